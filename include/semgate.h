@@ -1,0 +1,155 @@
+/* libsemgate — C ABI of the B200-native gated loop-closure retrieval path.
+ *
+ * The reference (wadewilliamsw1234/Multi-level-Indoor-SLAM) is pure Python and has
+ * no FFI of its own; its seam for this path is the method surface of
+ * scripts/semantic_gating/place_recognition.py and loop_closure_gate.py.  Each
+ * entry point below names the reference interface it replaces (file:line relative
+ * to scripts/semantic_gating/).  INTEGRATION.md shows the ctypes stub a maintainer
+ * of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no allocation of caller-visible memory inside;
+ *   - every function returns 0 on success, a negative SEMGATE_E* code or a positive
+ *     cudaError_t otherwise; semgate_last_error() gives a thread-local message;
+ *   - "device" pointers must live on the handle's GPU; *_host entry points take
+ *     host pointers (pinned or pageable) and do the copies themselves;
+ *   - sm_100a only: semgate_create fails on any other compute capability.  There
+ *     is no CPU or other-architecture fallback.
+ *   - floor labels are int32; SEMGATE_FLOOR_NONE encodes Python's floor_label=None
+ *     (place_recognition.py:78,898), which passes every gate.
+ */
+#ifndef SEMGATE_H_
+#define SEMGATE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEMGATE_VERSION 100
+#define SEMGATE_MAX_K 64
+#define SEMGATE_FLOOR_NONE INT32_MIN
+
+#define SEMGATE_EINVAL (-1)       /* bad argument */
+#define SEMGATE_EARCH (-2)        /* device is not compute capability 10.x */
+#define SEMGATE_ENOMEM (-3)       /* workspace / capacity too small */
+#define SEMGATE_EDRIVER (-4)      /* cuTensorMapEncodeTiled unavailable or failed */
+#define SEMGATE_EINDEX (-5)       /* candidate index outside the floor-label array */
+
+#define SEMGATE_GATE_FLAG 0       /* reference order: top-k, then flag cross-floor (place_recognition.py:888-899) */
+#define SEMGATE_GATE_MASK 1       /* exclude cross-floor columns before top-k */
+
+typedef struct semgate_ctx* semgate_handle_t;
+typedef void* semgate_stream_t;   /* cudaStream_t */
+
+/* Parameters of one gated top-k sweep.
+ * Mirrors the knobs of SemanticPlaceRecognition(similarity_threshold, min_time_gap)
+ * (place_recognition.py:814-818), find_loop_closures(enable_floor_gating, k) (:851-853),
+ * query(k, min_time_gap) (:117-121) and SemanticLoopClosureGate(strict_mode)
+ * (loop_closure_gate.py:42-44). */
+typedef struct semgate_topk_params {
+  float similarity_threshold;   /* keep s >= threshold, compared in fp32; -INFINITY disables (query()) */
+  double min_time_gap;          /* exclude |t_db - t_q| < gap (strict, fp64) */
+  int32_t k;                    /* 1..SEMGATE_MAX_K */
+  int32_t max_floor_diff;       /* -1 gating off; 0 strict; 1 non-strict */
+  int32_t gate_mode;            /* SEMGATE_GATE_FLAG | SEMGATE_GATE_MASK */
+  uint32_t db_index_offset;     /* global index of database row 0 (row-sharded multi-GPU) */
+  int32_t cta_group;            /* 0 = handle default; 1 = single-CTA tiles; 2 = CTA-pair tiles */
+} semgate_topk_params;
+
+int semgate_version(void);
+const char* semgate_last_error(void);
+
+/* ---- lifetime ---------------------------------------------------------- */
+int semgate_create(semgate_handle_t* out, int device);
+int semgate_destroy(semgate_handle_t h);
+int semgate_device_info(semgate_handle_t h, int* sm_count, int* cc_major, int* cc_minor);
+/* options: "cta_group" (1|2); "profile" (0|1): bracket every fused-kernel launch with CUDA
+ * events on its own stream */
+int semgate_set_option(semgate_handle_t h, const char* name, int64_t value);
+/* sum of the fused kernel's (K2) device durations since the last read, and how many
+ * launches that covers; synchronises on the recorded events and resets them. */
+int semgate_profile_read(semgate_handle_t h, double* total_ms, int64_t* n_launches);
+/* kernels launched through this handle since creation (bench.py's gpu_launches) */
+int64_t semgate_launch_count(semgate_handle_t h);
+
+/* descriptor length padded to the kernel's K granule (64) */
+int semgate_pad_dim(int d);
+
+/* ---- K1: row normalisation + bf16 cast ----------------------------------
+ * replaces `desc_matrix / (norms + 1e-8)` (place_recognition.py:186-187) and the
+ * per-query re-normalisation in _compute_similarity (:169-170).
+ * x: device fp32 [n, d], row stride ld elements.  out: device bf16 [n, d_pad]. */
+int semgate_normalize_cast(semgate_handle_t h, const float* x, int64_t n, int32_t d, int64_t ld, void* out_bf16,
+                           int32_t d_pad, semgate_stream_t stream);
+
+/* ---- K2+K3: fused similarity / exclusion window / gate / threshold / top-k ----
+ * replaces compute_all_pairwise_similarities + the per-row loop of
+ * find_loop_closures (place_recognition.py:868-899) and, with one query row,
+ * _compute_similarity + the mask + argsort of query() (:140-154).
+ *   q_bf16 [Q,d_pad], db_bf16 [N,d_pad]    normalised bf16 rows (K1 output)
+ *   q_ts/db_ts   fp64 or both NULL (no temporal mask, query(timestamp=None))
+ *   q_floor/db_floor  int32 or NULL (no gating)
+ *   workspace    >= semgate_topk_workspace_bytes(...)
+ * outputs, each [Q,k], any may be NULL:
+ *   out_keys    packed candidates (for semgate_merge_topk across GPUs)
+ *   out_scores  fp32 descending, -inf padded;  out_idx int32 global index, -1 padded
+ *   out_valid   uint8 floor flag;  out_count int32 [Q] */
+size_t semgate_topk_workspace_bytes(semgate_handle_t h, int64_t Q, int64_t N, int32_t d_pad, const semgate_topk_params* p);
+int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const void* db_bf16, int64_t N, int32_t d_pad,
+                       const double* q_ts, const double* db_ts, const int32_t* q_floor, const int32_t* db_floor,
+                       const semgate_topk_params* p, void* workspace, size_t workspace_bytes, uint64_t* out_keys,
+                       float* out_scores, int32_t* out_idx, uint8_t* out_valid, int32_t* out_count,
+                       semgate_stream_t stream);
+
+/* ---- K3 alone: merge G candidate lists per query (after an all-gather of out_keys) ----
+ * keys_in [G,Q,k] device; db_floor_all: floor labels of the WHOLE database (index = global). */
+int semgate_merge_topk(semgate_handle_t h, const uint64_t* keys_in, int32_t G, int64_t Q, int32_t k,
+                       const int32_t* q_floor, const int32_t* db_floor_all, int32_t max_floor_diff, uint64_t* out_keys,
+                       float* out_scores, int32_t* out_idx, uint8_t* out_valid, int32_t* out_count,
+                       semgate_stream_t stream);
+
+/* ---- K4: candidate compaction ----------------------------------------------
+ * replaces the PlaceMatch append loop (place_recognition.py:890-909): flat arrays
+ * ordered (query ascending, score descending).  Outputs need capacity Q*k.
+ * out_total: device int64.  workspace >= semgate_compact_workspace_bytes(Q). */
+size_t semgate_compact_workspace_bytes(int64_t Q);
+int semgate_compact(semgate_handle_t h, const float* scores, const int32_t* idx, const uint8_t* valid, const int32_t* count,
+                    int64_t Q, int32_t k, int32_t* out_query_idx, int32_t* out_match_idx, float* out_similarity,
+                    uint8_t* out_is_valid, int64_t* out_total, void* workspace, semgate_stream_t stream);
+
+/* ---- floor gate over explicit candidate pairs --------------------------------
+ * replaces SemanticLoopClosureGate.gate_candidates (loop_closure_gate.py:105-126).
+ * max_floor_diff: 0 = strict_mode True, 1 = strict_mode False.
+ * out_counts: device uint64[3] = accepted, rejected_cross_floor, out-of-range indices. */
+int semgate_gate_candidates(semgate_handle_t h, const int32_t* floor_labels, int64_t n_labels, const int32_t* query_idx,
+                            const int32_t* match_idx, int64_t M, int32_t max_floor_diff, uint8_t* out_is_valid,
+                            uint64_t* out_counts, semgate_stream_t stream);
+
+/* ---- host-buffer entry points (the reference-facing calls) ----------------------
+ * find_loop_closures over a whole database held in host memory
+ * (SemanticPlaceRecognition.find_loop_closures, place_recognition.py:851-911):
+ * H2D, K1, K2, K3, K4, D2H inside.  Output arrays need capacity >= min(n*k, capacity).
+ * Returns SEMGATE_ENOMEM (and the required size in *out_total) if capacity is short. */
+int semgate_find_loop_closures_host(semgate_handle_t h, const float* descriptors, int64_t n, int32_t d,
+                                    const double* timestamps, const int32_t* floor_labels,
+                                    const semgate_topk_params* p, int32_t* out_query_idx, int32_t* out_match_idx,
+                                    float* out_similarity, uint8_t* out_is_valid, int64_t capacity, int64_t* out_total);
+
+/* batched query() against a database in host memory (place_recognition.py:117-163):
+ * padded outputs [nq,k] + count[nq]. */
+int semgate_query_host(semgate_handle_t h, const float* queries, int64_t nq, const float* database, int64_t n, int32_t d,
+                       const double* q_ts, const double* db_ts, const semgate_topk_params* p, float* out_scores,
+                       int32_t* out_idx, int32_t* out_count);
+
+/* gate_candidates over host arrays; out_counts: host uint64[3]. */
+int semgate_gate_candidates_host(semgate_handle_t h, const int32_t* floor_labels, int64_t n_labels,
+                                 const int32_t* query_idx, const int32_t* match_idx, int64_t M, int32_t max_floor_diff,
+                                 uint8_t* out_is_valid, uint64_t* out_counts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEMGATE_H_ */

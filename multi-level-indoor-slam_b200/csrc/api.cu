@@ -1,0 +1,475 @@
+// C ABI of libsemgate (see include/semgate.h).
+#include "../../include/semgate.h"
+#include "launch.h"
+
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace semgate;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(static_cast<int>(e), "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define CUDA_TRY(expr)                                        \
+  do {                                                        \
+    cudaError_t _e = (expr);                                  \
+    if (_e != cudaSuccess) return cuda_fail(_e, #expr);       \
+  } while (0)
+
+#define RC_TRY(expr, what)                                                                  \
+  do {                                                                                      \
+    int _rc = (expr);                                                                       \
+    if (_rc > 0) return cuda_fail(static_cast<cudaError_t>(_rc), what);                     \
+    if (_rc < 0) return fail(SEMGATE_EDRIVER, "%s failed (driver rc %d)", what, _rc);       \
+  } while (0)
+
+constexpr int kNumBufs = 16;
+enum BufId { B_X = 0, B_BF16, B_TS, B_FL, B_WS, B_SC, B_IX, B_VA, B_CT, B_OQ, B_OM, B_OS, B_OV, B_TOT, B_CWS, B_QBF16 };
+
+inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+}  // namespace
+
+struct semgate_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  int cta_group = 1;
+  int64_t launches = 0;
+  cudaStream_t stream = nullptr;   // used by the *_host entry points
+  bool profile = false;            // record CUDA events around every K2 launch
+  std::vector<cudaEvent_t> prof_events;   // pairs (begin, end), on the launching stream
+  size_t prof_used = 0;
+  void* buf[kNumBufs] = {};
+  size_t cap[kNumBufs] = {};
+
+  int reserve(int id, size_t bytes, void** out) {
+    if (bytes == 0) bytes = 256;
+    if (cap[id] < bytes) {
+      if (buf[id]) cudaFree(buf[id]);
+      buf[id] = nullptr;
+      cap[id] = 0;
+      size_t want = align256(bytes + bytes / 8);
+      cudaError_t e = cudaMalloc(&buf[id], want);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc (scratch)");
+      cap[id] = want;
+    }
+    *out = buf[id];
+    return 0;
+  }
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int check_params(const semgate_topk_params* p) {
+  if (!p) return fail(SEMGATE_EINVAL, "params is NULL");
+  if (p->k < 1 || p->k > SEMGATE_MAX_K) return fail(SEMGATE_EINVAL, "k=%d outside 1..%d", p->k, SEMGATE_MAX_K);
+  if (p->max_floor_diff < -1) return fail(SEMGATE_EINVAL, "max_floor_diff=%d", p->max_floor_diff);
+  if (p->gate_mode != SEMGATE_GATE_FLAG && p->gate_mode != SEMGATE_GATE_MASK) return fail(SEMGATE_EINVAL, "gate_mode=%d", p->gate_mode);
+  if (p->cta_group != 0 && p->cta_group != 1 && p->cta_group != 2) return fail(SEMGATE_EINVAL, "cta_group=%d", p->cta_group);
+  if (std::isnan(p->similarity_threshold)) return fail(SEMGATE_EINVAL, "similarity_threshold is NaN");
+  return 0;
+}
+
+int resolve_cg(semgate_handle_t h, const semgate_topk_params* p) { return p->cta_group ? p->cta_group : h->cta_group; }
+
+}  // namespace
+
+extern "C" {
+
+int semgate_version(void) { return SEMGATE_VERSION; }
+const char* semgate_last_error(void) { return g_err; }
+int semgate_pad_dim(int d) { return d <= 0 ? 0 : ((d + 63) / 64) * 64; }
+
+int semgate_create(semgate_handle_t* out, int device) {
+  if (!out) return fail(SEMGATE_EINVAL, "out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(SEMGATE_EINVAL, "device %d out of range (%d visible)", device, ndev);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(SEMGATE_EARCH, "device %d (%s) is compute capability %d.%d; libsemgate is built for sm_100a only and has no fallback",
+                device, prop.name, prop.major, prop.minor);
+  semgate_ctx* h = new (std::nothrow) semgate_ctx();
+  if (!h) return fail(SEMGATE_ENOMEM, "out of host memory");
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->cc_major = prop.major;
+  h->cc_minor = prop.minor;
+  const char* env = getenv("SEMGATE_CTA_GROUP");
+  if (env && (env[0] == '1' || env[0] == '2')) h->cta_group = env[0] - '0';
+  DeviceGuard g(device);
+  cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate"); }
+  *out = h;
+  return 0;
+}
+
+int semgate_destroy(semgate_handle_t h) {
+  if (!h) return 0;
+  DeviceGuard g(h->device);
+  if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  for (int i = 0; i < kNumBufs; ++i) if (h->buf[i]) cudaFree(h->buf[i]);
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+  delete h;
+  return 0;
+}
+
+int semgate_device_info(semgate_handle_t h, int* sm_count, int* cc_major, int* cc_minor) {
+  if (!h) return fail(SEMGATE_EINVAL, "handle is NULL");
+  if (sm_count) *sm_count = h->sm_count;
+  if (cc_major) *cc_major = h->cc_major;
+  if (cc_minor) *cc_minor = h->cc_minor;
+  return 0;
+}
+
+int semgate_set_option(semgate_handle_t h, const char* name, int64_t value) {
+  if (!h || !name) return fail(SEMGATE_EINVAL, "NULL argument");
+  if (strcmp(name, "cta_group") == 0) {
+    if (value != 1 && value != 2) return fail(SEMGATE_EINVAL, "cta_group must be 1 or 2");
+    h->cta_group = static_cast<int>(value);
+    return 0;
+  }
+  if (strcmp(name, "profile") == 0) {
+    h->profile = value != 0;
+    return 0;
+  }
+  return fail(SEMGATE_EINVAL, "unknown option '%s'", name);
+}
+
+int64_t semgate_launch_count(semgate_handle_t h) { return h ? h->launches : 0; }
+
+int semgate_profile_read(semgate_handle_t h, double* total_ms, int64_t* n_launches) {
+  if (!h || !total_ms || !n_launches) return fail(SEMGATE_EINVAL, "NULL argument");
+  DeviceGuard g(h->device);
+  double sum = 0.0;
+  for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+    CUDA_TRY(cudaEventSynchronize(h->prof_events[i + 1]));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->prof_events[i], h->prof_events[i + 1]));
+    sum += ms;
+  }
+  *total_ms = sum;
+  *n_launches = static_cast<int64_t>(h->prof_used / 2);
+  h->prof_used = 0;
+  return 0;
+}
+
+// ---------------------------------------------------------------- K1
+int semgate_normalize_cast(semgate_handle_t h, const float* x, int64_t n, int32_t d, int64_t ld, void* out_bf16, int32_t d_pad,
+                           semgate_stream_t stream) {
+  if (!h) return fail(SEMGATE_EINVAL, "handle is NULL");
+  if (n < 0 || d <= 0 || ld < d || d_pad < d || d_pad % 64 != 0) return fail(SEMGATE_EINVAL, "normalize_cast: bad shape n=%lld d=%d ld=%lld d_pad=%d", (long long)n, d, (long long)ld, d_pad);
+  if (n == 0) return 0;
+  if (!x || !out_bf16) return fail(SEMGATE_EINVAL, "normalize_cast: NULL pointer");
+  DeviceGuard g(h->device);
+  RC_TRY(launch_normalize_cast(x, n, d, ld, out_bf16, d_pad, static_cast<cudaStream_t>(stream)), "normalize_cast launch");
+  h->launches += 1;
+  return 0;
+}
+
+// ---------------------------------------------------------------- K2 + K3
+size_t semgate_topk_workspace_bytes(semgate_handle_t h, int64_t Q, int64_t N, int32_t d_pad, const semgate_topk_params* p) {
+  if (!h || !p || Q <= 0 || N <= 0 || p->k < 1 || p->k > SEMGATE_MAX_K) return 256;
+  const int cg = resolve_cg(h, p);
+  Schedule sc = make_schedule(Q, N, d_pad, cg, h->sm_count);
+  return align256(topk_partial_bytes(sc, cg, p->k));
+}
+
+int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const void* db_bf16, int64_t N, int32_t d_pad,
+                       const double* q_ts, const double* db_ts, const int32_t* q_floor, const int32_t* db_floor,
+                       const semgate_topk_params* p, void* workspace, size_t workspace_bytes, uint64_t* out_keys,
+                       float* out_scores, int32_t* out_idx, uint8_t* out_valid, int32_t* out_count,
+                       semgate_stream_t stream) {
+  if (!h) return fail(SEMGATE_EINVAL, "handle is NULL");
+  int rc = check_params(p);
+  if (rc) return rc;
+  if (Q < 0 || N < 0 || Q > INT32_MAX || N > INT32_MAX) return fail(SEMGATE_EINVAL, "gated_topk: bad sizes Q=%lld N=%lld", (long long)Q, (long long)N);
+  if (d_pad <= 0 || d_pad % 64 != 0) return fail(SEMGATE_EINVAL, "gated_topk: d_pad=%d must be a positive multiple of 64", d_pad);
+  if ((q_ts == nullptr) != (db_ts == nullptr)) return fail(SEMGATE_EINVAL, "gated_topk: q_ts and db_ts must both be given or both be NULL");
+  if (static_cast<uint64_t>(p->db_index_offset) + static_cast<uint64_t>(N) > 0xFFFFFFFFull) return fail(SEMGATE_EINVAL, "gated_topk: global index overflows 32 bits");
+  if (Q == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DeviceGuard g(h->device);
+  const int cg = resolve_cg(h, p);
+  const int k = p->k;
+
+  MergeLaunch m{};
+  m.Q = Q; m.k = k;
+  m.keys_out = out_keys; m.scores = out_scores; m.idx = out_idx; m.valid = out_valid; m.count = out_count;
+  m.q_floor = q_floor; m.db_floor = db_floor; m.floor_index_offset = p->db_index_offset;
+  m.max_floor_diff = (q_floor && db_floor) ? p->max_floor_diff : -1;
+
+  if (N == 0) {   // empty database: every list is empty (place_recognition.py:134)
+    m.keys_in = nullptr; m.n_lists = 0; m.row_stride = 0; m.list_stride = 0;
+    RC_TRY(launch_merge_topk(m, st), "merge_topk launch");
+    h->launches += 1;
+    return 0;
+  }
+  if (!q_bf16 || !db_bf16) return fail(SEMGATE_EINVAL, "gated_topk: NULL descriptor pointer");
+  if ((reinterpret_cast<uintptr_t>(q_bf16) & 15) || (reinterpret_cast<uintptr_t>(db_bf16) & 15))
+    return fail(SEMGATE_EINVAL, "gated_topk: descriptor matrices must be 16-byte aligned");
+
+  Schedule sc = make_schedule(Q, N, d_pad, cg, h->sm_count);
+  const size_t need = topk_partial_bytes(sc, cg, k);
+  if (!workspace || workspace_bytes < need)
+    return fail(SEMGATE_ENOMEM, "gated_topk: workspace %zu < required %zu bytes", workspace_bytes, need);
+
+  TopkLaunch a{};
+  a.q_bf16 = q_bf16; a.Q = Q; a.db_bf16 = db_bf16; a.N = N; a.d_pad = d_pad;
+  a.q_ts = q_ts; a.db_ts = db_ts;
+  a.q_floor = q_floor; a.db_floor = db_floor;
+  a.threshold = p->similarity_threshold; a.gap = p->min_time_gap; a.k = k;
+  a.max_floor_diff = m.max_floor_diff; a.gate_mode = p->gate_mode;
+  a.db_index_offset = p->db_index_offset;
+  a.cta_group = cg; a.sm_count = h->sm_count;
+  int launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (h->profile) {
+    if (h->prof_used + 2 > h->prof_events.size()) {
+      cudaEvent_t e0, e1;
+      CUDA_TRY(cudaEventCreate(&e0));
+      CUDA_TRY(cudaEventCreate(&e1));
+      h->prof_events.push_back(e0);
+      h->prof_events.push_back(e1);
+    }
+    ev0 = h->prof_events[h->prof_used];
+    ev1 = h->prof_events[h->prof_used + 1];
+    h->prof_used += 2;
+    CUDA_TRY(cudaEventRecord(ev0, st));
+  }
+  RC_TRY(launch_gated_topk(a, sc, static_cast<uint64_t*>(workspace), st, &launches), "gated_topk launch");
+  if (ev1) CUDA_TRY(cudaEventRecord(ev1, st));
+  h->launches += launches;
+
+  m.keys_in = static_cast<const uint64_t*>(workspace);
+  m.row_stride = static_cast<int64_t>(sc.s_max) * k;
+  m.list_stride = k;
+  m.n_lists = -1; m.sc = sc; m.rows_per_mblock = 128 * cg;
+  RC_TRY(launch_merge_topk(m, st), "merge_topk launch");
+  h->launches += 1;
+  return 0;
+}
+
+int semgate_merge_topk(semgate_handle_t h, const uint64_t* keys_in, int32_t G, int64_t Q, int32_t k, const int32_t* q_floor,
+                       const int32_t* db_floor_all, int32_t max_floor_diff, uint64_t* out_keys, float* out_scores,
+                       int32_t* out_idx, uint8_t* out_valid, int32_t* out_count, semgate_stream_t stream) {
+  if (!h) return fail(SEMGATE_EINVAL, "handle is NULL");
+  if (G < 0 || Q < 0 || k < 1 || k > SEMGATE_MAX_K) return fail(SEMGATE_EINVAL, "merge_topk: bad sizes G=%d Q=%lld k=%d", G, (long long)Q, k);
+  if (Q == 0) return 0;
+  if (G > 0 && !keys_in) return fail(SEMGATE_EINVAL, "merge_topk: keys_in is NULL");
+  DeviceGuard g(h->device);
+  MergeLaunch m{};
+  m.keys_in = keys_in; m.Q = Q; m.k = k;
+  m.row_stride = k; m.list_stride = Q * k; m.n_lists = G;
+  m.keys_out = out_keys; m.scores = out_scores; m.idx = out_idx; m.valid = out_valid; m.count = out_count;
+  m.q_floor = q_floor; m.db_floor = db_floor_all; m.floor_index_offset = 0;
+  m.max_floor_diff = (q_floor && db_floor_all) ? max_floor_diff : -1;
+  RC_TRY(launch_merge_topk(m, static_cast<cudaStream_t>(stream)), "merge_topk launch");
+  h->launches += 1;
+  return 0;
+}
+
+// ---------------------------------------------------------------- K4
+size_t semgate_compact_workspace_bytes(int64_t Q) { return align256(compact_workspace_bytes(Q < 0 ? 0 : Q)); }
+
+int semgate_compact(semgate_handle_t h, const float* scores, const int32_t* idx, const uint8_t* valid, const int32_t* count,
+                    int64_t Q, int32_t k, int32_t* out_query_idx, int32_t* out_match_idx, float* out_similarity,
+                    uint8_t* out_is_valid, int64_t* out_total, void* workspace, semgate_stream_t stream) {
+  if (!h) return fail(SEMGATE_EINVAL, "handle is NULL");
+  if (Q < 0 || k < 1 || !out_total) return fail(SEMGATE_EINVAL, "compact: bad arguments");
+  if (Q > 0 && (!scores || !idx || !valid || !count || !out_query_idx || !out_match_idx || !out_similarity || !out_is_valid || !workspace))
+    return fail(SEMGATE_EINVAL, "compact: NULL pointer");
+  DeviceGuard g(h->device);
+  RC_TRY(launch_compact(scores, idx, valid, count, Q, k, out_query_idx, out_match_idx, out_similarity, out_is_valid, out_total,
+                        workspace, static_cast<cudaStream_t>(stream)), "compact launch");
+  h->launches += Q > 0 ? 3 : 0;
+  return 0;
+}
+
+// ---------------------------------------------------------------- gate over pairs
+int semgate_gate_candidates(semgate_handle_t h, const int32_t* floor_labels, int64_t n_labels, const int32_t* query_idx,
+                            const int32_t* match_idx, int64_t M, int32_t max_floor_diff, uint8_t* out_is_valid,
+                            uint64_t* out_counts, semgate_stream_t stream) {
+  if (!h) return fail(SEMGATE_EINVAL, "handle is NULL");
+  if (M < 0 || n_labels < 0 || max_floor_diff < 0 || !out_counts) return fail(SEMGATE_EINVAL, "gate_candidates: bad arguments");
+  if (M > 0 && (!floor_labels || !query_idx || !match_idx || !out_is_valid)) return fail(SEMGATE_EINVAL, "gate_candidates: NULL pointer");
+  DeviceGuard g(h->device);
+  RC_TRY(launch_gate_candidates(floor_labels, n_labels, query_idx, match_idx, M, max_floor_diff, out_is_valid,
+                                reinterpret_cast<unsigned long long*>(out_counts), static_cast<cudaStream_t>(stream)),
+         "gate_candidates launch");
+  h->launches += M > 0 ? 1 : 0;
+  return 0;
+}
+
+// ---------------------------------------------------------------- host-buffer entry points
+int semgate_find_loop_closures_host(semgate_handle_t h, const float* descriptors, int64_t n, int32_t d,
+                                    const double* timestamps, const int32_t* floor_labels, const semgate_topk_params* p,
+                                    int32_t* out_query_idx, int32_t* out_match_idx, float* out_similarity,
+                                    uint8_t* out_is_valid, int64_t capacity, int64_t* out_total) {
+  if (!h) return fail(SEMGATE_EINVAL, "handle is NULL");
+  int rc = check_params(p);
+  if (rc) return rc;
+  if (!out_total) return fail(SEMGATE_EINVAL, "out_total is NULL");
+  *out_total = 0;
+  if (n < 2) return 0;                                   // place_recognition.py:864
+  if (d <= 0 || !descriptors) return fail(SEMGATE_EINVAL, "find_loop_closures: bad descriptors");
+  DeviceGuard g(h->device);
+  cudaStream_t st = h->stream;
+  const int k = p->k;
+  const int d_pad = semgate_pad_dim(d);
+  void *dx, *dbf, *dts = nullptr, *dfl = nullptr, *ws, *sc, *ix, *va, *ct, *oq, *om, *os, *ov, *tot, *cws;
+  if ((rc = h->reserve(B_X, sizeof(float) * n * d, &dx))) return rc;
+  if ((rc = h->reserve(B_BF16, 2ull * n * d_pad, &dbf))) return rc;
+  if (timestamps && (rc = h->reserve(B_TS, 8ull * n, &dts))) return rc;
+  if (floor_labels && (rc = h->reserve(B_FL, 4ull * n, &dfl))) return rc;
+  const size_t wsb = semgate_topk_workspace_bytes(h, n, n, d_pad, p);
+  if ((rc = h->reserve(B_WS, wsb, &ws))) return rc;
+  const size_t nk = static_cast<size_t>(n) * k;
+  if ((rc = h->reserve(B_SC, 4 * nk, &sc)) || (rc = h->reserve(B_IX, 4 * nk, &ix)) || (rc = h->reserve(B_VA, nk, &va)) ||
+      (rc = h->reserve(B_CT, 4ull * n, &ct)) || (rc = h->reserve(B_OQ, 4 * nk, &oq)) || (rc = h->reserve(B_OM, 4 * nk, &om)) ||
+      (rc = h->reserve(B_OS, 4 * nk, &os)) || (rc = h->reserve(B_OV, nk, &ov)) || (rc = h->reserve(B_TOT, 8, &tot)) ||
+      (rc = h->reserve(B_CWS, semgate_compact_workspace_bytes(n), &cws)))
+    return rc;
+
+  // H2D in row chunks so that normalisation of chunk i overlaps the copy of chunk i+1
+  const int64_t chunk = std::max<int64_t>(1, (32ll << 20) / (static_cast<int64_t>(d) * 4));
+  for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+    const int64_t rows = std::min(chunk, n - r0);
+    CUDA_TRY(cudaMemcpyAsync(static_cast<float*>(dx) + r0 * d, descriptors + r0 * d, sizeof(float) * rows * d, cudaMemcpyHostToDevice, st));
+    if ((rc = semgate_normalize_cast(h, static_cast<float*>(dx) + r0 * d, rows, d, d, static_cast<char*>(dbf) + 2ull * r0 * d_pad, d_pad, st))) return rc;
+  }
+  if (dts) CUDA_TRY(cudaMemcpyAsync(dts, timestamps, 8ull * n, cudaMemcpyHostToDevice, st));
+  if (dfl) CUDA_TRY(cudaMemcpyAsync(dfl, floor_labels, 4ull * n, cudaMemcpyHostToDevice, st));
+  rc = semgate_gated_topk(h, dbf, n, dbf, n, d_pad, static_cast<double*>(dts), static_cast<double*>(dts),
+                          static_cast<int32_t*>(dfl), static_cast<int32_t*>(dfl), p, ws, h->cap[B_WS], nullptr,
+                          static_cast<float*>(sc), static_cast<int32_t*>(ix), static_cast<uint8_t*>(va),
+                          static_cast<int32_t*>(ct), st);
+  if (rc) return rc;
+  rc = semgate_compact(h, static_cast<float*>(sc), static_cast<int32_t*>(ix), static_cast<uint8_t*>(va), static_cast<int32_t*>(ct),
+                       n, k, static_cast<int32_t*>(oq), static_cast<int32_t*>(om), static_cast<float*>(os),
+                       static_cast<uint8_t*>(ov), static_cast<int64_t*>(tot), cws, st);
+  if (rc) return rc;
+  int64_t total = 0;
+  CUDA_TRY(cudaMemcpyAsync(&total, tot, 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  *out_total = total;
+  if (total > capacity) return fail(SEMGATE_ENOMEM, "find_loop_closures: %lld candidates exceed output capacity %lld", (long long)total, (long long)capacity);
+  if (total > 0) {
+    if (!out_query_idx || !out_match_idx || !out_similarity || !out_is_valid) return fail(SEMGATE_EINVAL, "find_loop_closures: NULL output");
+    CUDA_TRY(cudaMemcpyAsync(out_query_idx, oq, 4ull * total, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_match_idx, om, 4ull * total, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_similarity, os, 4ull * total, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_is_valid, ov, 1ull * total, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+int semgate_query_host(semgate_handle_t h, const float* queries, int64_t nq, const float* database, int64_t n, int32_t d,
+                       const double* q_ts, const double* db_ts, const semgate_topk_params* p, float* out_scores,
+                       int32_t* out_idx, int32_t* out_count) {
+  if (!h) return fail(SEMGATE_EINVAL, "handle is NULL");
+  int rc = check_params(p);
+  if (rc) return rc;
+  if (nq < 0 || n < 0 || d <= 0) return fail(SEMGATE_EINVAL, "query: bad sizes");
+  if (nq == 0) return 0;
+  if (!queries || !out_scores || !out_idx || !out_count) return fail(SEMGATE_EINVAL, "query: NULL pointer");
+  const int k = p->k;
+  if (n == 0) {                                          // place_recognition.py:134
+    for (int64_t i = 0; i < nq * k; ++i) { out_scores[i] = -INFINITY; out_idx[i] = -1; }
+    for (int64_t i = 0; i < nq; ++i) out_count[i] = 0;
+    return 0;
+  }
+  if (!database) return fail(SEMGATE_EINVAL, "query: NULL database");
+  DeviceGuard g(h->device);
+  cudaStream_t st = h->stream;
+  const int d_pad = semgate_pad_dim(d);
+  void *dx, *dbf, *qbf, *dts = nullptr, *ws, *sc, *ix, *ct;
+  if ((rc = h->reserve(B_X, sizeof(float) * std::max(n, nq) * d, &dx))) return rc;
+  if ((rc = h->reserve(B_BF16, 2ull * n * d_pad, &dbf))) return rc;
+  if ((rc = h->reserve(B_QBF16, 2ull * nq * d_pad, &qbf))) return rc;
+  const bool use_time = q_ts && db_ts;
+  if (use_time && (rc = h->reserve(B_TS, 8ull * (n + nq), &dts))) return rc;
+  const size_t wsb = semgate_topk_workspace_bytes(h, nq, n, d_pad, p);
+  const size_t nk = static_cast<size_t>(nq) * k;
+  if ((rc = h->reserve(B_WS, wsb, &ws)) || (rc = h->reserve(B_SC, 4 * nk, &sc)) || (rc = h->reserve(B_IX, 4 * nk, &ix)) ||
+      (rc = h->reserve(B_CT, 4ull * nq, &ct)))
+    return rc;
+  CUDA_TRY(cudaMemcpyAsync(dx, database, sizeof(float) * n * d, cudaMemcpyHostToDevice, st));
+  if ((rc = semgate_normalize_cast(h, static_cast<float*>(dx), n, d, d, dbf, d_pad, st))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(dx, queries, sizeof(float) * nq * d, cudaMemcpyHostToDevice, st));
+  if ((rc = semgate_normalize_cast(h, static_cast<float*>(dx), nq, d, d, qbf, d_pad, st))) return rc;
+  double* d_dbts = nullptr; double* d_qts = nullptr;
+  if (use_time) {
+    d_dbts = static_cast<double*>(dts); d_qts = d_dbts + n;
+    CUDA_TRY(cudaMemcpyAsync(d_dbts, db_ts, 8ull * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_qts, q_ts, 8ull * nq, cudaMemcpyHostToDevice, st));
+  }
+  semgate_topk_params pp = *p;
+  pp.max_floor_diff = -1;
+  rc = semgate_gated_topk(h, qbf, nq, dbf, n, d_pad, d_qts, d_dbts, nullptr, nullptr, &pp, ws, h->cap[B_WS], nullptr,
+                          static_cast<float*>(sc), static_cast<int32_t*>(ix), nullptr, static_cast<int32_t*>(ct), st);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(out_scores, sc, 4 * nk, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(out_idx, ix, 4 * nk, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(out_count, ct, 4ull * nq, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int semgate_gate_candidates_host(semgate_handle_t h, const int32_t* floor_labels, int64_t n_labels, const int32_t* query_idx,
+                                 const int32_t* match_idx, int64_t M, int32_t max_floor_diff, uint8_t* out_is_valid,
+                                 uint64_t* out_counts) {
+  if (!h) return fail(SEMGATE_EINVAL, "handle is NULL");
+  if (!out_counts || M < 0 || n_labels < 0 || max_floor_diff < 0) return fail(SEMGATE_EINVAL, "gate_candidates: bad arguments");
+  out_counts[0] = out_counts[1] = out_counts[2] = 0;
+  if (M == 0) return 0;
+  if (!floor_labels || !query_idx || !match_idx || !out_is_valid) return fail(SEMGATE_EINVAL, "gate_candidates: NULL pointer");
+  DeviceGuard g(h->device);
+  cudaStream_t st = h->stream;
+  int rc;
+  void *dfl, *dq, *dm, *dv, *dc;
+  if ((rc = h->reserve(B_FL, 4ull * std::max<int64_t>(n_labels, 1), &dfl)) || (rc = h->reserve(B_OQ, 4ull * M, &dq)) ||
+      (rc = h->reserve(B_OM, 4ull * M, &dm)) || (rc = h->reserve(B_OV, 1ull * M, &dv)) || (rc = h->reserve(B_TOT, 32, &dc)))
+    return rc;
+  CUDA_TRY(cudaMemcpyAsync(dfl, floor_labels, 4ull * n_labels, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(dq, query_idx, 4ull * M, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(dm, match_idx, 4ull * M, cudaMemcpyHostToDevice, st));
+  rc = semgate_gate_candidates(h, static_cast<int32_t*>(dfl), n_labels, static_cast<int32_t*>(dq), static_cast<int32_t*>(dm), M,
+                               max_floor_diff, static_cast<uint8_t*>(dv), static_cast<uint64_t*>(dc), st);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(out_is_valid, dv, 1ull * M, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(out_counts, dc, 24, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (out_counts[2] != 0) return fail(SEMGATE_EINDEX, "gate_candidates: %llu candidate indices fall outside the %lld floor labels", (unsigned long long)out_counts[2], (long long)n_labels);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,321 @@
+// K2 — fused similarity GEMM + temporal-exclusion / floor gate / threshold /
+// running top-k, sm_100a.
+//
+// Replaces, for a whole batch of query keyframes at once, the reference's
+//   sim_matrix = X_n X_n^T                       (place_recognition.py:190)
+//   per row: mask |t_j - t_i| < gap              (place_recognition.py:882-885)
+//            argsort()[::-1][:k]                 (place_recognition.py:888)
+//            drop sim < threshold                (place_recognition.py:891)
+// and the single-query form  DB_n q_n + mask + top-k (place_recognition.py:140-154).
+// The Q x N similarity matrix never leaves the SM: each 128 x 256 fp32 tile is
+// accumulated in TMEM by tcgen05.mma from TMA-staged bf16 tiles, read back by the
+// epilogue warps with tcgen05.ld, filtered and folded into a per-row top-k list
+// held in shared memory.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA
+// issuer, warps 2-5 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31 = tile rows).
+// CG = 1: one CTA computes a 128 x 256 tile.  CG = 2: a CTA pair (cta_group::2)
+// computes 256 x 256; each CTA stages its own 128 query rows and half of the
+// database tile, and keeps the accumulator rows of its own queries.
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace semgate {
+
+constexpr int BM = 128;          // query rows per CTA (= TMEM lanes)
+constexpr int BN = 256;          // database rows per tile (= TMEM columns per accumulator)
+constexpr int BK = 64;           // bf16 per 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
+
+struct TopkParams {
+  int Q;                 // query rows
+  int N;                 // database rows visible to this launch (local shard)
+  int kblocks;           // padded descriptor length / BK
+  int k;                 // list length (<= kMaxK)
+  int kstride;           // smem list row stride in keys (odd -> conflict-free)
+  int stages;            // smem ring depth
+  float threshold;       // keep s >= threshold (compared in fp32, like numpy's weak-scalar rule)
+  int use_time;          // 0: no temporal mask (query(timestamp=None), place_recognition.py:144)
+  double gap;            // min_time_gap
+  int max_floor_diff;    // -1 off, 0 strict, 1 non-strict
+  int gate_mode;         // 0 flag (reference order), 1 mask (exclude cross-floor before top-k)
+  uint32_t db_index_offset;   // global index of local database row 0 (multi-GPU shards)
+  const double* q_ts;
+  const double* db_ts;
+  const int32_t* q_floor;
+  const int32_t* db_floor;
+  uint64_t* partial;     // [mblocks*BM*CG rows][s_max][k] candidate keys
+  Schedule sc;
+};
+
+struct RowList {
+  uint64_t* keys;     // this thread's row in shared memory
+  int cnt;
+  int min_pos;
+  uint64_t min_key;
+  float f;            // current admission bound on the score
+
+  __device__ __forceinline__ void reset(float thr) { cnt = 0; min_pos = 0; min_key = 0; f = thr; }
+
+  __device__ __forceinline__ void rescan(int k) {
+    uint64_t mk = keys[0];
+    int mp = 0;
+    for (int i = 1; i < k; ++i) {
+      uint64_t v = keys[i];
+      if (v < mk) { mk = v; mp = i; }
+    }
+    min_key = mk; min_pos = mp; f = key_score(mk);
+  }
+
+  __device__ __forceinline__ void insert(uint64_t key, int k) {
+    if (cnt < k) {
+      keys[cnt++] = key;
+      if (cnt == k) rescan(k);
+    } else if (key > min_key) {
+      keys[min_pos] = key;
+      rescan(k);
+    }
+  }
+};
+
+template <int CG>
+__global__ void __launch_bounds__(kThreads, 1)
+gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
+                  const TopkParams p) {
+  constexpr uint32_t B_ROWS = BN / CG;
+  constexpr uint32_t B_STAGE_BYTES = B_ROWS * BK * 2;
+  constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr uint32_t kTmemCols = 512;   // two 256-column fp32 accumulators
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem base is only guaranteed 16-byte aligned by the ABI; realign for SWIZZLE_128B
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int stages = p.stages;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + static_cast<size_t>(stages) * A_STAGE_BYTES;
+  uint64_t* lists = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * STAGE_BYTES);
+  uint64_t* bars = lists + static_cast<size_t>(BM) * p.kstride;
+  // barrier slots: full[kMaxStages] empty[kMaxStages] tmem_full[2] tmem_empty[2]
+  const uint32_t bar_full = ptx::smem_u32(bars);
+  const uint32_t bar_empty = bar_full + 8 * kMaxStages;
+  const uint32_t bar_tfull = bar_empty + 8 * kMaxStages;
+  const uint32_t bar_tempty = bar_tfull + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+  const int unit = blockIdx.x / CG;
+
+  if constexpr (CG == 2) ptx::cluster_sync();   // peer must be resident before a pair-wide TMEM allocation
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&tmap_q);
+    ptx::prefetch_tensormap(&tmap_db);
+    for (int s = 0; s < stages; ++s) {
+      ptx::mbar_init(bar_full + 8 * s, CG);      // CG=2: leader's expect_tx arrive + peer's remote arrive
+      ptx::mbar_init(bar_empty + 8 * s, 1);      // one tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(bar_tfull + 8 * a, 1);      // one tcgen05.commit
+      ptx::mbar_init(bar_tempty + 8 * a, 4 * CG); // one arrive per epilogue warp (of both CTAs)
+    }
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+  }
+  if (warp == 1) ptx::tmem_alloc<CG>(ptx::smem_u32(tmem_slot), kTmemCols);
+  ptx::tc_fence_before();
+  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  const Schedule sc = p.sc;
+  const int n_sr = sc.n_full + (sc.r_last > 0 ? 1 : 0);
+
+  // ring / accumulator state (each role advances its own copy identically)
+  uint32_t stage = 0, phase = 0, it = 0;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      for (int sr = 0; sr < n_sr; ++sr) {
+        const bool full_sr = sr < sc.n_full;
+        const int r = full_sr ? sc.rm : sc.r_last;
+        const int S = full_sr ? sc.s_main : sc.s_last;
+        if (unit >= r * S) continue;
+        const int mb = sr * sc.rm + unit % r;
+        const int j = unit / r;
+        const int nt0 = split_begin(sc.ntiles, S, j), nt1 = split_begin(sc.ntiles, S, j + 1);
+        const int m0 = (mb * CG + static_cast<int>(cta_rank)) * BM;
+        for (int nt = nt0; nt < nt1; ++nt) {
+          const int n0 = nt * BN + static_cast<int>(cta_rank) * static_cast<int>(B_ROWS);
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            const uint32_t dst_a = ptx::smem_u32(smem_a + stage * A_STAGE_BYTES);
+            const uint32_t dst_b = ptx::smem_u32(smem_b + stage * B_STAGE_BYTES);
+            const uint32_t fb = bar_full + 8 * stage;
+            if constexpr (CG == 1) {
+              ptx::mbar_arrive_expect_tx(fb, STAGE_BYTES);
+              ptx::tma_load_2d(dst_a, &tmap_q, fb, kb * BK, m0);
+              ptx::tma_load_2d(dst_b, &tmap_db, fb, kb * BK, n0);
+            } else {
+              // both CTAs' bytes are accounted on the leader's barrier (its MMA reads both smems)
+              const uint32_t fb_leader = ptx::mapa(fb, 0);
+              if (leader) ptx::mbar_arrive_expect_tx(fb, 2 * STAGE_BYTES);
+              ptx::tma_load_2d_cg2(dst_a, &tmap_q, fb_leader, kb * BK, m0);
+              ptx::tma_load_2d_cg2(dst_b, &tmap_db, fb_leader, kb * BK, n0);
+              if (!leader) ptx::mbar_arrive_cluster(fb, 0);
+            }
+            if (++stage == static_cast<uint32_t>(stages)) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();   // reconverge before the (aligned) teardown barrier
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (leader CTA only)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(BM * CG, BN);
+      for (int sr = 0; sr < n_sr; ++sr) {
+        const bool full_sr = sr < sc.n_full;
+        const int r = full_sr ? sc.rm : sc.r_last;
+        const int S = full_sr ? sc.s_main : sc.s_last;
+        if (unit >= r * S) continue;
+        const int j = unit / r;
+        const int nt0 = split_begin(sc.ntiles, S, j), nt1 = split_begin(sc.ntiles, S, j + 1);
+        for (int nt = nt0; nt < nt1; ++nt, ++it) {
+          const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+          ptx::mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            ptx::mbar_wait(bar_full + 8 * stage, phase);
+            ptx::tc_fence_after();
+            const uint64_t adesc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * A_STAGE_BYTES));
+            const uint64_t bdesc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * B_STAGE_BYTES));
+#pragma unroll
+            for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+              // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in the >>4 address field
+              ptx::umma_bf16<CG>(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb | kk) != 0);
+            }
+            if constexpr (CG == 1) {
+              ptx::umma_commit_cg1(bar_empty + 8 * stage);
+              if (kb == p.kblocks - 1) ptx::umma_commit_cg1(bar_tfull + 8 * acc);
+            } else {
+              ptx::umma_commit_cg2_mc(bar_empty + 8 * stage, 0b11);
+              if (kb == p.kblocks - 1) ptx::umma_commit_cg2_mc(bar_tfull + 8 * acc, 0b11);
+            }
+            if (++stage == static_cast<uint32_t>(stages)) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+      if constexpr (CG == 2) {
+        // the peer's epilogue arrives remotely on our barriers: drain before teardown
+        if (it > 0) {
+          const uint32_t last = it - 1;
+          ptx::mbar_wait(bar_tempty + 8 * (last & 1), (last >> 1) & 1);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================== epilogue: gate + threshold + running top-k
+    const int quad = warp & 3;
+    const int row_in_tile = quad * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    RowList L;
+    L.keys = lists + static_cast<size_t>(row_in_tile) * p.kstride;
+    const int k = p.k;
+    const bool mask_mode = p.gate_mode == 1 && p.max_floor_diff >= 0 && p.q_floor != nullptr && p.db_floor != nullptr;
+    const bool use_time = p.use_time != 0;
+    const float pos_inf = __int_as_float(0x7f800000);
+
+    for (int sr = 0; sr < n_sr; ++sr) {
+      const bool full_sr = sr < sc.n_full;
+      const int r = full_sr ? sc.rm : sc.r_last;
+      const int S = full_sr ? sc.s_main : sc.s_last;
+      if (unit >= r * S) continue;
+      const int mb = sr * sc.rm + unit % r;
+      const int j = unit / r;
+      const int nt0 = split_begin(sc.ntiles, S, j), nt1 = split_begin(sc.ntiles, S, j + 1);
+      const int grow = (mb * CG + static_cast<int>(cta_rank)) * BM + row_in_tile;   // global query row
+      const bool row_live = grow < p.Q;
+      double tq = 0.0;
+      int32_t qf = kFloorNone;
+      if (row_live) {
+        if (use_time) tq = p.q_ts[grow];
+        if (mask_mode) qf = p.q_floor[grow];
+      }
+      L.reset(row_live ? p.threshold : pos_inf);
+
+      for (int nt = nt0; nt < nt1; ++nt, ++it) {
+        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t t_acc = t_lane + acc * BN;
+        const int col_base = nt * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(t_acc + c * 32, v);
+          ptx::tmem_wait_ld();
+          float mx = __uint_as_float(v[0]);
+#pragma unroll
+          for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+          const bool hit = mx >= L.f;
+          if (__any_sync(0xffffffffu, hit)) {
+            uint32_t m = 0;
+            if (hit) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) m |= (__uint_as_float(v[i]) >= L.f ? 1u : 0u) << i;
+            }
+            uint32_t wm = __reduce_or_sync(0xffffffffu, m);
+            while (wm) {                       // warp-uniform: tcgen05.ld is a warp-collective
+              const int i = __ffs(wm) - 1;
+              wm &= wm - 1;
+              const uint32_t bits = ptx::tmem_ld_32x1(t_acc + c * 32 + i);
+              ptx::tmem_wait_ld();
+              const float s = __uint_as_float(bits);
+              if (((m >> i) & 1u) && s >= L.f) {
+                const int col = col_base + c * 32 + i;     // local database row
+                if (col < p.N) {                            // TMA zero-fill beyond N must not score
+                  bool ok = true;
+                  if (use_time) ok = !time_excluded(__ldg(p.db_ts + col), tq, p.gap);
+                  if (ok && mask_mode) ok = floor_ok(qf, __ldg(p.db_floor + col), p.max_floor_diff);
+                  if (ok) L.insert(pack_key(s, static_cast<uint32_t>(col) + p.db_index_offset), k);
+                }
+              }
+            }
+          }
+        }
+        // accumulator drained: hand it back to the MMA issuer
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 1) ptx::mbar_arrive(bar_tempty + 8 * acc);
+          else ptx::mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
+        }
+      }
+
+      // flush this run's partial list (unsorted; empty slots are key 0)
+      if (row_live) {
+        uint64_t* out = p.partial + (static_cast<size_t>(grow) * sc.s_max + j) * k;
+        for (int i = 0; i < k; ++i) out[i] = i < L.cnt ? L.keys[i] : 0ull;
+      }
+    }
+  }
+
+  // ----------------------------------------------------------------- teardown
+  ptx::tc_fence_before();
+  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  ptx::tc_fence_after();
+  if (warp == 1) ptx::tmem_dealloc<CG>(tmem_base, kTmemCols);
+}
+
+}  // namespace semgate

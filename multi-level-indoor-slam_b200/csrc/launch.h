@@ -1,0 +1,61 @@
+// Internal host-side launch interface between the translation units of libsemgate.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "common.cuh"
+
+namespace semgate {
+
+struct TopkLaunch {
+  const void* q_bf16; int64_t Q;
+  const void* db_bf16; int64_t N;
+  int d_pad;
+  const double* q_ts; const double* db_ts;      // both null -> no temporal mask
+  const int32_t* q_floor; const int32_t* db_floor;
+  float threshold; double gap; int k;
+  int max_floor_diff; int gate_mode;
+  uint32_t db_index_offset;
+  int cta_group;                                  // 1 or 2
+  int sm_count;
+};
+
+// Tile schedule for a Q x N problem on `units` CTAs (CG=1) or CTA pairs (CG=2).
+Schedule make_schedule(int64_t Q, int64_t N, int d_pad, int cta_group, int sm_count);
+size_t topk_partial_bytes(const Schedule& sc, int cta_group, int k);
+
+// K2: fills `partial` ([rows_padded][s_max][k] keys). Returns cudaError as int.
+int launch_gated_topk(const TopkLaunch& a, const Schedule& sc, uint64_t* partial, cudaStream_t st,
+                      int* launches);
+
+// K1
+int launch_normalize_cast(const float* x, int64_t n, int d, int64_t ld, void* out_bf16, int d_pad, cudaStream_t st);
+
+// K3: merge `n_lists` candidate lists per row into one sorted list.
+struct MergeLaunch {
+  const uint64_t* keys_in;
+  int64_t Q; int k;
+  int64_t row_stride, list_stride;   // in keys
+  int n_lists;                       // >=0: constant; <0: per m-block from `sc`
+  Schedule sc; int rows_per_mblock;
+  // outputs (any may be null)
+  uint64_t* keys_out;                // [Q,k] sorted descending, 0 padded
+  float* scores; int32_t* idx; uint8_t* valid; int32_t* count;
+  const int32_t* q_floor; const int32_t* db_floor; int64_t floor_index_offset;  // valid = gate(q_floor[row], db_floor[idx - off])
+  int max_floor_diff;
+};
+int launch_merge_topk(const MergeLaunch& a, cudaStream_t st);
+
+// K4: padded [Q,k] lists -> flat candidate arrays (query asc, score desc)
+size_t compact_workspace_bytes(int64_t Q);
+int launch_compact(const float* scores, const int32_t* idx, const uint8_t* valid, const int32_t* count, int64_t Q, int k,
+                   int32_t* out_q, int32_t* out_m, float* out_s, uint8_t* out_v, int64_t* out_total, void* workspace,
+                   cudaStream_t st);
+
+// floor gate over explicit candidate pairs (loop_closure_gate.py:105-126)
+int launch_gate_candidates(const int32_t* floors, int64_t n_floors, const int32_t* q_idx, const int32_t* m_idx, int64_t M,
+                           int max_floor_diff, uint8_t* out_valid, unsigned long long* counts /*[3]: accepted, rejected, bad index*/,
+                           cudaStream_t st);
+
+}  // namespace semgate

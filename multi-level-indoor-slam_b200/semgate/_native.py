@@ -1,0 +1,366 @@
+"""ctypes binding of libsemgate.so (C ABI in include/semgate.h) + a thin torch-facing
+wrapper.  torch is used for device memory and streams only; all arithmetic on the
+path happens in the library's sm_100a kernels.  There is no CPU fallback: if the
+library is missing or the device is not a B200-class GPU, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsemgate.so")
+
+MAX_K = 64
+FLOOR_NONE = -2**31
+GATE_FLAG, GATE_MASK = 0, 1
+EINVAL, EARCH, ENOMEM, EDRIVER, EINDEX = -1, -2, -3, -4, -5
+
+# every symbol include/semgate.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "semgate_version", "semgate_last_error", "semgate_create", "semgate_destroy", "semgate_device_info",
+    "semgate_set_option", "semgate_profile_read", "semgate_launch_count", "semgate_pad_dim", "semgate_normalize_cast",
+    "semgate_topk_workspace_bytes", "semgate_gated_topk", "semgate_merge_topk", "semgate_compact_workspace_bytes",
+    "semgate_compact", "semgate_gate_candidates", "semgate_find_loop_closures_host", "semgate_query_host",
+    "semgate_gate_candidates_host",
+]
+
+
+class SemgateError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libsemgate error {code}: {message}")
+        self.code = code
+
+
+class TopkParams(C.Structure):
+    _fields_ = [
+        ("similarity_threshold", C.c_float),
+        ("min_time_gap", C.c_double),
+        ("k", C.c_int32),
+        ("max_floor_diff", C.c_int32),
+        ("gate_mode", C.c_int32),
+        ("db_index_offset", C.c_uint32),
+        ("cta_group", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def load_library():
+    """Load libsemgate.so; raises ImportError with the build command if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found. Build it with `python multi-level-indoor-slam_b200/build.py` "
+            "(nvcc, sm_100a). There is no fallback implementation.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, u32, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_size_t
+    P = C.POINTER
+    lib.semgate_version.restype = C.c_int
+    lib.semgate_last_error.restype = C.c_char_p
+    lib.semgate_create.argtypes = [P(vp), C.c_int]
+    lib.semgate_destroy.argtypes = [vp]
+    lib.semgate_device_info.argtypes = [vp, P(C.c_int), P(C.c_int), P(C.c_int)]
+    lib.semgate_set_option.argtypes = [vp, C.c_char_p, i64]
+    lib.semgate_profile_read.argtypes = [vp, P(C.c_double), P(i64)]
+    lib.semgate_launch_count.argtypes = [vp]
+    lib.semgate_launch_count.restype = i64
+    lib.semgate_pad_dim.argtypes = [C.c_int]
+    lib.semgate_normalize_cast.argtypes = [vp, vp, i64, i32, i64, vp, i32, vp]
+    lib.semgate_topk_workspace_bytes.argtypes = [vp, i64, i64, i32, P(TopkParams)]
+    lib.semgate_topk_workspace_bytes.restype = sz
+    lib.semgate_gated_topk.argtypes = [vp, vp, i64, vp, i64, i32, vp, vp, vp, vp, P(TopkParams), vp, sz,
+                                       vp, vp, vp, vp, vp, vp]
+    lib.semgate_merge_topk.argtypes = [vp, vp, i32, i64, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp]
+    lib.semgate_compact_workspace_bytes.argtypes = [i64]
+    lib.semgate_compact_workspace_bytes.restype = sz
+    lib.semgate_compact.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.semgate_gate_candidates.argtypes = [vp, vp, i64, vp, vp, i64, i32, vp, vp, vp]
+    lib.semgate_find_loop_closures_host.argtypes = [vp, vp, i64, i32, vp, vp, P(TopkParams), vp, vp, vp, vp, i64, P(i64)]
+    lib.semgate_query_host.argtypes = [vp, vp, i64, vp, i64, i32, vp, vp, P(TopkParams), vp, vp, vp]
+    lib.semgate_gate_candidates_host.argtypes = [vp, vp, i64, vp, vp, i64, i32, vp, vp]
+    for name in SYMBOLS:
+        getattr(lib, name)   # AttributeError here = the library is older than the header
+    _lib = lib
+    return lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise SemgateError(rc, load_library().semgate_last_error().decode("utf-8", "replace"))
+
+
+def pad_dim(d: int) -> int:
+    return ((int(d) + 63) // 64) * 64
+
+
+def make_params(k: int, similarity_threshold: float = -np.inf, min_time_gap: float = 10.0, max_floor_diff: int = -1,
+                gate_mode: int = GATE_FLAG, db_index_offset: int = 0, cta_group: int = 0) -> TopkParams:
+    if not (1 <= int(k) <= MAX_K):
+        raise ValueError(f"k={k} outside 1..{MAX_K}")
+    # the reference compares `sim < threshold` in the similarity dtype (fp32): same rounding here
+    thr = float(np.float32(similarity_threshold))
+    return TopkParams(thr, float(min_time_gap), int(k), int(max_floor_diff), int(gate_mode), int(db_index_offset),
+                      int(cta_group))
+
+
+def _np_ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+@dataclass
+class TopkResult:
+    scores: "object"   # [Q,k] fp32, descending, -inf padded
+    idx: "object"      # [Q,k] int32 global database index, -1 padded
+    valid: "object"    # [Q,k] uint8 floor flag
+    count: "object"    # [Q] int32
+    keys: "object" = None
+
+
+class Engine:
+    """One handle per GPU.  Device-pointer calls take torch CUDA tensors and run on
+    torch's current stream; `*_host` calls take numpy arrays."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self.device = int(device)
+        h = C.c_void_p()
+        _check(self.lib.semgate_create(C.byref(h), self.device))
+        self._h = h
+        sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
+        _check(self.lib.semgate_device_info(self._h, C.byref(sm), C.byref(ma), C.byref(mi)))
+        self.sm_count, self.cc = sm.value, (ma.value, mi.value)
+        self._ws = None   # grow-only torch workspace
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.semgate_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def set_option(self, name: str, value: int):
+        _check(self.lib.semgate_set_option(self._h, name.encode(), int(value)))
+
+    def profile_read(self):
+        """(total K2 milliseconds, launches) since the last read; needs set_option('profile', 1)."""
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        _check(self.lib.semgate_profile_read(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.semgate_launch_count(self._h))
+
+    def _torch(self):
+        import torch
+        return torch
+
+    def _stream(self):
+        torch = self._torch()
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self):
+        return self._torch().device("cuda", self.device)
+
+    @staticmethod
+    def _ptr(t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    def _expect(self, t, dtype, name, ndim=None):
+        torch = self._torch()
+        if t is None:
+            return
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.device.index == self.device):
+            raise TypeError(f"{name}: expected a CUDA tensor on device {self.device}")
+        if t.dtype != dtype:
+            raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+        if not t.is_contiguous():
+            raise ValueError(f"{name}: must be contiguous")
+        if ndim is not None and t.dim() != ndim:
+            raise ValueError(f"{name}: expected {ndim} dimensions")
+
+    def _workspace(self, nbytes: int):
+        torch = self._torch()
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, device=self._dev())
+        return self._ws
+
+    # ------------------------------------------------------------------ K1
+    def normalize_cast(self, x, out=None):
+        """fp32 [n,d] CUDA tensor -> row-normalised bf16 [n,pad64(d)] (zero padded)."""
+        torch = self._torch()
+        if x.dim() != 2 or x.dtype != torch.float32 or not x.is_cuda or x.stride(1) != 1:
+            raise TypeError("normalize_cast: expected a 2-D fp32 CUDA tensor with unit inner stride")
+        n, d = x.shape
+        dp = pad_dim(d)
+        if out is None:
+            out = torch.empty((n, dp), dtype=torch.bfloat16, device=x.device)
+        self._expect(out, torch.bfloat16, "out", 2)
+        if out.shape[0] < n or out.shape[1] != dp:
+            raise ValueError("normalize_cast: out has the wrong shape")
+        if n:
+            _check(self.lib.semgate_normalize_cast(self._h, self._ptr(x), n, d, x.stride(0), self._ptr(out), dp, self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ K2 + K3
+    def gated_topk(self, q_bf16, db_bf16, params: TopkParams, q_ts=None, db_ts=None, q_floor=None, db_floor=None,
+                   want_keys: bool = False, want_lists: bool = True) -> TopkResult:
+        torch = self._torch()
+        self._expect(q_bf16, torch.bfloat16, "q_bf16", 2)
+        self._expect(db_bf16, torch.bfloat16, "db_bf16", 2)
+        self._expect(q_ts, torch.float64, "q_ts", 1)
+        self._expect(db_ts, torch.float64, "db_ts", 1)
+        self._expect(q_floor, torch.int32, "q_floor", 1)
+        self._expect(db_floor, torch.int32, "db_floor", 1)
+        Q, dp = q_bf16.shape
+        N = db_bf16.shape[0]
+        if db_bf16.shape[1] != dp and N > 0:
+            raise ValueError("gated_topk: query and database descriptor lengths differ")
+        for t, n, name in ((q_ts, Q, "q_ts"), (q_floor, Q, "q_floor"), (db_ts, N, "db_ts"), (db_floor, N, "db_floor")):
+            if t is not None and t.shape[0] < n:
+                raise ValueError(f"gated_topk: {name} shorter than its matrix")
+        k = params.k
+        dev = q_bf16.device
+        keys = torch.empty((Q, k), dtype=torch.int64, device=dev) if want_keys else None
+        scores = idx = valid = count = None
+        if want_lists:
+            scores = torch.empty((Q, k), dtype=torch.float32, device=dev)
+            idx = torch.empty((Q, k), dtype=torch.int32, device=dev)
+            valid = torch.empty((Q, k), dtype=torch.uint8, device=dev)
+            count = torch.empty((Q,), dtype=torch.int32, device=dev)
+        if Q == 0:
+            return TopkResult(scores, idx, valid, count, keys)
+        wsb = int(self.lib.semgate_topk_workspace_bytes(self._h, Q, N, dp, C.byref(params)))
+        ws = self._workspace(wsb)
+        _check(self.lib.semgate_gated_topk(
+            self._h, self._ptr(q_bf16), Q, self._ptr(db_bf16), N, dp, self._ptr(q_ts), self._ptr(db_ts),
+            self._ptr(q_floor), self._ptr(db_floor), C.byref(params), self._ptr(ws), ws.numel(),
+            self._ptr(keys), self._ptr(scores), self._ptr(idx), self._ptr(valid), self._ptr(count), self._stream()))
+        return TopkResult(scores, idx, valid, count, keys)
+
+    def merge_topk(self, keys_gathered, k: int, q_floor=None, db_floor_all=None, max_floor_diff: int = -1,
+                   want_keys: bool = False) -> TopkResult:
+        """keys_gathered: int64 [G,Q,k] (all-gathered `keys` of per-shard sweeps)."""
+        torch = self._torch()
+        self._expect(keys_gathered, torch.int64, "keys_gathered", 3)
+        G, Q, kk = keys_gathered.shape
+        if kk != k:
+            raise ValueError("merge_topk: k mismatch")
+        dev = keys_gathered.device
+        scores = torch.empty((Q, k), dtype=torch.float32, device=dev)
+        idx = torch.empty((Q, k), dtype=torch.int32, device=dev)
+        valid = torch.empty((Q, k), dtype=torch.uint8, device=dev)
+        count = torch.empty((Q,), dtype=torch.int32, device=dev)
+        keys = torch.empty((Q, k), dtype=torch.int64, device=dev) if want_keys else None
+        if Q:
+            _check(self.lib.semgate_merge_topk(self._h, self._ptr(keys_gathered), G, Q, k, self._ptr(q_floor),
+                                               self._ptr(db_floor_all), max_floor_diff, self._ptr(keys), self._ptr(scores),
+                                               self._ptr(idx), self._ptr(valid), self._ptr(count), self._stream()))
+        return TopkResult(scores, idx, valid, count, keys)
+
+    # ------------------------------------------------------------------ K4
+    def compact(self, res: TopkResult):
+        """Padded lists -> (query_idx, match_idx, similarity, is_valid, total) CUDA tensors;
+        the arrays have capacity Q*k, the first `total` entries are meaningful."""
+        torch = self._torch()
+        Q, k = res.scores.shape
+        dev = res.scores.device
+        cap = max(Q * k, 1)
+        oq = torch.empty((cap,), dtype=torch.int32, device=dev)
+        om = torch.empty((cap,), dtype=torch.int32, device=dev)
+        os_ = torch.empty((cap,), dtype=torch.float32, device=dev)
+        ov = torch.empty((cap,), dtype=torch.uint8, device=dev)
+        total = torch.zeros((1,), dtype=torch.int64, device=dev)
+        wsb = int(self.lib.semgate_compact_workspace_bytes(Q))
+        ws = torch.empty((max(wsb, 256),), dtype=torch.uint8, device=dev)
+        _check(self.lib.semgate_compact(self._h, self._ptr(res.scores), self._ptr(res.idx), self._ptr(res.valid),
+                                        self._ptr(res.count), Q, k, self._ptr(oq), self._ptr(om), self._ptr(os_),
+                                        self._ptr(ov), self._ptr(total), self._ptr(ws), self._stream()))
+        return oq, om, os_, ov, total
+
+    # ------------------------------------------------------------------ gate
+    def gate_candidates(self, floor_labels, query_idx, match_idx, max_floor_diff: int):
+        torch = self._torch()
+        self._expect(floor_labels, torch.int32, "floor_labels", 1)
+        self._expect(query_idx, torch.int32, "query_idx", 1)
+        self._expect(match_idx, torch.int32, "match_idx", 1)
+        M = query_idx.shape[0]
+        if match_idx.shape[0] != M:
+            raise ValueError("gate_candidates: index arrays differ in length")
+        valid = torch.empty((M,), dtype=torch.uint8, device=query_idx.device)
+        counts = torch.zeros((3,), dtype=torch.int64, device=query_idx.device)
+        _check(self.lib.semgate_gate_candidates(self._h, self._ptr(floor_labels), floor_labels.shape[0], self._ptr(query_idx),
+                                                self._ptr(match_idx), M, max_floor_diff, self._ptr(valid), self._ptr(counts),
+                                                self._stream()))
+        return valid, counts
+
+    # ------------------------------------------------------------------ host-buffer calls
+    def find_loop_closures_host(self, descriptors: np.ndarray, timestamps: Optional[np.ndarray],
+                                floor_labels: Optional[np.ndarray], params: TopkParams, out=None):
+        """Whole find_loop_closures on host arrays (H2D, kernels, D2H inside the call).
+        Returns (query_idx, match_idx, similarity, is_valid) numpy arrays."""
+        desc = np.ascontiguousarray(descriptors, dtype=np.float32)
+        n, d = desc.shape if desc.ndim == 2 else (0, 0)
+        ts = None if timestamps is None else np.ascontiguousarray(timestamps, dtype=np.float64)
+        fl = None if floor_labels is None else np.ascontiguousarray(floor_labels, dtype=np.int32)
+        cap = max(n * params.k, 1)
+        if out is None:
+            out = (np.empty(cap, np.int32), np.empty(cap, np.int32), np.empty(cap, np.float32), np.empty(cap, np.uint8))
+        oq, om, os_, ov = out
+        total = C.c_int64(0)
+        _check(self.lib.semgate_find_loop_closures_host(self._h, _np_ptr(desc), n, d, _np_ptr(ts), _np_ptr(fl),
+                                                        C.byref(params), _np_ptr(oq), _np_ptr(om), _np_ptr(os_), _np_ptr(ov),
+                                                        min(cap, oq.shape[0]), C.byref(total)))
+        t = total.value
+        return oq[:t], om[:t], os_[:t], ov[:t].astype(bool)
+
+    def query_host(self, queries: np.ndarray, database: np.ndarray, params: TopkParams, q_ts=None, db_ts=None):
+        q = np.ascontiguousarray(np.atleast_2d(queries), dtype=np.float32)
+        db = np.ascontiguousarray(database, dtype=np.float32)
+        nq, d = q.shape
+        n = db.shape[0] if db.ndim == 2 else 0
+        qt = None if q_ts is None else np.ascontiguousarray(q_ts, dtype=np.float64)
+        dt = None if db_ts is None else np.ascontiguousarray(db_ts, dtype=np.float64)
+        k = params.k
+        scores = np.empty((nq, k), np.float32)
+        idx = np.empty((nq, k), np.int32)
+        count = np.empty((nq,), np.int32)
+        _check(self.lib.semgate_query_host(self._h, _np_ptr(q), nq, _np_ptr(db) if n else None, n, d, _np_ptr(qt), _np_ptr(dt),
+                                           C.byref(params), _np_ptr(scores), _np_ptr(idx), _np_ptr(count)))
+        return scores, idx, count
+
+    def gate_candidates_host(self, floor_labels: np.ndarray, query_idx: np.ndarray, match_idx: np.ndarray,
+                             max_floor_diff: int):
+        fl = np.ascontiguousarray(floor_labels, dtype=np.int32)
+        qi = np.ascontiguousarray(query_idx, dtype=np.int32)
+        mi = np.ascontiguousarray(match_idx, dtype=np.int32)
+        M = qi.shape[0]
+        valid = np.empty((max(M, 1),), np.uint8)
+        counts = np.zeros((3,), np.uint64)
+        _check(self.lib.semgate_gate_candidates_host(self._h, _np_ptr(fl), fl.shape[0], _np_ptr(qi), _np_ptr(mi), M,
+                                                     max_floor_diff, _np_ptr(valid), _np_ptr(counts)))
+        return valid[:M].astype(bool), int(counts[0]), int(counts[1])
+
+
+_engines = {}
+
+
+def get_engine(device: int = 0) -> Engine:
+    """Process-wide engine per device.  Raises if there is no usable B200."""
+    device = int(device)
+    if device not in _engines:
+        _engines[device] = Engine(device)
+    return _engines[device]

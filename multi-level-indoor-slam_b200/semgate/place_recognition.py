@@ -1,0 +1,361 @@
+"""Host-side mirror of the reference's place-recognition interface for the retrieval
+path, backed by libsemgate's sm_100a kernels.
+
+Same public names, argument meaning and error behaviour as the reference's
+scripts/semantic_gating/place_recognition.py (PlaceMatch :61-69, PlaceDescriptor
+:72-78, BasePlaceRecognition :81-190, SemanticPlaceRecognition :806-933), so code
+written against the reference keeps working:
+
+    spr = SemanticPlaceRecognition(vpr_method='mixvpr', device='cuda')
+    spr.add_image(descriptor, timestamp, floor_label)     # or append PlaceDescriptor
+    matches = spr.find_loop_closures(enable_floor_gating=True, k=10)
+
+What differs by design
+  * Descriptor *extraction* (MixVPR / SALAD / AnyLoc / CricaVPR model inference,
+    :193-803) is out of scope: `extract_descriptor` accepts an already extracted
+    descriptor vector of the method's dimensionality and returns it.
+  * The database lives on the GPU as row-normalised bf16 (packed incrementally, not
+    re-stacked per call as :140,:177 do) and the N x N matrix is never formed.
+  * `find_loop_closures(..., gate_mode="mask")` is an extension: cross-floor columns
+    are excluded before top-k.  The default "flag" keeps the reference's order
+    (top-k, threshold, then flag; :888-899).
+  * Tie order among exactly equal scores is (lower index first); the reference's
+    `np.argsort` leaves it unspecified.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import _native
+
+GATE_MODES = {"flag": _native.GATE_FLAG, "mask": _native.GATE_MASK}
+
+
+@dataclass
+class PlaceMatch:
+    """A place-recognition match between two keyframes."""
+    query_idx: int
+    match_idx: int
+    similarity: float
+    query_timestamp: Optional[float] = None
+    match_timestamp: Optional[float] = None
+    is_valid: bool = True  # cleared by the floor gate
+
+
+@dataclass
+class PlaceDescriptor:
+    """Global descriptor of one keyframe."""
+    timestamp: float
+    descriptor: np.ndarray
+    image_path: Optional[str] = None
+    floor_label: Optional[int] = None
+
+
+@dataclass
+class MatchArrays:
+    """Struct-of-arrays form of a match list (query ascending, similarity descending)."""
+    query_idx: np.ndarray
+    match_idx: np.ndarray
+    similarity: np.ndarray
+    is_valid: np.ndarray
+    query_timestamp: Optional[np.ndarray] = None
+    match_timestamp: Optional[np.ndarray] = None
+
+    def __len__(self):
+        return int(self.query_idx.shape[0])
+
+    def to_matches(self) -> List[PlaceMatch]:
+        qt = self.query_timestamp.tolist() if self.query_timestamp is not None else [None] * len(self)
+        mt = self.match_timestamp.tolist() if self.match_timestamp is not None else [None] * len(self)
+        return [PlaceMatch(q, m, s, a, b, v) for q, m, s, a, b, v in
+                zip(self.query_idx.tolist(), self.match_idx.tolist(), self.similarity.astype(np.float64).tolist(),
+                    qt, mt, self.is_valid.astype(bool).tolist())]
+
+    def as_gate_candidates(self) -> List[Tuple[int, int, float]]:
+        """`(query_idx, match_idx, score)` tuples, the input of SemanticLoopClosureGate.gate_candidates."""
+        return list(zip(self.query_idx.tolist(), self.match_idx.tolist(), self.similarity.astype(np.float64).tolist()))
+
+
+def _device_index(device) -> int:
+    if isinstance(device, int):
+        return device
+    s = str(device)
+    if s == "cpu":
+        raise RuntimeError("semgate has no CPU path: the retrieval kernels are sm_100a only (use device='cuda').")
+    if ":" in s:
+        return int(s.split(":")[1])
+    try:
+        import torch
+        return torch.cuda.current_device() if torch.cuda.is_available() else 0
+    except Exception:
+        return 0
+
+
+class _PackedDB:
+    """Device-resident database: bf16 normalised rows, fp64 timestamps, int32 floors,
+    grown geometrically and re-synchronised lazily from the Python descriptor list
+    (callers may append PlaceDescriptor objects directly, place_recognition.py:1015-1020)."""
+
+    def __init__(self, engine: "_native.Engine"):
+        self.engine = engine
+        self.n = 0
+        self.d = None
+        self.cap = 0
+        self.bf16 = self.ts = self.floor = None
+        self._ids: List[int] = []
+        self.has_floor = False
+
+    def _grow(self, need: int, d: int):
+        import torch
+        if self.d is not None and self.d != d:
+            raise ValueError(f"descriptor length changed from {self.d} to {d}")
+        if need <= self.cap:
+            return
+        cap = max(need, int(self.cap * 1.5), 1024)
+        dev = torch.device("cuda", self.engine.device)
+        dp = _native.pad_dim(d)
+        bf16 = torch.empty((cap, dp), dtype=torch.bfloat16, device=dev)
+        ts = torch.empty((cap,), dtype=torch.float64, device=dev)
+        fl = torch.empty((cap,), dtype=torch.int32, device=dev)
+        if self.n:
+            bf16[:self.n].copy_(self.bf16[:self.n])
+            ts[:self.n].copy_(self.ts[:self.n])
+            fl[:self.n].copy_(self.floor[:self.n])
+        self.bf16, self.ts, self.floor, self.cap, self.d = bf16, ts, fl, cap, d
+
+    def sync(self, descriptors: List[PlaceDescriptor]):
+        import torch
+        n = len(descriptors)
+        keep = min(self.n, n)
+        # cheap identity probes: first, last and a middle element of the packed prefix
+        probes = {0, keep - 1, keep // 2} if keep else set()
+        if n < self.n or any(self._ids[i] != id(descriptors[i]) for i in probes):
+            self.n, self._ids = 0, []
+            keep = 0
+        if n == keep:
+            return
+        new = descriptors[keep:]
+        x = np.ascontiguousarray(np.vstack([np.asarray(p.descriptor).reshape(1, -1) for p in new]), dtype=np.float32)
+        d = x.shape[1]
+        self._grow(n, d)
+        dev = self.bf16.device
+        xt = torch.from_numpy(x).to(dev, non_blocking=False)
+        self.engine.normalize_cast(xt, out=self.bf16[keep:n])
+        self.ts[keep:n] = torch.from_numpy(np.array([float(p.timestamp) for p in new], dtype=np.float64)).to(dev)
+        fl = np.array([_native.FLOOR_NONE if p.floor_label is None else int(p.floor_label) for p in new], dtype=np.int64)
+        real = fl[fl != _native.FLOOR_NONE]
+        if real.size and (real.max() > 2**31 - 1 or real.min() < -2**31 + 1):
+            raise ValueError("floor labels must fit in int32")
+        self.floor[keep:n] = torch.from_numpy(fl.astype(np.int32)).to(dev)
+        self._ids.extend(id(p) for p in new)
+        self.n = n
+
+
+class BasePlaceRecognition:
+    """Base class of the VPR methods (reference :81-190)."""
+
+    def __init__(self, descriptor_dim: int = 4096, device: str = 'cuda'):
+        self.descriptor_dim = descriptor_dim
+        self.device = device
+        self.model = None
+        self.descriptors: List[PlaceDescriptor] = []
+        self._db: Optional[_PackedDB] = None
+
+    # -- engine plumbing ---------------------------------------------------
+    def _engine(self) -> "_native.Engine":
+        return _native.get_engine(_device_index(self.device))
+
+    def _packed(self) -> _PackedDB:
+        if self._db is None:
+            self._db = _PackedDB(self._engine())
+        self._db.sync(self.descriptors)
+        return self._db
+
+    # -- reference interface ---------------------------------------------------
+    def extract_descriptor(self, image: np.ndarray) -> np.ndarray:
+        """Model inference is outside this package: pass the extracted descriptor."""
+        a = np.asarray(image)
+        if a.ndim == 1 and (self.descriptor_dim is None or a.shape[0] == self.descriptor_dim):
+            return a
+        raise NotImplementedError(
+            "descriptor extraction is not part of semgate; pass a 1-D descriptor of length "
+            f"{self.descriptor_dim} (got shape {a.shape})")
+
+    def add_image(self, image: np.ndarray, timestamp: float, floor_label: Optional[int] = None,
+                  image_path: Optional[str] = None) -> PlaceDescriptor:
+        descriptor = self.extract_descriptor(image)
+        pd = PlaceDescriptor(timestamp=timestamp, descriptor=descriptor, image_path=image_path, floor_label=floor_label)
+        self.descriptors.append(pd)
+        return pd
+
+    def query(self, image: np.ndarray, timestamp: Optional[float] = None, k: int = 5,
+              min_time_gap: float = 10.0) -> List[PlaceMatch]:
+        """Top-k most similar database keyframes (reference :117-163): temporal mask only
+        when `timestamp` is given, masked entries dropped, `query_idx = len(descriptors)`."""
+        if len(self.descriptors) == 0:
+            return []
+        q = np.asarray(self.extract_descriptor(image), dtype=np.float32).reshape(1, -1)
+        res = self.query_batch(q, None if timestamp is None else np.array([timestamp], dtype=np.float64), k, min_time_gap)
+        scores, idx, count = res
+        c = int(count[0])
+        nq = len(self.descriptors)
+        return [PlaceMatch(query_idx=nq, match_idx=int(idx[0, i]), similarity=float(scores[0, i]),
+                           query_timestamp=timestamp, match_timestamp=self.descriptors[int(idx[0, i])].timestamp)
+                for i in range(c)]
+
+    def query_batch(self, queries: np.ndarray, timestamps: Optional[np.ndarray] = None, k: int = 5,
+                    min_time_gap: float = 10.0):
+        """Batched `query`: (scores[nq,k], idx[nq,k], count[nq]) numpy arrays."""
+        import torch
+        db = self._packed()
+        eng = db.engine
+        dev = db.bf16.device
+        q = torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32)).to(dev)
+        if q.shape[1] != db.d:
+            raise ValueError(f"query length {q.shape[1]} != database descriptor length {db.d}")
+        qb = eng.normalize_cast(q)
+        params = _native.make_params(k=min(int(k), _native.MAX_K), similarity_threshold=-np.inf,
+                                     min_time_gap=min_time_gap, max_floor_diff=-1)
+        if k > _native.MAX_K:
+            raise ValueError(f"k={k} exceeds the kernel's list capacity {_native.MAX_K}")
+        q_ts = db_ts = None
+        if timestamps is not None:
+            q_ts = torch.from_numpy(np.ascontiguousarray(timestamps, dtype=np.float64)).to(dev)
+            db_ts = db.ts[:db.n]
+        r = eng.gated_topk(qb, db.bf16[:db.n], params, q_ts=q_ts, db_ts=db_ts)
+        return r.scores.cpu().numpy(), r.idx.cpu().numpy(), r.count.cpu().numpy()
+
+    def _compute_similarity(self, query: np.ndarray, database: np.ndarray) -> np.ndarray:
+        """Cosine similarity of one query against every database row (reference :165-171),
+        returned in full — computed as a top-N sweep in chunks of the kernel's list size is
+        not what this is for; prefer `query`.  Kept for interface parity."""
+        database = np.asarray(database, dtype=np.float32)
+        n = database.shape[0]
+        out = np.full((n,), -np.inf, dtype=np.float32)
+        if n == 0:
+            return out
+        eng = self._engine()
+        # sweep the database in windows of MAX_K rows so every score is returned
+        params = _native.make_params(k=_native.MAX_K, similarity_threshold=-np.inf, max_floor_diff=-1)
+        q = np.asarray(query, dtype=np.float32).reshape(1, -1)
+        for s in range(0, n, _native.MAX_K):
+            e = min(n, s + _native.MAX_K)
+            sc, ix, ct = eng.query_host(q, database[s:e], params)
+            c = int(ct[0])
+            out[s + ix[0, :c]] = sc[0, :c]
+        return out
+
+    def build_descriptor_matrix(self) -> np.ndarray:
+        if len(self.descriptors) == 0:
+            return np.array([])
+        return np.vstack([d.descriptor for d in self.descriptors])
+
+    def compute_all_pairwise_similarities(self) -> np.ndarray:
+        """The reference materialises the N x N matrix here (:179-190).  The fused path
+        never forms it; this method exists for interface parity and refuses sizes where
+        the matrix itself is the problem."""
+        n = len(self.descriptors)
+        if n == 0:
+            return np.array([])
+        if n > 8192:
+            raise MemoryError("compute_all_pairwise_similarities would materialise an N x N matrix; "
+                              "use find_loop_closures / query, which never form it")
+        m = self.build_descriptor_matrix().astype(np.float32)
+        return np.stack([self._compute_similarity(m[i], m) for i in range(n)])
+
+
+class MixVPR(BasePlaceRecognition):
+    def __init__(self, device: str = 'cuda', **_):
+        super().__init__(descriptor_dim=4096, device=device)   # reference :197
+
+
+class SALAD(BasePlaceRecognition):
+    def __init__(self, device: str = 'cuda', **_):
+        super().__init__(descriptor_dim=8448, device=device)   # reference :340
+
+
+class AnyLoc(BasePlaceRecognition):
+    def __init__(self, device: str = 'cuda', **_):
+        super().__init__(descriptor_dim=49152, device=device)  # reference :418
+
+
+class CricaVPR(BasePlaceRecognition):
+    def __init__(self, device: str = 'cuda', use_reranking: bool = True, **_):
+        super().__init__(descriptor_dim=10752, device=device)  # reference :513
+        self.use_reranking = use_reranking
+
+
+_METHODS = {'mixvpr': MixVPR, 'salad': SALAD, 'anyloc': AnyLoc, 'cricavpr': CricaVPR}
+
+
+class SemanticPlaceRecognition:
+    """Place recognition with floor gating (reference :806-933)."""
+
+    def __init__(self, vpr_method: str = 'mixvpr', device: str = 'cuda', similarity_threshold: float = 0.5,
+                 min_time_gap: float = 10.0, descriptor_dim: Optional[int] = None):
+        self.similarity_threshold = similarity_threshold
+        self.min_time_gap = min_time_gap
+        cls = _METHODS.get(vpr_method.lower())
+        if cls is None:
+            raise ValueError(f"Unknown VPR method: {vpr_method}. Available: mixvpr, salad, anyloc, cricavpr")
+        self.vpr = cls(device=device)
+        if descriptor_dim is not None:
+            self.vpr.descriptor_dim = descriptor_dim
+
+    def add_image(self, image: np.ndarray, timestamp: float, floor_label: int,
+                  image_path: Optional[str] = None) -> PlaceDescriptor:
+        return self.vpr.add_image(image, timestamp, floor_label, image_path)
+
+    def find_loop_closures(self, enable_floor_gating: bool = True, k: int = 10,
+                           gate_mode: str = "flag") -> List[PlaceMatch]:
+        """All loop-closure candidates of the database (reference :851-911)."""
+        return self.find_loop_closures_arrays(enable_floor_gating, k, gate_mode).to_matches()
+
+    def find_loop_closures_arrays(self, enable_floor_gating: bool = True, k: int = 10,
+                                  gate_mode: str = "flag") -> MatchArrays:
+        """Same result as struct-of-arrays (no per-match Python objects)."""
+        e = np.zeros(0, dtype=np.int32)
+        if len(self.vpr.descriptors) < 2:
+            return MatchArrays(e, e.copy(), np.zeros(0, np.float32), np.zeros(0, bool), np.zeros(0), np.zeros(0))
+        if gate_mode not in GATE_MODES:
+            raise ValueError(f"gate_mode must be one of {sorted(GATE_MODES)}")
+        if not (1 <= int(k) <= _native.MAX_K):
+            raise ValueError(f"k={k} outside the kernel's list capacity 1..{_native.MAX_K}")
+        db = self.vpr._packed()
+        eng = db.engine
+        n = db.n
+        params = _native.make_params(k=int(k), similarity_threshold=self.similarity_threshold,
+                                     min_time_gap=self.min_time_gap,
+                                     max_floor_diff=0 if enable_floor_gating else -1, gate_mode=GATE_MODES[gate_mode])
+        ts, fl = db.ts[:n], db.floor[:n]
+        r = eng.gated_topk(db.bf16[:n], db.bf16[:n], params, q_ts=ts, db_ts=ts, q_floor=fl, db_floor=fl)
+        oq, om, os_, ov, total = eng.compact(r)
+        t = int(total.item())
+        q = oq[:t].cpu().numpy()
+        m = om[:t].cpu().numpy()
+        tsh = ts.cpu().numpy()
+        return MatchArrays(q, m, os_[:t].cpu().numpy(), ov[:t].cpu().numpy().astype(bool), tsh[q], tsh[m])
+
+    def get_statistics(self, matches) -> Dict:
+        """Statistics of a match list (reference :913-933).  Accepts List[PlaceMatch] or MatchArrays."""
+        if isinstance(matches, MatchArrays):
+            valid_mask = matches.is_valid.astype(bool)
+            sims = matches.similarity.astype(np.float64)
+        else:
+            valid_mask = np.array([m.is_valid for m in matches], dtype=bool)
+            sims = np.array([m.similarity for m in matches], dtype=np.float64)
+        n = int(valid_mask.shape[0])
+        if n == 0:
+            return {'total_matches': 0, 'valid_matches': 0, 'rejected_matches': 0, 'rejection_rate': 0.0}
+        valid = int(valid_mask.sum())
+        return {
+            'total_matches': n,
+            'valid_matches': valid,
+            'rejected_matches': n - valid,
+            'rejection_rate': (n - valid) / n,
+            'mean_similarity': np.mean(sims),
+            'mean_valid_similarity': np.mean(sims[valid_mask]) if valid > 0 else 0.0,
+        }

@@ -1,0 +1,96 @@
+"""CPU tier: the C-ABI library builds, loads without a GPU, and exports every symbol
+include/semgate.h declares.  No compute calls here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "semgate.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(semgate_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "semgate_build", os.path.join(ROOT, "multi-level-indoor-slam_b200", "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    path = b.build()
+    lib = ctypes.CDLL(path)
+    declared = _declared_symbols()
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/semgate.h but not exported"
+    from semgate import _native
+    assert sorted(_native.SYMBOLS) == declared, "ctypes binding and header disagree"
+    lib.semgate_version.restype = ctypes.c_int
+    assert lib.semgate_version() == 100
+    assert lib.semgate_pad_dim(4096) == 4096 and lib.semgate_pad_dim(100) == 128 and lib.semgate_pad_dim(8448) == 8448
+
+
+def test_params_struct_layout():
+    from semgate import _native
+    # float, (pad), double, 5 x 32-bit -> 40 bytes with natural alignment
+    assert ctypes.sizeof(_native.TopkParams) == 40
+    assert _native.TopkParams.min_time_gap.offset == 8 and _native.TopkParams.k.offset == 16
+    p = _native.make_params(k=25, similarity_threshold=0.5, min_time_gap=10.0, max_floor_diff=0)
+    assert p.k == 25 and p.similarity_threshold == 0.5 and p.gate_mode == 0
+
+
+def test_no_gpu_fails_loudly():
+    """Without a usable sm_100 device the product path raises; it never falls back."""
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from semgate import _native, SemanticPlaceRecognition, PlaceDescriptor
+    with pytest.raises(_native.SemgateError):
+        _native.Engine(0)
+    spr = SemanticPlaceRecognition('mixvpr', 'cuda', descriptor_dim=8)
+    for i in range(3):
+        spr.vpr.descriptors.append(PlaceDescriptor(float(i), np.ones(8, np.float32), floor_label=1))
+    with pytest.raises(Exception):
+        spr.find_loop_closures()
+    with pytest.raises(RuntimeError):
+        SemanticPlaceRecognition('mixvpr', 'cpu', descriptor_dim=8).vpr._engine()
+
+
+def test_interface_parity_with_reference_signatures():
+    """Same constructor / method signatures as the reference classes
+    (place_recognition.py:61-190, :806-933; loop_closure_gate.py:16-148)."""
+    import inspect
+    import semgate
+
+    def sig(f):
+        return list(inspect.signature(f).parameters)
+
+    assert sig(semgate.PlaceMatch)[:6] == ["query_idx", "match_idx", "similarity", "query_timestamp",
+                                           "match_timestamp", "is_valid"]
+    assert sig(semgate.PlaceDescriptor) == ["timestamp", "descriptor", "image_path", "floor_label"]
+    assert sig(semgate.BasePlaceRecognition.add_image) == ["self", "image", "timestamp", "floor_label", "image_path"]
+    assert sig(semgate.BasePlaceRecognition.query) == ["self", "image", "timestamp", "k", "min_time_gap"]
+    assert sig(semgate.SemanticPlaceRecognition.__init__)[:5] == ["self", "vpr_method", "device",
+                                                                  "similarity_threshold", "min_time_gap"]
+    assert sig(semgate.SemanticPlaceRecognition.find_loop_closures)[:3] == ["self", "enable_floor_gating", "k"]
+    assert sig(semgate.SemanticLoopClosureGate.__init__)[:3] == ["self", "floor_labels", "strict_mode"]
+    assert sig(semgate.SemanticLoopClosureGate.gate_candidate) == ["self", "query_idx", "match_idx", "similarity_score"]
+    assert sig(semgate.LoopClosureCandidate) == ["query_idx", "match_idx", "similarity_score", "query_floor",
+                                                 "match_floor", "is_valid", "rejection_reason"]
+    d = inspect.signature(semgate.SemanticPlaceRecognition.__init__).parameters
+    assert d["similarity_threshold"].default == 0.5 and d["min_time_gap"].default == 10.0
+    assert inspect.signature(semgate.SemanticPlaceRecognition.find_loop_closures).parameters["k"].default == 10
+    assert inspect.signature(semgate.BasePlaceRecognition.query).parameters["k"].default == 5
+    spr = semgate.SemanticPlaceRecognition('salad')
+    assert spr.vpr.descriptor_dim == 8448
+    assert spr.get_statistics([]) == {'total_matches': 0, 'valid_matches': 0, 'rejected_matches': 0,
+                                      'rejection_rate': 0.0}
+    with pytest.raises(ValueError):
+        semgate.SemanticPlaceRecognition(vpr_method="nope")
+    g = semgate.SemanticLoopClosureGate([1, 2])
+    assert g.gate_candidates([]) == ([], []) and g.get_stats()["total_candidates"] == 0

@@ -1,0 +1,417 @@
+"""GPU tier (-m gpu): the sm_100a path, called through the C ABI, against the CPU oracle,
+the golden vectors produced by the unmodified reference, and size-independent
+properties at the benchmark's full size."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import parity
+from oracle import semgate_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FLC = sorted(glob.glob(os.path.join(GOLDEN, "flc_*.npz")))
+QRY = sorted(glob.glob(os.path.join(GOLDEN, "query_*.npz")))
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    assert torch.cuda.is_available(), "GPU tier needs a CUDA device"
+    from semgate import _native
+    return _native.get_engine(0)
+
+
+def _t(a, dtype=None):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def run_gpu(eng, q, db, k, thr=-np.inf, gap=10.0, q_ts=None, db_ts=None, q_fl=None, db_fl=None, mfd=-1,
+            mode=0, cg=1, offset=0):
+    """normalise + gated_topk on the GPU; returns the padded result as numpy."""
+    import torch
+    from semgate import _native
+    qb = eng.normalize_cast(_t(q, torch.float32))
+    dbb = qb if db is q else eng.normalize_cast(_t(db, torch.float32))
+    p = _native.make_params(k=k, similarity_threshold=thr, min_time_gap=gap, max_floor_diff=mfd, gate_mode=mode,
+                            db_index_offset=offset, cta_group=cg)
+    r = eng.gated_topk(qb, dbb, p,
+                       q_ts=None if q_ts is None else _t(q_ts, torch.float64),
+                       db_ts=None if db_ts is None else _t(db_ts, torch.float64),
+                       q_floor=None if q_fl is None else _t(q_fl, torch.int32),
+                       db_floor=None if db_fl is None else _t(db_fl, torch.int32), want_keys=True)
+    torch.cuda.synchronize()
+    return dict(scores=r.scores.cpu().numpy(), idx=r.idx.cpu().numpy().astype(np.int64),
+                valid=r.valid.cpu().numpy().astype(bool), count=r.count.cpu().numpy(), keys=r.keys.cpu().numpy())
+
+
+def check_padded(res, k):
+    """Structural invariants of the padded lists."""
+    sc, ix, ct = res["scores"], res["idx"], res["count"]
+    Q = sc.shape[0]
+    pos = np.arange(k)[None, :]
+    filled = pos < ct[:, None]
+    assert np.all(ix[filled] >= 0) and np.all(ix[~filled] == -1)
+    assert np.all(np.isneginf(sc[~filled]))
+    assert not np.any(res["valid"][~filled])
+    d = np.diff(sc, axis=1)
+    assert np.all(d[filled[:, 1:]] <= 0), "scores not descending"
+    for r in range(min(Q, 512)):
+        row = ix[r, :ct[r]]
+        assert len(set(row.tolist())) == len(row), "duplicate database index in a list"
+
+
+# --------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("n,d", [(1, 64), (37, 100), (300, 512), (64, 4096), (5, 8448), (3, 49152), (130, 33)])
+def test_normalize_cast(eng, n, d):
+    import torch
+    rng = np.random.default_rng(n * 1000 + d)
+    x = (rng.standard_normal((n, d)) * rng.uniform(0.1, 30, size=(n, 1))).astype(np.float32)
+    if n > 2:
+        x[1] = 0.0                                   # zero row: 0 / (0 + 1e-8) = 0
+    out = eng.normalize_cast(_t(x))
+    torch.cuda.synchronize()
+    dp = ((d + 63) // 64) * 64
+    assert out.shape == (n, dp) and out.dtype == torch.bfloat16
+    got = out.float().cpu().numpy()
+    want = O.bf16_round(O.l2_normalize(x))
+    assert np.all(got[:, d:] == 0), "padding must be zero"
+    # the row norm is summed in a different order than numpy's: allow one bf16 ulp
+    ulp = np.maximum(np.abs(want), 2.0 ** -126) * 2.0 ** -7
+    assert np.all(np.abs(got[:, :d] - want) <= ulp + 1e-30)
+    assert np.mean(got[:, :d] == want) > 0.98
+
+
+def test_normalize_cast_strided_and_unaligned(eng):
+    import torch
+    x = torch.randn(50, 200, device="cuda")
+    view = x[:, 3:103]                                # ld=200, offset 3 floats -> scalar path
+    out = eng.normalize_cast(view)
+    torch.cuda.synchronize()
+    want = O.bf16_round(O.l2_normalize(view.cpu().numpy()))
+    got = out.float().cpu().numpy()[:, :100]
+    assert np.max(np.abs(got - want)) <= 2.0 ** -7
+
+
+# --------------------------------------------------------------------------- K2/K3 vs oracle
+SHAPES = [
+    # Q,   N,    D,   k,  thr,  gap, floors
+    (128,  256,  64,  5,  0.3,  2.0, 3),      # exactly one tile
+    (100,  200,  64,  10, 0.5,  10.0, 3),     # ragged single tile
+    (300,  700,  128, 25, 0.5,  10.0, 3),     # several tiles, ragged edges
+    (257,  513,  96,  7,  0.2,  3.0, 4),      # D not a multiple of 64
+    (1000, 1000, 512, 25, 0.5,  10.0, 3),     # C1 slice
+    (64,   5000, 256, 32, 0.4,  5.0, 4),      # few queries, long database (split-N)
+    (1500, 300,  64,  3,  0.5,  1.0, 3),      # many query blocks, short database
+    (400,  2100, 320, 64, 0.1,  10.0, 3),     # k = 64
+]
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("shape", SHAPES, ids=[f"{s[0]}x{s[1]}x{s[2]}k{s[3]}" for s in SHAPES])
+def test_gated_topk_vs_oracle(eng, shape, cg):
+    from semgate import synthetic
+    Q, N, D, k, thr, gap, nf = shape
+    n = max(Q, N)
+    desc, ts, fl = synthetic.make_case(n, D, nf, seed=Q + N + D)
+    q, db = desc[:Q], desc[:N]
+    fl32 = fl.astype(np.int32)
+    got = run_gpu(eng, q, db, k, thr, gap, ts[:Q], ts[:N], fl32[:Q], fl32[:N], mfd=0, mode=0, cg=cg)
+    check_padded(got, k)
+    # (1) against the GPU arithmetic model: bf16 operands, wide accumulate -> tight
+    ref16 = O.gated_topk(q, db, ts[:Q], ts[:N], fl32[:Q], fl32[:N], k=k, threshold=thr, min_time_gap=gap,
+                         max_floor_diff=0, bf16=True)
+    rep = parity.compare_candidates(O.compact(ref16), O.compact(got), k, thr, tol=3e-5)
+    assert rep["max_score_err"] < 3e-5
+    # (2) against the reference arithmetic (fp32 operands): the north-star rule
+    ref32 = O.gated_topk(q, db, ts[:Q], ts[:N], fl32[:Q], fl32[:N], k=k, threshold=thr, min_time_gap=gap,
+                         max_floor_diff=0)
+    parity.compare_candidates(O.compact(ref32), O.compact(got), k, thr, tol=parity.SCORE_TOL)
+    # (3) bit-exact decisions on everything returned
+    c = O.compact(got)
+    parity.check_decisions_exact(c, ts[:N], fl32[:N], gap, 0, q_ts=ts[:Q], q_floors=fl32[:Q])
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+def test_mask_mode_and_nonstrict(eng, cg):
+    from semgate import synthetic
+    desc, ts, fl = synthetic.make_case(900, 128, 4, seed=77)
+    fl32 = fl.astype(np.int32)
+    for mfd in (0, 1):
+        got = run_gpu(eng, desc, desc, 6, 0.3, 4.0, ts, ts, fl32, fl32, mfd=mfd, mode=1, cg=cg)
+        check_padded(got, 6)
+        ref = O.gated_topk(desc, desc, ts, ts, fl32, fl32, k=6, threshold=0.3, min_time_gap=4.0,
+                           max_floor_diff=mfd, gate_mode=O.GATE_MASK, bf16=True)
+        parity.compare_candidates(O.compact(ref), O.compact(got), 6, 0.3, tol=3e-5)
+        c = O.compact(got)
+        assert c["is_valid"].all(), "mask mode returns floor-consistent pairs only"
+        parity.check_decisions_exact(c, ts, fl32, 4.0, mfd)
+
+
+def test_none_floors_and_gating_off(eng):
+    from semgate import synthetic
+    desc, ts, fl = synthetic.make_case(500, 64, 3, seed=5)
+    fl32 = fl.astype(np.int32)
+    fl32[::7] = O.FLOOR_NONE
+    got = run_gpu(eng, desc, desc, 8, 0.4, 4.0, ts, ts, fl32, fl32, mfd=0)
+    c = O.compact(got)
+    parity.check_decisions_exact(c, ts, fl32, 4.0, 0)
+    assert c["is_valid"][(fl32[c["query_idx"]] == O.FLOOR_NONE)].all()
+    off = run_gpu(eng, desc, desc, 8, 0.4, 4.0, ts, ts, fl32, fl32, mfd=-1)
+    assert O.compact(off)["is_valid"].all()
+    nofl = run_gpu(eng, desc, desc, 8, 0.4, 4.0, ts, ts, None, None, mfd=0)
+    assert O.compact(nofl)["is_valid"].all()
+    assert np.array_equal(nofl["idx"], got["idx"])
+
+
+def test_no_timestamps_and_unsorted_timestamps(eng):
+    from semgate import synthetic
+    desc, ts, fl = synthetic.make_case(600, 64, 3, seed=9)
+    got = run_gpu(eng, desc[:50], desc, 5)                      # query(timestamp=None): self match on top
+    assert np.array_equal(got["idx"][:, 0], np.arange(50))
+    assert np.allclose(got["scores"][:, 0], 1.0, atol=4e-3)
+    perm = np.random.default_rng(0).permutation(600)           # unsorted time stamps: per-pair fp64 predicate
+    tsp = ts[perm]
+    got = run_gpu(eng, desc, desc, 9, 0.3, 6.0, tsp, tsp)
+    ref = O.gated_topk(desc, desc, tsp, tsp, k=9, threshold=0.3, min_time_gap=6.0, max_floor_diff=-1, bf16=True)
+    parity.compare_candidates(O.compact(ref), O.compact(got), 9, 0.3, tol=3e-5)
+    parity.check_decisions_exact(O.compact(got), tsp, None, 6.0, -1)
+
+
+def test_epoch_scale_timestamps_need_fp64(eng):
+    """fp32 cannot resolve the window at epoch scale (128 s ulp); the decisions must
+    follow the fp64 predicate exactly, including pairs exactly `gap` apart (kept: strict <)."""
+    from semgate import synthetic
+    desc = synthetic.make_descriptors(400, 64, seed=3, places=4)     # many high-similarity pairs
+    ts = synthetic.EPOCH0 + 0.25 * np.arange(400)
+    got = run_gpu(eng, desc, desc, 25, -1.0, 2.5, ts, ts)
+    ref = O.gated_topk(desc, desc, ts, ts, k=25, threshold=-1.0, min_time_gap=2.5, max_floor_diff=-1, bf16=True)
+    parity.compare_candidates(O.compact(ref), O.compact(got), 25, -1.0, tol=3e-5)
+    c = O.compact(got)
+    parity.check_decisions_exact(c, ts, None, 2.5, -1)
+    d = np.abs(ts[c["match_idx"]] - ts[c["query_idx"]])
+    assert d.min() >= 2.5
+    ro = O.compact(ref)
+    dr = np.abs(ts[ro["match_idx"]] - ts[ro["query_idx"]])
+    assert (d == 2.5).sum() == (dr == 2.5).sum(), "pairs exactly min_time_gap apart are kept (strict <)"
+
+
+def test_adversarial_ascending_scores(eng):
+    """Every new column beats the current k-th score (threshold -1, similarity rising with
+    the index): the running list is replaced on every element."""
+    D, N, k = 64, 3000, 25
+    base = np.zeros(D, np.float32); base[0] = 1.0
+    other = np.zeros(D, np.float32); other[1] = 1.0
+    ang = np.linspace(np.pi / 2 - 0.01, 0.01, N).astype(np.float32)      # cos rises with the index
+    db = np.cos(ang)[:, None] * base[None, :] + np.sin(ang)[:, None] * other[None, :]
+    q = np.tile(base, (130, 1))
+    got = run_gpu(eng, q, db, k, -1.0)
+    check_padded(got, k)
+    want = np.arange(N - 1, N - 1 - k, -1)
+    assert np.array_equal(got["idx"][0], want) and np.array_equal(got["idx"][129], want)
+
+
+def test_ties_prefer_lower_index(eng):
+    rng = np.random.default_rng(1)
+    v = rng.standard_normal((1, 64)).astype(np.float32)
+    db = np.repeat(v, 700, axis=0)                      # identical rows -> identical scores
+    got = run_gpu(eng, v, db, 10)
+    assert np.array_equal(got["idx"][0], np.arange(10))
+
+
+def test_k_larger_than_database_and_tiny_inputs(eng):
+    from semgate import synthetic
+    desc, ts, fl = synthetic.make_case(6, 32, 3, seed=2)
+    got = run_gpu(eng, desc, desc, 25, -1.0, 0.6, ts, ts)
+    assert got["count"].max() <= 5
+    ref = O.gated_topk(desc, desc, ts, ts, k=25, threshold=-1.0, min_time_gap=0.6, max_floor_diff=-1, bf16=True)
+    parity.compare_candidates(O.compact(ref), O.compact(got), 25, -1.0, tol=3e-5)
+    one = run_gpu(eng, desc[:1], desc[:1], 3)
+    assert one["count"][0] == 1 and one["idx"][0, 0] == 0
+
+
+def test_db_index_offset_and_merge(eng):
+    """Row-sharded database: two shard sweeps + key merge == one sweep."""
+    import torch
+    from semgate import synthetic
+    desc, ts, fl = synthetic.make_case(1100, 128, 3, seed=31)
+    fl32 = fl.astype(np.int32)
+    whole = run_gpu(eng, desc, desc, 12, 0.3, 5.0, ts, ts, fl32, fl32, mfd=0)
+    cut = 600
+    a = run_gpu(eng, desc, desc[:cut], 12, 0.3, 5.0, ts, ts[:cut], fl32, fl32[:cut], mfd=0, offset=0)
+    b = run_gpu(eng, desc, desc[cut:], 12, 0.3, 5.0, ts, ts[cut:], fl32, fl32[cut:], mfd=0, offset=cut)
+    keys = torch.from_numpy(np.stack([a["keys"], b["keys"]])).cuda()
+    m = eng.merge_topk(keys, 12, q_floor=_t(fl32), db_floor_all=_t(fl32), max_floor_diff=0)
+    torch.cuda.synchronize()
+    assert np.array_equal(m.idx.cpu().numpy(), whole["idx"])
+    assert np.array_equal(m.scores.cpu().numpy(), whole["scores"])
+    assert np.array_equal(m.valid.cpu().numpy().astype(bool), whole["valid"])
+    assert np.array_equal(m.count.cpu().numpy(), whole["count"])
+
+
+# --------------------------------------------------------------------------- reference goldens through the mirrored API
+@pytest.mark.parametrize("path", FLC, ids=[os.path.basename(p)[:-4] for p in FLC])
+def test_find_loop_closures_golden(path):
+    from semgate import SemanticPlaceRecognition, PlaceDescriptor
+    c = parity.load_flc_case(path)
+    spr = SemanticPlaceRecognition('mixvpr', 'cuda', similarity_threshold=c["thr"], min_time_gap=c["gap"],
+                                   descriptor_dim=c["d"])
+    half = c["n"] // 2
+    for i in range(half):                                # add_image path ...
+        spr.add_image(c["desc"][i], float(c["ts"][i]), c["floors"][i])
+    for i in range(half, c["n"]):                        # ... and direct appends, as the reference demo does
+        spr.vpr.descriptors.append(PlaceDescriptor(float(c["ts"][i]), c["desc"][i], floor_label=c["floors"][i]))
+    matches = spr.find_loop_closures(enable_floor_gating=c["gating"], k=c["k"])
+    got = dict(query_idx=np.array([m.query_idx for m in matches], dtype=np.int64),
+               match_idx=np.array([m.match_idx for m in matches], dtype=np.int64),
+               similarity=np.array([m.similarity for m in matches]),
+               is_valid=np.array([m.is_valid for m in matches], dtype=bool))
+    parity.check_order(got)
+    rep = parity.compare_candidates(c["ref"], got, c["k"], c["thr"])
+    assert rep["max_score_err"] <= parity.SCORE_TOL
+    enc = O.encode_floors(c["floors"])
+    parity.check_decisions_exact(got, c["ts"], enc if c["gating"] else None, c["gap"], 0)
+    assert all(m.query_timestamp == c["ts"][m.query_idx] and m.match_timestamp == c["ts"][m.match_idx] for m in matches[:200])
+    st = spr.get_statistics(matches)
+    assert st["total_matches"] == len(matches) and st["valid_matches"] == int(got["is_valid"].sum())
+    # the composition the north star names: place recognition feeding the loop-closure gate
+    if c["gating"] and not any(f is None for f in c["floors"]):
+        from semgate import SemanticLoopClosureGate
+        gate = SemanticLoopClosureGate(np.array(c["floors"]), strict_mode=True)
+        valid, rejected = gate.gate_candidates([(m.query_idx, m.match_idx, m.similarity) for m in matches])
+        assert len(valid) == st["valid_matches"] and len(rejected) == st["rejected_matches"]
+
+
+@pytest.mark.parametrize("path", QRY, ids=[os.path.basename(p)[:-4] for p in QRY])
+def test_query_golden(path):
+    from semgate import BasePlaceRecognition, synthetic
+    g = np.load(path)
+    n, d, seed, k, with_ts = [int(v) for v in g["params"]]
+    gap = float(g["fparams"][0])
+    desc, ts, floors = synthetic.make_case(n + 4, d, 3, seed, 0.5)
+    vpr = BasePlaceRecognition(descriptor_dim=d, device='cuda')
+    for i in range(n):
+        vpr.add_image(desc[i], float(ts[i]), int(floors[i]))
+    for r, qi in enumerate(range(n, n + 4)):
+        tq = float(ts[(qi * 97) % n]) + 0.25 if with_ts else None
+        ms = vpr.query(desc[qi], tq, k=k, min_time_gap=gap)
+        cnt = int(g["count"][r])
+        ref = dict(query_idx=np.zeros(cnt, np.int64), match_idx=g["match_idx"][r, :cnt].astype(np.int64),
+                   similarity=g["similarity"][r, :cnt], is_valid=np.ones(cnt, bool))
+        got = dict(query_idx=np.zeros(len(ms), np.int64), match_idx=np.array([m.match_idx for m in ms], dtype=np.int64),
+                   similarity=np.array([m.similarity for m in ms]), is_valid=np.ones(len(ms), bool))
+        parity.compare_candidates(ref, got, k, None)
+        assert all(m.query_idx == n for m in ms)
+        if with_ts:
+            assert not np.any(np.abs(ts[got["match_idx"]] - tq) < gap)
+    assert BasePlaceRecognition(descriptor_dim=d, device='cuda').query(desc[0], 0.0) == []     # empty database
+
+
+@pytest.mark.parametrize("algo", ["lego_loam", "orb_slam3"])
+def test_gate_published_counts_gpu(algo):
+    """The reference's published gate counts through the gate class
+    (results/semantic_gating/{algo}_semantic_analysis.txt:20-22)."""
+    from semgate import SemanticLoopClosureGate
+    g = np.load(os.path.join(GOLDEN, f"gate_{algo}.npz"))
+    i, j = O.spatial_candidates(g["positions"], 2.0, 100)
+    total, acc, rej = [int(v) for v in g["published"]]
+    gate = SemanticLoopClosureGate(g["floor_labels"], strict_mode=True)
+    ok = gate.gate_arrays(i, j)
+    st = gate.get_stats()
+    assert (st["total_candidates"], st["accepted"], st["rejected_cross_floor"]) == (total, acc, rej)
+    want, _ = O.gate_candidates(g["floor_labels"], i, j, True)
+    assert np.array_equal(ok, want)
+    gate2 = SemanticLoopClosureGate(g["floor_labels"], strict_mode=False)
+    gate2.gate_arrays(i, j)
+    assert (gate2.stats["accepted"], gate2.stats["rejected_cross_floor"]) == tuple(int(v) for v in g["nonstrict"])
+    if algo == "lego_loam":                       # object interface on a slice, order preserved
+        cands = [(int(a), int(b), 0.5) for a, b in zip(i[:3000], j[:3000])]
+        gate3 = SemanticLoopClosureGate(g["floor_labels"], strict_mode=True)
+        valid, rejected = gate3.gate_candidates(cands)
+        assert len(valid) == int(want[:3000].sum()) and len(rejected) == 3000 - len(valid)
+        assert [c.query_idx for c in valid] == [int(a) for a, w in zip(i[:3000], want[:3000]) if w]
+        assert rejected and rejected[0].rejection_reason.startswith("Cross-floor: ")
+        one = gate3.gate_candidate(int(i[0]), int(j[0]), 0.9)
+        assert one.is_valid == bool(want[0]) and gate3.stats["total_candidates"] == 3001
+
+
+def test_host_abi_find_loop_closures(eng):
+    """The reference-facing C entry point on host buffers."""
+    from semgate import _native, synthetic
+    desc, ts, fl = synthetic.make_case(1200, 256, 3, seed=44)
+    p = _native.make_params(k=25, similarity_threshold=0.5, min_time_gap=10.0, max_floor_diff=0)
+    q, m, s, v = eng.find_loop_closures_host(desc, ts, fl.astype(np.int32), p)
+    got = dict(query_idx=q.astype(np.int64), match_idx=m.astype(np.int64), similarity=s, is_valid=v)
+    parity.check_order(got)
+    ref = O.find_loop_closures(desc, ts, fl.astype(np.int32), similarity_threshold=0.5, min_time_gap=10.0, k=25)
+    parity.compare_candidates(ref, got, 25, 0.5)
+    parity.check_decisions_exact(got, ts, fl.astype(np.int32), 10.0, 0)
+    # N < 2 -> no candidates (place_recognition.py:864)
+    q, m, s, v = eng.find_loop_closures_host(desc[:1], ts[:1], fl[:1].astype(np.int32), p)
+    assert len(q) == 0
+
+
+def test_errors(eng):
+    import torch
+    from semgate import _native
+    with pytest.raises(ValueError):
+        _native.make_params(k=0)
+    with pytest.raises(ValueError):
+        _native.make_params(k=65)
+    x = torch.zeros(4, 64, device="cuda", dtype=torch.bfloat16)
+    p = _native.make_params(k=3)
+    with pytest.raises(_native.SemgateError):
+        eng.gated_topk(x, x, p, q_ts=torch.zeros(4, device="cuda", dtype=torch.float64))   # one-sided timestamps
+    from semgate import SemanticPlaceRecognition, SemanticLoopClosureGate
+    with pytest.raises(ValueError):
+        SemanticPlaceRecognition(vpr_method="nope")
+    with pytest.raises(IndexError):
+        SemanticLoopClosureGate(np.array([1, 2, 3])).gate_arrays([0], [7])
+    assert SemanticPlaceRecognition('mixvpr').find_loop_closures() == []
+
+
+# --------------------------------------------------------------------------- full-size properties (BASELINE config 2)
+@pytest.mark.parametrize("cg", [1, 2])
+def test_full_size_properties_c2(eng, cg):
+    """20k x 4096-d all-pairs sweep: sampled rows against the oracle + structural properties."""
+    import torch
+    from semgate import _native, synthetic
+    n, d, k = 20000, 4096, 25
+    x = synthetic.make_descriptors_device(n, d, "cuda", seed=0)
+    ts = synthetic.make_timestamps(n)
+    fl = synthetic.make_floors(n, 3).astype(np.int32)
+    xb = eng.normalize_cast(x)
+    p = _native.make_params(k=k, similarity_threshold=0.5, min_time_gap=10.0, max_floor_diff=0, cta_group=cg)
+    tts, tfl = _t(ts), _t(fl)
+    r = eng.gated_topk(xb, xb, p, q_ts=tts, db_ts=tts, q_floor=tfl, db_floor=tfl)
+    r2 = eng.gated_topk(xb, xb, p, q_ts=tts, db_ts=tts, q_floor=tfl, db_floor=tfl)
+    torch.cuda.synchronize()
+    got = dict(scores=r.scores.cpu().numpy(), idx=r.idx.cpu().numpy().astype(np.int64),
+               valid=r.valid.cpu().numpy().astype(bool), count=r.count.cpu().numpy())
+    check_padded(got, k)
+    assert torch.equal(r.idx, r2.idx) and torch.equal(r.scores, r2.scores), "sweep must be deterministic"
+    c = O.compact(got)
+    parity.check_decisions_exact(c, ts, fl, 10.0, 0)
+    assert c["similarity"].min() >= np.float32(0.5)
+    # symmetry of the all-pairs sweep: (i,j) above threshold and not cut by k appears as (j,i)
+    rows = np.random.default_rng(0).choice(n, 96, replace=False)
+    xs = x[torch.from_numpy(rows).cuda()].cpu().numpy()
+    xa = x.cpu().numpy()
+    ref = O.gated_topk(xs, xa, ts[rows], ts, fl[rows], fl, k=k, threshold=0.5, min_time_gap=10.0, max_floor_diff=0)
+    sub = dict(scores=got["scores"][rows], idx=got["idx"][rows], valid=got["valid"][rows], count=got["count"][rows])
+    rep = parity.compare_candidates(O.compact(ref), O.compact(sub), k, 0.5)
+    assert rep["max_score_err"] <= parity.SCORE_TOL
+    oq, om, os_, ov, total = eng.compact(r)
+    t = int(total.item())
+    assert t == int(got["count"].sum())
+    flat = dict(query_idx=oq[:t].cpu().numpy(), match_idx=om[:t].cpu().numpy(), similarity=os_[:t].cpu().numpy(),
+                is_valid=ov[:t].cpu().numpy().astype(bool))
+    parity.check_order(flat)
+    assert np.array_equal(flat["match_idx"], c["match_idx"]) and np.array_equal(flat["is_valid"], c["is_valid"])
