@@ -1,0 +1,396 @@
+"""Benchmark of the gated loop-closure retrieval hot path (BASELINE.json metric:
+gated similarity pairs/s + queries/s at top-25; % of bf16 tensor peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE config 2, MixVPR shape): 20 000 query keyframes x 4096-d against a
+database of 20 000 keyframes PER GPU (N=1: the 20k all-pairs loop-closure sweep with floor
+gate; N>1: the database grows with N and is sharded by rows, per-GPU work is fixed ->
+"weak").  A step = one pass of the hot path over resident, already normalised bf16
+descriptors: fused tcgen05 sweep (K2) + list merge (K3) [+ NCCL all-gather + merge at N>1]
++ candidate compaction (K4).  `value` = query-database pairs scored per second, whole job.
+`e2e` = the same metric through the host-buffer C-ABI call (fp32 descriptors in pinned host
+memory -> candidates back in host memory: H2D, normalise, sweep, compaction, D2H all timed).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "multi-level-indoor-slam_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+N_Q = 20000          # query keyframes
+N_DB_PER_GPU = 20000  # database keyframes per GPU
+DIM = 4096           # MixVPR descriptor length (place_recognition.py:197)
+TOPK = 25
+THRESHOLD = 0.5      # SemanticPlaceRecognition default (place_recognition.py:817)
+MIN_TIME_GAP = 10.0  # (place_recognition.py:818)
+NUM_FLOORS = 3
+METRIC = "gated_similarity_pairs_per_s_top25"
+UNIT = "pairs/s"
+
+
+def workload_config(n_gpus: int):
+    return {
+        "workload": "BASELINE configs[1]: MixVPR-shape 4096-d, 20k-keyframe all-pairs loop-closure sweep with floor gate",
+        "queries": N_Q, "database_per_gpu": N_DB_PER_GPU, "database_total": N_DB_PER_GPU * n_gpus, "dim": DIM,
+        "top_k": TOPK, "similarity_threshold": THRESHOLD, "min_time_gap_s": MIN_TIME_GAP, "floors": NUM_FLOORS,
+        "gate": "strict floor gate, flag mode (reference order)", "sharding": f"db-rows x{n_gpus}" if n_gpus > 1 else "none",
+        "l2": "inputs larger than L2 (164 MB bf16 database vs 126 MB L2); no explicit flush",
+    }
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            j = json.load(open(p))
+            return float(j["bf16_tflops"]), float(j.get("hbm_gbs", 0.0)), "measured (MEASURED_PEAKS.json, burst)"
+        except Exception:
+            pass
+    return 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        loaded = sorted(sm)[len(sm) // 2:]          # upper half = samples under load
+        return {"sm_mhz": float(np.median(loaded)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU arm
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [i.get("num_threads", 0) for i in threadpool_info() if i.get("user_api") == "blas"]
+        if n:
+            return int(max(n))
+    except Exception:
+        pass
+    return os.cpu_count() or 1
+
+
+def cpu_inputs(n_db: int, seed: int = 0):
+    """Host copy of the workload: fp32 descriptors, timestamps, floors (same model as the GPU arm)."""
+    from semgate import synthetic
+    desc = synthetic.make_descriptors(n_db, DIM, seed=seed)
+    return desc, synthetic.make_timestamps(n_db), synthetic.make_floors(n_db, NUM_FLOORS).astype(np.int32)
+
+
+def cpu_sweep(desc, ts, fl, rows: int):
+    """The reference algorithm (oracle port, numpy/OpenBLAS on all host threads) on the first
+    `rows` query keyframes against the whole database.  Returns seconds."""
+    from oracle import semgate_oracle as O
+    t0 = time.perf_counter()
+    dbn = O.l2_normalize(desc)
+    res = O.gated_topk(dbn[:rows], dbn, ts[:rows], ts, fl[:rows], fl, k=TOPK, threshold=THRESHOLD,
+                       min_time_gap=MIN_TIME_GAP, max_floor_diff=0, normalize=False, block=1024)
+    O.compact(res)
+    return time.perf_counter() - t0
+
+
+def calibrate_rows(desc, ts, fl, target_s: float, lo: int = 256):
+    t = cpu_sweep(desc, ts, fl, lo)
+    # normalisation of the whole database is a fixed cost inside every sweep; scale the rest
+    rows = int(lo * max(target_s, t) / max(t, 1e-3))
+    return int(min(max(rows, lo), desc.shape[0], N_Q)), t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    desc, ts, fl = cpu_inputs(N_DB_PER_GPU)
+    budget = 150.0 / max(args.steps + args.warmup, 1)
+    rows, _ = calibrate_rows(desc, ts, fl, min(8.0, budget))
+    for _ in range(args.warmup):
+        cpu_sweep(desc, ts, fl, rows)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_sweep(desc, ts, fl, rows)
+    dt = time.perf_counter() - t0
+    value = rows * float(N_DB_PER_GPU) * args.steps / dt
+    sample = f"first {rows} of {N_Q} query keyframes against the full {N_DB_PER_GPU}-keyframe database per step"
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(1),
+        "queries_per_s": rows * args.steps / dt,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference algorithm (oracle/semgate_oracle.py, numpy + OpenBLAS, all host threads); the reference's own "
+                "Python loop (place_recognition.py:882-885) is ~25x slower than this port and cannot hold 20k x 20k",
+    }
+    print(json.dumps(out))
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from semgate import _native, synthetic
+    from semgate.dist import ShardedRetrieval, shard_bounds
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eng = _native.get_engine(local)
+    if args.cta_group:
+        eng.set_option("cta_group", args.cta_group)
+    eng.set_option("profile", 1)
+    sr = ShardedRetrieval(eng)
+
+    n_db_total = N_DB_PER_GPU * world
+    lo, hi = shard_bounds(n_db_total, world, rank)
+    dp = _native.pad_dim(DIM)
+
+    # ---- synthetic inputs, resident in HBM (anchors shared by all ranks; rank 0's shard = the queries)
+    g = torch.Generator(device=dev); g.manual_seed(1234)
+    places = max(8, n_db_total // 20)
+    anchors = torch.randn((places, DIM), generator=g, device=dev, dtype=torch.float32)
+
+    def make_rows(n, seed):
+        gg = torch.Generator(device=dev); gg.manual_seed(seed)
+        pid = torch.randint(0, places, (n,), generator=gg, device=dev)
+        x = anchors[pid]
+        x += 0.6 * torch.randn((n, DIM), generator=gg, device=dev, dtype=torch.float32)
+        return x
+
+    q_f32 = make_rows(N_Q, 1000)                       # == shard 0
+    db_f32 = q_f32 if rank == 0 else make_rows(hi - lo, 1000 + rank)
+    q_bf16 = eng.normalize_cast(q_f32)
+    db_bf16 = q_bf16 if rank == 0 else eng.normalize_cast(db_f32)
+    ts_all = torch.from_numpy(synthetic.make_timestamps(n_db_total)).to(dev)
+    fl_all = torch.from_numpy(synthetic.make_floors(n_db_total, NUM_FLOORS).astype(np.int32)).to(dev)
+    q_ts, q_fl = ts_all[:N_Q].contiguous(), fl_all[:N_Q].contiguous()
+    db_ts, db_fl = ts_all[lo:hi].contiguous(), fl_all[lo:hi].contiguous()
+
+    def mk(offset):
+        return _native.make_params(k=TOPK, similarity_threshold=THRESHOLD, min_time_gap=MIN_TIME_GAP, max_floor_diff=0,
+                                   gate_mode=_native.GATE_FLAG, db_index_offset=offset)
+
+    def step():
+        res = sr.sweep(q_bf16, db_bf16, mk, lo, q_ts=q_ts, db_ts_shard=db_ts, q_floor=q_fl, db_floor_shard=db_fl,
+                       db_floor_all=fl_all, max_floor_diff=0)
+        return eng.compact(res)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    barrier()
+    eng.profile_read()
+    launches0 = eng.launch_count
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count - launches0
+    k2_ms, k2_n = eng.profile_read()
+    clocks = sampler.stop() if rank == 0 else None
+    total_candidates = int(out[4].item())
+    if world > 1:
+        t = torch.tensor([ms, k2_ms / max(k2_n, 1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, k2_avg = float(t[0]), float(t[1])
+        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    else:
+        k2_avg = k2_ms / max(k2_n, 1)
+    pairs_per_step = float(N_Q) * float(n_db_total)
+    value = pairs_per_step * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (K2): algorithmic FLOPs = 2*Q*N_local*Dpad per launch
+    peak_tf, peak_hbm, peak_src = measured_peaks()
+    flops_per_launch = 2.0 * N_Q * (hi - lo) * dp
+    achieved_tf = flops_per_launch / (k2_avg * 1e-3) / 1e12 if k2_avg > 0 else 0.0
+    roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved_tf / peak_tf, "traffic": None, "kernel": "gated_topk_kernel (K2)",
+                "kernel_ms": k2_avg, "kernel_share_of_step": k2_avg / (ms / args.steps), "peak_source": peak_src,
+                "flops_per_launch": flops_per_launch}
+    prof = os.path.join(ROOT, "profiles", "k2_traffic.json")
+    if os.path.isfile(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- end to end through the public host-buffer API (pinned host memory in, host memory out)
+    e2e_steps = max(3, min(args.steps, 10))
+    q_host = torch.empty((N_Q, DIM), dtype=torch.float32, pin_memory=True)
+    q_host.copy_(q_f32)
+    ts_host = synthetic.make_timestamps(n_db_total)
+    fl_host = synthetic.make_floors(n_db_total, NUM_FLOORS).astype(np.int32)
+    cap = N_Q * TOPK
+    if world == 1:
+        outs = tuple(torch.empty((cap,), dtype=dt, pin_memory=True).numpy()
+                     for dt in (torch.int32, torch.int32, torch.float32, torch.uint8))
+        qh = q_host.numpy()
+        p = mk(0)
+
+        def e2e_step():
+            r = eng.find_loop_closures_host(qh, ts_host, fl_host, p, out=outs)   # semgate_find_loop_closures_host
+            return len(r[0])
+        h2d = qh.nbytes + ts_host.nbytes + fl_host.nbytes
+    else:
+        db_host = q_host if rank == 0 else torch.empty((hi - lo, DIM), dtype=torch.float32, pin_memory=True)
+        if rank != 0:
+            db_host.copy_(db_f32)
+        tsh = torch.from_numpy(ts_host).pin_memory()
+        flh = torch.from_numpy(fl_host).pin_memory()
+        ho = [torch.empty((cap,), dtype=dt, pin_memory=True) for dt in (torch.int32, torch.int32, torch.float32, torch.uint8)]
+
+        def e2e_step():
+            qd = q_host.to(dev, non_blocking=True)
+            qb = eng.normalize_cast(qd)
+            dbb = qb if rank == 0 else eng.normalize_cast(db_host.to(dev, non_blocking=True))
+            tsd, fld = tsh.to(dev, non_blocking=True), flh.to(dev, non_blocking=True)
+            res = sr.sweep(qb, dbb, mk, lo, q_ts=tsd[:N_Q], db_ts_shard=tsd[lo:hi], q_floor=fld[:N_Q],
+                           db_floor_shard=fld[lo:hi], db_floor_all=fld, max_floor_diff=0)
+            oq, om, os_, ov, tot = eng.compact(res)
+            t = int(tot.item())
+            if rank == 0:
+                for h, d in zip(ho, (oq, om, os_, ov)):
+                    h[:t].copy_(d[:t], non_blocking=True)
+                torch.cuda.synchronize()
+            return t
+        h2d = q_host.numel() * 4 * (2 * world - 1) + (ts_host.nbytes + fl_host.nbytes) * world
+    del q_f32, db_f32
+    n_e2e = e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        n_e2e = e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt[0])
+    e2e = {"value": pairs_per_step * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(n_e2e * 13 + 8), "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
+           "api": "semgate_find_loop_closures_host (C ABI, pinned host buffers)" if world == 1 else
+                  "semgate python API: pinned host -> device, normalise, sharded sweep, NCCL merge, compaction, D2H"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        desc = q_host.numpy()
+        rows, _ = calibrate_rows(desc, ts_host, fl_host, 10.0)
+        dt = cpu_sweep(desc, ts_host, fl_host, rows)
+        cpu = {"value": rows * float(N_DB_PER_GPU) / dt, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+               "sample": f"first {rows} of {N_Q} query keyframes against the full {N_DB_PER_GPU}-keyframe database "
+                         f"({dt:.1f} s, oracle/semgate_oracle.py: numpy + OpenBLAS)",
+               "host_cpus": os.cpu_count()}
+
+    out_json = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
+        "queries_per_s": N_Q * args.steps / (ms * 1e-3), "candidates_per_step": total_candidates,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "cta_group": args.cta_group or int(os.environ.get("SEMGATE_CTA_GROUP", "1")),
+    }
+    print(json.dumps(out_json))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cta-group", type=int, default=0, choices=[0, 1, 2])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "ours" and args.gpus != world:
+        if args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
