@@ -47,8 +47,10 @@ class ShardedRetrieval:
                                        db_floor=db_floor_shard, want_keys=True, want_lists=False)
         Q, k = local.keys.shape
         buf = self._gather_buf
-        if buf is None or buf.shape != (self.world, Q, k) or buf.device != local.keys.device:
-            buf = torch.empty((self.world, Q, k), dtype=torch.int64, device=local.keys.device)
+        if buf is None or buf.shape != (self.world * Q, k) or buf.device != local.keys.device:
+            # concatenation along dim 0 is the layout every backend accepts; viewed as [G,Q,k] below
+            buf = torch.empty((self.world * Q, k), dtype=torch.int64, device=local.keys.device)
             self._gather_buf = buf
         self.dist.all_gather_into_tensor(buf, local.keys, group=self.group)
-        return self.engine.merge_topk(buf, k, q_floor=q_floor, db_floor_all=db_floor_all, max_floor_diff=max_floor_diff)
+        return self.engine.merge_topk(buf.view(self.world, Q, k), k, q_floor=q_floor, db_floor_all=db_floor_all,
+                                      max_floor_diff=max_floor_diff)

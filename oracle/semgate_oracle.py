@@ -262,3 +262,40 @@ def statistics(is_valid, similarity):
     return {"total_matches": n, "valid_matches": v, "rejected_matches": n - v,
             "rejection_rate": (n - v) / n, "mean_similarity": float(sim.mean()),
             "mean_valid_similarity": float(sim[np.asarray(is_valid, bool)].mean()) if v > 0 else 0.0}
+
+
+# ----------------------------------------------------------------------------
+# candidate keys (the wire format of the multi-GPU all-gather; csrc/common.cuh)
+# ----------------------------------------------------------------------------
+def pack_keys(scores, idx):
+    """(fp32 score, global index) -> int64 key whose unsigned order is (score desc, index asc);
+    empty slots (idx < 0) -> 0.  Mirrors pack_key() in csrc/common.cuh."""
+    s = np.ascontiguousarray(scores, dtype=np.float32)
+    u = s.view(np.uint32).astype(np.uint64)
+    neg = (u & np.uint64(0x80000000)) != 0
+    o = np.where(neg, (~u) & np.uint64(0xFFFFFFFF), u | np.uint64(0x80000000))
+    ix = np.asarray(idx, dtype=np.int64)
+    key = (o << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - np.where(ix >= 0, ix, 0).astype(np.uint64))
+    key = np.where(ix >= 0, key, np.uint64(0))
+    return key.view(np.int64)
+
+
+def unpack_keys(keys):
+    """int64 keys -> (scores fp32 with -inf for empty, idx int64 with -1 for empty)."""
+    k = np.ascontiguousarray(keys).view(np.uint64)
+    o = (k >> np.uint64(32)).astype(np.uint32)
+    pos = (o & np.uint32(0x80000000)) != 0
+    u = np.where(pos, o & np.uint32(0x7FFFFFFF), ~o)
+    s = u.astype(np.uint32).view(np.float32)
+    ix = (np.uint64(0xFFFFFFFF) - (k & np.uint64(0xFFFFFFFF))).astype(np.int64)
+    empty = k == 0
+    return np.where(empty, -np.inf, s).astype(np.float32), np.where(empty, -1, ix)
+
+
+def merge_keys(keys_gathered, k):
+    """[G,Q,k] keys -> [Q,k] largest keys per row, descending, 0 padded (K3's merge)."""
+    g = np.ascontiguousarray(keys_gathered).view(np.uint64)
+    G, Q, kk = g.shape
+    allk = np.transpose(g, (1, 0, 2)).reshape(Q, G * kk)
+    srt = np.sort(allk, axis=1)[:, ::-1][:, :k]
+    return np.ascontiguousarray(srt).view(np.int64)

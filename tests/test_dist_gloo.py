@@ -1,0 +1,129 @@
+"""CPU tier: the row-sharded multi-rank path (semgate/dist.py) with world_size 2 over gloo.
+
+The orchestration under test is the product's: shard bounds, global column offsets, the
+all-gather of per-rank candidate keys and the merge call.  The two kernels it drives
+(K2 sweep, K3 merge) need a GPU, so a stand-in engine restates them with the oracle on
+CPU tensors; the same merge is checked against the real K3 kernel in tests/test_gpu_parity.py.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import semgate_oracle as O
+from semgate import synthetic
+from semgate.dist import ShardedRetrieval, shard_bounds
+
+
+class _Res:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+class OracleEngine:
+    """Stand-in for semgate._native.Engine on CPU tensors (test double)."""
+
+    def __init__(self, desc_q, desc_db_all):
+        self.q, self.db_all = desc_q, desc_db_all
+
+    def gated_topk(self, q_bf16, db_bf16, params, q_ts=None, db_ts=None, q_floor=None, db_floor=None,
+                   want_keys=False, want_lists=True):
+        lo, n = params["offset"], db_bf16.shape[0]
+        r = O.gated_topk(q_bf16.numpy(), db_bf16.numpy(), None if q_ts is None else q_ts.numpy(),
+                         None if db_ts is None else db_ts.numpy(), None if q_floor is None else q_floor.numpy(),
+                         None if db_floor is None else db_floor.numpy(), k=params["k"], threshold=params["thr"],
+                         min_time_gap=params["gap"], max_floor_diff=params["mfd"], db_index_offset=lo, normalize=True)
+        keys = torch.from_numpy(O.pack_keys(r["scores"], r["idx"]))
+        return _Res(keys=keys, scores=torch.from_numpy(r["scores"]), idx=torch.from_numpy(r["idx"]),
+                    valid=torch.from_numpy(r["valid"]), count=torch.from_numpy(r["count"]))
+
+    def merge_topk(self, keys_gathered, k, q_floor=None, db_floor_all=None, max_floor_diff=-1):
+        merged = O.merge_keys(keys_gathered.numpy(), k)
+        sc, ix = O.unpack_keys(merged)
+        got = ix >= 0
+        valid = got.copy()
+        if q_floor is not None and db_floor_all is not None and max_floor_diff >= 0:
+            mf = db_floor_all.numpy()[np.where(got, ix, 0)]
+            valid = got & O.floor_ok(q_floor.numpy()[:, None], mf, max_floor_diff)
+        return _Res(scores=torch.from_numpy(sc), idx=torch.from_numpy(ix), valid=torch.from_numpy(valid),
+                    count=torch.from_numpy(got.sum(axis=1).astype(np.int32)), keys=torch.from_numpy(merged))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_db, n_q, d, k = 1301, 257, 48, 9
+        desc, ts, fl = synthetic.make_case(n_db, d, 4, seed=3)
+        fl = fl.astype(np.int32)
+        lo, hi = shard_bounds(n_db, world, rank)
+        sr = ShardedRetrieval(OracleEngine(desc[:n_q], desc))
+        assert sr.world == world and sr.rank == rank
+        t = torch.from_numpy
+        res = sr.sweep(t(desc[:n_q]), t(desc[lo:hi]), lambda off: dict(offset=off, k=k, thr=0.3, gap=5.0, mfd=0), lo,
+                       q_ts=t(ts[:n_q]), db_ts_shard=t(ts[lo:hi]), q_floor=t(fl[:n_q]), db_floor_shard=t(fl[lo:hi]),
+                       db_floor_all=t(fl), max_floor_diff=0)
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), scores=res.scores.numpy(), idx=res.idx.numpy(),
+                 valid=res.valid.numpy(), count=res.count.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_bounds_cover_exactly():
+    for n in (0, 1, 7, 1000, 1000003):
+        for w in (1, 2, 3, 8):
+            b = [shard_bounds(n, w, r) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(10, 2, 2)
+
+
+def test_key_roundtrip_and_order():
+    rng = np.random.default_rng(0)
+    s = rng.standard_normal((50, 8)).astype(np.float32)
+    s[0, :3] = [0.0, -0.0, np.inf]
+    s[1, :2] = 0.25                                     # tie: lower index must win
+    ix = rng.permutation(400).reshape(50, 8).astype(np.int64)
+    ix[1, :2] = [7, 3]
+    keys = O.pack_keys(s, ix)
+    s2, i2 = O.unpack_keys(keys)
+    assert np.array_equal(s2, s) and np.array_equal(i2, ix)
+    ku = keys.view(np.uint64)
+    assert ku[1, 1] > ku[1, 0]                          # same score, index 3 beats index 7
+    order = np.argsort(-ku[2].astype(np.float64), kind="stable")
+    assert np.all(np.diff(s[2][order]) <= 0)
+    empty = O.pack_keys(np.array([-np.inf], np.float32), np.array([-1]))
+    assert empty[0] == 0 and O.unpack_keys(empty)[1][0] == -1
+
+
+def test_sharded_sweep_world2_gloo(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    n_db, n_q, d, k = 1301, 257, 48, 9
+    desc, ts, fl = synthetic.make_case(n_db, d, 4, seed=3)
+    fl = fl.astype(np.int32)
+    whole = O.gated_topk(desc[:n_q], desc, ts[:n_q], ts, fl[:n_q], fl, k=k, threshold=0.3, min_time_gap=5.0,
+                         max_floor_diff=0)
+    r0 = np.load(tmp_path / "rank0.npz")
+    r1 = np.load(tmp_path / "rank1.npz")
+    for key in ("scores", "idx", "valid", "count"):
+        assert np.array_equal(r0[key], r1[key]), f"ranks disagree on {key}"
+    # shard sweeps normalise their own slice: identical arithmetic per row -> identical result
+    assert np.array_equal(r0["idx"], whole["idx"])
+    assert np.array_equal(r0["scores"], whole["scores"])
+    assert np.array_equal(r0["valid"], whole["valid"])
+    assert np.array_equal(r0["count"], whole["count"])

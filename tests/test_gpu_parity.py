@@ -210,18 +210,31 @@ def test_epoch_scale_timestamps_need_fp64(eng):
 
 
 def test_adversarial_ascending_scores(eng):
-    """Every new column beats the current k-th score (threshold -1, similarity rising with
-    the index): the running list is replaced on every element."""
+    """Every new column beats the current k-th score (threshold -1, similarity strictly rising
+    with the index): the running list is replaced on every element.  Operands are fed as raw
+    bf16 so that all 3000 scores are exactly representable and distinct."""
+    import torch
+    from semgate import _native
     D, N, k = 64, 3000, 25
-    base = np.zeros(D, np.float32); base[0] = 1.0
-    other = np.zeros(D, np.float32); other[1] = 1.0
-    ang = np.linspace(np.pi / 2 - 0.01, 0.01, N).astype(np.float32)      # cos rises with the index
-    db = np.cos(ang)[:, None] * base[None, :] + np.sin(ang)[:, None] * other[None, :]
-    q = np.tile(base, (130, 1))
-    got = run_gpu(eng, q, db, k, -1.0)
-    check_padded(got, k)
-    want = np.arange(N - 1, N - 1 - k, -1)
-    assert np.array_equal(got["idx"][0], want) and np.array_equal(got["idx"][129], want)
+    i = np.arange(N)
+    db = np.zeros((N, D), np.float32)
+    db[:, 0] = (128 + i // 32) / 256.0            # bf16-exact
+    db[:, 1] = (i % 32) / 32.0                    # bf16-exact
+    q = np.zeros((130, D), np.float32)
+    q[:, 0] = 1.0
+    q[:, 1] = 1.0 / 256.0                         # score_i = (128 + i//32)/256 + (i%32)/8192, exact in fp32
+    qb = torch.from_numpy(q).cuda().to(torch.bfloat16)
+    dbb = torch.from_numpy(db).cuda().to(torch.bfloat16)
+    assert torch.equal(dbb.float().cpu(), torch.from_numpy(db))
+    for cg in (1, 2):
+        r = eng.gated_topk(qb, dbb, _native.make_params(k=k, similarity_threshold=-1.0, cta_group=cg))
+        torch.cuda.synchronize()
+        got = dict(scores=r.scores.cpu().numpy(), idx=r.idx.cpu().numpy().astype(np.int64),
+                   valid=r.valid.cpu().numpy().astype(bool), count=r.count.cpu().numpy())
+        check_padded(got, k)
+        want = np.arange(N - 1, N - 1 - k, -1)
+        assert np.array_equal(got["idx"][0], want) and np.array_equal(got["idx"][129], want)
+        assert np.array_equal(got["scores"][0], (db[want, 0] + db[want, 1] / 256.0).astype(np.float32))
 
 
 def test_ties_prefer_lower_index(eng):
@@ -253,6 +266,7 @@ def test_db_index_offset_and_merge(eng):
     cut = 600
     a = run_gpu(eng, desc, desc[:cut], 12, 0.3, 5.0, ts, ts[:cut], fl32, fl32[:cut], mfd=0, offset=0)
     b = run_gpu(eng, desc, desc[cut:], 12, 0.3, 5.0, ts, ts[cut:], fl32, fl32[cut:], mfd=0, offset=cut)
+    assert np.array_equal(a["keys"], O.pack_keys(a["scores"], a["idx"])), "key wire format differs from the oracle's"
     keys = torch.from_numpy(np.stack([a["keys"], b["keys"]])).cuda()
     m = eng.merge_topk(keys, 12, q_floor=_t(fl32), db_floor_all=_t(fl32), max_floor_diff=0)
     torch.cuda.synchronize()
