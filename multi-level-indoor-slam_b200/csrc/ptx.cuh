@@ -47,12 +47,14 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster.
+// Default (cta-scope) semantics on purpose: a `.release.cluster` arrive compiles to
+// MEMBAR.ALL.GPU + ERRBAR in the issuing thread, which drains the TMA pipeline every stage.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(bar), "r"(cta) : "memory");
 }
 
