@@ -128,6 +128,19 @@ int semgate_gate_candidates(semgate_handle_t h, const int32_t* floor_labels, int
                             const int32_t* match_idx, int64_t M, int32_t max_floor_diff, uint8_t* out_is_valid,
                             uint64_t* out_counts, semgate_stream_t stream);
 
+/* ---- spatial-proximity candidate generator (radius join over poses) ----------------
+ * replaces detect_loop_closure_candidates (orb_slam3_integration.py:167-217 and the
+ * droid_slam / lego_loam twins): pairs i < j with ||p_i - p_j|| <= radius (fp64) and
+ * j - i >= min_index_gap, sorted by (i, j).  positions: device fp64 [n,3].
+ * Two phases: _count fills the workspace and *out_total (device int64); _fill writes the
+ * first `capacity` pairs (out_dist may be NULL). */
+size_t semgate_spatial_workspace_bytes(int64_t n);
+int semgate_spatial_count(semgate_handle_t h, const double* positions, int64_t n, double radius, int64_t min_index_gap,
+                          void* workspace, int64_t* out_total, semgate_stream_t stream);
+int semgate_spatial_fill(semgate_handle_t h, const double* positions, int64_t n, double radius, int64_t min_index_gap,
+                         const void* workspace, int32_t* out_i, int32_t* out_j, double* out_dist, int64_t capacity,
+                         semgate_stream_t stream);
+
 /* ---- host-buffer entry points (the reference-facing calls) ----------------------
  * find_loop_closures over a whole database held in host memory
  * (SemanticPlaceRecognition.find_loop_closures, place_recognition.py:851-911):
@@ -148,6 +161,13 @@ int semgate_query_host(semgate_handle_t h, const float* queries, int64_t nq, con
 int semgate_gate_candidates_host(semgate_handle_t h, const int32_t* floor_labels, int64_t n_labels,
                                  const int32_t* query_idx, const int32_t* match_idx, int64_t M, int32_t max_floor_diff,
                                  uint8_t* out_is_valid, uint64_t* out_counts);
+
+/* detect_loop_closure_candidates over host arrays.  *out_total always receives the number
+ * of pairs; if it exceeds `capacity` (or the outputs are NULL) nothing is written and
+ * SEMGATE_ENOMEM is returned, so a caller can size its buffers with a first call. */
+int semgate_spatial_candidates_host(semgate_handle_t h, const double* positions, int64_t n, double radius,
+                                    int64_t min_index_gap, int32_t* out_i, int32_t* out_j, double* out_dist,
+                                    int64_t capacity, int64_t* out_total);
 
 #ifdef __cplusplus
 }

@@ -328,6 +328,35 @@ int semgate_gate_candidates(semgate_handle_t h, const int32_t* floor_labels, int
   return 0;
 }
 
+// ---------------------------------------------------------------- spatial radius join
+size_t semgate_spatial_workspace_bytes(int64_t n) { return align256(spatial_workspace_bytes(n < 0 ? 0 : n)); }
+
+int semgate_spatial_count(semgate_handle_t h, const double* positions, int64_t n, double radius, int64_t min_index_gap,
+                          void* workspace, int64_t* out_total, semgate_stream_t stream) {
+  if (!h) return fail(SEMGATE_EINVAL, "handle is NULL");
+  if (n < 0 || n > INT32_MAX || !out_total || !(radius >= 0.0)) return fail(SEMGATE_EINVAL, "spatial_count: bad arguments");
+  if (n > 0 && (!positions || !workspace)) return fail(SEMGATE_EINVAL, "spatial_count: NULL pointer");
+  DeviceGuard g(h->device);
+  RC_TRY(launch_spatial_count(positions, n, radius, min_index_gap, workspace, out_total, static_cast<cudaStream_t>(stream)),
+         "spatial_count launch");
+  h->launches += n > 0 ? 4 : 0;
+  return 0;
+}
+
+int semgate_spatial_fill(semgate_handle_t h, const double* positions, int64_t n, double radius, int64_t min_index_gap,
+                         const void* workspace, int32_t* out_i, int32_t* out_j, double* out_dist, int64_t capacity,
+                         semgate_stream_t stream) {
+  if (!h) return fail(SEMGATE_EINVAL, "handle is NULL");
+  if (n < 0 || capacity < 0) return fail(SEMGATE_EINVAL, "spatial_fill: bad arguments");
+  if (n == 0 || capacity == 0) return 0;
+  if (!positions || !workspace || !out_i || !out_j) return fail(SEMGATE_EINVAL, "spatial_fill: NULL pointer");
+  DeviceGuard g(h->device);
+  RC_TRY(launch_spatial_fill(positions, n, radius, min_index_gap, workspace, out_i, out_j, out_dist, capacity,
+                             static_cast<cudaStream_t>(stream)), "spatial_fill launch");
+  h->launches += 1;
+  return 0;
+}
+
 // ---------------------------------------------------------------- host-buffer entry points
 int semgate_find_loop_closures_host(semgate_handle_t h, const float* descriptors, int64_t n, int32_t d,
                                     const double* timestamps, const int32_t* floor_labels, const semgate_topk_params* p,
@@ -469,6 +498,43 @@ int semgate_gate_candidates_host(semgate_handle_t h, const int32_t* floor_labels
   CUDA_TRY(cudaMemcpyAsync(out_counts, dc, 24, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   if (out_counts[2] != 0) return fail(SEMGATE_EINDEX, "gate_candidates: %llu candidate indices fall outside the %lld floor labels", (unsigned long long)out_counts[2], (long long)n_labels);
+  return 0;
+}
+
+int semgate_spatial_candidates_host(semgate_handle_t h, const double* positions, int64_t n, double radius,
+                                    int64_t min_index_gap, int32_t* out_i, int32_t* out_j, double* out_dist,
+                                    int64_t capacity, int64_t* out_total) {
+  if (!h) return fail(SEMGATE_EINVAL, "handle is NULL");
+  if (!out_total || n < 0) return fail(SEMGATE_EINVAL, "spatial_candidates: bad arguments");
+  *out_total = 0;
+  if (n == 0) return 0;
+  if (!positions) return fail(SEMGATE_EINVAL, "spatial_candidates: NULL positions");
+  DeviceGuard g(h->device);
+  cudaStream_t st = h->stream;
+  int rc;
+  void *dp, *ws, *tot;
+  if ((rc = h->reserve(B_X, 24ull * n, &dp)) || (rc = h->reserve(B_WS, semgate_spatial_workspace_bytes(n), &ws)) ||
+      (rc = h->reserve(B_TOT, 32, &tot)))
+    return rc;
+  CUDA_TRY(cudaMemcpyAsync(dp, positions, 24ull * n, cudaMemcpyHostToDevice, st));
+  if ((rc = semgate_spatial_count(h, static_cast<double*>(dp), n, radius, min_index_gap, ws, static_cast<int64_t*>(tot), st))) return rc;
+  int64_t total = 0;
+  CUDA_TRY(cudaMemcpyAsync(&total, tot, 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  *out_total = total;
+  if (total == 0) return 0;
+  if (total > capacity || !out_i || !out_j)
+    return fail(SEMGATE_ENOMEM, "spatial_candidates: %lld pairs exceed output capacity %lld", (long long)total, (long long)capacity);
+  void *di, *dj, *dd = nullptr;
+  if ((rc = h->reserve(B_OQ, 4ull * total, &di)) || (rc = h->reserve(B_OM, 4ull * total, &dj))) return rc;
+  if (out_dist && (rc = h->reserve(B_SC, 8ull * total, &dd))) return rc;
+  if ((rc = semgate_spatial_fill(h, static_cast<double*>(dp), n, radius, min_index_gap, ws, static_cast<int32_t*>(di),
+                                 static_cast<int32_t*>(dj), static_cast<double*>(dd), total, st)))
+    return rc;
+  CUDA_TRY(cudaMemcpyAsync(out_i, di, 4ull * total, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(out_j, dj, 4ull * total, cudaMemcpyDeviceToHost, st));
+  if (out_dist) CUDA_TRY(cudaMemcpyAsync(out_dist, dd, 8ull * total, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
   return 0;
 }
 

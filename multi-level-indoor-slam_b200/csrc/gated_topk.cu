@@ -4,6 +4,7 @@
 
 #include <cudaTypedefs.h>
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 namespace semgate {
@@ -19,7 +20,9 @@ Schedule make_schedule(int64_t Q, int64_t N, int d_pad, int cta_group, int sm_co
   // Query blocks resident per super-row are re-read from L2 once per database
   // tile; keep them comfortably inside the 126 MB L2 next to the database tiles.
   const int64_t a_bytes = static_cast<int64_t>(bm_unit) * d_pad * 2;
-  const int rm_cap = static_cast<int>(std::max<int64_t>(1, (48ll << 20) / std::max<int64_t>(a_bytes, 1)));
+  int64_t cap_mb = 48;
+  if (const char* e = getenv("SEMGATE_RM_CAP_MB")) { const long v = atol(e); if (v > 0) cap_mb = v; }
+  const int rm_cap = static_cast<int>(std::max<int64_t>(1, (cap_mb << 20) / std::max<int64_t>(a_bytes, 1)));
   const int rm_hi = std::min({sc.mblocks, units, rm_cap});
   int64_t best_cost = -1;
   int best_rm = 1;

@@ -142,24 +142,24 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   uint32_t stage = 0, phase = 0, it = 0;
 
   if (warp == 0) {
-    // ===================================================== TMA producer
-    if (lane == 0) {
-      for (int sr = 0; sr < n_sr; ++sr) {
-        const bool full_sr = sr < sc.n_full;
-        const int r = full_sr ? sc.rm : sc.r_last;
-        const int S = full_sr ? sc.s_main : sc.s_last;
-        if (unit >= r * S) continue;
-        const int mb = sr * sc.rm + unit % r;
-        const int j = unit / r;
-        const int nt0 = split_begin(sc.ntiles, S, j), nt1 = split_begin(sc.ntiles, S, j + 1);
-        const int m0 = (mb * CG + static_cast<int>(cta_rank)) * BM;
-        for (int nt = nt0; nt < nt1; ++nt) {
-          const int n0 = nt * BN + static_cast<int>(cta_rank) * static_cast<int>(B_ROWS);
-          for (int kb = 0; kb < p.kblocks; ++kb) {
-            ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-            const uint32_t dst_a = ptx::smem_u32(smem_a + stage * A_STAGE_BYTES);
-            const uint32_t dst_b = ptx::smem_u32(smem_b + stage * B_STAGE_BYTES);
-            const uint32_t fb = bar_full + 8 * stage;
+    // ===================================================== TMA producer (whole warp loops, one lane issues)
+    for (int sr = 0; sr < n_sr; ++sr) {
+      const bool full_sr = sr < sc.n_full;
+      const int r = full_sr ? sc.rm : sc.r_last;
+      const int S = full_sr ? sc.s_main : sc.s_last;
+      if (unit >= r * S) continue;
+      const int mb = sr * sc.rm + unit % r;
+      const int j = unit / r;
+      const int nt0 = split_begin(sc.ntiles, S, j), nt1 = split_begin(sc.ntiles, S, j + 1);
+      const int m0 = (mb * CG + static_cast<int>(cta_rank)) * BM;
+      for (int nt = nt0; nt < nt1; ++nt) {
+        const int n0 = nt * BN + static_cast<int>(cta_rank) * static_cast<int>(B_ROWS);
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t dst_a = ptx::smem_u32(smem_a) + stage * A_STAGE_BYTES;
+          const uint32_t dst_b = ptx::smem_u32(smem_b) + stage * B_STAGE_BYTES;
+          const uint32_t fb = bar_full + 8 * stage;
+          if (ptx::elect_one()) {
             if constexpr (CG == 1) {
               ptx::mbar_arrive_expect_tx(fb, STAGE_BYTES);
               ptx::tma_load_2d(dst_a, &tmap_q, fb, kb * BK, m0);
@@ -172,16 +172,18 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
               ptx::tma_load_2d_cg2(dst_b, &tmap_db, fb_leader, kb * BK, n0);
               if (!leader) ptx::mbar_arrive_cluster(fb, 0);
             }
-            if (++stage == static_cast<uint32_t>(stages)) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == static_cast<uint32_t>(stages)) { stage = 0; phase ^= 1; }
         }
       }
     }
-    __syncwarp();   // reconverge before the (aligned) teardown barrier
   } else if (warp == 1) {
     // ===================================================== MMA issuer (leader CTA only)
-    if (lane == 0 && leader) {
+    if (leader) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(BM * CG, BN);
+      const uint64_t adesc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a));
+      const uint64_t bdesc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b));
       for (int sr = 0; sr < n_sr; ++sr) {
         const bool full_sr = sr < sc.n_full;
         const int r = full_sr ? sc.rm : sc.r_last;
@@ -197,20 +199,24 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           for (int kb = 0; kb < p.kblocks; ++kb) {
             ptx::mbar_wait(bar_full + 8 * stage, phase);
             ptx::tc_fence_after();
-            const uint64_t adesc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * A_STAGE_BYTES));
-            const uint64_t bdesc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * B_STAGE_BYTES));
+            // descriptors differ from stage 0's only in the (address >> 4) field
+            const uint64_t adesc = adesc0 + static_cast<uint64_t>((stage * A_STAGE_BYTES) >> 4);
+            const uint64_t bdesc = bdesc0 + static_cast<uint64_t>((stage * B_STAGE_BYTES) >> 4);
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-              // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in the >>4 address field
-              ptx::umma_bf16<CG>(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb | kk) != 0);
+              for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in the >>4 address field
+                ptx::umma_bf16<CG>(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb | kk) != 0);
+              }
+              if constexpr (CG == 1) {
+                ptx::umma_commit_cg1(bar_empty + 8 * stage);
+                if (kb == p.kblocks - 1) ptx::umma_commit_cg1(bar_tfull + 8 * acc);
+              } else {
+                ptx::umma_commit_cg2_mc(bar_empty + 8 * stage, 0b11);
+                if (kb == p.kblocks - 1) ptx::umma_commit_cg2_mc(bar_tfull + 8 * acc, 0b11);
+              }
             }
-            if constexpr (CG == 1) {
-              ptx::umma_commit_cg1(bar_empty + 8 * stage);
-              if (kb == p.kblocks - 1) ptx::umma_commit_cg1(bar_tfull + 8 * acc);
-            } else {
-              ptx::umma_commit_cg2_mc(bar_empty + 8 * stage, 0b11);
-              if (kb == p.kblocks - 1) ptx::umma_commit_cg2_mc(bar_tfull + 8 * acc, 0b11);
-            }
+            __syncwarp();
             if (++stage == static_cast<uint32_t>(stages)) { stage = 0; phase ^= 1; }
           }
         }

@@ -58,4 +58,11 @@ int launch_gate_candidates(const int32_t* floors, int64_t n_floors, const int32_
                            int max_floor_diff, uint8_t* out_valid, unsigned long long* counts /*[3]: accepted, rejected, bad index*/,
                            cudaStream_t st);
 
+// spatial radius join (orb_slam3_integration.py:167-217): count+scan, then fill
+size_t spatial_workspace_bytes(int64_t n);
+int launch_spatial_count(const double* pos, int64_t n, double radius, int64_t gap, void* workspace, int64_t* total,
+                         cudaStream_t st);
+int launch_spatial_fill(const double* pos, int64_t n, double radius, int64_t gap, const void* workspace, int32_t* out_i,
+                        int32_t* out_j, double* out_dist, int64_t capacity, cudaStream_t st);
+
 }  // namespace semgate

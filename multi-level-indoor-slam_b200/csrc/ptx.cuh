@@ -24,6 +24,19 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   return r;
 }
 
+// One lane of a converged warp gets `true`.  Keeping role loops warp-uniform and electing
+// only around the asynchronous instruction lets ptxas keep addresses/descriptors in uniform
+// registers instead of a per-instruction R2UR waterfall.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

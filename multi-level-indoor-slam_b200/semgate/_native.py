@@ -26,7 +26,8 @@ SYMBOLS = [
     "semgate_set_option", "semgate_profile_read", "semgate_launch_count", "semgate_pad_dim", "semgate_normalize_cast",
     "semgate_topk_workspace_bytes", "semgate_gated_topk", "semgate_merge_topk", "semgate_compact_workspace_bytes",
     "semgate_compact", "semgate_gate_candidates", "semgate_find_loop_closures_host", "semgate_query_host",
-    "semgate_gate_candidates_host",
+    "semgate_gate_candidates_host", "semgate_spatial_workspace_bytes", "semgate_spatial_count", "semgate_spatial_fill",
+    "semgate_spatial_candidates_host",
 ]
 
 
@@ -86,6 +87,11 @@ def load_library():
     lib.semgate_find_loop_closures_host.argtypes = [vp, vp, i64, i32, vp, vp, P(TopkParams), vp, vp, vp, vp, i64, P(i64)]
     lib.semgate_query_host.argtypes = [vp, vp, i64, vp, i64, i32, vp, vp, P(TopkParams), vp, vp, vp]
     lib.semgate_gate_candidates_host.argtypes = [vp, vp, i64, vp, vp, i64, i32, vp, vp]
+    lib.semgate_spatial_workspace_bytes.argtypes = [i64]
+    lib.semgate_spatial_workspace_bytes.restype = sz
+    lib.semgate_spatial_count.argtypes = [vp, vp, i64, C.c_double, i64, vp, vp, vp]
+    lib.semgate_spatial_fill.argtypes = [vp, vp, i64, C.c_double, i64, vp, vp, vp, vp, i64, vp]
+    lib.semgate_spatial_candidates_host.argtypes = [vp, vp, i64, C.c_double, i64, vp, vp, vp, i64, P(i64)]
     for name in SYMBOLS:
         getattr(lib, name)   # AttributeError here = the library is older than the header
     _lib = lib
@@ -353,6 +359,26 @@ class Engine:
         _check(self.lib.semgate_gate_candidates_host(self._h, _np_ptr(fl), fl.shape[0], _np_ptr(qi), _np_ptr(mi), M,
                                                      max_floor_diff, _np_ptr(valid), _np_ptr(counts)))
         return valid[:M].astype(bool), int(counts[0]), int(counts[1])
+
+
+    def spatial_candidates_host(self, positions: np.ndarray, radius: float, min_index_gap: int, want_dist: bool = True):
+        """Radius join over poses: (i, j, dist) with i < j, j - i >= gap, ||p_i - p_j|| <= radius, sorted by (i, j)."""
+        pos = np.ascontiguousarray(positions, dtype=np.float64)
+        if pos.ndim != 2 or pos.shape[1] != 3:
+            raise ValueError("positions must be [n, 3]")
+        n = pos.shape[0]
+        total = C.c_int64(0)
+        rc = self.lib.semgate_spatial_candidates_host(self._h, _np_ptr(pos), n, float(radius), int(min_index_gap),
+                                                      None, None, None, 0, C.byref(total))
+        if rc not in (0, ENOMEM):
+            _check(rc)
+        t = total.value
+        oi, oj = np.empty(max(t, 1), np.int32), np.empty(max(t, 1), np.int32)
+        od = np.empty(max(t, 1), np.float64) if want_dist else None
+        if t:
+            _check(self.lib.semgate_spatial_candidates_host(self._h, _np_ptr(pos), n, float(radius), int(min_index_gap),
+                                                            _np_ptr(oi), _np_ptr(oj), _np_ptr(od), t, C.byref(total)))
+        return oi[:t], oj[:t], (od[:t] if want_dist else None)
 
 
 _engines = {}

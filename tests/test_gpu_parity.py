@@ -362,6 +362,35 @@ def test_gate_published_counts_gpu(algo):
         assert one.is_valid == bool(want[0]) and gate3.stats["total_candidates"] == 3001
 
 
+@pytest.mark.parametrize("algo", ["lego_loam", "orb_slam3"])
+def test_spatial_candidates_and_gate_end_to_end(algo):
+    """Poses -> radius join -> floor gate, all on the GPU, against the reference's published
+    counts and the oracle's pair list (orb_slam3_integration.py:167-281)."""
+    from semgate import spatial
+    g = np.load(os.path.join(GOLDEN, f"gate_{algo}.npz"))
+    i, j, d = spatial.detect_loop_closure_candidates_arrays(g["positions"], 2.0, 100)
+    oi, oj = O.spatial_candidates(g["positions"], 2.0, 100)
+    assert np.array_equal(i, oi) and np.array_equal(j, oj), "candidate pairs differ from the KD-tree join"
+    want_d = np.linalg.norm(g["positions"][oi] - g["positions"][oj], axis=1)
+    assert np.allclose(d, want_d, rtol=1e-13, atol=0) and d.max() <= 2.0
+    a, gate, ok = spatial.apply_floor_gating(i, j, g["floor_labels"], strict_mode=True, max_pairs=5)
+    total, acc, rej = [int(v) for v in g["published"]]
+    assert (a.total_candidates, a.same_floor_candidates, a.cross_floor_candidates) == (total, acc, rej)
+    assert (gate.stats["accepted"], gate.stats["rejected_cross_floor"]) == (acc, rej)
+    assert len(a.cross_floor_pairs) == 5 and all(p[2] != p[3] for p in a.cross_floor_pairs)
+    a2, gate2, _ = spatial.apply_floor_gating(i, j, g["floor_labels"], strict_mode=False)
+    assert (gate2.stats["accepted"], gate2.stats["rejected_cross_floor"]) == tuple(int(v) for v in g["nonstrict"])
+    assert a2.same_floor_candidates == acc
+    # small cases incl. gap <= 0 and an empty result
+    pos = g["positions"][:300]
+    for r, gap in ((0.5, 0), (1.0, 1), (3.0, 250), (1e-9, 5)):
+        gi, gj, _ = spatial.detect_loop_closure_candidates_arrays(pos, r, gap)
+        ri, rj = O.spatial_candidates(pos, r, max(gap, 1))
+        assert np.array_equal(gi, ri) and np.array_equal(gj, rj)
+    tup = spatial.detect_loop_closure_candidates(pos, 1.0, 50)
+    assert all(b - a_ >= 50 and a_ < b for a_, b, _ in tup)
+
+
 def test_host_abi_find_loop_closures(eng):
     """The reference-facing C entry point on host buffers."""
     from semgate import _native, synthetic
