@@ -366,7 +366,7 @@ def run_ours(args):
         "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
         "queries_per_s": N_Q * args.steps / (ms * 1e-3), "candidates_per_step": total_candidates,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "cta_group": args.cta_group or int(os.environ.get("SEMGATE_CTA_GROUP", "1")),
+        "cta_group": args.cta_group or os.environ.get("SEMGATE_CTA_GROUP", "auto (2 for Q >= 4096)"),
     }
     print(json.dumps(out_json))
     if world > 1:

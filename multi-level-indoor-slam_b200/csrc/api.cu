@@ -52,7 +52,7 @@ struct semgate_ctx {
   int device = 0;
   int sm_count = 0;
   int cc_major = 0, cc_minor = 0;
-  int cta_group = 1;
+  int cta_group = 0;               // 0 = auto (by problem size), 1, 2
   int64_t launches = 0;
   cudaStream_t stream = nullptr;   // used by the *_host entry points
   bool profile = false;            // record CUDA events around every K2 launch
@@ -95,7 +95,13 @@ int check_params(const semgate_topk_params* p) {
   return 0;
 }
 
-int resolve_cg(semgate_handle_t h, const semgate_topk_params* p) { return p->cta_group ? p->cta_group : h->cta_group; }
+// CTA-pair tiles (cta_group::2) halve the database-tile traffic per SM and win a few percent on
+// large sweeps; with few query rows half of every 256-row pair tile would be padding.
+int resolve_cg(semgate_handle_t h, const semgate_topk_params* p, int64_t Q) {
+  const int want = p->cta_group ? p->cta_group : h->cta_group;
+  if (want == 1 || want == 2) return want;
+  return Q >= 4096 ? 2 : 1;
+}
 
 }  // namespace
 
@@ -152,7 +158,7 @@ int semgate_device_info(semgate_handle_t h, int* sm_count, int* cc_major, int* c
 int semgate_set_option(semgate_handle_t h, const char* name, int64_t value) {
   if (!h || !name) return fail(SEMGATE_EINVAL, "NULL argument");
   if (strcmp(name, "cta_group") == 0) {
-    if (value != 1 && value != 2) return fail(SEMGATE_EINVAL, "cta_group must be 1 or 2");
+    if (value != 0 && value != 1 && value != 2) return fail(SEMGATE_EINVAL, "cta_group must be 0 (auto), 1 or 2");
     h->cta_group = static_cast<int>(value);
     return 0;
   }
@@ -197,7 +203,7 @@ int semgate_normalize_cast(semgate_handle_t h, const float* x, int64_t n, int32_
 // ---------------------------------------------------------------- K2 + K3
 size_t semgate_topk_workspace_bytes(semgate_handle_t h, int64_t Q, int64_t N, int32_t d_pad, const semgate_topk_params* p) {
   if (!h || !p || Q <= 0 || N <= 0 || p->k < 1 || p->k > SEMGATE_MAX_K) return 256;
-  const int cg = resolve_cg(h, p);
+  const int cg = resolve_cg(h, p, Q);
   Schedule sc = make_schedule(Q, N, d_pad, cg, h->sm_count);
   return align256(topk_partial_bytes(sc, cg, p->k));
 }
@@ -217,7 +223,7 @@ int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const 
   if (Q == 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DeviceGuard g(h->device);
-  const int cg = resolve_cg(h, p);
+  const int cg = resolve_cg(h, p, Q);
   const int k = p->k;
 
   MergeLaunch m{};
