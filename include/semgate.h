@@ -57,6 +57,8 @@ typedef struct semgate_topk_params {
   int32_t gate_mode;            /* SEMGATE_GATE_FLAG | SEMGATE_GATE_MASK */
   uint32_t db_index_offset;     /* global index of database row 0 (row-sharded multi-GPU) */
   int32_t cta_group;            /* 0 = handle default (auto by size); 1 = single-CTA tiles; 2 = CTA-pair tiles */
+  int32_t accumulate;           /* 1: out_keys already holds each query's list over OTHER database rows (earlier
+                                   sweeps of disjoint slices); merge this sweep into it in place */
 } semgate_topk_params;
 
 int semgate_version(void);

@@ -41,8 +41,8 @@ int cuda_fail(cudaError_t e, const char* what) {
     if (_rc < 0) return fail(SEMGATE_EDRIVER, "%s failed (driver rc %d)", what, _rc);       \
   } while (0)
 
-constexpr int kNumBufs = 16;
-enum BufId { B_X = 0, B_BF16, B_TS, B_FL, B_WS, B_SC, B_IX, B_VA, B_CT, B_OQ, B_OM, B_OS, B_OV, B_TOT, B_CWS, B_QBF16 };
+constexpr int kNumBufs = 17;
+enum BufId { B_X = 0, B_BF16, B_TS, B_FL, B_WS, B_SC, B_IX, B_VA, B_CT, B_OQ, B_OM, B_OS, B_OV, B_TOT, B_CWS, B_QBF16, B_KEYS };
 
 inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
@@ -54,7 +54,9 @@ struct semgate_ctx {
   int cc_major = 0, cc_minor = 0;
   int cta_group = 0;               // 0 = auto (by problem size), 1, 2
   int64_t launches = 0;
-  cudaStream_t stream = nullptr;   // used by the *_host entry points
+  cudaStream_t stream = nullptr;   // used by the *_host entry points (compute)
+  cudaStream_t copy_stream = nullptr;   // H2D + normalisation of the next chunk, overlapped with the sweep
+  std::vector<cudaEvent_t> chunk_events;
   bool profile = false;            // record CUDA events around every K2 launch
   std::vector<cudaEvent_t> prof_events;   // pairs (begin, end), on the launching stream
   size_t prof_used = 0;
@@ -91,6 +93,7 @@ int check_params(const semgate_topk_params* p) {
   if (p->max_floor_diff < -1) return fail(SEMGATE_EINVAL, "max_floor_diff=%d", p->max_floor_diff);
   if (p->gate_mode != SEMGATE_GATE_FLAG && p->gate_mode != SEMGATE_GATE_MASK) return fail(SEMGATE_EINVAL, "gate_mode=%d", p->gate_mode);
   if (p->cta_group != 0 && p->cta_group != 1 && p->cta_group != 2) return fail(SEMGATE_EINVAL, "cta_group=%d", p->cta_group);
+  if (p->accumulate != 0 && p->accumulate != 1) return fail(SEMGATE_EINVAL, "accumulate=%d", p->accumulate);
   if (std::isnan(p->similarity_threshold)) return fail(SEMGATE_EINVAL, "similarity_threshold is NaN");
   return 0;
 }
@@ -133,6 +136,8 @@ int semgate_create(semgate_handle_t* out, int device) {
   DeviceGuard g(device);
   cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate"); }
+  e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { cudaStreamDestroy(h->stream); delete h; return cuda_fail(e, "cudaStreamCreate"); }
   *out = h;
   return 0;
 }
@@ -141,6 +146,8 @@ int semgate_destroy(semgate_handle_t h) {
   if (!h) return 0;
   DeviceGuard g(h->device);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+  for (cudaEvent_t e : h->chunk_events) cudaEventDestroy(e);
   for (int i = 0; i < kNumBufs; ++i) if (h->buf[i]) cudaFree(h->buf[i]);
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   delete h;
@@ -221,6 +228,7 @@ int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const 
   if ((q_ts == nullptr) != (db_ts == nullptr)) return fail(SEMGATE_EINVAL, "gated_topk: q_ts and db_ts must both be given or both be NULL");
   if (static_cast<uint64_t>(p->db_index_offset) + static_cast<uint64_t>(N) > 0xFFFFFFFFull) return fail(SEMGATE_EINVAL, "gated_topk: global index overflows 32 bits");
   if (Q == 0) return 0;
+  if (p->accumulate && !out_keys) return fail(SEMGATE_EINVAL, "gated_topk: accumulate needs out_keys");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DeviceGuard g(h->device);
   const int cg = resolve_cg(h, p, Q);
@@ -229,6 +237,7 @@ int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const 
   MergeLaunch m{};
   m.Q = Q; m.k = k;
   m.keys_out = out_keys; m.scores = out_scores; m.idx = out_idx; m.valid = out_valid; m.count = out_count;
+  m.seed_keys = p->accumulate ? out_keys : nullptr;
   m.q_floor = q_floor; m.db_floor = db_floor; m.floor_index_offset = p->db_index_offset;
   m.max_floor_diff = (q_floor && db_floor) ? p->max_floor_diff : -1;
 
@@ -384,8 +393,6 @@ int semgate_find_loop_closures_host(semgate_handle_t h, const float* descriptors
   if ((rc = h->reserve(B_BF16, 2ull * n * d_pad, &dbf))) return rc;
   if (timestamps && (rc = h->reserve(B_TS, 8ull * n, &dts))) return rc;
   if (floor_labels && (rc = h->reserve(B_FL, 4ull * n, &dfl))) return rc;
-  const size_t wsb = semgate_topk_workspace_bytes(h, n, n, d_pad, p);
-  if ((rc = h->reserve(B_WS, wsb, &ws))) return rc;
   const size_t nk = static_cast<size_t>(n) * k;
   if ((rc = h->reserve(B_SC, 4 * nk, &sc)) || (rc = h->reserve(B_IX, 4 * nk, &ix)) || (rc = h->reserve(B_VA, nk, &va)) ||
       (rc = h->reserve(B_CT, 4ull * n, &ct)) || (rc = h->reserve(B_OQ, 4 * nk, &oq)) || (rc = h->reserve(B_OM, 4 * nk, &om)) ||
@@ -393,17 +400,60 @@ int semgate_find_loop_closures_host(semgate_handle_t h, const float* descriptors
       (rc = h->reserve(B_CWS, semgate_compact_workspace_bytes(n), &cws)))
     return rc;
 
-  // H2D in row chunks so that normalisation of chunk i overlaps the copy of chunk i+1
-  const int64_t chunk = std::max<int64_t>(1, (32ll << 20) / (static_cast<int64_t>(d) * 4));
-  for (int64_t r0 = 0; r0 < n; r0 += chunk) {
-    const int64_t rows = std::min(chunk, n - r0);
-    CUDA_TRY(cudaMemcpyAsync(static_cast<float*>(dx) + r0 * d, descriptors + r0 * d, sizeof(float) * rows * d, cudaMemcpyHostToDevice, st));
-    if ((rc = semgate_normalize_cast(h, static_cast<float*>(dx) + r0 * d, rows, d, d, static_cast<char*>(dbf) + 2ull * r0 * d_pad, d_pad, st))) return rc;
+  // Pipeline over row chunks: while chunk c+1 crosses PCIe (copy stream: H2D + K1), the compute
+  // stream sweeps everything that chunk c completes: queries of chunk c against database rows
+  // [0, end of c), and the earlier queries against chunk c's rows, accumulated into the per-query
+  // key lists.  Top-k under a total order is an associative merge, so the result equals one sweep.
+  const int64_t bytes_per_row = static_cast<int64_t>(d) * 4;
+  int64_t nchunks = std::min<int64_t>(8, std::max<int64_t>(1, (n * bytes_per_row) / (24ll << 20)));
+  if (n < 4096) nchunks = 1;
+  const int64_t chunk = (n + nchunks - 1) / nchunks;
+  while (static_cast<int64_t>(h->chunk_events.size()) < nchunks) {
+    cudaEvent_t ev;
+    CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    h->chunk_events.push_back(ev);
   }
+  void* keys;
+  if ((rc = h->reserve(B_KEYS, 8 * nk, &keys))) return rc;
+  // workspace: the largest any sub-sweep needs
+  size_t ws_need = 0;
+  for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+    const int64_t r1 = std::min(n, r0 + chunk);
+    ws_need = std::max(ws_need, semgate_topk_workspace_bytes(h, r1 - r0, r1, d_pad, p));
+    if (r0 > 0) ws_need = std::max(ws_need, semgate_topk_workspace_bytes(h, r0, r1 - r0, d_pad, p));
+  }
+  if ((rc = h->reserve(B_WS, ws_need, &ws))) return rc;
+  cudaStream_t cs = h->copy_stream;
   if (dts) CUDA_TRY(cudaMemcpyAsync(dts, timestamps, 8ull * n, cudaMemcpyHostToDevice, st));
   if (dfl) CUDA_TRY(cudaMemcpyAsync(dfl, floor_labels, 4ull * n, cudaMemcpyHostToDevice, st));
-  rc = semgate_gated_topk(h, dbf, n, dbf, n, d_pad, static_cast<double*>(dts), static_cast<double*>(dts),
-                          static_cast<int32_t*>(dfl), static_cast<int32_t*>(dfl), p, ws, h->cap[B_WS], nullptr,
+  double* d_ts = static_cast<double*>(dts);
+  int32_t* d_fl = static_cast<int32_t*>(dfl);
+  char* bf = static_cast<char*>(dbf);
+  uint64_t* d_keys = static_cast<uint64_t*>(keys);
+  int64_t ci = 0;
+  for (int64_t r0 = 0; r0 < n; r0 += chunk, ++ci) {
+    const int64_t r1 = std::min(n, r0 + chunk), rows = r1 - r0;
+    CUDA_TRY(cudaMemcpyAsync(static_cast<float*>(dx) + r0 * d, descriptors + r0 * d, sizeof(float) * rows * d, cudaMemcpyHostToDevice, cs));
+    if ((rc = semgate_normalize_cast(h, static_cast<float*>(dx) + r0 * d, rows, d, d, bf + 2ull * r0 * d_pad, d_pad, cs))) return rc;
+    CUDA_TRY(cudaEventRecord(h->chunk_events[ci], cs));
+    CUDA_TRY(cudaStreamWaitEvent(st, h->chunk_events[ci], 0));
+    semgate_topk_params pa = *p;
+    pa.db_index_offset = 0; pa.accumulate = 0;
+    rc = semgate_gated_topk(h, bf + 2ull * r0 * d_pad, rows, bf, r1, d_pad, d_ts ? d_ts + r0 : nullptr, d_ts,
+                            d_fl ? d_fl + r0 : nullptr, d_fl, &pa, ws, h->cap[B_WS], d_keys + r0 * k, nullptr, nullptr,
+                            nullptr, nullptr, st);
+    if (rc) return rc;
+    if (r0 > 0) {
+      semgate_topk_params pb = *p;
+      pb.db_index_offset = static_cast<uint32_t>(r0); pb.accumulate = 1;
+      rc = semgate_gated_topk(h, bf, r0, bf + 2ull * r0 * d_pad, rows, d_pad, d_ts, d_ts ? d_ts + r0 : nullptr, d_fl,
+                              d_fl ? d_fl + r0 : nullptr, &pb, ws, h->cap[B_WS], d_keys, nullptr, nullptr, nullptr,
+                              nullptr, st);
+      if (rc) return rc;
+    }
+  }
+  // decode the final key lists, apply the floor flag
+  rc = semgate_merge_topk(h, d_keys, 1, n, k, d_fl, d_fl, (d_fl != nullptr) ? p->max_floor_diff : -1, nullptr,
                           static_cast<float*>(sc), static_cast<int32_t*>(ix), static_cast<uint8_t*>(va),
                           static_cast<int32_t*>(ct), st);
   if (rc) return rc;

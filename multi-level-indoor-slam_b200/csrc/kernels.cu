@@ -118,6 +118,11 @@ merge_topk_kernel(const MergeLaunch a) {
   const int total = n_lists * k;
 
   uint64_t run[2] = {0ull, 0ull};          // running list: rank t lives in run[t>>5] of lane t&31
+  if (a.seed_keys != nullptr) {            // already sorted descending: rank t -> lane t&31, slot t>>5
+    const uint64_t* seed = a.seed_keys + row * k;
+    if (lane < k) run[0] = seed[lane];
+    if (lane + 32 < k) run[1] = seed[lane + 32];
+  }
   for (int b0 = 0; b0 < total; b0 += 32 * kBatchPerLane) {
     uint64_t c[kBatchPerLane + 2];
 #pragma unroll

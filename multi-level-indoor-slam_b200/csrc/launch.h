@@ -39,6 +39,7 @@ struct MergeLaunch {
   int64_t row_stride, list_stride;   // in keys
   int n_lists;                       // >=0: constant; <0: per m-block from `sc`
   Schedule sc; int rows_per_mblock;
+  const uint64_t* seed_keys;         // optional [Q,k]: one more list per row (may alias keys_out)
   // outputs (any may be null)
   uint64_t* keys_out;                // [Q,k] sorted descending, 0 padded
   float* scores; int32_t* idx; uint8_t* valid; int32_t* count;

@@ -46,6 +46,7 @@ class TopkParams(C.Structure):
         ("gate_mode", C.c_int32),
         ("db_index_offset", C.c_uint32),
         ("cta_group", C.c_int32),
+        ("accumulate", C.c_int32),
     ]
 
 
@@ -108,13 +109,14 @@ def pad_dim(d: int) -> int:
 
 
 def make_params(k: int, similarity_threshold: float = -np.inf, min_time_gap: float = 10.0, max_floor_diff: int = -1,
-                gate_mode: int = GATE_FLAG, db_index_offset: int = 0, cta_group: int = 0) -> TopkParams:
+                gate_mode: int = GATE_FLAG, db_index_offset: int = 0, cta_group: int = 0,
+                accumulate: bool = False) -> TopkParams:
     if not (1 <= int(k) <= MAX_K):
         raise ValueError(f"k={k} outside 1..{MAX_K}")
     # the reference compares `sim < threshold` in the similarity dtype (fp32): same rounding here
     thr = float(np.float32(similarity_threshold))
     return TopkParams(thr, float(min_time_gap), int(k), int(max_floor_diff), int(gate_mode), int(db_index_offset),
-                      int(cta_group))
+                      int(cta_group), 1 if accumulate else 0)
 
 
 def _np_ptr(a: Optional[np.ndarray]):
@@ -223,7 +225,8 @@ class Engine:
 
     # ------------------------------------------------------------------ K2 + K3
     def gated_topk(self, q_bf16, db_bf16, params: TopkParams, q_ts=None, db_ts=None, q_floor=None, db_floor=None,
-                   want_keys: bool = False, want_lists: bool = True) -> TopkResult:
+                   want_keys: bool = False, want_lists: bool = True, keys=None) -> TopkResult:
+        """`keys`: int64 [Q,k] to write the key lists into (and, with params.accumulate, to merge with)."""
         torch = self._torch()
         self._expect(q_bf16, torch.bfloat16, "q_bf16", 2)
         self._expect(db_bf16, torch.bfloat16, "db_bf16", 2)
@@ -240,7 +243,14 @@ class Engine:
                 raise ValueError(f"gated_topk: {name} shorter than its matrix")
         k = params.k
         dev = q_bf16.device
-        keys = torch.empty((Q, k), dtype=torch.int64, device=dev) if want_keys else None
+        if keys is not None:
+            self._expect(keys, torch.int64, "keys", 2)
+            if tuple(keys.shape) != (Q, k):
+                raise ValueError("gated_topk: keys must be [Q, k]")
+        elif want_keys or params.accumulate:
+            if params.accumulate:
+                raise ValueError("gated_topk: accumulate needs the previous `keys`")
+            keys = torch.empty((Q, k), dtype=torch.int64, device=dev)
         scores = idx = valid = count = None
         if want_lists:
             scores = torch.empty((Q, k), dtype=torch.float32, device=dev)

@@ -276,6 +276,53 @@ def test_db_index_offset_and_merge(eng):
     assert np.array_equal(m.count.cpu().numpy(), whole["count"])
 
 
+def test_accumulate_over_database_slices(eng):
+    """Sweeping disjoint database slices one after the other with `accumulate` == one sweep."""
+    import torch
+    from semgate import _native, synthetic
+    desc, ts, fl = synthetic.make_case(2300, 128, 3, seed=8)
+    fl32 = fl.astype(np.int32)
+    xb = eng.normalize_cast(_t(desc))
+    tts, tfl = _t(ts), _t(fl32)
+    kw = dict(k=20, similarity_threshold=0.3, min_time_gap=5.0, max_floor_diff=0)
+    whole = eng.gated_topk(xb, xb, _native.make_params(**kw), q_ts=tts, db_ts=tts, q_floor=tfl, db_floor=tfl, want_keys=True)
+    keys = None
+    for lo, hi in ((0, 700), (700, 1500), (1500, 2300)):
+        p = _native.make_params(db_index_offset=lo, accumulate=keys is not None, **kw)
+        # hand the previous keys back in: the binding allocates `keys` unless we pass them
+        r = eng.gated_topk(xb, xb[lo:hi], p, q_ts=tts, db_ts=tts[lo:hi].contiguous(), q_floor=tfl,
+                           db_floor=tfl[lo:hi].contiguous(), want_keys=True, want_lists=False, keys=keys)
+        keys = r.keys
+    torch.cuda.synchronize()
+    assert torch.equal(keys, whole.keys)
+    m = eng.merge_topk(keys.unsqueeze(0).contiguous(), 20, q_floor=tfl, db_floor_all=tfl, max_floor_diff=0)
+    torch.cuda.synchronize()
+    assert torch.equal(m.idx, whole.idx) and torch.equal(m.scores, whole.scores) and torch.equal(m.valid, whole.valid)
+
+
+def test_host_abi_chunked_pipeline(eng):
+    """Large enough that semgate_find_loop_closures_host pipelines H2D chunks against partial sweeps."""
+    from semgate import _native, synthetic
+    desc, ts, fl = synthetic.make_case(9000, 2048, 3, seed=45)          # 74 MB -> 3 chunks
+    fl32 = fl.astype(np.int32)
+    p = _native.make_params(k=25, similarity_threshold=0.5, min_time_gap=10.0, max_floor_diff=0)
+    q, m, s, v = eng.find_loop_closures_host(desc, ts, fl32, p)
+    got = dict(query_idx=q.astype(np.int64), match_idx=m.astype(np.int64), similarity=s, is_valid=v)
+    parity.check_order(got)
+    ref = O.find_loop_closures(desc, ts, fl32, similarity_threshold=0.5, min_time_gap=10.0, k=25, bf16=True)
+    rep = parity.compare_candidates(ref, got, 25, 0.5, tol=BF16_MODEL_TOL)
+    assert rep["boundary_diffs"] <= 2
+    parity.check_decisions_exact(got, ts, fl32, 10.0, 0)
+    # and it equals the resident-data path exactly
+    import torch
+    xb = eng.normalize_cast(_t(desc))
+    tts, tfl = _t(ts), _t(fl32)
+    r = eng.gated_topk(xb, xb, p, q_ts=tts, db_ts=tts, q_floor=tfl, db_floor=tfl)
+    oq, om, os_, ov, tot = eng.compact(r)
+    t = int(tot.item())
+    assert t == len(q) and np.array_equal(om[:t].cpu().numpy(), m) and np.array_equal(os_[:t].cpu().numpy(), s)
+
+
 # --------------------------------------------------------------------------- reference goldens through the mirrored API
 @pytest.mark.parametrize("path", FLC, ids=[os.path.basename(p)[:-4] for p in FLC])
 def test_find_loop_closures_golden(path):
