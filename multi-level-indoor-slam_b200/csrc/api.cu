@@ -404,10 +404,29 @@ int semgate_find_loop_closures_host(semgate_handle_t h, const float* descriptors
   // stream sweeps everything that chunk c completes: queries of chunk c against database rows
   // [0, end of c), and the earlier queries against chunk c's rows, accumulated into the per-query
   // key lists.  Top-k under a total order is an associative merge, so the result equals one sweep.
+  // Chunk sizes shrink towards the end: what cannot overlap with PCIe is the work the LAST chunk
+  // completes, and that is proportional to its size.
   const int64_t bytes_per_row = static_cast<int64_t>(d) * 4;
-  int64_t nchunks = std::min<int64_t>(8, std::max<int64_t>(1, (n * bytes_per_row) / (24ll << 20)));
-  if (n < 4096) nchunks = 1;
-  const int64_t chunk = (n + nchunks - 1) / nchunks;
+  const int64_t approx_chunks = (n * bytes_per_row) / (24ll << 20);
+  std::vector<int64_t> bounds;   // chunk c = rows [bounds[c], bounds[c+1])
+  bounds.push_back(0);
+  if (n < 4096 || approx_chunks < 2) {
+    bounds.push_back(n);
+  } else {
+    static const int kWeights[10] = {4, 4, 4, 4, 3, 3, 2, 2, 1, 1};
+    const int nw = static_cast<int>(std::min<int64_t>(10, std::max<int64_t>(2, approx_chunks)));
+    int wsum = 0;
+    for (int i = 0; i < nw; ++i) wsum += kWeights[10 - nw + i];
+    int acc = 0;
+    for (int i = 0; i < nw; ++i) {
+      acc += kWeights[10 - nw + i];
+      int64_t b = (i == nw - 1) ? n : ((n * acc / wsum + 127) / 128) * 128;   // 128-row aligned cuts
+      b = std::min(b, n);
+      if (b > bounds.back()) bounds.push_back(b);
+    }
+    if (bounds.back() != n) bounds.push_back(n);
+  }
+  const int64_t nchunks = static_cast<int64_t>(bounds.size()) - 1;
   while (static_cast<int64_t>(h->chunk_events.size()) < nchunks) {
     cudaEvent_t ev;
     CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -417,8 +436,8 @@ int semgate_find_loop_closures_host(semgate_handle_t h, const float* descriptors
   if ((rc = h->reserve(B_KEYS, 8 * nk, &keys))) return rc;
   // workspace: the largest any sub-sweep needs
   size_t ws_need = 0;
-  for (int64_t r0 = 0; r0 < n; r0 += chunk) {
-    const int64_t r1 = std::min(n, r0 + chunk);
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const int64_t r0 = bounds[c], r1 = bounds[c + 1];
     ws_need = std::max(ws_need, semgate_topk_workspace_bytes(h, r1 - r0, r1, d_pad, p));
     if (r0 > 0) ws_need = std::max(ws_need, semgate_topk_workspace_bytes(h, r0, r1 - r0, d_pad, p));
   }
@@ -430,9 +449,8 @@ int semgate_find_loop_closures_host(semgate_handle_t h, const float* descriptors
   int32_t* d_fl = static_cast<int32_t*>(dfl);
   char* bf = static_cast<char*>(dbf);
   uint64_t* d_keys = static_cast<uint64_t*>(keys);
-  int64_t ci = 0;
-  for (int64_t r0 = 0; r0 < n; r0 += chunk, ++ci) {
-    const int64_t r1 = std::min(n, r0 + chunk), rows = r1 - r0;
+  for (int64_t ci = 0; ci < nchunks; ++ci) {
+    const int64_t r0 = bounds[ci], r1 = bounds[ci + 1], rows = r1 - r0;
     CUDA_TRY(cudaMemcpyAsync(static_cast<float*>(dx) + r0 * d, descriptors + r0 * d, sizeof(float) * rows * d, cudaMemcpyHostToDevice, cs));
     if ((rc = semgate_normalize_cast(h, static_cast<float*>(dx) + r0 * d, rows, d, d, bf + 2ull * r0 * d_pad, d_pad, cs))) return rc;
     CUDA_TRY(cudaEventRecord(h->chunk_events[ci], cs));

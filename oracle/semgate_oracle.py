@@ -10,12 +10,12 @@ this file computes the same decisions blocked over query rows.
 Pinning status
   * floor gate (integer decisions): PINNED by the reference's published counts
     (`results/semantic_gating/lego_loam_semantic_analysis.txt:20-22`,
-    `orb_slam3_semantic_analysis.txt:20-22`) — see tests/test_gate_golden.py.
+    `orb_slam3_semantic_analysis.txt:20-22`) — see tests/test_oracle_golden.py.
   * similarity / temporal mask / top-k: the reference ships no golden vectors
     or tests for them; PINNED instead against outputs of the unmodified
     reference code run in the build container (`tests/golden/make_golden.py`
     -> `tests/golden/*.npz`) and, when /root/reference is present, live in
-    tests/test_oracle_vs_reference.py.
+    tests/test_oracle_golden.py::test_live_reference_random_cases.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 reference legs may import this module.  The product package never does.
