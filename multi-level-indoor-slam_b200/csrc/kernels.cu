@@ -79,9 +79,62 @@ normalize_cast_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ld,
   }
 }
 
+// Long rows (d > 4096, e.g. SALAD 8448-d, AnyLoc 49152-d): one 1024-thread block per row, the row
+// is staged in shared memory so that DRAM is touched once (read 4*d, write 2*d_pad).
+constexpr int kNormBigThreads = 1024;
+
+__global__ void __launch_bounds__(kNormBigThreads)
+normalize_cast_smem_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ld, __nv_bfloat16* __restrict__ out, int d_pad) {
+  extern __shared__ __align__(16) float row_s[];
+  __shared__ float red[32];
+  const int tid = threadIdx.x;
+  const int nv = d >> 2;
+  for (int64_t row = blockIdx.x; row < n; row += gridDim.x) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * ld);
+    __nv_bfloat16* orow = out + row * static_cast<int64_t>(d_pad);
+    float ss = 0.f;
+    int i = tid;
+    for (; i + 3 * kNormBigThreads < nv; i += 4 * kNormBigThreads) {      // 4 independent 16-byte loads in flight
+      const float4 a = __ldg(xr + i), b = __ldg(xr + i + kNormBigThreads), c = __ldg(xr + i + 2 * kNormBigThreads),
+                   e = __ldg(xr + i + 3 * kNormBigThreads);
+      reinterpret_cast<float4*>(row_s)[i] = a;
+      reinterpret_cast<float4*>(row_s)[i + kNormBigThreads] = b;
+      reinterpret_cast<float4*>(row_s)[i + 2 * kNormBigThreads] = c;
+      reinterpret_cast<float4*>(row_s)[i + 3 * kNormBigThreads] = e;
+      ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w +
+            c.x * c.x + c.y * c.y + c.z * c.z + c.w * c.w + e.x * e.x + e.y * e.y + e.z * e.z + e.w * e.w;
+    }
+    for (; i < nv; i += kNormBigThreads) {
+      const float4 a = __ldg(xr + i);
+      reinterpret_cast<float4*>(row_s)[i] = a;
+      ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    }
+    const float denom = sqrtf(block_sum(ss, red)) + 1e-8f;     // block_sum's barriers also publish row_s
+    for (int j = tid; j < nv; j += kNormBigThreads) {
+      const float4 v = reinterpret_cast<const float4*>(row_s)[j];
+      store_bf16x4(orow + 4 * j, v.x / denom, v.y / denom, v.z / denom, v.w / denom);
+    }
+    for (int j = nv + tid; j < (d_pad >> 2); j += kNormBigThreads) store_bf16x4(orow + 4 * j, 0.f, 0.f, 0.f, 0.f);
+    __syncthreads();                                            // row_s is reused by the next row
+  }
+}
+
 int launch_normalize_cast(const float* x, int64_t n, int d, int64_t ld, void* out_bf16, int d_pad, cudaStream_t st) {
   if (n <= 0) return 0;
   const bool vec = (d % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  const size_t row_bytes = static_cast<size_t>(d) * 4;
+  if (vec && d > kNormCache * kNormThreads * 4 && row_bytes <= 200 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(normalize_cast_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      attr_set = true;
+    }
+    const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(2, (220 * 1024) / (row_bytes + 1024))));
+    const unsigned grid = static_cast<unsigned>(std::min<int64_t>(n, 148 * per_sm));
+    normalize_cast_smem_kernel<<<grid, kNormBigThreads, row_bytes, st>>>(x, n, d, ld, static_cast<__nv_bfloat16*>(out_bf16), d_pad);
+    return static_cast<int>(cudaGetLastError());
+  }
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(n, 148 * 16));
   if (vec)
     normalize_cast_kernel<true><<<grid, kNormThreads, 0, st>>>(x, n, d, ld, static_cast<__nv_bfloat16*>(out_bf16), d_pad);
