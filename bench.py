@@ -325,7 +325,7 @@ def run_ours(args):
         except Exception:
             pass
 
-    if STRONG or args.no_e2e:
+    if STRONG or args.no_e2e or args.workload != "c2":
         if rank == 0:
             out_json = {
                 "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -388,7 +388,7 @@ int semgate_find_loop_closures_host(semgate_handle_t h, const float* descriptors
   cudaStream_t st = h->stream;
   const int k = p->k;
   const int d_pad = semgate_pad_dim(d);
-  void *dx, *dbf, *dts = nullptr, *dfl = nullptr, *ws, *sc, *ix, *va, *ct, *oq, *om, *os, *ov, *tot, *cws;
+  void *dx = nullptr, *dbf = nullptr, *dts = nullptr, *dfl = nullptr, *ws = nullptr, *sc = nullptr, *ix = nullptr, *va = nullptr, *ct = nullptr, *oq = nullptr, *om = nullptr, *os = nullptr, *ov = nullptr, *tot = nullptr, *cws = nullptr;
   if ((rc = h->reserve(B_X, sizeof(float) * n * d, &dx))) return rc;
   if ((rc = h->reserve(B_BF16, 2ull * n * d_pad, &dbf))) return rc;
   if (timestamps && (rc = h->reserve(B_TS, 8ull * n, &dts))) return rc;
@@ -514,7 +514,7 @@ int semgate_query_host(semgate_handle_t h, const float* queries, int64_t nq, con
   DeviceGuard g(h->device);
   cudaStream_t st = h->stream;
   const int d_pad = semgate_pad_dim(d);
-  void *dx, *dbf, *qbf, *dts = nullptr, *ws, *sc, *ix, *ct;
+  void *dx = nullptr, *dbf = nullptr, *qbf = nullptr, *dts = nullptr, *ws = nullptr, *sc = nullptr, *ix = nullptr, *ct = nullptr;
   if ((rc = h->reserve(B_X, sizeof(float) * std::max(n, nq) * d, &dx))) return rc;
   if ((rc = h->reserve(B_BF16, 2ull * n * d_pad, &dbf))) return rc;
   if ((rc = h->reserve(B_QBF16, 2ull * nq * d_pad, &qbf))) return rc;
@@ -558,7 +558,7 @@ int semgate_gate_candidates_host(semgate_handle_t h, const int32_t* floor_labels
   DeviceGuard g(h->device);
   cudaStream_t st = h->stream;
   int rc;
-  void *dfl, *dq, *dm, *dv, *dc;
+  void *dfl = nullptr, *dq = nullptr, *dm = nullptr, *dv = nullptr, *dc = nullptr;
   if ((rc = h->reserve(B_FL, 4ull * std::max<int64_t>(n_labels, 1), &dfl)) || (rc = h->reserve(B_OQ, 4ull * M, &dq)) ||
       (rc = h->reserve(B_OM, 4ull * M, &dm)) || (rc = h->reserve(B_OV, 1ull * M, &dv)) || (rc = h->reserve(B_TOT, 32, &dc)))
     return rc;
@@ -586,7 +586,7 @@ int semgate_spatial_candidates_host(semgate_handle_t h, const double* positions,
   DeviceGuard g(h->device);
   cudaStream_t st = h->stream;
   int rc;
-  void *dp, *ws, *tot;
+  void *dp = nullptr, *ws = nullptr, *tot = nullptr;
   if ((rc = h->reserve(B_X, 24ull * n, &dp)) || (rc = h->reserve(B_WS, semgate_spatial_workspace_bytes(n), &ws)) ||
       (rc = h->reserve(B_TOT, 32, &tot)))
     return rc;

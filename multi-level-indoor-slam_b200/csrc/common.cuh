@@ -60,6 +60,11 @@ __host__ __device__ __forceinline__ bool time_excluded(double t_db, double t_q, 
 // keeps one running top-k list per query row; the `s` partial lists of a row
 // are merged afterwards.  The last super-row may hold fewer m-blocks and is
 // split finer.
+// Long databases are additionally cut into `n_panels` column panels that fit
+// in L2, visited panel-major (for panel: for super-row: run): units that drift
+// apart over a long sweep still find the panel's tiles in L2 instead of each
+// streaming them from DRAM.  A row's list is carried from panel to panel through
+// its partial-list slot in HBM.
 struct Schedule {
   int mblocks;      // ceil(Q / BM)            (for pairs: counted in pair-rows of 2*BM)
   int ntiles;       // ceil(N / BN)
@@ -69,6 +74,7 @@ struct Schedule {
   int r_last;       // m-blocks in the trailing partial super-row (0 if none)
   int s_last;       // splits per m-block there
   int s_max;        // max(s_main, s_last): slot stride of the partial lists
+  int n_panels;     // column panels (>= 1); every panel holds >= s_max tiles
 };
 
 __host__ __device__ __forceinline__ int sched_slots(const Schedule& sc, int mb) {
@@ -78,6 +84,37 @@ __host__ __device__ __forceinline__ int sched_slots(const Schedule& sc, int mb) 
 // balanced contiguous split of [0, n) into s parts
 __host__ __device__ __forceinline__ int split_begin(int n, int s, int j) {
   return static_cast<int>((static_cast<int64_t>(n) * j) / s);
+}
+
+// One unit's work list, identical for every warp role: f(mb, slot, nt0, nt1, carry).
+struct Run {
+  int mb;      // m-block (pair-row for CG = 2)
+  int slot;    // which of the m-block's runs (partial-list slot)
+  int nt0;     // first n-tile
+  int nt1;     // one past the last n-tile
+  bool carry;  // the row lists continue from an earlier panel
+};
+
+template <typename F>
+__device__ __forceinline__ void for_each_run(const Schedule& sc, int unit, F&& f) {
+  const int n_sr = sc.n_full + (sc.r_last > 0 ? 1 : 0);
+  for (int p = 0; p < sc.n_panels; ++p) {
+    const int pt0 = split_begin(sc.ntiles, sc.n_panels, p);
+    const int len = split_begin(sc.ntiles, sc.n_panels, p + 1) - pt0;
+    for (int sr = 0; sr < n_sr; ++sr) {
+      const bool full_sr = sr < sc.n_full;
+      const int r = full_sr ? sc.rm : sc.r_last;
+      const int S = full_sr ? sc.s_main : sc.s_last;
+      if (unit >= r * S) continue;
+      Run run;
+      run.mb = sr * sc.rm + unit % r;
+      run.slot = unit / r;
+      run.nt0 = pt0 + split_begin(len, S, run.slot);
+      run.nt1 = pt0 + split_begin(len, S, run.slot + 1);
+      run.carry = p > 0;
+      if (run.nt0 < run.nt1) f(run);
+    }
+  }
 }
 
 }  // namespace semgate

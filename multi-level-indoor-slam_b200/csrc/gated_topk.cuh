@@ -136,23 +136,15 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
   const Schedule sc = p.sc;
-  const int n_sr = sc.n_full + (sc.r_last > 0 ? 1 : 0);
 
   // ring / accumulator state (each role advances its own copy identically)
   uint32_t stage = 0, phase = 0, it = 0;
 
   if (warp == 0) {
     // ===================================================== TMA producer (whole warp loops, one lane issues)
-    for (int sr = 0; sr < n_sr; ++sr) {
-      const bool full_sr = sr < sc.n_full;
-      const int r = full_sr ? sc.rm : sc.r_last;
-      const int S = full_sr ? sc.s_main : sc.s_last;
-      if (unit >= r * S) continue;
-      const int mb = sr * sc.rm + unit % r;
-      const int j = unit / r;
-      const int nt0 = split_begin(sc.ntiles, S, j), nt1 = split_begin(sc.ntiles, S, j + 1);
-      const int m0 = (mb * CG + static_cast<int>(cta_rank)) * BM;
-      for (int nt = nt0; nt < nt1; ++nt) {
+    for_each_run(sc, unit, [&](const Run& run) {
+      const int m0 = (run.mb * CG + static_cast<int>(cta_rank)) * BM;
+      for (int nt = run.nt0; nt < run.nt1; ++nt) {
         const int n0 = nt * BN + static_cast<int>(cta_rank) * static_cast<int>(B_ROWS);
         for (int kb = 0; kb < p.kblocks; ++kb) {
           ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -177,21 +169,15 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           if (++stage == static_cast<uint32_t>(stages)) { stage = 0; phase ^= 1; }
         }
       }
-    }
+    });
   } else if (warp == 1) {
     // ===================================================== MMA issuer (leader CTA only)
     if (leader) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(BM * CG, BN);
       const uint64_t adesc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a));
       const uint64_t bdesc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b));
-      for (int sr = 0; sr < n_sr; ++sr) {
-        const bool full_sr = sr < sc.n_full;
-        const int r = full_sr ? sc.rm : sc.r_last;
-        const int S = full_sr ? sc.s_main : sc.s_last;
-        if (unit >= r * S) continue;
-        const int j = unit / r;
-        const int nt0 = split_begin(sc.ntiles, S, j), nt1 = split_begin(sc.ntiles, S, j + 1);
-        for (int nt = nt0; nt < nt1; ++nt, ++it) {
+      for_each_run(sc, unit, [&](const Run& run) {
+        for (int nt = run.nt0; nt < run.nt1; ++nt, ++it) {
           const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
           ptx::mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
           ptx::tc_fence_after();
@@ -220,7 +206,7 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             if (++stage == static_cast<uint32_t>(stages)) { stage = 0; phase ^= 1; }
           }
         }
-      }
+      });
       if constexpr (CG == 2) {
         // the peer's epilogue arrives remotely on our barriers: drain before teardown
         if (it > 0) {
@@ -242,16 +228,10 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const bool use_time = p.use_time != 0;
     const float pos_inf = __int_as_float(0x7f800000);
 
-    for (int sr = 0; sr < n_sr; ++sr) {
-      const bool full_sr = sr < sc.n_full;
-      const int r = full_sr ? sc.rm : sc.r_last;
-      const int S = full_sr ? sc.s_main : sc.s_last;
-      if (unit >= r * S) continue;
-      const int mb = sr * sc.rm + unit % r;
-      const int j = unit / r;
-      const int nt0 = split_begin(sc.ntiles, S, j), nt1 = split_begin(sc.ntiles, S, j + 1);
-      const int grow = (mb * CG + static_cast<int>(cta_rank)) * BM + row_in_tile;   // global query row
+    for_each_run(sc, unit, [&](const Run& run) {
+      const int grow = (run.mb * CG + static_cast<int>(cta_rank)) * BM + row_in_tile;   // global query row
       const bool row_live = grow < p.Q;
+      uint64_t* slot = p.partial + (static_cast<size_t>(row_live ? grow : 0) * sc.s_max + run.slot) * k;
       double tq = 0.0;
       int32_t qf = kFloorNone;
       if (row_live) {
@@ -259,8 +239,19 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         if (mask_mode) qf = p.q_floor[grow];
       }
       L.reset(row_live ? p.threshold : pos_inf);
+      if (run.carry && row_live) {
+        // continue the list this row built over earlier panels (entries are packed at the front)
+        int c = 0;
+        for (int i = 0; i < k; ++i) {
+          const uint64_t key = slot[i];
+          L.keys[i] = key;
+          c += key != 0ull ? 1 : 0;
+        }
+        L.cnt = c;
+        if (c == k) L.rescan(k);
+      }
 
-      for (int nt = nt0; nt < nt1; ++nt, ++it) {
+      for (int nt = run.nt0; nt < run.nt1; ++nt, ++it) {
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase);
         ptx::tc_fence_after();
@@ -309,12 +300,11 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
       }
 
-      // flush this run's partial list (unsorted; empty slots are key 0)
+      // flush this run's list (unsorted, packed at the front; empty slots are key 0)
       if (row_live) {
-        uint64_t* out = p.partial + (static_cast<size_t>(grow) * sc.s_max + j) * k;
-        for (int i = 0; i < k; ++i) out[i] = i < L.cnt ? L.keys[i] : 0ull;
+        for (int i = 0; i < k; ++i) slot[i] = i < L.cnt ? L.keys[i] : 0ull;
       }
-    }
+    });
   }
 
   // ----------------------------------------------------------------- teardown

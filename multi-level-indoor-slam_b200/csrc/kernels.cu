@@ -123,7 +123,8 @@ int launch_normalize_cast(const float* x, int64_t n, int d, int64_t ld, void* ou
   if (n <= 0) return 0;
   const bool vec = (d % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   const size_t row_bytes = static_cast<size_t>(d) * 4;
-  if (vec && d > kNormCache * kNormThreads * 4 && row_bytes <= 200 * 1024) {
+  // mid-length rows (8448-d = 33 KB) do better re-reading from L2 with many small blocks per SM
+  if (vec && row_bytes >= 64 * 1024 && row_bytes <= 200 * 1024) {
     static bool attr_set = false;
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(normalize_cast_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -276,6 +276,26 @@ def test_db_index_offset_and_merge(eng):
     assert np.array_equal(m.count.cpu().numpy(), whole["count"])
 
 
+@pytest.mark.parametrize("cg", [1, 2])
+def test_column_panels_carry_lists(eng, cg, monkeypatch):
+    """Long databases are swept in L2-sized column panels with the row lists carried through HBM
+    between panels; forced here at a small size (the schedule reads SEMGATE_PANEL_MB per call)."""
+    from semgate import synthetic
+    monkeypatch.setenv("SEMGATE_PANEL_MB", "1")
+    Q, N, D, k = 700, 45000, 64, 25
+    desc, ts, fl = synthetic.make_case(N, D, 4, seed=123)
+    fl32 = fl.astype(np.int32)
+    got = run_gpu(eng, desc[:Q], desc, k, 0.45, 10.0, ts[:Q], ts, fl32[:Q], fl32, mfd=0, cg=cg)
+    check_padded(got, k)
+    ref = O.gated_topk(desc[:Q], desc, ts[:Q], ts, fl32[:Q], fl32, k=k, threshold=0.45, min_time_gap=10.0,
+                       max_floor_diff=0, bf16=True)
+    rep = parity.compare_candidates(O.compact(ref), O.compact(got), k, 0.45, tol=BF16_MODEL_TOL)
+    assert rep["boundary_diffs"] <= 2
+    monkeypatch.delenv("SEMGATE_PANEL_MB")
+    one = run_gpu(eng, desc[:Q], desc, k, 0.45, 10.0, ts[:Q], ts, fl32[:Q], fl32, mfd=0, cg=cg)
+    assert np.array_equal(one["idx"], got["idx"]) and np.array_equal(one["scores"], got["scores"])
+
+
 def test_accumulate_over_database_slices(eng):
     """Sweeping disjoint database slices one after the other with `accumulate` == one sweep."""
     import torch
