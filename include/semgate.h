@@ -143,6 +143,25 @@ int semgate_spatial_fill(semgate_handle_t h, const double* positions, int64_t n,
                          const void* workspace, int32_t* out_i, int32_t* out_j, double* out_dist, int64_t capacity,
                          semgate_stream_t stream);
 
+/* ---- K5: CricaVPR cross-correlation re-rank ------------------------------------------
+ * replaces compute_cross_correlation_score (place_recognition.py:669-710) over a batch of
+ * (query, candidate) pairs and the score combination of rerank_candidates (:748).
+ *   local_feats  device bf16 [n_feat, P, dl_pad]: patch features, rows L2-normalised
+ *                (semgate_normalize_cast over the [n_feat*P, dl] matrix), dl_pad % 64 == 0
+ *   query_idx / match_idx  int32 [M] keyframe numbers; a negative or out-of-range entry means
+ *                "no cached local features" -> cross = NaN, combined = global (:749)
+ *   out_cross[M] = sqrt(mean(row maxima) * mean(column maxima)) of q m^T
+ *   out_combined[M] = 0.5 * global_sim + 0.5 * cross */
+int semgate_rerank_scores(semgate_handle_t h, const void* local_feats, int64_t n_feat, int32_t P, int32_t dl_pad,
+                          const int32_t* query_idx, const int32_t* match_idx, const float* global_sim, int64_t M,
+                          float* out_cross, float* out_combined, semgate_stream_t stream);
+/* per-query stable sort by combined score, descending, keep top_k (place_recognition.py:753-757).
+ * cand_idx / combined: [Q, kc] padded lists (kc <= 64) with count[Q] live entries each;
+ * outputs [Q, top_k] (-1 / -inf padded) and out_count[Q]. */
+int semgate_rerank_select(semgate_handle_t h, const int32_t* cand_idx, const float* combined, const int32_t* count,
+                          int64_t Q, int32_t kc, int32_t top_k, int32_t* out_idx, float* out_score, int32_t* out_count,
+                          semgate_stream_t stream);
+
 /* ---- host-buffer entry points (the reference-facing calls) ----------------------
  * find_loop_closures over a whole database held in host memory
  * (SemanticPlaceRecognition.find_loop_closures, place_recognition.py:851-911):

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "semgate", "libsemgate.so")
-SOURCES = ["api.cu", "gated_topk.cu", "kernels.cu", "spatial.cu"]
+SOURCES = ["api.cu", "gated_topk.cu", "kernels.cu", "spatial.cu", "rerank.cu"]
 HEADERS = ["common.cuh", "ptx.cuh", "gated_topk.cuh", "launch.h", os.path.join("..", "..", "include", "semgate.h")]
 
 

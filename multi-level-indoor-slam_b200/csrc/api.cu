@@ -372,6 +372,44 @@ int semgate_spatial_fill(semgate_handle_t h, const double* positions, int64_t n,
   return 0;
 }
 
+// ---------------------------------------------------------------- K5 re-rank
+int semgate_rerank_scores(semgate_handle_t h, const void* local_feats, int64_t n_feat, int32_t P, int32_t dl_pad,
+                          const int32_t* query_idx, const int32_t* match_idx, const float* global_sim, int64_t M,
+                          float* out_cross, float* out_combined, semgate_stream_t stream) {
+  if (!h) return fail(SEMGATE_EINVAL, "handle is NULL");
+  if (M < 0 || n_feat < 0 || n_feat > INT32_MAX) return fail(SEMGATE_EINVAL, "rerank_scores: bad sizes");
+  if (M == 0) return 0;
+  if (P < 1 || P > 4096) return fail(SEMGATE_EINVAL, "rerank_scores: P=%d outside 1..4096", P);
+  if (dl_pad <= 0 || dl_pad % 64 != 0) return fail(SEMGATE_EINVAL, "rerank_scores: dl_pad=%d must be a positive multiple of 64", dl_pad);
+  if (!query_idx || !match_idx || !global_sim || !out_cross || !out_combined) return fail(SEMGATE_EINVAL, "rerank_scores: NULL pointer");
+  if (n_feat > 0 && (!local_feats || (reinterpret_cast<uintptr_t>(local_feats) & 15)))
+    return fail(SEMGATE_EINVAL, "rerank_scores: local_feats must be a 16-byte aligned device pointer");
+  DeviceGuard g(h->device);
+  if (n_feat == 0) {
+    // no features at all: every pair falls back to its global score; the kernel handles it through
+    // the out-of-range path, but a tensor map needs a valid base -> use the index array as a stand-in
+    local_feats = query_idx;
+  }
+  RC_TRY(launch_rerank(local_feats, static_cast<int>(std::max<int64_t>(n_feat, 1)), P, dl_pad, query_idx, match_idx, global_sim, M,
+                       out_cross, out_combined, h->sm_count, static_cast<cudaStream_t>(stream)), "rerank launch");
+  h->launches += 1;
+  return 0;
+}
+
+int semgate_rerank_select(semgate_handle_t h, const int32_t* cand_idx, const float* combined, const int32_t* count,
+                          int64_t Q, int32_t kc, int32_t top_k, int32_t* out_idx, float* out_score, int32_t* out_count,
+                          semgate_stream_t stream) {
+  if (!h) return fail(SEMGATE_EINVAL, "handle is NULL");
+  if (Q < 0 || kc < 1 || kc > 64 || top_k < 1 || top_k > 64) return fail(SEMGATE_EINVAL, "rerank_select: bad sizes");
+  if (Q == 0) return 0;
+  if (!cand_idx || !combined || !count || !out_idx || !out_score || !out_count) return fail(SEMGATE_EINVAL, "rerank_select: NULL pointer");
+  DeviceGuard g(h->device);
+  RC_TRY(launch_rerank_select(cand_idx, combined, count, Q, kc, top_k, out_idx, out_score, out_count,
+                              static_cast<cudaStream_t>(stream)), "rerank_select launch");
+  h->launches += 1;
+  return 0;
+}
+
 // ---------------------------------------------------------------- host-buffer entry points
 int semgate_find_loop_closures_host(semgate_handle_t h, const float* descriptors, int64_t n, int32_t d,
                                     const double* timestamps, const int32_t* floor_labels, const semgate_topk_params* p,

@@ -66,4 +66,11 @@ int launch_spatial_count(const double* pos, int64_t n, double radius, int64_t ga
 int launch_spatial_fill(const double* pos, int64_t n, double radius, int64_t gap, const void* workspace, int32_t* out_i,
                         int32_t* out_j, double* out_dist, int64_t capacity, cudaStream_t st);
 
+// K5: CricaVPR cross-correlation score per candidate pair + per-query selection (place_recognition.py:669-757)
+int launch_rerank(const void* feats_bf16, int n_feat, int P, int dl_pad, const int32_t* q_idx, const int32_t* m_idx,
+                  const float* global_sim, int64_t M, float* out_cross, float* out_combined, int sm_count,
+                  cudaStream_t st);
+int launch_rerank_select(const int32_t* cand_idx, const float* combined, const int32_t* count, int64_t Q, int kc, int top_k,
+                         int32_t* out_idx, float* out_score, int32_t* out_count, cudaStream_t st);
+
 }  // namespace semgate

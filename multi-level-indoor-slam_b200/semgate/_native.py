@@ -27,7 +27,7 @@ SYMBOLS = [
     "semgate_topk_workspace_bytes", "semgate_gated_topk", "semgate_merge_topk", "semgate_compact_workspace_bytes",
     "semgate_compact", "semgate_gate_candidates", "semgate_find_loop_closures_host", "semgate_query_host",
     "semgate_gate_candidates_host", "semgate_spatial_workspace_bytes", "semgate_spatial_count", "semgate_spatial_fill",
-    "semgate_spatial_candidates_host",
+    "semgate_spatial_candidates_host", "semgate_rerank_scores", "semgate_rerank_select",
 ]
 
 
@@ -93,6 +93,8 @@ def load_library():
     lib.semgate_spatial_count.argtypes = [vp, vp, i64, C.c_double, i64, vp, vp, vp]
     lib.semgate_spatial_fill.argtypes = [vp, vp, i64, C.c_double, i64, vp, vp, vp, vp, i64, vp]
     lib.semgate_spatial_candidates_host.argtypes = [vp, vp, i64, C.c_double, i64, vp, vp, vp, i64, P(i64)]
+    lib.semgate_rerank_scores.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, i64, vp, vp, vp]
+    lib.semgate_rerank_select.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, vp, vp, vp]
     for name in SYMBOLS:
         getattr(lib, name)   # AttributeError here = the library is older than the header
     _lib = lib
@@ -322,6 +324,43 @@ class Engine:
                                                 self._ptr(match_idx), M, max_floor_diff, self._ptr(valid), self._ptr(counts),
                                                 self._stream()))
         return valid, counts
+
+    # ------------------------------------------------------------------ K5 re-rank
+    def rerank_scores(self, local_feats, query_idx, match_idx, global_sim):
+        """local_feats: bf16 [n_feat, P, dl_pad] (rows normalised); index / score vectors [M] on the device.
+        Returns (cross[M], combined[M]) fp32; negative indices mean "no cached features"."""
+        torch = self._torch()
+        self._expect(local_feats, torch.bfloat16, "local_feats", 3)
+        self._expect(query_idx, torch.int32, "query_idx", 1)
+        self._expect(match_idx, torch.int32, "match_idx", 1)
+        self._expect(global_sim, torch.float32, "global_sim", 1)
+        M = query_idx.shape[0]
+        if match_idx.shape[0] != M or global_sim.shape[0] != M:
+            raise ValueError("rerank_scores: vectors differ in length")
+        n_feat, P, dlp = local_feats.shape
+        cross = torch.empty((M,), dtype=torch.float32, device=query_idx.device)
+        comb = torch.empty((M,), dtype=torch.float32, device=query_idx.device)
+        if M:
+            _check(self.lib.semgate_rerank_scores(self._h, self._ptr(local_feats), n_feat, P, dlp, self._ptr(query_idx),
+                                                  self._ptr(match_idx), self._ptr(global_sim), M, self._ptr(cross),
+                                                  self._ptr(comb), self._stream()))
+        return cross, comb
+
+    def rerank_select(self, cand_idx, combined, count, top_k: int):
+        """[Q,kc] padded candidate lists -> ([Q,top_k] idx, [Q,top_k] score, [Q] count), stable sort by score desc."""
+        torch = self._torch()
+        self._expect(cand_idx, torch.int32, "cand_idx", 2)
+        self._expect(combined, torch.float32, "combined", 2)
+        self._expect(count, torch.int32, "count", 1)
+        Q, kc = cand_idx.shape
+        dev = cand_idx.device
+        oi = torch.empty((Q, top_k), dtype=torch.int32, device=dev)
+        os_ = torch.empty((Q, top_k), dtype=torch.float32, device=dev)
+        oc = torch.empty((Q,), dtype=torch.int32, device=dev)
+        if Q:
+            _check(self.lib.semgate_rerank_select(self._h, self._ptr(cand_idx), self._ptr(combined), self._ptr(count), Q, kc,
+                                                  int(top_k), self._ptr(oi), self._ptr(os_), self._ptr(oc), self._stream()))
+        return oi, os_, oc
 
     # ------------------------------------------------------------------ host-buffer calls
     def find_loop_closures_host(self, descriptors: np.ndarray, timestamps: Optional[np.ndarray],

@@ -73,3 +73,21 @@ def make_descriptors_device(n: int, d: int, device, seed: int = 0, noise: float 
         out[s:e] = anchors[pid]
         out[s:e] += noise * torch.randn((e - s, d), generator=g, device=device, dtype=torch.float32)
     return out
+
+
+def make_local_features(n: int, patches: int, dim: int, seed: int = 0, places: int | None = None, noise: float = 0.8):
+    """Patch-level local features `[n, patches, dim]` fp32 (CricaVPR / DINOv2 style: 529 x 768 at
+    322x322 input, place_recognition.py:655,784): every place has its own set of patch anchors,
+    a keyframe is a noisy, partly permuted copy (viewpoint change moves patches around)."""
+    rng = np.random.default_rng(seed)
+    p = places if places is not None else max(2, n // 4)
+    anchors = rng.standard_normal((p, patches, dim), dtype=np.float32)
+    pid = rng.integers(0, p, size=n)
+    out = np.empty((n, patches, dim), dtype=np.float32)
+    for i in range(n):
+        perm = np.arange(patches)
+        sw = rng.integers(0, patches, size=(patches // 4, 2))
+        perm[sw[:, 0]], perm[sw[:, 1]] = perm[sw[:, 1]], perm[sw[:, 0]]
+        out[i] = anchors[pid[i]][perm] + np.float32(noise) * rng.standard_normal((patches, dim), dtype=np.float32)
+        out[i] *= rng.uniform(0.5, 3.0, size=(patches, 1)).astype(np.float32)
+    return out, pid

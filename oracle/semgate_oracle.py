@@ -299,3 +299,43 @@ def merge_keys(keys_gathered, k):
     allk = np.transpose(g, (1, 0, 2)).reshape(Q, G * kk)
     srt = np.sort(allk, axis=1)[:, ::-1][:, :k]
     return np.ascontiguousarray(srt).view(np.int64)
+
+
+# ----------------------------------------------------------------------------
+# CricaVPR cross-correlation re-rank (place_recognition.py:669-757)
+# ----------------------------------------------------------------------------
+def cross_correlation_score(query_features, match_features, bf16=False):
+    """compute_cross_correlation_score (place_recognition.py:669-710): L2-normalise the patch
+    rows (`x / (||x|| + 1e-8)`), correlation = q m^T, mean of the row maxima times mean of the
+    column maxima, square root.  fp32 like the reference's torch-CPU path."""
+    q = np.asarray(query_features, dtype=np.float32)
+    m = np.asarray(match_features, dtype=np.float32)
+    if q.ndim == 3:
+        q = q[0]
+    if m.ndim == 3:
+        m = m[0]
+    q = q / (np.linalg.norm(q, axis=-1, keepdims=True) + np.float32(1e-8))
+    m = m / (np.linalg.norm(m, axis=-1, keepdims=True) + np.float32(1e-8))
+    if bf16:
+        q, m = bf16_round(q), bf16_round(m)
+    corr = q @ m.T
+    with np.errstate(invalid="ignore"):
+        return np.float32(np.sqrt(corr.max(axis=1).mean(dtype=np.float32) * corr.max(axis=0).mean(dtype=np.float32)))
+
+
+def rerank_candidates(features, query_idx, candidates, top_k=5, use_reranking=True, bf16=False):
+    """rerank_candidates (place_recognition.py:712-757).  `features`: dict index -> [P,D] (or
+    [1,P,D]) local features; `candidates`: list of (match_idx, global_similarity).  Combined score
+    0.5*global + 0.5*cross when the match has cached features, else the global score; stable sort
+    descending; first top_k."""
+    if not use_reranking or query_idx not in features:
+        return list(candidates[:top_k])
+    out = []
+    for match_idx, global_sim in candidates:
+        if match_idx in features:
+            cc = float(cross_correlation_score(features[query_idx], features[match_idx], bf16=bf16))
+            out.append((match_idx, 0.5 * global_sim + 0.5 * cc))
+        else:
+            out.append((match_idx, global_sim))
+    out.sort(key=lambda x: x[1], reverse=True)
+    return out[:top_k]

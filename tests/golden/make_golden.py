@@ -9,6 +9,7 @@ Writes (all small, compressed):
                 synthetic cases: inputs are regenerated from (n, d, floors, seed) by
                 semgate.synthetic, outputs are the reference PlaceMatch fields.
   query_*.npz   BasePlaceRecognition.query outputs (place_recognition.py:117-163).
+  rerank_*.npz  CricaVPR cross-correlation scores and re-ranked lists (place_recognition.py:669-757).
   gate_lego_loam.npz / gate_orb_slam3.npz
                 positions + file-membership floor labels of the shipped trajectories
                 (results/trajectories/{lego_loam,orb_slam3}/*.txt; label order 5,1,4,2 from
@@ -141,9 +142,61 @@ def gen_gate():
         print(f"gate_{algo}: {total} / {acc} / {rej} == published; non-strict {nonstrict}")
 
 
+# (name, n keyframes, patches, dim, seed, top_k, candidates per query, missing-feature index or -1)
+RERANK_CASES = [
+    ("small", 24, 48, 64, 3, 5, 10, -1),
+    ("missing", 20, 33, 40, 4, 3, 8, 5),
+    ("dinov2_shape", 10, 529, 768, 5, 5, 6, -1),
+]
+
+
+def gen_rerank():
+    """CricaVPR.compute_cross_correlation_score / rerank_candidates (place_recognition.py:669-757) run
+    verbatim (torch CPU).  The class constructor would load models; the two methods only touch
+    `use_reranking` and `_feature_cache`."""
+    PR = ref_loader.place_recognition()
+    for name, n, patches, dim, seed, top_k, ncand, missing in RERANK_CASES:
+        feats, _ = synthetic.make_local_features(n, patches, dim, seed)
+        crica = PR.CricaVPR.__new__(PR.CricaVPR)
+        crica.use_reranking = True
+        crica._feature_cache = {i: feats[i][None] for i in range(n) if i != missing}   # [1,P,D] like extract_local_features
+        rng = np.random.default_rng(seed + 100)
+        q_idx, cand_idx, cand_sim, cross, out_idx, out_score, out_cnt = [], [], [], [], [], [], []
+        for q in range(0, n, 2):
+            if q == missing:
+                continue
+            cands = [int(c) for c in rng.choice([i for i in range(n) if i != q], size=ncand, replace=False)]
+            sims = rng.uniform(0.3, 0.95, size=ncand).astype(np.float32)
+            cl = [(c, float(s_)) for c, s_ in zip(cands, sims)]
+            rr = crica.rerank_candidates(q, cl, top_k=top_k)
+            q_idx.append(q)
+            cand_idx.append(cands)
+            cand_sim.append(sims)
+            cross.append([crica.compute_cross_correlation_score(feats[q][None], feats[c][None]) if c != missing else np.nan
+                          for c in cands])
+            out_idx.append([m for m, _ in rr] + [-1] * (top_k - len(rr)))
+            out_score.append([sc for _, sc in rr] + [np.nan] * (top_k - len(rr)))
+            out_cnt.append(len(rr))
+        np.savez_compressed(
+            os.path.join(HERE, f"rerank_{name}.npz"),
+            params=np.array([n, patches, dim, seed, top_k, ncand, missing], dtype=np.int64),
+            query_idx=np.array(q_idx, dtype=np.int32), cand_idx=np.array(cand_idx, dtype=np.int32),
+            cand_sim=np.array(cand_sim, dtype=np.float32), cross=np.array(cross, dtype=np.float32),
+            out_idx=np.array(out_idx, dtype=np.int32), out_score=np.array(out_score, dtype=np.float64),
+            out_count=np.array(out_cnt, dtype=np.int32))
+        print(f"rerank_{name}: {len(q_idx)} queries x {ncand} candidates, cross in "
+              f"[{np.nanmin(cross):.3f}, {np.nanmax(cross):.3f}]")
+
+
 if __name__ == "__main__":
     if not ref_loader.available():
         sys.exit("reference not present; golden vectors can only be generated in the build container")
-    gen_flc()
-    gen_query()
-    gen_gate()
+    only = sys.argv[1:] or ["flc", "query", "gate", "rerank"]
+    if "flc" in only:
+        gen_flc()
+    if "query" in only:
+        gen_query()
+    if "gate" in only:
+        gen_gate()
+    if "rerank" in only:
+        gen_rerank()

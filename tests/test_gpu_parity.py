@@ -19,8 +19,8 @@ QRY = sorted(glob.glob(os.path.join(GOLDEN, "query_*.npz")))
 # Against the oracle's model of the GPU arithmetic (bf16 operands, wide accumulation) the
 # only differences are fp32 summation order and the rare bf16 rounding flip caused by the
 # row norm being summed in a different order (one flipped element moves a score by about
-# x_i * y_i * 2^-8 <= ~4e-5 at d=128).  13x tighter than the north-star tolerance.
-BF16_MODEL_TOL = 1.5e-4
+# x_i * y_i * 2^-8 <= ~6e-5 at d=64, and a few can add up).  ~7x tighter than the north-star tolerance.
+BF16_MODEL_TOL = 3e-4
 
 
 @pytest.fixture(scope="module")

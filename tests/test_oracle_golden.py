@@ -122,3 +122,33 @@ def test_live_reference_random_cases():
         got = O.find_loop_closures(desc, ts, fl.astype(np.int32), similarity_threshold=thr, min_time_gap=gap, k=k)
         rep = parity.compare_candidates(ref, got, k, thr, tol=1e-5)
         assert rep["boundary_diffs"] == 0
+
+
+RER = sorted(glob.glob(os.path.join(GOLDEN, "rerank_*.npz")))
+
+
+@pytest.mark.parametrize("path", RER, ids=[os.path.basename(p)[:-4] for p in RER])
+def test_rerank_matches_reference(path):
+    """CricaVPR cross-correlation re-rank (place_recognition.py:669-757) against the reference's own outputs."""
+    from semgate import synthetic
+    g = np.load(path)
+    n, patches, dim, seed, top_k, ncand, missing = [int(v) for v in g["params"]]
+    feats, _ = synthetic.make_local_features(n, patches, dim, seed)
+    cache = {i: feats[i] for i in range(n) if i != missing}
+    for r, q in enumerate(g["query_idx"].tolist()):
+        cands = [(int(c), float(s)) for c, s in zip(g["cand_idx"][r], g["cand_sim"][r])]
+        for ci, (c, _) in enumerate(cands):
+            if c != missing:
+                assert abs(float(O.cross_correlation_score(feats[q], feats[c])) - float(g["cross"][r, ci])) < 2e-6
+        rr = O.rerank_candidates(cache, q, cands, top_k=top_k)
+        cnt = int(g["out_count"][r])
+        assert len(rr) == cnt
+        assert [m for m, _ in rr] == g["out_idx"][r, :cnt].tolist()
+        assert np.allclose([s for _, s in rr], g["out_score"][r, :cnt], atol=2e-6)
+    # the bf16 model of the GPU arithmetic stays inside the 2e-3 tolerance
+    a = O.cross_correlation_score(feats[0], feats[1])
+    b = O.cross_correlation_score(feats[0], feats[1], bf16=True)
+    assert abs(float(a) - float(b)) < 2e-3
+    # no cached query features / re-ranking off -> the input order is kept (place_recognition.py:733-737)
+    assert O.rerank_candidates({}, 0, [(1, 0.5), (2, 0.9)], top_k=1) == [(1, 0.5)]
+    assert O.rerank_candidates(cache, 0, [(1, 0.5), (2, 0.9)], top_k=5, use_reranking=False) == [(1, 0.5), (2, 0.9)]
