@@ -43,18 +43,21 @@ Schedule make_schedule(int64_t Q, int64_t N, int d_pad, int cta_group, int sm_co
   sc.r_last = sc.mblocks % sc.rm;
   sc.s_last = sc.r_last > 0 ? std::min(sc.ntiles, units / sc.r_last) : 0;
   sc.s_max = std::max(sc.n_full > 0 ? sc.s_main : 0, sc.s_last);
-  // Column panels: only when a run would be long enough for units to drift out of each other's
-  // L2 window.  Panel width = a multiple of the split count (no ceiling loss) whose tiles fit the cap.
-  int64_t panel_mb = 40;
-  if (const char* e = getenv("SEMGATE_PANEL_MB")) { const long v = atol(e); if (v > 0) panel_mb = v; }
-  const int64_t tile_bytes = static_cast<int64_t>(BN) * d_pad * 2;
-  const int smax = std::max(sc.s_max, 1);
-  int w_cap = static_cast<int>(std::max<int64_t>(1, (panel_mb << 20) / tile_bytes));
-  w_cap = std::max(smax, (w_cap / smax) * smax);
+  // Column panels (off unless SEMGATE_PANEL_MB is set): panel width = a multiple of the split count
+  // (no ceiling loss) whose tiles fit the given number of megabytes.
   sc.n_panels = 1;
-  if (sc.ntiles > 4 * w_cap) {
-    sc.n_panels = (sc.ntiles + w_cap - 1) / w_cap;
-    sc.n_panels = std::max(1, std::min(sc.n_panels, sc.ntiles / smax));   // every panel keeps >= s_max tiles
+  if (const char* e = getenv("SEMGATE_PANEL_MB")) {
+    const long panel_mb = atol(e);
+    if (panel_mb > 0) {
+      const int64_t tile_bytes = static_cast<int64_t>(BN) * d_pad * 2;
+      const int smax = std::max(sc.s_max, 1);
+      int w_cap = static_cast<int>(std::max<int64_t>(1, (static_cast<int64_t>(panel_mb) << 20) / tile_bytes));
+      w_cap = std::max(smax, (w_cap / smax) * smax);
+      if (sc.ntiles > 4 * w_cap) {
+        sc.n_panels = (sc.ntiles + w_cap - 1) / w_cap;
+        sc.n_panels = std::max(1, std::min(sc.n_panels, sc.ntiles / smax));   // every panel keeps >= s_max tiles
+      }
+    }
   }
   return sc;
 }

@@ -282,10 +282,152 @@ class AnyLoc(BasePlaceRecognition):
         super().__init__(descriptor_dim=49152, device=device)  # reference :418
 
 
+class _LocalStore:
+    """Device-resident patch features: bf16 [cap, P, pad64(D)], rows L2-normalised once per
+    keyframe (place_recognition.py:695-699 re-normalises them for every pair)."""
+
+    def __init__(self, engine: "_native.Engine"):
+        self.engine = engine
+        self.slot: Dict[int, int] = {}     # keyframe index -> row of `feats`
+        self._ids: Dict[int, int] = {}     # keyframe index -> id() of the cached array
+        self.feats = None
+        self.P = self.D = None
+
+    def sync(self, cache: Dict[int, np.ndarray]):
+        import torch
+        new = [k for k, v in cache.items() if self._ids.get(k) != id(v)]
+        if not new:
+            return
+        first = np.asarray(cache[new[0]])
+        P, D = first.shape[-2], first.shape[-1]
+        if self.P is not None and (P, D) != (self.P, self.D):
+            raise ValueError(f"local feature shape changed from {(self.P, self.D)} to {(P, D)}")
+        self.P, self.D = P, D
+        need = len(self.slot) + sum(1 for k in new if k not in self.slot)
+        dev = torch.device("cuda", self.engine.device)
+        dp = _native.pad_dim(D)
+        if self.feats is None or self.feats.shape[0] < need:
+            cap = max(need, 64, 0 if self.feats is None else int(self.feats.shape[0] * 1.5))
+            grown = torch.empty((cap, P, dp), dtype=torch.bfloat16, device=dev)
+            if self.feats is not None and len(self.slot):
+                grown[:self.feats.shape[0]].copy_(self.feats)
+            self.feats = grown
+        for k in new:
+            a = np.asarray(cache[k], dtype=np.float32).reshape(-1, D)
+            if a.shape[0] != P:
+                raise ValueError("every keyframe needs the same number of patches")
+            if k not in self.slot:
+                self.slot[k] = len(self.slot)
+            self.engine.normalize_cast(torch.from_numpy(np.ascontiguousarray(a)).to(dev), out=self.feats[self.slot[k]])
+            self._ids[k] = id(cache[k])
+
+
 class CricaVPR(BasePlaceRecognition):
+    """CricaVPR interface (reference :508-803) for the retrieval + cross-correlation re-rank part.
+    Model inference is out of scope: global descriptors and patch-level local features are
+    passed in (`add_image(descriptor, ..., local_features=patches)`)."""
+
     def __init__(self, device: str = 'cuda', use_reranking: bool = True, **_):
         super().__init__(descriptor_dim=10752, device=device)  # reference :513
         self.use_reranking = use_reranking
+        self._feature_cache: Dict[int, np.ndarray] = {}
+        self._store: Optional[_LocalStore] = None
+
+    def extract_local_features(self, image: np.ndarray) -> np.ndarray:
+        """Accepts already extracted patch features `[P, D]` / `[1, P, D]`; returns `[1, P, D]` (reference :655-667)."""
+        a = np.asarray(image)
+        if a.ndim == 2:
+            return a[None]
+        if a.ndim == 3 and a.shape[0] == 1:
+            return a
+        raise NotImplementedError("local feature extraction is not part of semgate; pass [P, D] patch features")
+
+    def add_image(self, image: np.ndarray, timestamp: float, floor_label: Optional[int] = None,
+                  image_path: Optional[str] = None, local_features: Optional[np.ndarray] = None) -> PlaceDescriptor:
+        pd = super().add_image(image, timestamp, floor_label, image_path)
+        if self.use_reranking and local_features is not None:
+            self._feature_cache[len(self.descriptors) - 1] = self.extract_local_features(local_features)
+        return pd
+
+    def _local(self) -> _LocalStore:
+        if self._store is None:
+            self._store = _LocalStore(self._engine())
+        self._store.sync(self._feature_cache)
+        return self._store
+
+    def _pair_scores(self, q_idx: np.ndarray, m_idx: np.ndarray, global_sim: np.ndarray):
+        """(cross, combined) fp32 arrays for keyframe-index pairs; indices without cached features
+        get cross = NaN and combined = global (reference :741-749)."""
+        import torch
+        st = self._local()
+        dev = torch.device("cuda", st.engine.device)
+        slot = st.slot
+        qs = np.array([slot.get(int(i), -1) for i in q_idx], dtype=np.int32)
+        ms = np.array([slot.get(int(i), -1) for i in m_idx], dtype=np.int32)
+        if st.feats is None:
+            return np.full(len(qs), np.nan, np.float32), np.asarray(global_sim, dtype=np.float32).copy()
+        cross, comb = st.engine.rerank_scores(st.feats, torch.from_numpy(qs).to(dev), torch.from_numpy(ms).to(dev),
+                                              torch.from_numpy(np.ascontiguousarray(global_sim, dtype=np.float32)).to(dev))
+        return cross.cpu().numpy(), comb.cpu().numpy()
+
+    def compute_cross_correlation_score(self, query_features: np.ndarray, match_features: np.ndarray) -> float:
+        """Cross-correlation score of two patch-feature sets (reference :669-710)."""
+        import torch
+        eng = self._engine()
+        dev = torch.device("cuda", eng.device)
+        q = np.asarray(query_features, dtype=np.float32)
+        m = np.asarray(match_features, dtype=np.float32)
+        q = q.reshape(-1, q.shape[-1])
+        m = m.reshape(-1, m.shape[-1])
+        if q.shape != m.shape:
+            raise ValueError("the kernel scores equally shaped patch sets (same P and D)")
+        both = torch.from_numpy(np.ascontiguousarray(np.concatenate([q, m]))).to(dev)
+        feats = eng.normalize_cast(both).view(2, q.shape[0], -1)
+        z = torch.zeros(1, dtype=torch.int32, device=dev)
+        cross, _ = eng.rerank_scores(feats, z, z + 1, torch.zeros(1, dtype=torch.float32, device=dev))
+        return float(cross.item())
+
+    def rerank_candidates(self, query_idx: int, candidates: List[Tuple[int, float]], top_k: int = 5) -> List[Tuple[int, float]]:
+        """Re-rank `(match_idx, global_similarity)` candidates of one query (reference :712-757)."""
+        if not self.use_reranking or query_idx not in self._feature_cache or not candidates:
+            return candidates[:top_k]
+        m = np.array([c[0] for c in candidates], dtype=np.int64)
+        g = np.array([c[1] for c in candidates], dtype=np.float32)
+        _, comb = self._pair_scores(np.full(len(m), query_idx), m, g)
+        order = sorted(range(len(m)), key=lambda i: comb[i], reverse=True)      # stable, like list.sort (:754)
+        return [(int(m[i]), float(comb[i])) for i in order[:top_k]]
+
+    def rerank_batch(self, query_idx: np.ndarray, cand_idx: np.ndarray, global_sim: np.ndarray, count: np.ndarray,
+                     top_k: int = 5):
+        """All queries at once: padded `[Q, kc]` candidate lists (kc <= 64) -> (idx [Q,top_k], score [Q,top_k],
+        count [Q]).  Queries without cached features keep their input order."""
+        import torch
+        st = self._local()
+        eng = st.engine
+        dev = torch.device("cuda", eng.device)
+        Q, kc = cand_idx.shape
+        live = np.arange(kc)[None, :] < np.asarray(count)[:, None]
+        qq = np.repeat(np.asarray(query_idx, dtype=np.int64)[:, None], kc, axis=1)
+        has_q = np.array([int(q) in st.slot for q in query_idx])
+        m = np.where(live, cand_idx, -1)
+        m = np.where(has_q[:, None] & self.use_reranking, m, -1)       # no query features: global score only
+        _, comb = self._pair_scores(qq.ravel(), m.ravel(), np.where(live, global_sim, 0).astype(np.float32).ravel())
+        comb = comb.reshape(Q, kc)
+        # rows that must keep their order (reference :733-737): give them strictly decreasing keys
+        keep = ~(has_q & self.use_reranking)
+        keys = np.where(keep[:, None], -np.arange(kc, dtype=np.float32)[None, :], comb)
+        oi, _, oc = eng.rerank_select(torch.from_numpy(np.ascontiguousarray(cand_idx, dtype=np.int32)).to(dev),
+                                      torch.from_numpy(np.ascontiguousarray(keys, dtype=np.float32)).to(dev),
+                                      torch.from_numpy(np.ascontiguousarray(count, dtype=np.int32)).to(dev), top_k)
+        oi, oc = oi.cpu().numpy(), oc.cpu().numpy()
+        # scores of the selected entries (for kept-order rows the global similarity)
+        pos = {(r, int(c)): j for r in range(Q) for j, c in enumerate(cand_idx[r, :count[r]])}
+        src = np.where(keep[:, None], global_sim, comb)
+        os_ = np.full((Q, top_k), -np.inf, np.float32)
+        for r in range(Q):
+            for t in range(oc[r]):
+                os_[r, t] = src[r, pos[(r, int(oi[r, t]))]]
+        return oi, os_, oc
 
 
 _METHODS = {'mixvpr': MixVPR, 'salad': SALAD, 'anyloc': AnyLoc, 'cricavpr': CricaVPR}

@@ -94,3 +94,24 @@ def test_interface_parity_with_reference_signatures():
         semgate.SemanticPlaceRecognition(vpr_method="nope")
     g = semgate.SemanticLoopClosureGate([1, 2])
     assert g.gate_candidates([]) == ([], []) and g.get_stats()["total_candidates"] == 0
+
+
+def test_cricavpr_host_logic_without_gpu():
+    """Feature caching and the no-rerank short cuts never touch the device (reference :733-737, :768-777)."""
+    import numpy as np
+    import semgate
+    v = semgate.CricaVPR(device='cuda', use_reranking=True)
+    lf = np.ones((7, 16), np.float32)
+    v.add_image(np.zeros(v.descriptor_dim, np.float32), 0.0, 1, local_features=lf)
+    v.add_image(np.zeros(v.descriptor_dim, np.float32), 1.0, 1)
+    assert list(v._feature_cache) == [0] and v._feature_cache[0].shape == (1, 7, 16)
+    assert v.extract_local_features(lf[None]).shape == (1, 7, 16)
+    with pytest.raises(NotImplementedError):
+        v.extract_local_features(np.zeros((2, 3, 4, 5)))
+    cands = [(0, 0.9), (1, 0.8), (2, 0.7)]
+    assert v.rerank_candidates(5, cands, top_k=2) == cands[:2]          # query without cached features
+    v.use_reranking = False
+    assert v.rerank_candidates(0, cands, top_k=5) == cands
+    w = semgate.CricaVPR(use_reranking=False)
+    w.add_image(np.zeros(w.descriptor_dim, np.float32), 0.0, 1, local_features=lf)
+    assert w._feature_cache == {}

@@ -531,3 +531,75 @@ def test_full_size_properties_c2(eng, cg):
                 is_valid=ov[:t].cpu().numpy().astype(bool))
     parity.check_order(flat)
     assert np.array_equal(flat["match_idx"], c["match_idx"]) and np.array_equal(flat["is_valid"], c["is_valid"])
+
+
+# --------------------------------------------------------------------------- K5: CricaVPR cross-correlation re-rank
+RER = sorted(glob.glob(os.path.join(GOLDEN, "rerank_*.npz")))
+
+
+@pytest.mark.parametrize("path", RER, ids=[os.path.basename(p)[:-4] for p in RER])
+def test_rerank_golden(path):
+    """compute_cross_correlation_score / rerank_candidates (place_recognition.py:669-757) against the
+    reference's own outputs: scores within 2e-3, re-ranked lists equal up to that tolerance."""
+    from semgate import CricaVPR, synthetic
+    g = np.load(path)
+    n, patches, dim, seed, top_k, ncand, missing = [int(v) for v in g["params"]]
+    feats, _ = synthetic.make_local_features(n, patches, dim, seed)
+    vpr = CricaVPR(device='cuda', use_reranking=True)
+    for i in range(n):
+        vpr.add_image(np.zeros(vpr.descriptor_dim, np.float32), float(i), 1,
+                      local_features=None if i == missing else feats[i])
+    assert (missing in vpr._feature_cache) is False and len(vpr._feature_cache) == n - (1 if missing >= 0 else 0)
+    for r, q in enumerate(g["query_idx"].tolist()):
+        cands = [(int(c), float(s)) for c, s in zip(g["cand_idx"][r], g["cand_sim"][r])]
+        m = np.array([c for c, _ in cands])
+        cross, comb = vpr._pair_scores(np.full(len(m), q), m, g["cand_sim"][r])
+        ref_cross = g["cross"][r]
+        has = m != missing
+        assert np.all(np.isnan(cross[~has])) and np.array_equal(comb[~has], g["cand_sim"][r][~has])
+        assert np.max(np.abs(cross[has] - ref_cross[has])) <= parity.SCORE_TOL
+        want16 = np.array([O.cross_correlation_score(feats[q], feats[c], bf16=True) for c in m[has]])
+        assert np.max(np.abs(cross[has] - want16)) <= BF16_MODEL_TOL
+        rr = vpr.rerank_candidates(q, cands, top_k=top_k)
+        cnt = int(g["out_count"][r])
+        assert len(rr) == cnt
+        ref_list = list(zip(g["out_idx"][r, :cnt].tolist(), g["out_score"][r, :cnt].tolist()))
+        ref_all = dict(O.rerank_candidates({i: feats[i] for i in range(n) if i != missing}, q, cands, top_k=len(cands)))
+        for (gi, gs), (ri, rs) in zip(rr, ref_list):
+            assert abs(gs - ref_all[gi]) <= parity.SCORE_TOL          # every returned score is right
+            assert gi == ri or abs(ref_all[gi] - rs) <= 2 * parity.SCORE_TOL   # order differs only inside the tolerance
+    # single-pair entry point and the untouched-order cases
+    s = vpr.compute_cross_correlation_score(feats[0], feats[1][None])
+    assert abs(s - float(O.cross_correlation_score(feats[0], feats[1]))) <= parity.SCORE_TOL
+    assert vpr.rerank_candidates(10 ** 6, [(1, 0.5), (2, 0.9)], top_k=1) == [(1, 0.5)]
+    vpr.use_reranking = False
+    assert vpr.rerank_candidates(0, [(1, 0.5), (2, 0.9)], top_k=5) == [(1, 0.5), (2, 0.9)]
+
+
+def test_rerank_batch_dinov2_shape(eng):
+    """529 patches x 768-d (DINOv2 at 322x322): a batch of pairs against the oracle, and the batched
+    per-query selection against per-query Python sorting."""
+    import torch
+    from semgate import CricaVPR, synthetic
+    n, P, D, kc, top_k = 40, 529, 768, 12, 5
+    feats, _ = synthetic.make_local_features(n, P, D, seed=9)
+    vpr = CricaVPR(device='cuda')
+    for i in range(n):
+        vpr.add_image(np.zeros(vpr.descriptor_dim, np.float32), float(i), 1, local_features=feats[i] if i % 9 != 4 else None)
+    rng = np.random.default_rng(0)
+    Q = 16
+    query_idx = rng.choice(n, Q, replace=False)
+    cand = np.stack([rng.choice(n, kc, replace=False) for _ in range(Q)]).astype(np.int32)
+    gsim = rng.uniform(0.3, 0.9, size=(Q, kc)).astype(np.float32)
+    count = rng.integers(3, kc + 1, size=Q).astype(np.int32)
+    oi, os_, oc = vpr.rerank_batch(query_idx, cand, gsim, count, top_k=top_k)
+    cache = {i: feats[i] for i in vpr._feature_cache}
+    for r in range(Q):
+        cl = [(int(c), float(s)) for c, s in zip(cand[r, :count[r]], gsim[r, :count[r]])]
+        ref = O.rerank_candidates(cache, int(query_idx[r]), cl, top_k=top_k, bf16=True)
+        full = dict(O.rerank_candidates(cache, int(query_idx[r]), cl, top_k=len(cl), bf16=True))
+        assert oc[r] == len(ref)
+        for t in range(oc[r]):
+            assert abs(os_[r, t] - full[int(oi[r, t])]) <= BF16_MODEL_TOL
+            assert int(oi[r, t]) == ref[t][0] or abs(full[int(oi[r, t])] - ref[t][1]) <= 2 * BF16_MODEL_TOL
+        assert np.all(oi[r, oc[r]:] == -1)
