@@ -18,7 +18,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -87,53 +86,67 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons sampled through NVML every ~2 ms DURING the timed region
+    (the default timed region is tens of milliseconds; `nvidia-smi -lms` cannot sample faster than 100 ms)."""
 
     def __init__(self, index: int):
         self.index = index
-        self.lines = []
-        self.proc = None
+        self.samples = []
+        self.reasons = set()
+        self.running = False
+        self.thread = None
+        self.nv = None
+        self.h = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = self.index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                phys = int(vis.split(",")[self.index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            self.nv = None
+            return
+        self.running = True
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        nv = self.nv
+        names = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                 ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                 ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+        while self.running:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                watts = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((float(mhz), float(watts), float(util)))
+                for nm, bit in names:
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, f[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
+        if self.nv is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        loaded = sorted(sm)[len(sm) // 2:]          # upper half = samples under load
-        return {"sm_mhz": float(np.median(loaded)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        self.running = False
+        self.thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        a = np.array(self.samples)
+        return {"sm_mhz": float(np.median(a[:, 0])), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": int(a.shape[0]), "power_w": float(np.median(a[:, 1]))}
 
 
 # --------------------------------------------------------------------------- CPU arm
@@ -285,7 +298,6 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()

@@ -87,6 +87,14 @@ int semgate_pad_dim(int d);
 int semgate_normalize_cast(semgate_handle_t h, const float* x, int64_t n, int32_t d, int64_t ld, void* out_bf16,
                            int32_t d_pad, semgate_stream_t stream);
 
+/* ---- dense similarity matrix (interface parity only) ---------------------
+ * replaces `desc_matrix_norm @ desc_matrix_norm.T` (place_recognition.py:190) and
+ * `np.dot(database_norm, query_norm)` (:171) for callers that really want the scores
+ * themselves: out[i * ld_out + j] = <q_i, db_j>, fp32, same tcgen05 main loop as K2
+ * with a store epilogue.  The retrieval path never calls this. */
+int semgate_similarity_matrix(semgate_handle_t h, const void* q_bf16, int64_t Q, const void* db_bf16, int64_t N,
+                              int32_t d_pad, float* out, int64_t ld_out, semgate_stream_t stream);
+
 /* ---- K2+K3: fused similarity / exclusion window / gate / threshold / top-k ----
  * replaces compute_all_pairwise_similarities + the per-row loop of
  * find_loop_closures (place_recognition.py:868-899) and, with one query row,

@@ -212,7 +212,7 @@ size_t semgate_topk_workspace_bytes(semgate_handle_t h, int64_t Q, int64_t N, in
   if (!h || !p || Q <= 0 || N <= 0 || p->k < 1 || p->k > SEMGATE_MAX_K) return 256;
   const int cg = resolve_cg(h, p, Q);
   Schedule sc = make_schedule(Q, N, d_pad, cg, h->sm_count);
-  return align256(topk_partial_bytes(sc, cg, p->k));
+  return align256(topk_workspace_bytes(sc, cg, p->k));
 }
 
 int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const void* db_bf16, int64_t N, int32_t d_pad,
@@ -252,7 +252,7 @@ int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const 
     return fail(SEMGATE_EINVAL, "gated_topk: descriptor matrices must be 16-byte aligned");
 
   Schedule sc = make_schedule(Q, N, d_pad, cg, h->sm_count);
-  const size_t need = topk_partial_bytes(sc, cg, k);
+  const size_t need = topk_workspace_bytes(sc, cg, k);
   if (!workspace || workspace_bytes < need)
     return fail(SEMGATE_ENOMEM, "gated_topk: workspace %zu < required %zu bytes", workspace_bytes, need);
 
@@ -308,6 +308,31 @@ int semgate_merge_topk(semgate_handle_t h, const uint64_t* keys_in, int32_t G, i
   m.max_floor_diff = (q_floor && db_floor_all) ? max_floor_diff : -1;
   RC_TRY(launch_merge_topk(m, static_cast<cudaStream_t>(stream)), "merge_topk launch");
   h->launches += 1;
+  return 0;
+}
+
+// ---------------------------------------------------------------- dense similarity (interface parity)
+int semgate_similarity_matrix(semgate_handle_t h, const void* q_bf16, int64_t Q, const void* db_bf16, int64_t N, int32_t d_pad,
+                              float* out, int64_t ld_out, semgate_stream_t stream) {
+  if (!h) return fail(SEMGATE_EINVAL, "handle is NULL");
+  if (Q < 0 || N < 0 || Q > INT32_MAX || N > INT32_MAX) return fail(SEMGATE_EINVAL, "similarity_matrix: bad sizes Q=%lld N=%lld", (long long)Q, (long long)N);
+  if (d_pad <= 0 || d_pad % 64 != 0) return fail(SEMGATE_EINVAL, "similarity_matrix: d_pad=%d must be a positive multiple of 64", d_pad);
+  if (Q == 0 || N == 0) return 0;
+  if (!q_bf16 || !db_bf16 || !out) return fail(SEMGATE_EINVAL, "similarity_matrix: NULL pointer");
+  if (ld_out < N) return fail(SEMGATE_EINVAL, "similarity_matrix: ld_out=%lld < N=%lld", (long long)ld_out, (long long)N);
+  if ((reinterpret_cast<uintptr_t>(q_bf16) & 15) || (reinterpret_cast<uintptr_t>(db_bf16) & 15))
+    return fail(SEMGATE_EINVAL, "similarity_matrix: descriptor matrices must be 16-byte aligned");
+  DeviceGuard g(h->device);
+  const int cg = 1;
+  Schedule sc = make_schedule(Q, N, d_pad, cg, h->sm_count);
+  TopkLaunch a{};
+  a.q_bf16 = q_bf16; a.Q = Q; a.db_bf16 = db_bf16; a.N = N; a.d_pad = d_pad;
+  a.threshold = 0.f; a.gap = 0.0; a.k = 1; a.max_floor_diff = -1; a.gate_mode = 0; a.db_index_offset = 0;
+  a.cta_group = cg; a.sm_count = h->sm_count;
+  a.dense = out; a.dense_ld = ld_out;
+  int launches = 0;
+  RC_TRY(launch_gated_topk(a, sc, nullptr, static_cast<cudaStream_t>(stream), &launches), "similarity_matrix launch");
+  h->launches += launches;
   return 0;
 }
 

@@ -56,15 +56,20 @@ __host__ __device__ __forceinline__ bool time_excluded(double t_db, double t_q, 
 // super-rows of `rm` consecutive m-blocks; inside a super-row every m-block's
 // database range is split into `s` contiguous runs of n-tiles, one run per
 // CTA (or CTA pair), so that rm*s <= units.  All units of a super-row stream
-// the same database tiles at about the same time (L2 reuse) and each unit
-// keeps one running top-k list per query row; the `s` partial lists of a row
-// are merged afterwards.  The last super-row may hold fewer m-blocks and is
-// split finer.
-// Long databases are additionally cut into `n_panels` column panels that fit
-// in L2, visited panel-major (for panel: for super-row: run): units that drift
-// apart over a long sweep still find the panel's tiles in L2 instead of each
-// streaming them from DRAM.  A row's list is carried from panel to panel through
-// its partial-list slot in HBM.
+// the same `s` database tiles at about the same time (each tile is fetched from
+// DRAM once and served to the other rm - 1 readers by L2) and each unit keeps
+// one running top-k list per query row; the `s` partial lists of a row are
+// merged afterwards.  The last super-row may hold fewer m-blocks and is split
+// finer.
+//
+// Pacing.  The L2 only helps while the units of a super-row stay close together.
+// Every unit counts the chunks (`pace_kb` k-blocks of one tile) it has issued on a
+// per-super-row counter array, and does not start chunk p before ALL units of the
+// super-row have issued chunk p - sync_window.  The window is sized so that the
+// streamed operands of the whole grid inside it fit in L2 next to the resident
+// query blocks.  With very long descriptors (query blocks no longer L2-resident,
+// `a_resident` = 0) both operands are streamed and the same lock-step makes every
+// k-slice of every operand come from DRAM once per super-row step.
 struct Schedule {
   int mblocks;      // ceil(Q / BM)            (for pairs: counted in pair-rows of 2*BM)
   int ntiles;       // ceil(N / BN)
@@ -74,8 +79,17 @@ struct Schedule {
   int r_last;       // m-blocks in the trailing partial super-row (0 if none)
   int s_last;       // splits per m-block there
   int s_max;        // max(s_main, s_last): slot stride of the partial lists
-  int n_panels;     // column panels (>= 1); every panel holds >= s_max tiles
+  int a_resident;   // the super-row's query blocks stay in L2 across database tiles
+  int sync_window;  // pacing window in chunks (0 = pacing off)
+  int pace_kb;      // k-blocks per chunk
+  int cpt;          // chunks per tile = ceil(kblocks / pace_kb)
+  int len_main;     // ceil(ntiles / s_main): longest run of a full super-row, in tiles
+  int len_last;     // ceil(ntiles / s_last)
 };
+
+__host__ __device__ __forceinline__ int64_t sched_sync_counters(const Schedule& sc) {
+  return (static_cast<int64_t>(sc.n_full) * sc.len_main + sc.len_last) * sc.cpt;
+}
 
 __host__ __device__ __forceinline__ int sched_slots(const Schedule& sc, int mb) {
   return mb < sc.n_full * sc.rm ? sc.s_main : sc.s_last;
@@ -86,34 +100,38 @@ __host__ __device__ __forceinline__ int split_begin(int n, int s, int j) {
   return static_cast<int>((static_cast<int64_t>(n) * j) / s);
 }
 
-// One unit's work list, identical for every warp role: f(mb, slot, nt0, nt1, carry).
+// One unit's work list, identical for every warp role.
 struct Run {
   int mb;      // m-block (pair-row for CG = 2)
   int slot;    // which of the m-block's runs (partial-list slot)
   int nt0;     // first n-tile
   int nt1;     // one past the last n-tile
-  bool carry;  // the row lists continue from an earlier panel
+  // pacing: counters of this super-row; all `units_all` units reach tile ordinal < short_len,
+  // only the `units_long` units with the longer runs reach ordinal == short_len
+  int64_t sync_base;
+  int short_len;
+  int units_all;
+  int units_long;
 };
 
 template <typename F>
 __device__ __forceinline__ void for_each_run(const Schedule& sc, int unit, F&& f) {
   const int n_sr = sc.n_full + (sc.r_last > 0 ? 1 : 0);
-  for (int p = 0; p < sc.n_panels; ++p) {
-    const int pt0 = split_begin(sc.ntiles, sc.n_panels, p);
-    const int len = split_begin(sc.ntiles, sc.n_panels, p + 1) - pt0;
-    for (int sr = 0; sr < n_sr; ++sr) {
-      const bool full_sr = sr < sc.n_full;
-      const int r = full_sr ? sc.rm : sc.r_last;
-      const int S = full_sr ? sc.s_main : sc.s_last;
-      if (unit >= r * S) continue;
-      Run run;
-      run.mb = sr * sc.rm + unit % r;
-      run.slot = unit / r;
-      run.nt0 = pt0 + split_begin(len, S, run.slot);
-      run.nt1 = pt0 + split_begin(len, S, run.slot + 1);
-      run.carry = p > 0;
-      if (run.nt0 < run.nt1) f(run);
-    }
+  for (int sr = 0; sr < n_sr; ++sr) {
+    const bool full_sr = sr < sc.n_full;
+    const int r = full_sr ? sc.rm : sc.r_last;
+    const int S = full_sr ? sc.s_main : sc.s_last;
+    if (unit >= r * S) continue;
+    Run run;
+    run.mb = sr * sc.rm + unit % r;
+    run.slot = unit / r;
+    run.nt0 = split_begin(sc.ntiles, S, run.slot);
+    run.nt1 = split_begin(sc.ntiles, S, run.slot + 1);
+    run.sync_base = (full_sr ? static_cast<int64_t>(sr) * sc.len_main : static_cast<int64_t>(sc.n_full) * sc.len_main) * sc.cpt;
+    run.short_len = sc.ntiles / S;
+    run.units_all = r * S;
+    run.units_long = r * (sc.ntiles % S);
+    if (run.nt0 < run.nt1) f(run);
   }
 }
 

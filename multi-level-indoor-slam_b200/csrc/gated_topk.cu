@@ -6,10 +6,16 @@
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 
 namespace semgate {
 
 // ------------------------------------------------------------------ schedule
+static long env_long(const char* name, long dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atol(e) : dflt;
+}
+
 Schedule make_schedule(int64_t Q, int64_t N, int d_pad, int cta_group, int sm_count) {
   Schedule sc{};
   const int units = std::max(1, sm_count / cta_group);
@@ -17,53 +23,72 @@ Schedule make_schedule(int64_t Q, int64_t N, int d_pad, int cta_group, int sm_co
   sc.mblocks = static_cast<int>((Q + bm_unit - 1) / bm_unit);
   sc.ntiles = static_cast<int>((N + BN - 1) / BN);
   if (sc.mblocks <= 0 || sc.ntiles <= 0) { sc.mblocks = std::max(sc.mblocks, 0); return sc; }
-  // Query blocks resident per super-row are re-read from L2 once per database
-  // tile; keep them comfortably inside the 126 MB L2 next to the database tiles.
+  // A super-row's query blocks are re-read once per database tile.  While they fit in L2
+  // (`cap`; measured: the usable share of the 126 MB is about one die's half minus the streamed
+  // tiles) only the database tiles come from DRAM: s * BN rows per tile-time.  Beyond that
+  // both operands stream: s * BN + rm * BM rows.  Among the super-row heights whose makespan is
+  // within 4 % of the best, take the one with the least DRAM traffic.
   const int64_t a_bytes = static_cast<int64_t>(bm_unit) * d_pad * 2;
-  int64_t cap_mb = 48;
-  if (const char* e = getenv("SEMGATE_RM_CAP_MB")) { const long v = atol(e); if (v > 0) cap_mb = v; }
-  const int rm_cap = static_cast<int>(std::max<int64_t>(1, (cap_mb << 20) / std::max<int64_t>(a_bytes, 1)));
-  const int rm_hi = std::min({sc.mblocks, units, rm_cap});
+  const int64_t cap = env_long("SEMGATE_RM_CAP_MB", 40) << 20;
+  const int rm_hi = std::min(sc.mblocks, units);
+  std::vector<int64_t> cost(rm_hi + 1, 0);
   int64_t best_cost = -1;
-  int best_rm = 1;
   for (int rm = 1; rm <= rm_hi; ++rm) {
     const int s_main = std::min(sc.ntiles, units / rm);
     const int n_full = sc.mblocks / rm;
     const int r_last = sc.mblocks % rm;
-    int64_t cost = static_cast<int64_t>(n_full) * ((sc.ntiles + s_main - 1) / s_main);
+    int64_t c = static_cast<int64_t>(n_full) * ((sc.ntiles + s_main - 1) / s_main);
     if (r_last > 0) {
       const int s_last = std::min(sc.ntiles, units / r_last);
-      cost += (sc.ntiles + s_last - 1) / s_last;
+      c += (sc.ntiles + s_last - 1) / s_last;
     }
-    if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best_rm = rm; }   // ties -> larger rm (fewer DRAM passes)
+    cost[rm] = c;
+    if (best_cost < 0 || c < best_cost) best_cost = c;
+  }
+  int best_rm = 1;
+  int64_t best_rows = -1;
+  for (int rm = 1; rm <= rm_hi; ++rm) {
+    if (cost[rm] * 100 > best_cost * 104) continue;
+    const int s_main = std::min(sc.ntiles, units / rm);
+    const bool resident = rm * a_bytes <= cap;
+    const int64_t rows = static_cast<int64_t>(s_main) * BN + (resident ? 0 : static_cast<int64_t>(rm) * bm_unit);
+    if (best_rows < 0 || rows < best_rows || (rows == best_rows && cost[rm] <= cost[best_rm])) { best_rows = rows; best_rm = rm; }
   }
   sc.rm = best_rm;
+  sc.a_resident = sc.rm * a_bytes <= cap ? 1 : 0;
   sc.s_main = std::min(sc.ntiles, units / sc.rm);
   sc.n_full = sc.mblocks / sc.rm;
   sc.r_last = sc.mblocks % sc.rm;
   sc.s_last = sc.r_last > 0 ? std::min(sc.ntiles, units / sc.r_last) : 0;
   sc.s_max = std::max(sc.n_full > 0 ? sc.s_main : 0, sc.s_last);
-  // Column panels (off unless SEMGATE_PANEL_MB is set): panel width = a multiple of the split count
-  // (no ceiling loss) whose tiles fit the given number of megabytes.
-  sc.n_panels = 1;
-  if (const char* e = getenv("SEMGATE_PANEL_MB")) {
-    const long panel_mb = atol(e);
-    if (panel_mb > 0) {
-      const int64_t tile_bytes = static_cast<int64_t>(BN) * d_pad * 2;
-      const int smax = std::max(sc.s_max, 1);
-      int w_cap = static_cast<int>(std::max<int64_t>(1, (static_cast<int64_t>(panel_mb) << 20) / tile_bytes));
-      w_cap = std::max(smax, (w_cap / smax) * smax);
-      if (sc.ntiles > 4 * w_cap) {
-        sc.n_panels = (sc.ntiles + w_cap - 1) / w_cap;
-        sc.n_panels = std::max(1, std::min(sc.n_panels, sc.ntiles / smax));   // every panel keeps >= s_max tiles
-      }
-    }
-  }
+  sc.len_main = sc.n_full > 0 ? (sc.ntiles + sc.s_main - 1) / sc.s_main : 0;
+  sc.len_last = sc.r_last > 0 ? (sc.ntiles + sc.s_last - 1) / sc.s_last : 0;
+
+  // Pacing: chunks of 16 k-blocks; the window holds `SEMGATE_WINDOW_MB` of streamed operands of the
+  // whole grid.  Off for short runs (nothing to drift) and with SEMGATE_WINDOW_MB=0.
+  const int kblocks = d_pad / BK;
+  sc.pace_kb = std::min(kblocks, 16);
+  sc.cpt = (kblocks + sc.pace_kb - 1) / sc.pace_kb;
+  const int64_t window_bytes = env_long("SEMGATE_WINDOW_MB", 24) << 20;
+  const int64_t stream_rows = static_cast<int64_t>(sc.s_main) * BN + (sc.a_resident ? 0 : static_cast<int64_t>(sc.rm) * bm_unit);
+  const int64_t chunk_bytes = stream_rows * sc.pace_kb * BK * 2;
+  int window = static_cast<int>(std::min<int64_t>(64, std::max<int64_t>(2, window_bytes / std::max<int64_t>(chunk_bytes, 1))));
+  const int64_t run_chunks = static_cast<int64_t>(std::max(sc.len_main, sc.len_last)) * sc.cpt;
+  sc.sync_window = (window_bytes > 0 && run_chunks > 4 * window) ? window : 0;
   return sc;
 }
 
 size_t topk_partial_bytes(const Schedule& sc, int cta_group, int k) {
-  return static_cast<size_t>(sc.mblocks) * BM * cta_group * std::max(sc.s_max, 1) * k * sizeof(uint64_t);
+  const size_t b = static_cast<size_t>(sc.mblocks) * BM * cta_group * std::max(sc.s_max, 1) * k * sizeof(uint64_t);
+  return (b + 255) & ~static_cast<size_t>(255);
+}
+
+size_t topk_sync_bytes(const Schedule& sc) {
+  return sc.sync_window > 0 ? static_cast<size_t>(sched_sync_counters(sc)) * sizeof(uint32_t) : 0;
+}
+
+size_t topk_workspace_bytes(const Schedule& sc, int cta_group, int k) {
+  return topk_partial_bytes(sc, cta_group, k) + topk_sync_bytes(sc);
 }
 
 // ------------------------------------------------------------------ tensor maps
@@ -123,6 +148,20 @@ int launch_gated_topk(const TopkLaunch& a, const Schedule& sc, uint64_t* partial
   p.q_ts = a.q_ts; p.db_ts = a.db_ts; p.q_floor = a.q_floor; p.db_floor = a.db_floor;
   p.partial = partial;
   p.sc = sc;
+  p.dense = a.dense; p.dense_ld = a.dense_ld;
+  if (a.dense != nullptr) p.sc.sync_window = 0;   // no workspace in dense mode
+  p.sync = nullptr;
+  if (p.sc.sync_window > 0) {
+    // the pacing counters live behind the partial lists in the caller's workspace
+    p.sync = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(partial) + topk_partial_bytes(sc, cg, a.k));
+    cudaError_t me = cudaMemsetAsync(p.sync, 0, topk_sync_bytes(sc), st);
+    if (me != cudaSuccess) return static_cast<int>(me);
+    if (launches) ++*launches;
+  }
+  // query blocks are re-read from L2 for every database tile: keep them; database tiles stream through
+  const int hint = static_cast<int>(env_long("SEMGATE_L2_HINT", 2));
+  p.policy_q = ((hint == 1 || hint == 2) && sc.a_resident) ? ptx::kL2EvictLast : ptx::kL2EvictNormal;
+  p.policy_db = (hint >= 2 && sc.a_resident) ? ptx::kL2EvictFirst : ptx::kL2EvictNormal;
 
   // deepest ring that fits the 227 KB per-CTA limit
   const size_t limit = 232448;

@@ -49,6 +49,11 @@ struct TopkParams {
   const int32_t* q_floor;
   const int32_t* db_floor;
   uint64_t* partial;     // [mblocks*BM*CG rows][s_max][k] candidate keys
+  float* dense;          // non-null: write the raw fp32 similarity tiles to dense[row * dense_ld + col] instead of
+  int64_t dense_ld;      //           building lists (compute_all_pairwise_similarities, place_recognition.py:179-190)
+  uint32_t* sync;        // pacing counters (zeroed per launch) or null: see Schedule::sync_window
+  uint64_t policy_q;     // L2 eviction priority of the query-block loads (re-read once per database tile)
+  uint64_t policy_db;    // ... of the streamed database tiles
   Schedule sc;
 };
 
@@ -142,11 +147,38 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 
   if (warp == 0) {
     // ===================================================== TMA producer (whole warp loops, one lane issues)
+    const int window = (p.sync != nullptr) ? sc.sync_window : 0;
+    const int pace_kb = sc.pace_kb, cpt = sc.cpt;
     for_each_run(sc, unit, [&](const Run& run) {
       const int m0 = (run.mb * CG + static_cast<int>(cta_rank)) * BM;
+      uint32_t* const pace = p.sync + run.sync_base;
       for (int nt = run.nt0; nt < run.nt1; ++nt) {
         const int n0 = nt * BN + static_cast<int>(cta_rank) * static_cast<int>(B_ROWS);
+        int chunk = (nt - run.nt0) * cpt;            // position of this unit in its run, in chunks
+        int kb_next_chunk = 0;
         for (int kb = 0; kb < p.kblocks; ++kb) {
+          if (window > 0 && kb == kb_next_chunk) {
+            if (kb > 0) {                              // previous chunk fully issued
+              if (ptx::elect_one()) ptx::red_add_relaxed_gpu(pace + chunk, 1u);
+              ++chunk;
+            }
+            kb_next_chunk += pace_kb;
+            const int back = chunk - window;
+            if (back >= 0) {
+              // stay within `window` chunks of the slowest unit of this super-row
+              const uint32_t need = static_cast<uint32_t>((back / cpt) < run.short_len ? run.units_all : run.units_long) * CG;
+              uint32_t spins = 0;
+              uint64_t t0 = 0;
+              while (ptx::ld_relaxed_gpu(pace + back) < need) {
+                ptx::nanosleep(100);
+                if ((++spins & 0x3FFu) == 0) {
+                  const uint64_t now = ptx::globaltimer_ns();
+                  if (t0 == 0) t0 = now;
+                  else if (now - t0 > SEMGATE_WAIT_TIMEOUT_NS) __trap();
+                }
+              }
+            }
+          }
           ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t dst_a = ptx::smem_u32(smem_a) + stage * A_STAGE_BYTES;
           const uint32_t dst_b = ptx::smem_u32(smem_b) + stage * B_STAGE_BYTES;
@@ -154,20 +186,22 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           if (ptx::elect_one()) {
             if constexpr (CG == 1) {
               ptx::mbar_arrive_expect_tx(fb, STAGE_BYTES);
-              ptx::tma_load_2d(dst_a, &tmap_q, fb, kb * BK, m0);
-              ptx::tma_load_2d(dst_b, &tmap_db, fb, kb * BK, n0);
+              ptx::tma_load_2d(dst_a, &tmap_q, fb, kb * BK, m0, p.policy_q);
+              ptx::tma_load_2d(dst_b, &tmap_db, fb, kb * BK, n0, p.policy_db);
             } else {
               // both CTAs' bytes are accounted on the leader's barrier (its MMA reads both smems)
               const uint32_t fb_leader = ptx::mapa(fb, 0);
               if (leader) ptx::mbar_arrive_expect_tx(fb, 2 * STAGE_BYTES);
-              ptx::tma_load_2d_cg2(dst_a, &tmap_q, fb_leader, kb * BK, m0);
-              ptx::tma_load_2d_cg2(dst_b, &tmap_db, fb_leader, kb * BK, n0);
+              ptx::tma_load_2d_cg2(dst_a, &tmap_q, fb_leader, kb * BK, m0, p.policy_q);
+              ptx::tma_load_2d_cg2(dst_b, &tmap_db, fb_leader, kb * BK, n0, p.policy_db);
               if (!leader) ptx::mbar_arrive_cluster(fb, 0);
             }
           }
           __syncwarp();
           if (++stage == static_cast<uint32_t>(stages)) { stage = 0; phase ^= 1; }
         }
+        if (window > 0 && ptx::elect_one()) ptx::red_add_relaxed_gpu(pace + chunk, 1u);   // last chunk of the tile
+        __syncwarp();
       }
     });
   } else if (warp == 1) {
@@ -239,17 +273,6 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         if (mask_mode) qf = p.q_floor[grow];
       }
       L.reset(row_live ? p.threshold : pos_inf);
-      if (run.carry && row_live) {
-        // continue the list this row built over earlier panels (entries are packed at the front)
-        int c = 0;
-        for (int i = 0; i < k; ++i) {
-          const uint64_t key = slot[i];
-          L.keys[i] = key;
-          c += key != 0ull ? 1 : 0;
-        }
-        L.cnt = c;
-        if (c == k) L.rescan(k);
-      }
 
       for (int nt = run.nt0; nt < run.nt1; ++nt, ++it) {
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -262,6 +285,23 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           uint32_t v[32];
           ptx::tmem_ld_32x32(t_acc + c * 32, v);
           ptx::tmem_wait_ld();
+          if (p.dense != nullptr) {
+            // dense output: this thread owns 32 consecutive columns of its row
+            const int col0 = col_base + c * 32;
+            if (row_live && col0 < p.N) {
+              float* dst = p.dense + static_cast<int64_t>(grow) * p.dense_ld + col0;
+              if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                  *reinterpret_cast<uint4*>(dst + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (col0 + i < p.N) dst[i] = __uint_as_float(v[i]);
+              }
+            }
+            continue;
+          }
           float mx = __uint_as_float(v[0]);
 #pragma unroll
           for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
@@ -301,7 +341,7 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       }
 
       // flush this run's list (unsorted, packed at the front; empty slots are key 0)
-      if (row_live) {
+      if (row_live && p.dense == nullptr) {
         for (int i = 0; i < k; ++i) slot[i] = i < L.cnt ? L.keys[i] : 0ull;
       }
     });

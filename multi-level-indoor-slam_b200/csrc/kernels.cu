@@ -79,62 +79,85 @@ normalize_cast_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ld,
   }
 }
 
-// Long rows (d > 4096, e.g. SALAD 8448-d, AnyLoc 49152-d): one 1024-thread block per row, the row
-// is staged in shared memory so that DRAM is touched once (read 4*d, write 2*d_pad).
-constexpr int kNormBigThreads = 1024;
+// Long rows (d > 4096, e.g. SALAD 8448-d, AnyLoc 49152-d): a row is split over the CTAs of a
+// thread-block cluster (<= 8), every thread keeps its 12 float4 in registers between the two
+// passes, and the per-CTA partial sums of squares are exchanged through distributed shared
+// memory.  DRAM is touched once (read 4*d, write 2*d_pad), several rows are in flight per SM, and
+// every CTA adds the partials in rank order, so all of them divide by the same denominator.
+constexpr int kNormLongCache = 12;                                   // float4 per thread
+constexpr int kNormLongChunk = kNormThreads * kNormLongCache * 4;    // 12288 floats per CTA
 
-__global__ void __launch_bounds__(kNormBigThreads)
-normalize_cast_smem_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ld, __nv_bfloat16* __restrict__ out, int d_pad) {
-  extern __shared__ __align__(16) float row_s[];
+__device__ __forceinline__ float ld_dsmem_f32(const float* local, uint32_t cta) {
+  uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(local)), remote;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(cta));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kNormThreads)
+normalize_cast_cluster_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ld, __nv_bfloat16* __restrict__ out,
+                              int d_pad, int csize) {
   __shared__ float red[32];
+  __shared__ float partial[2];
   const int tid = threadIdx.x;
-  const int nv = d >> 2;
-  for (int64_t row = blockIdx.x; row < n; row += gridDim.x) {
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int64_t cluster_id = blockIdx.x / csize, n_clusters = gridDim.x / csize;
+  const int nv = d >> 2;                                  // float4 per row (d % 4 == 0)
+  const int v0 = static_cast<int>(rank) * (kNormLongChunk >> 2);   // this CTA's first float4 of the row
+  int par = 0;
+  for (int64_t row = cluster_id; row < n; row += n_clusters, par ^= 1) {
     const float4* xr = reinterpret_cast<const float4*>(x + row * ld);
     __nv_bfloat16* orow = out + row * static_cast<int64_t>(d_pad);
+    float4 cache[kNormLongCache];
     float ss = 0.f;
-    int i = tid;
-    for (; i + 3 * kNormBigThreads < nv; i += 4 * kNormBigThreads) {      // 4 independent 16-byte loads in flight
-      const float4 a = __ldg(xr + i), b = __ldg(xr + i + kNormBigThreads), c = __ldg(xr + i + 2 * kNormBigThreads),
-                   e = __ldg(xr + i + 3 * kNormBigThreads);
-      reinterpret_cast<float4*>(row_s)[i] = a;
-      reinterpret_cast<float4*>(row_s)[i + kNormBigThreads] = b;
-      reinterpret_cast<float4*>(row_s)[i + 2 * kNormBigThreads] = c;
-      reinterpret_cast<float4*>(row_s)[i + 3 * kNormBigThreads] = e;
-      ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w +
-            c.x * c.x + c.y * c.y + c.z * c.z + c.w * c.w + e.x * e.x + e.y * e.y + e.z * e.z + e.w * e.w;
+#pragma unroll
+    for (int c = 0; c < kNormLongCache; ++c) {
+      const int i = v0 + c * kNormThreads + tid;
+      cache[c] = i < nv ? __ldcs(xr + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (; i < nv; i += kNormBigThreads) {
-      const float4 a = __ldg(xr + i);
-      reinterpret_cast<float4*>(row_s)[i] = a;
-      ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+#pragma unroll
+    for (int c = 0; c < kNormLongCache; ++c)
+      ss += cache[c].x * cache[c].x + cache[c].y * cache[c].y + cache[c].z * cache[c].z + cache[c].w * cache[c].w;
+    ss = block_sum(ss, red);
+    float total = ss;
+    if (csize > 1) {
+      if (tid == 0) partial[par] = ss;
+      asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+      total = 0.f;
+      for (int r = 0; r < csize; ++r) total += ld_dsmem_f32(&partial[par], static_cast<uint32_t>(r));
     }
-    const float denom = sqrtf(block_sum(ss, red)) + 1e-8f;     // block_sum's barriers also publish row_s
-    for (int j = tid; j < nv; j += kNormBigThreads) {
-      const float4 v = reinterpret_cast<const float4*>(row_s)[j];
-      store_bf16x4(orow + 4 * j, v.x / denom, v.y / denom, v.z / denom, v.w / denom);
+    const float denom = sqrtf(total) + 1e-8f;
+#pragma unroll
+    for (int c = 0; c < kNormLongCache; ++c) {
+      const int i = v0 + c * kNormThreads + tid;
+      if (i < nv) store_bf16x4(orow + 4 * i, cache[c].x / denom, cache[c].y / denom, cache[c].z / denom, cache[c].w / denom);
+      else if (i < (d_pad >> 2)) store_bf16x4(orow + 4 * i, 0.f, 0.f, 0.f, 0.f);
     }
-    for (int j = nv + tid; j < (d_pad >> 2); j += kNormBigThreads) store_bf16x4(orow + 4 * j, 0.f, 0.f, 0.f, 0.f);
-    __syncthreads();                                            // row_s is reused by the next row
   }
+  // a peer may still be reading this CTA's partial sum of the last row
+  if (csize > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 int launch_normalize_cast(const float* x, int64_t n, int d, int64_t ld, void* out_bf16, int d_pad, cudaStream_t st) {
   if (n <= 0) return 0;
   const bool vec = (d % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  const size_t row_bytes = static_cast<size_t>(d) * 4;
-  // mid-length rows (8448-d = 33 KB) do better re-reading from L2 with many small blocks per SM
-  if (vec && row_bytes >= 64 * 1024 && row_bytes <= 200 * 1024) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(normalize_cast_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      if (e != cudaSuccess) return static_cast<int>(e);
-      attr_set = true;
-    }
-    const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(2, (220 * 1024) / (row_bytes + 1024))));
-    const unsigned grid = static_cast<unsigned>(std::min<int64_t>(n, 148 * per_sm));
-    normalize_cast_smem_kernel<<<grid, kNormBigThreads, row_bytes, st>>>(x, n, d, ld, static_cast<__nv_bfloat16*>(out_bf16), d_pad);
-    return static_cast<int>(cudaGetLastError());
+  if (vec && d > 4096 && d_pad <= 8 * kNormLongChunk) {
+    int csize = (d_pad + kNormLongChunk - 1) / kNormLongChunk;       // 1, 2, 3..8 -> round up to a power of two
+    while (csize & (csize - 1)) ++csize;
+    const int64_t clusters = std::min<int64_t>(n, std::max(1, (148 * 3) / csize));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(clusters * csize));
+    cfg.blockDim = dim3(kNormThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = static_cast<unsigned>(csize); attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return static_cast<int>(cudaLaunchKernelEx(&cfg, normalize_cast_cluster_kernel, x, n, d, ld,
+                                               static_cast<__nv_bfloat16*>(out_bf16), d_pad, csize));
   }
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(n, 148 * 16));
   if (vec)
@@ -145,23 +168,40 @@ int launch_normalize_cast(const float* x, int64_t n, int d, int64_t ld, void* ou
 }
 
 // =========================================================================== K3
-// One warp per query row.  Candidates are consumed in batches of 256 keys (8 per
-// lane) next to the running list (<= 64 keys, 2 per lane); k rounds of warp-wide
-// arg-max extract the new running list in descending order.  Keys are unique
+// One warp per query row.  Every lane keeps P candidate keys sorted descending in
+// registers (a fixed compare-exchange network); then k rounds of "warp-wide max over
+// the lanes' heads, the winning lane pops" emit the merged list in descending order.
+// A batch is 32*P keys: the running list (<= 64 keys, 2 per lane) plus new ones; the
+// common case (s*k <= 128 keys) is a single batch with P = 4.  Keys are unique
 // (distinct database rows), 0 = empty.
 constexpr int kMergeWarps = 8;
-constexpr int kBatchPerLane = 8;
 
-__device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
-  const uint32_t hi = static_cast<uint32_t>(v >> 32);
-  const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
-  const uint32_t lo = hi == mh ? static_cast<uint32_t>(v) : 0u;
-  const uint32_t ml = __reduce_max_sync(0xffffffffu, lo);
-  return (static_cast<uint64_t>(mh) << 32) | ml;
+__device__ __forceinline__ void cmp_swap_desc(uint64_t& a, uint64_t& b) {
+  const bool sw = a < b;
+  const uint64_t hi = sw ? b : a, lo = sw ? a : b;
+  a = hi; b = lo;
 }
 
+template <int P>
+__device__ __forceinline__ void sort_desc(uint64_t (&c)[P]) {
+  if constexpr (P == 4) {
+    cmp_swap_desc(c[0], c[1]); cmp_swap_desc(c[2], c[3]);
+    cmp_swap_desc(c[0], c[2]); cmp_swap_desc(c[1], c[3]);
+    cmp_swap_desc(c[1], c[2]);
+  } else {   // P == 8: Batcher's odd-even merge sort, 19 comparators
+    cmp_swap_desc(c[0], c[1]); cmp_swap_desc(c[2], c[3]); cmp_swap_desc(c[4], c[5]); cmp_swap_desc(c[6], c[7]);
+    cmp_swap_desc(c[0], c[2]); cmp_swap_desc(c[1], c[3]); cmp_swap_desc(c[4], c[6]); cmp_swap_desc(c[5], c[7]);
+    cmp_swap_desc(c[1], c[2]); cmp_swap_desc(c[5], c[6]);
+    cmp_swap_desc(c[0], c[4]); cmp_swap_desc(c[1], c[5]); cmp_swap_desc(c[2], c[6]); cmp_swap_desc(c[3], c[7]);
+    cmp_swap_desc(c[2], c[4]); cmp_swap_desc(c[3], c[5]);
+    cmp_swap_desc(c[1], c[2]); cmp_swap_desc(c[3], c[4]); cmp_swap_desc(c[5], c[6]);
+  }
+}
+
+template <int P>
 __global__ void __launch_bounds__(kMergeWarps * 32)
 merge_topk_kernel(const MergeLaunch a) {
+  static_assert(P == 4 || P == 8, "keys per lane");
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * kMergeWarps + (threadIdx.x >> 5);
   if (row >= a.Q) return;
@@ -172,34 +212,42 @@ merge_topk_kernel(const MergeLaunch a) {
   const int total = n_lists * k;
 
   uint64_t run[2] = {0ull, 0ull};          // running list: rank t lives in run[t>>5] of lane t&31
-  if (a.seed_keys != nullptr) {            // already sorted descending: rank t -> lane t&31, slot t>>5
+  bool have_run = false;
+  if (a.seed_keys != nullptr) {            // one more list per row (order irrelevant here)
     const uint64_t* seed = a.seed_keys + row * k;
     if (lane < k) run[0] = seed[lane];
     if (lane + 32 < k) run[1] = seed[lane + 32];
+    have_run = true;
   }
-  for (int b0 = 0; b0 < total; b0 += 32 * kBatchPerLane) {
-    uint64_t c[kBatchPerLane + 2];
+  int b0 = 0;
+  do {
+    const int nnew = have_run ? P - 2 : P;   // key slots per lane for new candidates
+    uint64_t c[P];
 #pragma unroll
-    for (int i = 0; i < kBatchPerLane; ++i) {
+    for (int i = 0; i < P; ++i) {
       const int e = b0 + i * 32 + lane;
-      c[i] = e < total ? base[static_cast<int64_t>(e / k) * a.list_stride + (e % k)] : 0ull;
+      uint64_t v = 0ull;
+      if (i < nnew && e < total) v = base[static_cast<int64_t>(e / k) * a.list_stride + (e % k)];
+      c[i] = v;
     }
-    c[kBatchPerLane] = run[0];
-    c[kBatchPerLane + 1] = run[1];
-    uint64_t nr[2] = {0ull, 0ull};
+    if (have_run) { c[P - 2] = run[0]; c[P - 1] = run[1]; }
+    b0 += 32 * nnew;
+    sort_desc<P>(c);
+    run[0] = run[1] = 0ull;
     for (int t = 0; t < k; ++t) {
-      uint64_t lm = c[0];
+      // warp-wide max of the heads (64-bit as two 32-bit reductions)
+      const uint32_t hi = static_cast<uint32_t>(c[0] >> 32), lo = static_cast<uint32_t>(c[0]);
+      const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+      const uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+      if ((mh | ml) == 0u) break;                        // warp-uniform: nothing left
+      const bool mine = hi == mh && lo == ml;
 #pragma unroll
-      for (int i = 1; i < kBatchPerLane + 2; ++i) lm = c[i] > lm ? c[i] : lm;
-      const uint64_t best = warp_max_u64(lm);
-      if (best == 0ull) break;                           // warp-uniform
-#pragma unroll
-      for (int i = 0; i < kBatchPerLane + 2; ++i) if (c[i] == best) c[i] = 0ull;
-      if ((t & 31) == lane) nr[t >> 5] = best;
+      for (int i = 0; i + 1 < P; ++i) c[i] = mine ? c[i + 1] : c[i];
+      c[P - 1] = mine ? 0ull : c[P - 1];
+      if ((t & 31) == lane) run[t >> 5] = (static_cast<uint64_t>(mh) << 32) | ml;
     }
-    run[0] = nr[0];
-    run[1] = nr[1];
-  }
+    have_run = true;
+  } while (b0 < total);
 
   int cnt = 0;
 #pragma unroll
@@ -232,7 +280,13 @@ merge_topk_kernel(const MergeLaunch a) {
 int launch_merge_topk(const MergeLaunch& a, cudaStream_t st) {
   if (a.Q <= 0) return 0;
   const unsigned grid = static_cast<unsigned>((a.Q + kMergeWarps - 1) / kMergeWarps);
-  merge_topk_kernel<<<grid, kMergeWarps * 32, 0, st>>>(a);
+  // 4 keys per lane cover one batch of 128 new keys (64 when a seeded list rides along)
+  const int lists = a.n_lists >= 0 ? a.n_lists : std::max(a.sc.s_main, a.sc.s_last);
+  const int64_t keys = static_cast<int64_t>(lists) * a.k;
+  if (keys <= (a.seed_keys ? 64 : 128))
+    merge_topk_kernel<4><<<grid, kMergeWarps * 32, 0, st>>>(a);
+  else
+    merge_topk_kernel<8><<<grid, kMergeWarps * 32, 0, st>>>(a);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -335,25 +389,43 @@ int launch_compact(const float* scores, const int32_t* idx, const uint8_t* valid
 }
 
 // =========================================================================== floor gate over pairs
+// the gate class has no None labels and no "off" switch: diff > max -> reject (loop_closure_gate.py:89-101)
+__device__ __forceinline__ uint32_t gate_one(const int32_t* __restrict__ floors, int64_t n_floors, int32_t q, int32_t m,
+                                             int max_floor_diff, unsigned& acc, unsigned& rej, unsigned& bad) {
+  if (q < 0 || q >= n_floors || m < 0 || m >= n_floors) { ++bad; return 0u; }
+  int64_t dfl = static_cast<int64_t>(__ldg(floors + q)) - static_cast<int64_t>(__ldg(floors + m));
+  if (dfl < 0) dfl = -dfl;
+  const bool ok = dfl <= max_floor_diff;
+  if (ok) ++acc; else ++rej;
+  return ok ? 1u : 0u;
+}
+
+// VEC: four candidates per thread per step (16-byte index loads, eight label gathers in
+// flight, one 4-byte store); needs 16-byte aligned index arrays and a 4-byte aligned output.
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 gate_candidates_kernel(const int32_t* __restrict__ floors, int64_t n_floors, const int32_t* __restrict__ q_idx,
                        const int32_t* __restrict__ m_idx, int64_t M, int max_floor_diff, uint8_t* __restrict__ out_valid,
                        unsigned long long* __restrict__ counts) {
   unsigned acc = 0, rej = 0, bad = 0;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < M;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t q = q_idx[i], m = m_idx[i];
-    bool ok = false;
-    if (q < 0 || q >= n_floors || m < 0 || m >= n_floors) {
-      ++bad;
-    } else {
-      // the gate class has no None labels and no "off" switch: diff > max -> reject (loop_closure_gate.py:89-101)
-      int64_t dfl = static_cast<int64_t>(__ldg(floors + q)) - static_cast<int64_t>(__ldg(floors + m));
-      if (dfl < 0) dfl = -dfl;
-      ok = dfl <= max_floor_diff;
-      if (ok) ++acc; else ++rej;
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthreads = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  if constexpr (VEC) {
+    const int64_t M4 = M >> 2;
+    for (int64_t i = tid; i < M4; i += nthreads) {
+      const int4 q = __ldcs(reinterpret_cast<const int4*>(q_idx) + i);
+      const int4 m = __ldcs(reinterpret_cast<const int4*>(m_idx) + i);
+      uint32_t r = gate_one(floors, n_floors, q.x, m.x, max_floor_diff, acc, rej, bad);
+      r |= gate_one(floors, n_floors, q.y, m.y, max_floor_diff, acc, rej, bad) << 8;
+      r |= gate_one(floors, n_floors, q.z, m.z, max_floor_diff, acc, rej, bad) << 16;
+      r |= gate_one(floors, n_floors, q.w, m.w, max_floor_diff, acc, rej, bad) << 24;
+      __stcs(reinterpret_cast<uint32_t*>(out_valid) + i, r);
     }
-    out_valid[i] = ok ? 1 : 0;
+    for (int64_t i = (M4 << 2) + tid; i < M; i += nthreads)
+      out_valid[i] = static_cast<uint8_t>(gate_one(floors, n_floors, q_idx[i], m_idx[i], max_floor_diff, acc, rej, bad));
+  } else {
+    for (int64_t i = tid; i < M; i += nthreads)
+      out_valid[i] = static_cast<uint8_t>(gate_one(floors, n_floors, q_idx[i], m_idx[i], max_floor_diff, acc, rej, bad));
   }
   acc = __reduce_add_sync(0xffffffffu, acc);
   rej = __reduce_add_sync(0xffffffffu, rej);
@@ -371,8 +443,14 @@ int launch_gate_candidates(const int32_t* floors, int64_t n_floors, const int32_
   cudaError_t e = cudaMemsetAsync(counts, 0, 3 * sizeof(unsigned long long), st);
   if (e != cudaSuccess) return static_cast<int>(e);
   if (M <= 0) return 0;
-  const unsigned grid = static_cast<unsigned>(std::min<int64_t>((M + 255) / 256, 148 * 8));
-  gate_candidates_kernel<<<grid, 256, 0, st>>>(floors, n_floors, q_idx, m_idx, M, max_floor_diff, out_valid, counts);
+  const bool vec = ((reinterpret_cast<uintptr_t>(q_idx) | reinterpret_cast<uintptr_t>(m_idx)) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out_valid) & 3) == 0;
+  const int64_t work = vec ? (M + 3) / 4 : M;
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>((work + 255) / 256, 148 * 8));
+  if (vec)
+    gate_candidates_kernel<true><<<grid, 256, 0, st>>>(floors, n_floors, q_idx, m_idx, M, max_floor_diff, out_valid, counts);
+  else
+    gate_candidates_kernel<false><<<grid, 256, 0, st>>>(floors, n_floors, q_idx, m_idx, M, max_floor_diff, out_valid, counts);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -19,13 +19,16 @@ struct TopkLaunch {
   uint32_t db_index_offset;
   int cta_group;                                  // 1 or 2
   int sm_count;
+  float* dense; int64_t dense_ld;                 // non-null: dense fp32 similarity output instead of lists
 };
 
 // Tile schedule for a Q x N problem on `units` CTAs (CG=1) or CTA pairs (CG=2).
 Schedule make_schedule(int64_t Q, int64_t N, int d_pad, int cta_group, int sm_count);
-size_t topk_partial_bytes(const Schedule& sc, int cta_group, int k);
+size_t topk_partial_bytes(const Schedule& sc, int cta_group, int k);      // candidate-key lists (256-byte multiple)
+size_t topk_workspace_bytes(const Schedule& sc, int cta_group, int k);    // lists + pacing counters
 
-// K2: fills `partial` ([rows_padded][s_max][k] keys). Returns cudaError as int.
+// K2: fills `partial` ([rows_padded][s_max][k] keys; the workspace also holds the pacing counters).
+// Returns cudaError as int.
 int launch_gated_topk(const TopkLaunch& a, const Schedule& sc, uint64_t* partial, cudaStream_t st,
                       int* launches);
 

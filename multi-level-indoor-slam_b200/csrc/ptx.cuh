@@ -108,20 +108,36 @@ __device__ __forceinline__ void prefetch_tensormap(const void* desc) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(desc) : "memory");
 }
 
+// L2 eviction-priority policies for TMA loads (createpolicy.fractional encodings, fraction 1.0).
+constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull;
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
+
 // 2D tile load global -> this CTA's smem, completion on this CTA's mbarrier.
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1, uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1) : "memory");
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1), "l"(policy) : "memory");
 }
 
 // Same, issued from a CTA of a cta_group::2 pair.  `dst`/`bar` are shared::cluster
 // addresses (the barrier may live in the peer CTA).
-__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1, uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1) : "memory");
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1), "l"(policy) : "memory");
 }
+
+// gpu-scope relaxed counter access for the pacing counters (no data is published through them)
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_add_relaxed_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void nanosleep(uint32_t ns) { asm volatile("nanosleep.u32 %0;" ::"r"(ns)); }
 
 // Multicast variant: the tile lands at the same smem offset in every CTA of `mask`
 // and each destination CTA's barrier (same offset) receives the complete_tx.

@@ -27,7 +27,7 @@ SYMBOLS = [
     "semgate_topk_workspace_bytes", "semgate_gated_topk", "semgate_merge_topk", "semgate_compact_workspace_bytes",
     "semgate_compact", "semgate_gate_candidates", "semgate_find_loop_closures_host", "semgate_query_host",
     "semgate_gate_candidates_host", "semgate_spatial_workspace_bytes", "semgate_spatial_count", "semgate_spatial_fill",
-    "semgate_spatial_candidates_host", "semgate_rerank_scores", "semgate_rerank_select",
+    "semgate_spatial_candidates_host", "semgate_rerank_scores", "semgate_rerank_select", "semgate_similarity_matrix",
 ]
 
 
@@ -95,6 +95,7 @@ def load_library():
     lib.semgate_spatial_candidates_host.argtypes = [vp, vp, i64, C.c_double, i64, vp, vp, vp, i64, P(i64)]
     lib.semgate_rerank_scores.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, i64, vp, vp, vp]
     lib.semgate_rerank_select.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, vp, vp, vp]
+    lib.semgate_similarity_matrix.argtypes = [vp, vp, i64, vp, i64, i32, vp, i64, vp]
     for name in SYMBOLS:
         getattr(lib, name)   # AttributeError here = the library is older than the header
     _lib = lib
@@ -268,6 +269,26 @@ class Engine:
             self._ptr(q_floor), self._ptr(db_floor), C.byref(params), self._ptr(ws), ws.numel(),
             self._ptr(keys), self._ptr(scores), self._ptr(idx), self._ptr(valid), self._ptr(count), self._stream()))
         return TopkResult(scores, idx, valid, count, keys)
+
+    def similarity_matrix(self, q_bf16, db_bf16, out=None):
+        """Dense fp32 [Q,N] similarity of normalised bf16 rows (interface parity with
+        compute_all_pairwise_similarities / _compute_similarity; the retrieval path never forms it)."""
+        torch = self._torch()
+        self._expect(q_bf16, torch.bfloat16, "q_bf16", 2)
+        self._expect(db_bf16, torch.bfloat16, "db_bf16", 2)
+        Q, dp = q_bf16.shape
+        N = db_bf16.shape[0]
+        if N > 0 and db_bf16.shape[1] != dp:
+            raise ValueError("similarity_matrix: query and database descriptor lengths differ")
+        if out is None:
+            out = torch.empty((Q, N), dtype=torch.float32, device=q_bf16.device)
+        self._expect(out, torch.float32, "out", 2)
+        if tuple(out.shape) != (Q, N):
+            raise ValueError("similarity_matrix: out must be [Q, N]")
+        if Q and N:
+            _check(self.lib.semgate_similarity_matrix(self._h, self._ptr(q_bf16), Q, self._ptr(db_bf16), N, dp,
+                                                      self._ptr(out), out.stride(0), self._stream()))
+        return out
 
     def merge_topk(self, keys_gathered, k: int, q_floor=None, db_floor_all=None, max_floor_diff: int = -1,
                    want_keys: bool = False) -> TopkResult:

@@ -229,24 +229,20 @@ class BasePlaceRecognition:
         return r.scores.cpu().numpy(), r.idx.cpu().numpy(), r.count.cpu().numpy()
 
     def _compute_similarity(self, query: np.ndarray, database: np.ndarray) -> np.ndarray:
-        """Cosine similarity of one query against every database row (reference :165-171),
-        returned in full — computed as a top-N sweep in chunks of the kernel's list size is
-        not what this is for; prefer `query`.  Kept for interface parity."""
-        database = np.asarray(database, dtype=np.float32)
-        n = database.shape[0]
-        out = np.full((n,), -np.inf, dtype=np.float32)
-        if n == 0:
-            return out
+        """Cosine similarity of one query against every row of `database` (reference :165-171):
+        both sides normalised as `x / (|x| + 1e-8)`, fp32 result of length N."""
+        import torch
+        database = np.ascontiguousarray(database, dtype=np.float32)
+        if database.ndim != 2 or database.shape[0] == 0:
+            return np.zeros((0,), dtype=np.float32)
         eng = self._engine()
-        # sweep the database in windows of MAX_K rows so every score is returned
-        params = _native.make_params(k=_native.MAX_K, similarity_threshold=-np.inf, max_floor_diff=-1)
-        q = np.asarray(query, dtype=np.float32).reshape(1, -1)
-        for s in range(0, n, _native.MAX_K):
-            e = min(n, s + _native.MAX_K)
-            sc, ix, ct = eng.query_host(q, database[s:e], params)
-            c = int(ct[0])
-            out[s + ix[0, :c]] = sc[0, :c]
-        return out
+        dev = torch.device("cuda", eng.device)
+        q = np.ascontiguousarray(np.asarray(query, dtype=np.float32).reshape(1, -1))
+        if q.shape[1] != database.shape[1]:
+            raise ValueError("shapes not aligned")           # numpy's dot raises ValueError too
+        qb = eng.normalize_cast(torch.from_numpy(q).to(dev))
+        db = eng.normalize_cast(torch.from_numpy(database).to(dev))
+        return eng.similarity_matrix(qb, db)[0].cpu().numpy()
 
     def build_descriptor_matrix(self) -> np.ndarray:
         if len(self.descriptors) == 0:
@@ -254,17 +250,19 @@ class BasePlaceRecognition:
         return np.vstack([d.descriptor for d in self.descriptors])
 
     def compute_all_pairwise_similarities(self) -> np.ndarray:
-        """The reference materialises the N x N matrix here (:179-190).  The fused path
-        never forms it; this method exists for interface parity and refuses sizes where
-        the matrix itself is the problem."""
+        """N x N cosine similarities (reference :179-190) from the packed device database.  The
+        retrieval path (find_loop_closures / query) never forms this matrix; here it is the product,
+        so it must fit in device and host memory (4*N*N bytes)."""
+        import torch
         n = len(self.descriptors)
         if n == 0:
             return np.array([])
-        if n > 8192:
-            raise MemoryError("compute_all_pairwise_similarities would materialise an N x N matrix; "
+        db = self._packed()
+        free, _ = torch.cuda.mem_get_info(db.bf16.device)
+        if 4 * n * n > free:
+            raise MemoryError(f"a {n} x {n} fp32 similarity matrix does not fit in device memory; "
                               "use find_loop_closures / query, which never form it")
-        m = self.build_descriptor_matrix().astype(np.float32)
-        return np.stack([self._compute_similarity(m[i], m) for i in range(n)])
+        return db.engine.similarity_matrix(db.bf16[:n], db.bf16[:n]).cpu().numpy()
 
 
 class MixVPR(BasePlaceRecognition):

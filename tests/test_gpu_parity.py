@@ -276,12 +276,64 @@ def test_db_index_offset_and_merge(eng):
     assert np.array_equal(m.count.cpu().numpy(), whole["count"])
 
 
+@pytest.mark.parametrize("G,k,fill", [(1, 25, 1.0), (4, 25, 0.6), (5, 25, 1.0), (6, 25, 1.0), (8, 64, 0.9), (29, 25, 0.3), (3, 1, 1.0)])
+def test_merge_topk_kernel_exact(eng, G, k, fill):
+    """K3 against a numpy sort of the same keys: one batch (<= 128 keys, 4 per lane), multi-batch
+    (8 per lane), partially filled and empty lists, unsorted inputs."""
+    import torch
+    rng = np.random.default_rng(G * 100 + k)
+    Q = 777
+    sc = rng.uniform(-1, 1, size=(G, Q, k)).astype(np.float32)
+    ix = rng.permutation(G * Q * k).reshape(G, Q, k).astype(np.int64) % (2 ** 31 - 1)
+    ix[rng.uniform(size=ix.shape) > fill] = -1                  # empty slots anywhere in a list
+    ix[:, 5] = -1                                               # a row with no candidates at all
+    keys = O.pack_keys(sc, ix)
+    m = eng.merge_topk(torch.from_numpy(keys).cuda(), k, want_keys=True)
+    torch.cuda.synchronize()
+    flat = keys.view(np.uint64).transpose(1, 0, 2).reshape(Q, G * k)
+    want = np.sort(flat, axis=1)[:, ::-1][:, :k]                # uint64 sort, descending
+    got = m.keys.cpu().numpy().view(np.uint64)
+    pad = np.zeros((Q, max(0, k - want.shape[1])), np.uint64)
+    assert np.array_equal(got, np.concatenate([want, pad], axis=1))
+    cnt = (want != 0).sum(axis=1)
+    assert np.array_equal(m.count.cpu().numpy(), cnt)
+    assert m.count.cpu().numpy()[5] == 0 and np.all(m.idx.cpu().numpy()[5] == -1)
+
+
+def test_similarity_matrix_dense(eng):
+    """Dense-output mode of the fused kernel vs numpy (place_recognition.py:171, :190), ragged shapes,
+    and the mirrored _compute_similarity / compute_all_pairwise_similarities."""
+    import torch
+    from semgate import BasePlaceRecognition, PlaceDescriptor, synthetic
+    for (Q, N, D) in ((300, 1000, 512), (1, 777, 100), (129, 257, 64), (5, 4099, 4096)):
+        desc, _, _ = synthetic.make_case(max(Q, N), D, 3, seed=Q + N)
+        qb = eng.normalize_cast(_t(desc[:Q]))
+        db = eng.normalize_cast(_t(desc[:N]))
+        got = eng.similarity_matrix(qb, db).cpu().numpy()
+        a = qb.float().cpu().numpy().astype(np.float64)
+        b = db.float().cpu().numpy().astype(np.float64)
+        assert got.shape == (Q, N) and np.max(np.abs(got - a @ b.T)) <= 2e-5        # same bf16 operands
+        ref = O.l2_normalize(desc[:Q]) @ O.l2_normalize(desc[:N]).T
+        assert np.max(np.abs(got - ref)) <= parity.SCORE_TOL
+    desc, ts, fl = synthetic.make_case(500, 256, 3, seed=3)
+    vpr = BasePlaceRecognition(descriptor_dim=256)
+    for i in range(500):
+        vpr.descriptors.append(PlaceDescriptor(float(ts[i]), desc[i], floor_label=int(fl[i])))
+    S = vpr.compute_all_pairwise_similarities()
+    ref = O.l2_normalize(desc) @ O.l2_normalize(desc).T
+    assert S.shape == (500, 500) and S.dtype == np.float32 and np.max(np.abs(S - ref)) <= parity.SCORE_TOL
+    row = vpr._compute_similarity(desc[7] * 3.0, desc)                                # unnormalised query
+    assert row.shape == (500,) and np.max(np.abs(row - ref[7])) <= parity.SCORE_TOL
+    assert BasePlaceRecognition().compute_all_pairwise_similarities().size == 0
+
+
 @pytest.mark.parametrize("cg", [1, 2])
-def test_column_panels_carry_lists(eng, cg, monkeypatch):
-    """Long databases are swept in L2-sized column panels with the row lists carried through HBM
-    between panels; forced here at a small size (the schedule reads SEMGATE_PANEL_MB per call)."""
+@pytest.mark.parametrize("window_mb", ["1", "0"])
+def test_paced_long_runs(eng, cg, window_mb, monkeypatch):
+    """Long runs are paced through per-super-row chunk counters (the units of a super-row stay inside an
+    L2-sized window).  Forced on at a small size by a 1 MB window, off by 0: the result never depends on it."""
     from semgate import synthetic
-    monkeypatch.setenv("SEMGATE_PANEL_MB", "1")
+    monkeypatch.setenv("SEMGATE_WINDOW_MB", window_mb)
     Q, N, D, k = 700, 45000, 64, 25
     desc, ts, fl = synthetic.make_case(N, D, 4, seed=123)
     fl32 = fl.astype(np.int32)
@@ -291,9 +343,14 @@ def test_column_panels_carry_lists(eng, cg, monkeypatch):
                        max_floor_diff=0, bf16=True)
     rep = parity.compare_candidates(O.compact(ref), O.compact(got), k, 0.45, tol=BF16_MODEL_TOL)
     assert rep["boundary_diffs"] <= 2
-    monkeypatch.delenv("SEMGATE_PANEL_MB")
+    # all-pairs with a ragged tail super-row (units with runs of different length share the counters)
+    n2 = 9000
+    got2 = run_gpu(eng, desc[:n2], desc[:n2], k, 0.45, 10.0, ts[:n2], ts[:n2], fl32[:n2], fl32[:n2], mfd=0, cg=cg)
+    monkeypatch.delenv("SEMGATE_WINDOW_MB")
     one = run_gpu(eng, desc[:Q], desc, k, 0.45, 10.0, ts[:Q], ts, fl32[:Q], fl32, mfd=0, cg=cg)
     assert np.array_equal(one["idx"], got["idx"]) and np.array_equal(one["scores"], got["scores"])
+    one2 = run_gpu(eng, desc[:n2], desc[:n2], k, 0.45, 10.0, ts[:n2], ts[:n2], fl32[:n2], fl32[:n2], mfd=0, cg=cg)
+    assert np.array_equal(one2["idx"], got2["idx"]) and np.array_equal(one2["scores"], got2["scores"])
 
 
 def test_accumulate_over_database_slices(eng):
@@ -427,6 +484,27 @@ def test_gate_published_counts_gpu(algo):
         assert rejected and rejected[0].rejection_reason.startswith("Cross-floor: ")
         one = gate3.gate_candidate(int(i[0]), int(j[0]), 0.9)
         assert one.is_valid == bool(want[0]) and gate3.stats["total_candidates"] == 3001
+
+
+@pytest.mark.parametrize("M,shift", [(1, 0), (3, 0), (4, 0), (1027, 0), (100003, 0), (4099, 1), (4099, 3)])
+def test_gate_candidates_kernel_paths(eng, M, shift):
+    """Vector path (4 candidates per thread), its tail, and the scalar path taken for index arrays that
+    are only 4-byte aligned; decisions and counters bit-exact against loop_closure_gate.py:89-101."""
+    import torch
+    rng = np.random.default_rng(M + shift)
+    nl = 5000
+    fl = rng.choice([1, 2, 4, 5], size=nl).astype(np.int32)
+    q = rng.integers(0, nl, size=M + shift).astype(np.int32)
+    m = rng.integers(0, nl, size=M + shift).astype(np.int32)
+    for mfd in (0, 1):
+        v, c = eng.gate_candidates(_t(fl), _t(q)[shift:], _t(m)[shift:], mfd)
+        torch.cuda.synchronize()
+        want = np.abs(fl[q[shift:]].astype(np.int64) - fl[m[shift:]]) <= mfd
+        assert np.array_equal(v.cpu().numpy().astype(bool), want)
+        assert c.cpu().numpy().tolist() == [int(want.sum()), int((~want).sum()), 0]
+    q[shift] = nl                                                     # out of range -> counted, flagged invalid
+    v, c = eng.gate_candidates(_t(fl), _t(q)[shift:], _t(m)[shift:], 0)
+    assert int(c[2].item()) == 1 and int(v[0].item()) == 0
 
 
 @pytest.mark.parametrize("algo", ["lego_loam", "orb_slam3"])
