@@ -267,10 +267,16 @@ def run_ours(args):
         q_bf16 = make_bf16(N_Q, 1000)                  # same seed on every rank: identical matrix
         db_bf16 = q_bf16[lo:hi]                        # this rank's slice of the database rows
     else:
-        q_f32 = make_rows(N_Q, 1000)                   # == shard 0
-        db_f32 = q_f32 if rank == 0 else make_rows(hi - lo, 1000 + rank)
+        # the query keyframes are the first N_Q rows of the database (rank 0's shard starts with them)
+        q_f32 = make_rows(N_Q, 1000)
+        if rank == 0 and N_Q == hi - lo:
+            db_f32 = q_f32
+        else:
+            db_f32 = make_rows(hi - lo, 2000 + rank)
+            if rank == 0:
+                db_f32[:min(N_Q, hi - lo)] = q_f32[:min(N_Q, hi - lo)]
         q_bf16 = eng.normalize_cast(q_f32)
-        db_bf16 = q_bf16 if rank == 0 else eng.normalize_cast(db_f32)
+        db_bf16 = q_bf16 if db_f32 is q_f32 else eng.normalize_cast(db_f32)
     ts_all = torch.from_numpy(synthetic.make_timestamps(n_db_total)).to(dev)
     fl_all = torch.from_numpy(synthetic.make_floors(n_db_total, NUM_FLOORS).astype(np.int32)).to(dev)
     q_ts, q_fl = ts_all[:N_Q].contiguous(), fl_all[:N_Q].contiguous()
@@ -445,7 +451,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cta-group", type=int, default=0, choices=[0, 1, 2])
+    ap.add_argument("--cta-group", type=int, default=0, choices=[0, 1, 2, 4])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg")
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c5"],

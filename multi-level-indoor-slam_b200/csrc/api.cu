@@ -92,7 +92,7 @@ int check_params(const semgate_topk_params* p) {
   if (p->k < 1 || p->k > SEMGATE_MAX_K) return fail(SEMGATE_EINVAL, "k=%d outside 1..%d", p->k, SEMGATE_MAX_K);
   if (p->max_floor_diff < -1) return fail(SEMGATE_EINVAL, "max_floor_diff=%d", p->max_floor_diff);
   if (p->gate_mode != SEMGATE_GATE_FLAG && p->gate_mode != SEMGATE_GATE_MASK) return fail(SEMGATE_EINVAL, "gate_mode=%d", p->gate_mode);
-  if (p->cta_group != 0 && p->cta_group != 1 && p->cta_group != 2) return fail(SEMGATE_EINVAL, "cta_group=%d", p->cta_group);
+  if (p->cta_group != 0 && p->cta_group != 1 && p->cta_group != 2 && p->cta_group != 4) return fail(SEMGATE_EINVAL, "cta_group=%d", p->cta_group);
   if (p->accumulate != 0 && p->accumulate != 1) return fail(SEMGATE_EINVAL, "accumulate=%d", p->accumulate);
   if (std::isnan(p->similarity_threshold)) return fail(SEMGATE_EINVAL, "similarity_threshold is NaN");
   return 0;
@@ -102,7 +102,7 @@ int check_params(const semgate_topk_params* p) {
 // large sweeps; with few query rows half of every 256-row pair tile would be padding.
 int resolve_cg(semgate_handle_t h, const semgate_topk_params* p, int64_t Q) {
   const int want = p->cta_group ? p->cta_group : h->cta_group;
-  if (want == 1 || want == 2) return want;
+  if (want == 1 || want == 2 || want == 4) return want;
   return Q >= 4096 ? 2 : 1;
 }
 
@@ -132,7 +132,7 @@ int semgate_create(semgate_handle_t* out, int device) {
   h->cc_major = prop.major;
   h->cc_minor = prop.minor;
   const char* env = getenv("SEMGATE_CTA_GROUP");
-  if (env && (env[0] == '1' || env[0] == '2')) h->cta_group = env[0] - '0';
+  if (env && (env[0] == '1' || env[0] == '2' || env[0] == '4')) h->cta_group = env[0] - '0';
   DeviceGuard g(device);
   cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate"); }
@@ -165,7 +165,7 @@ int semgate_device_info(semgate_handle_t h, int* sm_count, int* cc_major, int* c
 int semgate_set_option(semgate_handle_t h, const char* name, int64_t value) {
   if (!h || !name) return fail(SEMGATE_EINVAL, "NULL argument");
   if (strcmp(name, "cta_group") == 0) {
-    if (value != 0 && value != 1 && value != 2) return fail(SEMGATE_EINVAL, "cta_group must be 0 (auto), 1 or 2");
+    if (value != 0 && value != 1 && value != 2 && value != 4) return fail(SEMGATE_EINVAL, "cta_group must be 0 (auto), 1, 2 or 4");
     h->cta_group = static_cast<int>(value);
     return 0;
   }
@@ -284,9 +284,9 @@ int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const 
   h->launches += launches;
 
   m.keys_in = static_cast<const uint64_t*>(workspace);
-  m.row_stride = static_cast<int64_t>(sc.s_max) * k;
+  m.row_stride = 0;   // per-row offsets follow the schedule (n_lists < 0)
   m.list_stride = k;
-  m.n_lists = -1; m.sc = sc; m.rows_per_mblock = 128 * cg;
+  m.n_lists = -1; m.sc = sc; m.rows_per_mblock = 128 * cg;   // cg = CTAs (128-row query blocks) per schedule unit
   RC_TRY(launch_merge_topk(m, st), "merge_topk launch");
   h->launches += 1;
   return 0;

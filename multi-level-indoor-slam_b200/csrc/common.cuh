@@ -78,7 +78,7 @@ struct Schedule {
   int n_full;       // number of full super-rows
   int r_last;       // m-blocks in the trailing partial super-row (0 if none)
   int s_last;       // splits per m-block there
-  int s_max;        // max(s_main, s_last): slot stride of the partial lists
+  int s_max;        // max(s_main, s_last)
   int a_resident;   // the super-row's query blocks stay in L2 across database tiles
   int sync_window;  // pacing window in chunks (0 = pacing off)
   int pace_kb;      // k-blocks per chunk
@@ -93,6 +93,16 @@ __host__ __device__ __forceinline__ int64_t sched_sync_counters(const Schedule& 
 
 __host__ __device__ __forceinline__ int sched_slots(const Schedule& sc, int mb) {
   return mb < sc.n_full * sc.rm ? sc.s_main : sc.s_last;
+}
+
+// Partial lists of the fused kernel: row r keeps one k-entry list per run of its m-block, rows of
+// full super-rows (s_main lists each) first, then the rows of the tail super-row (s_last lists each).
+__host__ __device__ __forceinline__ int64_t sched_list_offset(const Schedule& sc, int64_t row, int rows_per_mblock, int k) {
+  const int64_t rows_full = static_cast<int64_t>(sc.n_full) * sc.rm * rows_per_mblock;
+  return row < rows_full ? row * sc.s_main * k : (rows_full * sc.s_main + (row - rows_full) * sc.s_last) * k;
+}
+__host__ __device__ __forceinline__ int64_t sched_list_keys(const Schedule& sc, int rows_per_mblock, int k) {
+  return sched_list_offset(sc, static_cast<int64_t>(sc.mblocks) * rows_per_mblock, rows_per_mblock, k);
 }
 
 // balanced contiguous split of [0, n) into s parts

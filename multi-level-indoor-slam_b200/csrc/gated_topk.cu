@@ -16,9 +16,38 @@ static long env_long(const char* name, long dflt) {
   return (e && *e) ? atol(e) : dflt;
 }
 
+static size_t smem_bytes_for(int cg, int stages, int kstride);
+constexpr size_t kSmemLimit = 232448;   // 227 KB per CTA
+
+// Schedule units (CTAs, CTA pairs, or 4-CTA clusters of two pairs) that are co-resident.  A cluster
+// must sit inside one GPC, so 4-CTA clusters may not cover every SM: ask the occupancy calculator.
+int topk_units(int cta_group, int sm_count) {
+  if (cta_group != 4) return std::max(1, sm_count / cta_group);
+  static int cached = -1;
+  static std::once_flag once;
+  std::call_once(once, [&] {
+    int stages = kMaxStages;                       // same ring-depth rule as the launch (largest list size)
+    while (stages > 2 && smem_bytes_for(2, stages, kMaxK | 1) > kSmemLimit) --stages;
+    const size_t smem = smem_bytes_for(2, stages, kMaxK | 1);
+    if (cudaFuncSetAttribute(gated_topk_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(4 * sm_count));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gated_topk_kernel<2, 2>, &cfg) == cudaSuccess) cached = n;
+  });
+  cudaGetLastError();
+  return std::max(1, cached > 0 ? cached : sm_count / 4 - 5);   // conservative if the query failed
+}
+
 Schedule make_schedule(int64_t Q, int64_t N, int d_pad, int cta_group, int sm_count) {
   Schedule sc{};
-  const int units = std::max(1, sm_count / cta_group);
+  const int units = topk_units(cta_group, sm_count);
   const int bm_unit = BM * cta_group;
   sc.mblocks = static_cast<int>((Q + bm_unit - 1) / bm_unit);
   sc.ntiles = static_cast<int>((N + BN - 1) / BN);
@@ -69,17 +98,20 @@ Schedule make_schedule(int64_t Q, int64_t N, int d_pad, int cta_group, int sm_co
   const int kblocks = d_pad / BK;
   sc.pace_kb = std::min(kblocks, 16);
   sc.cpt = (kblocks + sc.pace_kb - 1) / sc.pace_kb;
-  const int64_t window_bytes = env_long("SEMGATE_WINDOW_MB", 24) << 20;
+  const int64_t window_bytes = env_long("SEMGATE_WINDOW_MB", 8) << 20;
   const int64_t stream_rows = static_cast<int64_t>(sc.s_main) * BN + (sc.a_resident ? 0 : static_cast<int64_t>(sc.rm) * bm_unit);
   const int64_t chunk_bytes = stream_rows * sc.pace_kb * BK * 2;
   int window = static_cast<int>(std::min<int64_t>(64, std::max<int64_t>(2, window_bytes / std::max<int64_t>(chunk_bytes, 1))));
   const int64_t run_chunks = static_cast<int64_t>(std::max(sc.len_main, sc.len_last)) * sc.cpt;
   sc.sync_window = (window_bytes > 0 && run_chunks > 4 * window) ? window : 0;
+  // test knob: force a window of that many chunks wherever a run is longer than the window
+  const int forced = static_cast<int>(env_long("SEMGATE_WINDOW_CHUNKS", 0));
+  if (forced > 0) sc.sync_window = run_chunks > forced ? forced : 0;
   return sc;
 }
 
 size_t topk_partial_bytes(const Schedule& sc, int cta_group, int k) {
-  const size_t b = static_cast<size_t>(sc.mblocks) * BM * cta_group * std::max(sc.s_max, 1) * k * sizeof(uint64_t);
+  const size_t b = static_cast<size_t>(sched_list_keys(sc, BM * cta_group, k)) * sizeof(uint64_t);
   return (b + 255) & ~static_cast<size_t>(255);
 }
 
@@ -120,7 +152,7 @@ static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int d_pad, 
 }
 
 static size_t smem_bytes_for(int cg, int stages, int kstride) {
-  const size_t stage = A_STAGE_BYTES + static_cast<size_t>(BN / cg) * BK * 2;
+  const size_t stage = A_STAGE_BYTES + static_cast<size_t>(BN / std::min(cg, 2)) * BK * 2;
   return 1024 /*realign slack*/ + stages * stage + static_cast<size_t>(BM) * kstride * 8 + 256 /*barriers + tmem slot*/;
 }
 
@@ -130,7 +162,7 @@ int launch_gated_topk(const TopkLaunch& a, const Schedule& sc, uint64_t* partial
   CUtensorMap tq, tdb;
   int rc = make_tmap(&tq, a.q_bf16, a.Q, a.d_pad, BM);
   if (rc) return rc;
-  rc = make_tmap(&tdb, a.db_bf16, a.N, a.d_pad, BN / cg);
+  rc = make_tmap(&tdb, a.db_bf16, a.N, a.d_pad, BN / cg);   // rows one CTA fetches per k-block
   if (rc) return rc;
 
   TopkParams p{};
@@ -164,14 +196,13 @@ int launch_gated_topk(const TopkLaunch& a, const Schedule& sc, uint64_t* partial
   p.policy_db = (hint >= 2 && sc.a_resident) ? ptx::kL2EvictFirst : ptx::kL2EvictNormal;
 
   // deepest ring that fits the 227 KB per-CTA limit
-  const size_t limit = 232448;
   int stages = kMaxStages;
-  while (stages > 2 && smem_bytes_for(cg, stages, p.kstride) > limit) --stages;
+  while (stages > 2 && smem_bytes_for(cg, stages, p.kstride) > kSmemLimit) --stages;
   stages = std::min(stages, std::max(2, p.kblocks));
   p.stages = stages;
   const size_t smem = smem_bytes_for(cg, stages, p.kstride);
 
-  const int units = std::max(1, a.sm_count / cg);
+  const int units = topk_units(cg, a.sm_count);
   // only units that receive work in some super-row need to exist
   int used = 0;
   if (sc.n_full > 0) used = std::max(used, sc.rm * sc.s_main);
@@ -184,20 +215,18 @@ int launch_gated_topk(const TopkLaunch& a, const Schedule& sc, uint64_t* partial
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(cg); attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = cg > 1 ? 1 : 0;
   cudaError_t e;
-  if (cg == 2) {
-    e = cudaFuncSetAttribute(gated_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, gated_topk_kernel<2>, tq, tdb, p);
-  } else {
-    e = cudaFuncSetAttribute(gated_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return static_cast<int>(e);
-    cfg.attrs = nullptr; cfg.numAttrs = 0;
-    e = cudaLaunchKernelEx(&cfg, gated_topk_kernel<1>, tq, tdb, p);
-  }
+  auto launch = [&](auto kernel) -> cudaError_t {
+    cudaError_t ee = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (ee != cudaSuccess) return ee;
+    return cudaLaunchKernelEx(&cfg, kernel, tq, tdb, p);
+  };
+  if (cg == 4) e = launch(gated_topk_kernel<2, 2>);
+  else if (cg == 2) e = launch(gated_topk_kernel<2, 1>);
+  else e = launch(gated_topk_kernel<1, 1>);
   if (e != cudaSuccess) return static_cast<int>(e);
   if (launches) ++*launches;
   return 0;

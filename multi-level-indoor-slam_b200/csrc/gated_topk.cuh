@@ -17,6 +17,11 @@
 // CG = 1: one CTA computes a 128 x 256 tile.  CG = 2: a CTA pair (cta_group::2)
 // computes 256 x 256; each CTA stages its own 128 query rows and half of the
 // database tile, and keeps the accumulator rows of its own queries.
+// MC = 2 (with CG = 2): a cluster of two CTA pairs computes 512 x 256; the pairs own
+// adjacent query blocks and share the database tile, every CTA fetches a quarter of it
+// and TMA-multicasts it into the CTA of the other pair that needs it, which cuts the
+// L2 -> SM traffic per FLOP by a quarter (the fused kernel sits at the L2 slice
+// throughput at boost clocks).  The two pairs advance in lock-step through the stage ring.
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
@@ -30,6 +35,7 @@ constexpr int UMMA_K = 16;
 constexpr int kThreads = 192;
 constexpr int kMaxStages = 8;
 constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
+constexpr uint64_t kPaceGiveUpNs = 2000000ull;    // 2 ms
 
 struct TopkParams {
   int Q;                 // query rows
@@ -48,7 +54,7 @@ struct TopkParams {
   const double* db_ts;
   const int32_t* q_floor;
   const int32_t* db_floor;
-  uint64_t* partial;     // [mblocks*BM*CG rows][s_max][k] candidate keys
+  uint64_t* partial;     // candidate keys, one k-entry list per (row, run): see sched_list_offset()
   float* dense;          // non-null: write the raw fp32 similarity tiles to dense[row * dense_ld + col] instead of
   int64_t dense_ld;      //           building lists (compute_all_pairwise_similarities, place_recognition.py:179-190)
   uint32_t* sync;        // pacing counters (zeroed per launch) or null: see Schedule::sync_window
@@ -87,11 +93,14 @@ struct RowList {
   }
 };
 
-template <int CG>
+template <int CG, int MC>
 __global__ void __launch_bounds__(kThreads, 1)
 gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
                   const TopkParams p) {
-  constexpr uint32_t B_ROWS = BN / CG;
+  static_assert(MC == 1 || (MC == 2 && CG == 2), "multicast needs CTA pairs");
+  constexpr int CSIZE = CG * MC;                 // CTAs per cluster = per schedule unit
+  constexpr uint32_t B_ROWS = BN / CG;           // database rows held by one CTA
+  constexpr uint32_t B_LOAD_ROWS = B_ROWS / MC;  // ... of which it fetches this many itself
   constexpr uint32_t B_STAGE_BYTES = B_ROWS * BK * 2;
   constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   constexpr uint32_t kTmemCols = 512;   // two 256-column fp32 accumulators
@@ -114,18 +123,21 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0;
-  const bool leader = cta_rank == 0;
-  const int unit = blockIdx.x / CG;
+  const uint32_t cta_rank = (CSIZE > 1) ? ptx::cluster_ctarank() : 0;
+  const uint32_t half = cta_rank & 1u;           // position inside the CTA pair
+  const uint32_t pair = cta_rank >> 1;           // which pair of the cluster
+  const uint32_t pair_leader = cta_rank & ~1u;   // cluster rank of this pair's MMA-issuing CTA
+  const bool leader = half == 0;
+  const int unit = blockIdx.x / CSIZE;
 
-  if constexpr (CG == 2) ptx::cluster_sync();   // peer must be resident before a pair-wide TMEM allocation
+  if constexpr (CSIZE > 1) ptx::cluster_sync();   // peers must be resident before a pair-wide TMEM allocation
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&tmap_q);
     ptx::prefetch_tensormap(&tmap_db);
     for (int s = 0; s < stages; ++s) {
       ptx::mbar_init(bar_full + 8 * s, CG);      // CG=2: leader's expect_tx arrive + peer's remote arrive
-      ptx::mbar_init(bar_empty + 8 * s, 1);      // one tcgen05.commit
+      ptx::mbar_init(bar_empty + 8 * s, MC);     // one tcgen05.commit per pair that reads what lands here
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(bar_tfull + 8 * a, 1);      // one tcgen05.commit
@@ -136,7 +148,7 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   }
   if (warp == 1) ptx::tmem_alloc<CG>(ptx::smem_u32(tmem_slot), kTmemCols);
   ptx::tc_fence_before();
-  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  if constexpr (CSIZE > 1) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
@@ -150,10 +162,16 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const int window = (p.sync != nullptr) ? sc.sync_window : 0;
     const int pace_kb = sc.pace_kb, cpt = sc.cpt;
     for_each_run(sc, unit, [&](const Run& run) {
-      const int m0 = (run.mb * CG + static_cast<int>(cta_rank)) * BM;
+      const int m0 = (run.mb * CSIZE + static_cast<int>(cta_rank)) * BM;
       uint32_t* const pace = p.sync + run.sync_base;
+      // Pacing is a hint, never a dependency: a unit that has waited kPaceGiveUpNs for the others
+      // (e.g. one that idles through the full super-rows and reaches the tail super-row seconds
+      // before anybody else) stops pacing for the rest of the run and just streams.
+      bool paced = window > 0;
       for (int nt = run.nt0; nt < run.nt1; ++nt) {
-        const int n0 = nt * BN + static_cast<int>(cta_rank) * static_cast<int>(B_ROWS);
+        // rows of the database tile this CTA fetches: its half of the tile, and with MC = 2 the
+        // quarter of that half that its pair is responsible for
+        const int n0 = nt * BN + static_cast<int>(half * B_ROWS + (MC == 2 ? pair * B_LOAD_ROWS : 0u));
         int chunk = (nt - run.nt0) * cpt;            // position of this unit in its run, in chunks
         int kb_next_chunk = 0;
         for (int kb = 0; kb < p.kblocks; ++kb) {
@@ -164,17 +182,17 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             }
             kb_next_chunk += pace_kb;
             const int back = chunk - window;
-            if (back >= 0) {
+            if (paced && back >= 0) {
               // stay within `window` chunks of the slowest unit of this super-row
-              const uint32_t need = static_cast<uint32_t>((back / cpt) < run.short_len ? run.units_all : run.units_long) * CG;
+              const uint32_t need = static_cast<uint32_t>((back / cpt) < run.short_len ? run.units_all : run.units_long) * CSIZE;
               uint32_t spins = 0;
               uint64_t t0 = 0;
               while (ptx::ld_relaxed_gpu(pace + back) < need) {
                 ptx::nanosleep(100);
-                if ((++spins & 0x3FFu) == 0) {
+                if ((++spins & 0x3Fu) == 0) {
                   const uint64_t now = ptx::globaltimer_ns();
                   if (t0 == 0) t0 = now;
-                  else if (now - t0 > SEMGATE_WAIT_TIMEOUT_NS) __trap();
+                  else if (now - t0 > kPaceGiveUpNs) { paced = false; break; }
                 }
               }
             }
@@ -188,13 +206,23 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
               ptx::mbar_arrive_expect_tx(fb, STAGE_BYTES);
               ptx::tma_load_2d(dst_a, &tmap_q, fb, kb * BK, m0, p.policy_q);
               ptx::tma_load_2d(dst_b, &tmap_db, fb, kb * BK, n0, p.policy_db);
-            } else {
+            } else if constexpr (MC == 1) {
               // both CTAs' bytes are accounted on the leader's barrier (its MMA reads both smems)
               const uint32_t fb_leader = ptx::mapa(fb, 0);
               if (leader) ptx::mbar_arrive_expect_tx(fb, 2 * STAGE_BYTES);
               ptx::tma_load_2d_cg2(dst_a, &tmap_q, fb_leader, kb * BK, m0, p.policy_q);
               ptx::tma_load_2d_cg2(dst_b, &tmap_db, fb_leader, kb * BK, n0, p.policy_db);
               if (!leader) ptx::mbar_arrive_cluster(fb, 0);
+            } else {
+              // two pairs: the query rows are private, the database quarter goes to this CTA and to the
+              // CTA at the same position of the other pair; every destination's bytes are accounted on
+              // its own pair leader's barrier (2 * STAGE_BYTES per pair: 2 query blocks + 4 quarters)
+              const uint32_t fb_leader = ptx::pair_leader_addr(fb);
+              if (leader) ptx::mbar_arrive_expect_tx(fb, 2 * STAGE_BYTES);
+              ptx::tma_load_2d_cg2(dst_a, &tmap_q, fb_leader, kb * BK, m0, p.policy_q);
+              ptx::tma_load_2d_cg2_mc(dst_b + pair * (B_LOAD_ROWS * BK * 2), &tmap_db, fb_leader, kb * BK, n0,
+                                      static_cast<uint16_t>((1u << half) | (1u << (half + 2))), p.policy_db);
+              if (!leader) ptx::mbar_arrive_cluster(fb, pair_leader);
             }
           }
           __syncwarp();
@@ -232,8 +260,10 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 ptx::umma_commit_cg1(bar_empty + 8 * stage);
                 if (kb == p.kblocks - 1) ptx::umma_commit_cg1(bar_tfull + 8 * acc);
               } else {
-                ptx::umma_commit_cg2_mc(bar_empty + 8 * stage, 0b11);
-                if (kb == p.kblocks - 1) ptx::umma_commit_cg2_mc(bar_tfull + 8 * acc, 0b11);
+                // the stage is refilled by every CTA of the cluster that multicasts into this pair;
+                // the accumulator is read by this pair's epilogues only
+                ptx::umma_commit_cg2_mc(bar_empty + 8 * stage, static_cast<uint16_t>((1u << CSIZE) - 1u));
+                if (kb == p.kblocks - 1) ptx::umma_commit_cg2_mc(bar_tfull + 8 * acc, static_cast<uint16_t>(0b11u << pair_leader));
               }
             }
             __syncwarp();
@@ -263,9 +293,9 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const float pos_inf = __int_as_float(0x7f800000);
 
     for_each_run(sc, unit, [&](const Run& run) {
-      const int grow = (run.mb * CG + static_cast<int>(cta_rank)) * BM + row_in_tile;   // global query row
+      const int grow = (run.mb * CSIZE + static_cast<int>(cta_rank)) * BM + row_in_tile;   // global query row
       const bool row_live = grow < p.Q;
-      uint64_t* slot = p.partial + (static_cast<size_t>(row_live ? grow : 0) * sc.s_max + run.slot) * k;
+      uint64_t* slot = p.partial + sched_list_offset(sc, row_live ? grow : 0, BM * CSIZE, k) + static_cast<int64_t>(run.slot) * k;
       double tq = 0.0;
       int32_t qf = kFloorNone;
       if (row_live) {
@@ -336,7 +366,7 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         __syncwarp();
         if (lane == 0) {
           if constexpr (CG == 1) ptx::mbar_arrive(bar_tempty + 8 * acc);
-          else ptx::mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
+          else ptx::mbar_arrive_cluster(bar_tempty + 8 * acc, pair_leader);
         }
       }
 
@@ -349,7 +379,7 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 
   // ----------------------------------------------------------------- teardown
   ptx::tc_fence_before();
-  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  if constexpr (CSIZE > 1) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   if (warp == 1) ptx::tmem_dealloc<CG>(tmem_base, kTmemCols);
 }

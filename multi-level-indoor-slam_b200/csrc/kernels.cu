@@ -146,7 +146,9 @@ int launch_normalize_cast(const float* x, int64_t n, int d, int64_t ld, void* ou
   if (vec && d > 4096 && d_pad <= 8 * kNormLongChunk) {
     int csize = (d_pad + kNormLongChunk - 1) / kNormLongChunk;       // 1, 2, 3..8 -> round up to a power of two
     while (csize & (csize - 1)) ++csize;
-    const int64_t clusters = std::min<int64_t>(n, std::max(1, (148 * 3) / csize));
+    // one cluster per row (grid-stride only beyond 2^20 rows): residency of the clusters is the
+    // hardware scheduler's business, nothing here assumes they are all co-resident
+    const int64_t clusters = std::min<int64_t>(n, 1 << 20);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(clusters * csize));
     cfg.blockDim = dim3(kNormThreads);
@@ -198,28 +200,12 @@ __device__ __forceinline__ void sort_desc(uint64_t (&c)[P]) {
   }
 }
 
+// Merge the keys base[(e / kk) * list_stride + e % kk], e in [e0, e1), into `run` (the warp's running
+// top-k list: rank t lives in run[t>>5] of lane t&31).  `have_run`: run already holds keys.
 template <int P>
-__global__ void __launch_bounds__(kMergeWarps * 32)
-merge_topk_kernel(const MergeLaunch a) {
-  static_assert(P == 4 || P == 8, "keys per lane");
-  const int lane = threadIdx.x & 31;
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * kMergeWarps + (threadIdx.x >> 5);
-  if (row >= a.Q) return;
-  const int k = a.k;
-  int n_lists = a.n_lists;
-  if (n_lists < 0) n_lists = sched_slots(a.sc, static_cast<int>(row / a.rows_per_mblock));
-  const uint64_t* base = a.keys_in + row * a.row_stride;
-  const int total = n_lists * k;
-
-  uint64_t run[2] = {0ull, 0ull};          // running list: rank t lives in run[t>>5] of lane t&31
-  bool have_run = false;
-  if (a.seed_keys != nullptr) {            // one more list per row (order irrelevant here)
-    const uint64_t* seed = a.seed_keys + row * k;
-    if (lane < k) run[0] = seed[lane];
-    if (lane + 32 < k) run[1] = seed[lane + 32];
-    have_run = true;
-  }
-  int b0 = 0;
+__device__ __forceinline__ void merge_range(const uint64_t* __restrict__ base, int e0, int e1, int kk, int64_t list_stride,
+                                            int k, int lane, uint64_t (&run)[2], bool have_run) {
+  int b0 = e0;
   do {
     const int nnew = have_run ? P - 2 : P;   // key slots per lane for new candidates
     uint64_t c[P];
@@ -227,7 +213,7 @@ merge_topk_kernel(const MergeLaunch a) {
     for (int i = 0; i < P; ++i) {
       const int e = b0 + i * 32 + lane;
       uint64_t v = 0ull;
-      if (i < nnew && e < total) v = base[static_cast<int64_t>(e / k) * a.list_stride + (e % k)];
+      if (i < nnew && e < e1) v = base[static_cast<int64_t>(e / kk) * list_stride + (e % kk)];
       c[i] = v;
     }
     if (have_run) { c[P - 2] = run[0]; c[P - 1] = run[1]; }
@@ -244,10 +230,58 @@ merge_topk_kernel(const MergeLaunch a) {
 #pragma unroll
       for (int i = 0; i + 1 < P; ++i) c[i] = mine ? c[i + 1] : c[i];
       c[P - 1] = mine ? 0ull : c[P - 1];
-      if ((t & 31) == lane) run[t >> 5] = (static_cast<uint64_t>(mh) << 32) | ml;
+      const uint64_t best = (static_cast<uint64_t>(mh) << 32) | ml;
+      if (t == lane) run[0] = best;                      // static register indices: no local-memory array
+      if (t == lane + 32) run[1] = best;
     }
     have_run = true;
-  } while (b0 < total);
+  } while (b0 < e1);
+}
+
+// ROWBLOCK = false: one warp per row.  ROWBLOCK = true (few rows, many lists: a single streaming
+// query leaves one list per SM): one block per row, every warp merges a slice of the row's keys and
+// warp 0 merges the eight intermediate lists from shared memory.
+template <int P, bool ROWBLOCK>
+__global__ void __launch_bounds__(kMergeWarps * 32)
+merge_topk_kernel(const MergeLaunch a) {
+  static_assert(P == 4 || P == 8, "keys per lane");
+  __shared__ uint64_t stage[ROWBLOCK ? kMergeWarps * 64 : 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t row = ROWBLOCK ? static_cast<int64_t>(blockIdx.x) : static_cast<int64_t>(blockIdx.x) * kMergeWarps + warp;
+  if (row >= a.Q) return;
+  const int k = a.k;
+  int n_lists = a.n_lists;
+  const uint64_t* base = a.keys_in + row * a.row_stride;
+  if (n_lists < 0) {   // the fused kernel's partial lists: list count and offset follow the tile schedule
+    n_lists = sched_slots(a.sc, static_cast<int>(row / a.rows_per_mblock));
+    base = a.keys_in + sched_list_offset(a.sc, row, a.rows_per_mblock, a.k);
+  }
+  const int total = n_lists * k;
+
+  uint64_t run[2] = {0ull, 0ull};
+  bool have_run = false;
+  if (a.seed_keys != nullptr && (!ROWBLOCK || warp == 0)) {   // one more list per row (order irrelevant here)
+    const uint64_t* seed = a.seed_keys + row * k;
+    if (lane < k) run[0] = seed[lane];
+    if (lane + 32 < k) run[1] = seed[lane + 32];
+    have_run = true;
+  }
+  if constexpr (!ROWBLOCK) {
+    // rows with few lists (most rows: the tail super-row is split finer than the others) take the
+    // cheaper 4-keys-per-lane network; warp-uniform choice
+    if (P == 8 && total + (have_run ? 64 : 0) <= 128) merge_range<4>(base, 0, total, k, a.list_stride, k, lane, run, have_run);
+    else merge_range<P>(base, 0, total, k, a.list_stride, k, lane, run, have_run);
+  } else {
+    const int per = (total + kMergeWarps - 1) / kMergeWarps;
+    const int e0 = min(total, warp * per), e1 = min(total, e0 + per);
+    merge_range<P>(base, e0, e1, k, a.list_stride, k, lane, run, have_run);
+    stage[warp * 64 + lane] = run[0];
+    stage[warp * 64 + 32 + lane] = run[1];
+    __syncthreads();
+    if (warp != 0) return;
+    run[0] = run[1] = 0ull;
+    merge_range<P>(stage, 0, kMergeWarps * 64, 64, 64, k, lane, run, false);
+  }
 
   int cnt = 0;
 #pragma unroll
@@ -283,10 +317,12 @@ int launch_merge_topk(const MergeLaunch& a, cudaStream_t st) {
   // 4 keys per lane cover one batch of 128 new keys (64 when a seeded list rides along)
   const int lists = a.n_lists >= 0 ? a.n_lists : std::max(a.sc.s_main, a.sc.s_last);
   const int64_t keys = static_cast<int64_t>(lists) * a.k;
-  if (keys <= (a.seed_keys ? 64 : 128))
-    merge_topk_kernel<4><<<grid, kMergeWarps * 32, 0, st>>>(a);
+  if (a.Q <= 2048 && keys >= 1024)
+    merge_topk_kernel<8, true><<<static_cast<unsigned>(a.Q), kMergeWarps * 32, 0, st>>>(a);
+  else if (keys <= (a.seed_keys ? 64 : 128))
+    merge_topk_kernel<4, false><<<grid, kMergeWarps * 32, 0, st>>>(a);
   else
-    merge_topk_kernel<8><<<grid, kMergeWarps * 32, 0, st>>>(a);
+    merge_topk_kernel<8, false><<<grid, kMergeWarps * 32, 0, st>>>(a);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -17,12 +17,13 @@ struct TopkLaunch {
   float threshold; double gap; int k;
   int max_floor_diff; int gate_mode;
   uint32_t db_index_offset;
-  int cta_group;                                  // 1 or 2
+  int cta_group;                                  // CTAs per schedule unit: 1, 2 (cta_group::2 pair) or 4 (two pairs, multicast)
   int sm_count;
   float* dense; int64_t dense_ld;                 // non-null: dense fp32 similarity output instead of lists
 };
 
-// Tile schedule for a Q x N problem on `units` CTAs (CG=1) or CTA pairs (CG=2).
+// Tile schedule for a Q x N problem on `units` CTAs (1), CTA pairs (2) or two-pair clusters (4).
+int topk_units(int cta_group, int sm_count);
 Schedule make_schedule(int64_t Q, int64_t N, int d_pad, int cta_group, int sm_count);
 size_t topk_partial_bytes(const Schedule& sc, int cta_group, int k);      // candidate-key lists (256-byte multiple)
 size_t topk_workspace_bytes(const Schedule& sc, int cta_group, int k);    // lists + pacing counters
@@ -40,7 +41,7 @@ struct MergeLaunch {
   const uint64_t* keys_in;
   int64_t Q; int k;
   int64_t row_stride, list_stride;   // in keys
-  int n_lists;                       // >=0: constant; <0: per m-block from `sc`
+  int n_lists;                       // >=0: constant; <0: per m-block from `sc` (offsets too: sched_list_offset)
   Schedule sc; int rows_per_mblock;
   const uint64_t* seed_keys;         // optional [Q,k]: one more list per row (may alias keys_out)
   // outputs (any may be null)

@@ -139,15 +139,20 @@ __device__ __forceinline__ void red_add_relaxed_gpu(uint32_t* p, uint32_t v) {
 }
 __device__ __forceinline__ void nanosleep(uint32_t ns) { asm volatile("nanosleep.u32 %0;" ::"r"(ns)); }
 
-// Multicast variant: the tile lands at the same smem offset in every CTA of `mask`
-// and each destination CTA's barrier (same offset) receives the complete_tx.
+// Multicast variant: the tile lands at the same smem offset in every CTA of `mask`; with
+// cta_group::2 the complete_tx of each destination goes to the barrier at `bar`'s offset in the
+// even (leader) CTA of that destination's pair when `bar` has its peer bit cleared (pair_leader_addr).
 __device__ __forceinline__ void tma_load_2d_cg2_mc(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1,
-                                                    uint16_t mask) {
+                                                    uint16_t mask, uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5, %6;"
+      ::"r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1), "h"(mask), "l"(policy) : "memory");
 }
+
+// A CTA's own shared-window address names its smem inside the cluster; bit 24 selects the odd CTA
+// of a cta_group::2 pair.  Clearing it addresses the same offset in the pair's leader.
+__device__ __forceinline__ uint32_t pair_leader_addr(uint32_t addr) { return addr & 0xFEFFFFFFu; }
 
 __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t cta) {
   uint32_t r;

@@ -120,7 +120,7 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("cg", [1, 2, 4])
 @pytest.mark.parametrize("shape", SHAPES, ids=[f"{s[0]}x{s[1]}x{s[2]}k{s[3]}" for s in SHAPES])
 def test_gated_topk_vs_oracle(eng, shape, cg):
     from semgate import synthetic
@@ -145,7 +145,7 @@ def test_gated_topk_vs_oracle(eng, shape, cg):
     parity.check_decisions_exact(c, ts[:N], fl32[:N], gap, 0, q_ts=ts[:Q], q_floors=fl32[:Q])
 
 
-@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("cg", [1, 2, 4])
 def test_mask_mode_and_nonstrict(eng, cg):
     from semgate import synthetic
     desc, ts, fl = synthetic.make_case(900, 128, 4, seed=77)
@@ -327,30 +327,32 @@ def test_similarity_matrix_dense(eng):
     assert BasePlaceRecognition().compute_all_pairwise_similarities().size == 0
 
 
-@pytest.mark.parametrize("cg", [1, 2])
-@pytest.mark.parametrize("window_mb", ["1", "0"])
-def test_paced_long_runs(eng, cg, window_mb, monkeypatch):
-    """Long runs are paced through per-super-row chunk counters (the units of a super-row stay inside an
-    L2-sized window).  Forced on at a small size by a 1 MB window, off by 0: the result never depends on it."""
+@pytest.mark.parametrize("cg", [1, 2, 4])
+@pytest.mark.parametrize("chunks", ["1", "3"])
+def test_paced_runs(eng, cg, chunks, monkeypatch):
+    """The units of a super-row advance in lock-step through per-super-row chunk counters (L2 pacing).
+    Forced on at test sizes with a window of 1 / 3 chunks: ragged tail super-rows, runs of different
+    length sharing the counters, several chunks per tile (d = 2048 -> 2), one k-block per tile (d = 64).
+    The result never depends on the pacing."""
     from semgate import synthetic
-    monkeypatch.setenv("SEMGATE_WINDOW_MB", window_mb)
-    Q, N, D, k = 700, 45000, 64, 25
-    desc, ts, fl = synthetic.make_case(N, D, 4, seed=123)
-    fl32 = fl.astype(np.int32)
-    got = run_gpu(eng, desc[:Q], desc, k, 0.45, 10.0, ts[:Q], ts, fl32[:Q], fl32, mfd=0, cg=cg)
-    check_padded(got, k)
-    ref = O.gated_topk(desc[:Q], desc, ts[:Q], ts, fl32[:Q], fl32, k=k, threshold=0.45, min_time_gap=10.0,
-                       max_floor_diff=0, bf16=True)
-    rep = parity.compare_candidates(O.compact(ref), O.compact(got), k, 0.45, tol=BF16_MODEL_TOL)
-    assert rep["boundary_diffs"] <= 2
-    # all-pairs with a ragged tail super-row (units with runs of different length share the counters)
-    n2 = 9000
-    got2 = run_gpu(eng, desc[:n2], desc[:n2], k, 0.45, 10.0, ts[:n2], ts[:n2], fl32[:n2], fl32[:n2], mfd=0, cg=cg)
-    monkeypatch.delenv("SEMGATE_WINDOW_MB")
-    one = run_gpu(eng, desc[:Q], desc, k, 0.45, 10.0, ts[:Q], ts, fl32[:Q], fl32, mfd=0, cg=cg)
-    assert np.array_equal(one["idx"], got["idx"]) and np.array_equal(one["scores"], got["scores"])
-    one2 = run_gpu(eng, desc[:n2], desc[:n2], k, 0.45, 10.0, ts[:n2], ts[:n2], fl32[:n2], fl32[:n2], mfd=0, cg=cg)
-    assert np.array_equal(one2["idx"], got2["idx"]) and np.array_equal(one2["scores"], got2["scores"])
+    cases = [(700, 45000, 64, 4), (9000, 9000, 64, 3), (1500, 5000, 2048, 3), (333, 7777, 192, 2)]
+    for Q, N, D, F in cases:
+        desc, ts, fl = synthetic.make_case(max(Q, N), D, F, seed=Q + D)
+        fl32 = fl.astype(np.int32)
+        args = (desc[:Q], desc[:N], 25, 0.45, 10.0, ts[:Q], ts[:N], fl32[:Q], fl32[:N])
+        monkeypatch.setenv("SEMGATE_WINDOW_CHUNKS", chunks)
+        got = run_gpu(eng, *args, mfd=0, cg=cg)
+        monkeypatch.delenv("SEMGATE_WINDOW_CHUNKS")
+        monkeypatch.setenv("SEMGATE_WINDOW_MB", "0")
+        one = run_gpu(eng, *args, mfd=0, cg=cg)
+        monkeypatch.delenv("SEMGATE_WINDOW_MB")
+        check_padded(got, 25)
+        assert np.array_equal(one["idx"], got["idx"]) and np.array_equal(one["scores"], got["scores"])
+        if D == 64 and Q == 700:
+            ref = O.gated_topk(desc[:Q], desc[:N], ts[:Q], ts[:N], fl32[:Q], fl32[:N], k=25, threshold=0.45,
+                               min_time_gap=10.0, max_floor_diff=0, bf16=True)
+            rep = parity.compare_candidates(O.compact(ref), O.compact(got), 25, 0.45, tol=BF16_MODEL_TOL)
+            assert rep["boundary_diffs"] <= 2
 
 
 def test_accumulate_over_database_slices(eng):
@@ -572,7 +574,7 @@ def test_errors(eng):
 
 
 # --------------------------------------------------------------------------- full-size properties (BASELINE config 2)
-@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("cg", [1, 2, 4])
 def test_full_size_properties_c2(eng, cg):
     """20k x 4096-d all-pairs sweep: sampled rows against the oracle + structural properties."""
     import torch
