@@ -385,12 +385,8 @@ def run_ours(args):
         ho = [torch.empty((cap,), dtype=dt, pin_memory=True) for dt in (torch.int32, torch.int32, torch.float32, torch.uint8)]
 
         def e2e_step():
-            qd = q_host.to(dev, non_blocking=True)
-            qb = eng.normalize_cast(qd)
-            dbb = qb if rank == 0 else eng.normalize_cast(db_host.to(dev, non_blocking=True))
-            tsd, fld = tsh.to(dev, non_blocking=True), flh.to(dev, non_blocking=True)
-            res = sr.sweep(qb, dbb, mk, lo, q_ts=tsd[:N_Q], db_ts_shard=tsd[lo:hi], q_floor=fld[:N_Q],
-                           db_floor_shard=fld[lo:hi], db_floor_all=fld, max_floor_diff=0)
+            # queries cross PCIe once (rank 0, they are its shard) and travel on as bf16 over NVLink
+            res = sr.sweep_from_host(q_host if rank == 0 else None, db_host, tsh, flh, mk, lo, hi, N_Q, max_floor_diff=0)
             oq, om, os_, ov, tot = eng.compact(res)
             t = int(tot.item())
             if rank == 0:
@@ -398,7 +394,7 @@ def run_ours(args):
                     h[:t].copy_(d[:t], non_blocking=True)
                 torch.cuda.synchronize()
             return t
-        h2d = q_host.numel() * 4 * (2 * world - 1) + (ts_host.nbytes + fl_host.nbytes) * world
+        h2d = q_host.numel() * 4 * world + (ts_host.nbytes + fl_host.nbytes) * world   # one fp32 shard per rank
     del q_f32, db_f32
     n_e2e = e2e_step()
     barrier()
@@ -414,7 +410,7 @@ def run_ours(args):
     e2e = {"value": pairs_per_step * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(n_e2e * 13 + 8), "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
            "api": "semgate_find_loop_closures_host (C ABI, pinned host buffers)" if world == 1 else
-                  "semgate python API: pinned host -> device, normalise, sharded sweep, NCCL merge, compaction, D2H"}
+                  "semgate python API (ShardedRetrieval.sweep_from_host): pinned host shard -> device per rank, normalise, NVLink broadcast of the bf16 queries, sharded sweep, NCCL merge, compaction, D2H"}
 
     if rank != 0:
         if world > 1:

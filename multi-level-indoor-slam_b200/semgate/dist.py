@@ -54,3 +54,32 @@ class ShardedRetrieval:
         self.dist.all_gather_into_tensor(buf, local.keys, group=self.group)
         return self.engine.merge_topk(buf.view(self.world, Q, k), k, q_floor=q_floor, db_floor_all=db_floor_all,
                                       max_floor_diff=max_floor_diff)
+
+    def sweep_from_host(self, q_host, db_shard_host, ts_all_host, floor_all_host, make_params, shard_lo: int,
+                        shard_hi: int, n_q: int, max_floor_diff: int = -1, src: int = 0):
+        """End-to-end form of `sweep` for inputs that live in pinned HOST memory.
+
+        Every rank uploads and normalises only its own database shard (fp32 `[hi-lo, D]`); the query
+        descriptors (fp32 `[n_q, D]`, given on rank `src` only, may be the same tensor as its shard)
+        cross PCIe once, on `src`, and reach the other GPUs as normalised bf16 rows through an NCCL
+        broadcast over NVLink instead of `world` more host copies.  Timestamps / floor labels (12 B per
+        keyframe) are uploaded by every rank.  Returns the merged TopkResult (identical on every rank)."""
+        import torch
+        eng = self.engine
+        dev = getattr(eng, "torch_device", None) or torch.device("cuda", eng.device)
+        same = self.rank == src and q_host is db_shard_host
+        db_bf16 = eng.normalize_cast(db_shard_host.to(dev, non_blocking=True))
+        if self.rank == src:
+            q_bf16 = db_bf16 if same else eng.normalize_cast(q_host.to(dev, non_blocking=True))
+            if q_bf16.shape[0] != n_q:
+                q_bf16 = q_bf16[:n_q].contiguous()
+        else:
+            q_bf16 = torch.empty((n_q, db_bf16.shape[1]), dtype=db_bf16.dtype, device=dev)
+        if self.world > 1:
+            self.dist.broadcast(q_bf16, src=src, group=self.group)
+        ts = ts_all_host.to(dev, non_blocking=True) if ts_all_host is not None else None
+        fl = floor_all_host.to(dev, non_blocking=True) if floor_all_host is not None else None
+        return self.sweep(q_bf16, db_bf16, make_params, shard_lo,
+                          q_ts=None if ts is None else ts[:n_q], db_ts_shard=None if ts is None else ts[shard_lo:shard_hi],
+                          q_floor=None if fl is None else fl[:n_q], db_floor_shard=None if fl is None else fl[shard_lo:shard_hi],
+                          db_floor_all=fl, max_floor_diff=max_floor_diff)

@@ -27,8 +27,14 @@ class _Res:
 class OracleEngine:
     """Stand-in for semgate._native.Engine on CPU tensors (test double)."""
 
+    torch_device = torch.device("cpu")
+    device = 0
+
     def __init__(self, desc_q, desc_db_all):
         self.q, self.db_all = desc_q, desc_db_all
+
+    def normalize_cast(self, x, out=None):
+        return x          # the stand-in sweep normalises inside the oracle call
 
     def gated_topk(self, q_bf16, db_bf16, params, q_ts=None, db_ts=None, q_floor=None, db_floor=None,
                    want_keys=False, want_lists=True):
@@ -77,6 +83,12 @@ def _worker(rank, world, port, out_dir):
                        db_floor_all=t(fl), max_floor_diff=0)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), scores=res.scores.numpy(), idx=res.idx.numpy(),
                  valid=res.valid.numpy(), count=res.count.numpy())
+        # host-input form: only rank 0 holds the queries, the others receive them by broadcast
+        mk = lambda off: dict(offset=off, k=k, thr=0.3, gap=5.0, mfd=0)
+        res2 = sr.sweep_from_host(t(desc[:n_q].copy()) if rank == 0 else None, t(desc[lo:hi].copy()), t(ts), t(fl), mk, lo, hi,
+                                  n_q, max_floor_diff=0)
+        for a, b in ((res.scores, res2.scores), (res.idx, res2.idx), (res.valid, res2.valid), (res.count, res2.count)):
+            assert torch.equal(a, b), "sweep_from_host differs from sweep"
     finally:
         dist.destroy_process_group()
 
