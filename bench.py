@@ -216,6 +216,17 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------- GPU arm
+def exchange_info(sr, world):
+    if world == 1:
+        return {}
+    peer = sr._symm is not None
+    d = {"exchange": "peer memory: merge kernel reads the per-GPU lists in place over NVLink" if peer
+         else "NCCL all-gather of the per-GPU lists, then merge"}
+    if sr.peer_error:
+        d["peer_exchange_unavailable"] = sr.peer_error
+    return d
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -235,7 +246,7 @@ def run_ours(args):
     if args.cta_group:
         eng.set_option("cta_group", args.cta_group)
     eng.set_option("profile", 1)
-    sr = ShardedRetrieval(eng)
+    sr = ShardedRetrieval(eng, exchange=args.exchange)
 
     n_db_total = db_total(world)
     lo, hi = shard_bounds(n_db_total, world, rank)
@@ -354,6 +365,7 @@ def run_ours(args):
                 "gpu_launches": int(launches), "clocks": clocks,
                 "note": "non-default workload: e2e / cpu_baseline legs are only run for the default configuration",
             }
+            out_json.update(exchange_info(sr, world))
             print(json.dumps(out_json))
         if world > 1:
             dist.destroy_process_group()
@@ -436,6 +448,7 @@ def run_ours(args):
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "cta_group": args.cta_group or os.environ.get("SEMGATE_CTA_GROUP", "auto (2 for Q >= 4096)"),
     }
+    out_json.update(exchange_info(sr, world))
     print(json.dumps(out_json))
     if world > 1:
         dist.destroy_process_group()
@@ -448,6 +461,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cta-group", type=int, default=0, choices=[0, 1, 2, 4])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "peer"],
+                    help="N>1: how the per-GPU candidate lists meet (NCCL all-gather, or read in place over NVLink by the merge kernel)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg")
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c5"],

@@ -121,6 +121,16 @@ int semgate_merge_topk(semgate_handle_t h, const uint64_t* keys_in, int32_t G, i
                        float* out_scores, int32_t* out_idx, uint8_t* out_valid, int32_t* out_count,
                        semgate_stream_t stream);
 
+/* Same merge with the G per-GPU lists read IN PLACE: peer_keys is a DEVICE array of G device
+ * pointers, list g of query row r = peer_keys[g] + r*k.  With the other ranks' buffers mapped into
+ * this process (CUDA IPC / torch symmetric memory) the kernel pulls them over NVLink while it
+ * merges, so the all-gather and its G*Q*k gathered copy disappear (semgate/dist.py, exchange="peer").
+ * The caller orders the peers' writes before this launch (a cross-GPU barrier on the stream). */
+int semgate_merge_topk_peers(semgate_handle_t h, const uint64_t* const* peer_keys, int32_t G, int64_t Q, int32_t k,
+                             const int32_t* q_floor, const int32_t* db_floor_all, int32_t max_floor_diff,
+                             uint64_t* out_keys, float* out_scores, int32_t* out_idx, uint8_t* out_valid,
+                             int32_t* out_count, semgate_stream_t stream);
+
 /* ---- K4: candidate compaction ----------------------------------------------
  * replaces the PlaceMatch append loop (place_recognition.py:890-909): flat arrays
  * ordered (query ascending, score descending).  Outputs need capacity Q*k.

@@ -311,6 +311,27 @@ int semgate_merge_topk(semgate_handle_t h, const uint64_t* keys_in, int32_t G, i
   return 0;
 }
 
+// merge of per-GPU lists read in place from the peers' memory (NVLink P2P): no gathered copy
+int semgate_merge_topk_peers(semgate_handle_t h, const uint64_t* const* peer_keys, int32_t G, int64_t Q, int32_t k,
+                             const int32_t* q_floor, const int32_t* db_floor_all, int32_t max_floor_diff, uint64_t* out_keys,
+                             float* out_scores, int32_t* out_idx, uint8_t* out_valid, int32_t* out_count,
+                             semgate_stream_t stream) {
+  if (!h) return fail(SEMGATE_EINVAL, "handle is NULL");
+  if (G < 1 || Q < 0 || k < 1 || k > SEMGATE_MAX_K) return fail(SEMGATE_EINVAL, "merge_topk_peers: bad sizes G=%d Q=%lld k=%d", G, (long long)Q, k);
+  if (Q == 0) return 0;
+  if (!peer_keys) return fail(SEMGATE_EINVAL, "merge_topk_peers: peer_keys is NULL");
+  DeviceGuard g(h->device);
+  MergeLaunch m{};
+  m.keys_in = nullptr; m.list_ptrs = peer_keys; m.Q = Q; m.k = k;
+  m.row_stride = 0; m.list_stride = 0; m.n_lists = G;
+  m.keys_out = out_keys; m.scores = out_scores; m.idx = out_idx; m.valid = out_valid; m.count = out_count;
+  m.q_floor = q_floor; m.db_floor = db_floor_all; m.floor_index_offset = 0;
+  m.max_floor_diff = (q_floor && db_floor_all) ? max_floor_diff : -1;
+  RC_TRY(launch_merge_topk(m, static_cast<cudaStream_t>(stream)), "merge_topk launch");
+  h->launches += 1;
+  return 0;
+}
+
 // ---------------------------------------------------------------- dense similarity (interface parity)
 int semgate_similarity_matrix(semgate_handle_t h, const void* q_bf16, int64_t Q, const void* db_bf16, int64_t N, int32_t d_pad,
                               float* out, int64_t ld_out, semgate_stream_t stream) {

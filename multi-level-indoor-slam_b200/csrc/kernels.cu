@@ -202,9 +202,11 @@ __device__ __forceinline__ void sort_desc(uint64_t (&c)[P]) {
 
 // Merge the keys base[(e / kk) * list_stride + e % kk], e in [e0, e1), into `run` (the warp's running
 // top-k list: rank t lives in run[t>>5] of lane t&31).  `have_run`: run already holds keys.
+// `ptrs` != nullptr: list g lives at ptrs[g] + base_off (peer GPUs' buffers), else at base + g * list_stride.
 template <int P>
 __device__ __forceinline__ void merge_range(const uint64_t* __restrict__ base, int e0, int e1, int kk, int64_t list_stride,
-                                            int k, int lane, uint64_t (&run)[2], bool have_run) {
+                                            int k, int lane, uint64_t (&run)[2], bool have_run,
+                                            const uint64_t* const* __restrict__ ptrs = nullptr, int64_t base_off = 0) {
   int b0 = e0;
   do {
     const int nnew = have_run ? P - 2 : P;   // key slots per lane for new candidates
@@ -213,7 +215,10 @@ __device__ __forceinline__ void merge_range(const uint64_t* __restrict__ base, i
     for (int i = 0; i < P; ++i) {
       const int e = b0 + i * 32 + lane;
       uint64_t v = 0ull;
-      if (i < nnew && e < e1) v = base[static_cast<int64_t>(e / kk) * list_stride + (e % kk)];
+      if (i < nnew && e < e1) {
+        const int g = e / kk, j = e - g * kk;
+        v = ptrs ? ptrs[g][base_off + j] : base[static_cast<int64_t>(g) * list_stride + j];
+      }
       c[i] = v;
     }
     if (have_run) { c[P - 2] = run[0]; c[P - 1] = run[1]; }
@@ -269,12 +274,14 @@ merge_topk_kernel(const MergeLaunch a) {
   if constexpr (!ROWBLOCK) {
     // rows with few lists (most rows: the tail super-row is split finer than the others) take the
     // cheaper 4-keys-per-lane network; warp-uniform choice
-    if (P == 8 && total + (have_run ? 64 : 0) <= 128) merge_range<4>(base, 0, total, k, a.list_stride, k, lane, run, have_run);
-    else merge_range<P>(base, 0, total, k, a.list_stride, k, lane, run, have_run);
+    if (P == 8 && total + (have_run ? 64 : 0) <= 128)
+      merge_range<4>(base, 0, total, k, a.list_stride, k, lane, run, have_run, a.list_ptrs, row * k);
+    else
+      merge_range<P>(base, 0, total, k, a.list_stride, k, lane, run, have_run, a.list_ptrs, row * k);
   } else {
     const int per = (total + kMergeWarps - 1) / kMergeWarps;
     const int e0 = min(total, warp * per), e1 = min(total, e0 + per);
-    merge_range<P>(base, e0, e1, k, a.list_stride, k, lane, run, have_run);
+    merge_range<P>(base, e0, e1, k, a.list_stride, k, lane, run, have_run, a.list_ptrs, row * k);
     stage[warp * 64 + lane] = run[0];
     stage[warp * 64 + 32 + lane] = run[1];
     __syncthreads();
@@ -327,7 +334,8 @@ int launch_merge_topk(const MergeLaunch& a, cudaStream_t st) {
 }
 
 // =========================================================================== K4
-constexpr int kScanBlock = 1024;
+constexpr int kScanBlock = 128;     // rows per block of the count / scatter kernels (many small blocks: all SMs busy)
+constexpr int kScanThreads = 1024;  // threads of the single-block scan over the block sums
 
 __device__ __forceinline__ int block_exclusive_scan(int v, int* smem /*>=32*/, int* total) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -360,13 +368,13 @@ compact_count_kernel(const int32_t* __restrict__ count, int64_t Q, int64_t* __re
   if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
 }
 
-__global__ void __launch_bounds__(kScanBlock)
+__global__ void __launch_bounds__(kScanThreads)
 compact_scan_kernel(int64_t* __restrict__ block_sums, int64_t nblocks, int64_t* __restrict__ out_total) {
   // serial-in-chunks exclusive scan; nblocks = ceil(Q/1024) is small
   __shared__ int sm[32];
   __shared__ int tot;
   int64_t carry = 0;
-  for (int64_t b0 = 0; b0 < nblocks; b0 += kScanBlock) {
+  for (int64_t b0 = 0; b0 < nblocks; b0 += kScanThreads) {
     const int64_t i = b0 + threadIdx.x;
     const int v = i < nblocks ? static_cast<int>(block_sums[i]) : 0;
     const int ex = block_exclusive_scan(v, sm, &tot);
@@ -418,7 +426,7 @@ int launch_compact(const float* scores, const int32_t* idx, const uint8_t* valid
   const int64_t nb = (Q + kScanBlock - 1) / kScanBlock;
   int64_t* bs = static_cast<int64_t*>(workspace);
   compact_count_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, st>>>(count, Q, bs);
-  compact_scan_kernel<<<1, kScanBlock, 0, st>>>(bs, nb, out_total);
+  compact_scan_kernel<<<1, kScanThreads, 0, st>>>(bs, nb, out_total);
   compact_scatter_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, st>>>(scores, idx, valid, count, Q, k, bs, out_q, out_m,
                                                                           out_s, out_v);
   return static_cast<int>(cudaGetLastError());

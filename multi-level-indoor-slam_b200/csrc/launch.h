@@ -43,6 +43,8 @@ struct MergeLaunch {
   int64_t row_stride, list_stride;   // in keys
   int n_lists;                       // >=0: constant; <0: per m-block from `sc` (offsets too: sched_list_offset)
   Schedule sc; int rows_per_mblock;
+  const uint64_t* const* list_ptrs;  // optional device array of n_lists pointers: list g of row r = list_ptrs[g] + r*k
+                                     // (per-GPU lists read in place over NVLink peer memory; keys_in unused)
   const uint64_t* seed_keys;         // optional [Q,k]: one more list per row (may alias keys_out)
   // outputs (any may be null)
   uint64_t* keys_out;                // [Q,k] sorted descending, 0 padded

@@ -238,12 +238,6 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "r"(taddr) : "memory");
 }
 
-__device__ __forceinline__ uint32_t tmem_ld_32x1(uint32_t taddr) {
-  uint32_t r;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
-  return r;
-}
-
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle, rows of
 // 64 bf16 (128 B) packed contiguously; 8-row groups are 1024 B apart (SBO).

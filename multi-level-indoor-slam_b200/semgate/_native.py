@@ -28,6 +28,7 @@ SYMBOLS = [
     "semgate_compact", "semgate_gate_candidates", "semgate_find_loop_closures_host", "semgate_query_host",
     "semgate_gate_candidates_host", "semgate_spatial_workspace_bytes", "semgate_spatial_count", "semgate_spatial_fill",
     "semgate_spatial_candidates_host", "semgate_rerank_scores", "semgate_rerank_select", "semgate_similarity_matrix",
+    "semgate_merge_topk_peers",
 ]
 
 
@@ -96,6 +97,7 @@ def load_library():
     lib.semgate_rerank_scores.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, i64, vp, vp, vp]
     lib.semgate_rerank_select.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, vp, vp, vp]
     lib.semgate_similarity_matrix.argtypes = [vp, vp, i64, vp, i64, i32, vp, i64, vp]
+    lib.semgate_merge_topk_peers.argtypes = [vp, vp, i32, i64, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp]
     for name in SYMBOLS:
         getattr(lib, name)   # AttributeError here = the library is older than the header
     _lib = lib
@@ -308,6 +310,24 @@ class Engine:
             _check(self.lib.semgate_merge_topk(self._h, self._ptr(keys_gathered), G, Q, k, self._ptr(q_floor),
                                                self._ptr(db_floor_all), max_floor_diff, self._ptr(keys), self._ptr(scores),
                                                self._ptr(idx), self._ptr(valid), self._ptr(count), self._stream()))
+        return TopkResult(scores, idx, valid, count, keys)
+
+    def merge_topk_peers(self, peer_ptrs_dev: int, G: int, Q: int, k: int, q_floor=None, db_floor_all=None,
+                         max_floor_diff: int = -1, want_keys: bool = False) -> TopkResult:
+        """`peer_ptrs_dev`: address of a device array of G pointers to the ranks' `[Q,k]` key buffers
+        (this rank's own and the peers' mapped over NVLink); merged in place, no gathered copy."""
+        torch = self._torch()
+        dev = self._dev()
+        scores = torch.empty((Q, k), dtype=torch.float32, device=dev)
+        idx = torch.empty((Q, k), dtype=torch.int32, device=dev)
+        valid = torch.empty((Q, k), dtype=torch.uint8, device=dev)
+        count = torch.empty((Q,), dtype=torch.int32, device=dev)
+        keys = torch.empty((Q, k), dtype=torch.int64, device=dev) if want_keys else None
+        if Q:
+            _check(self.lib.semgate_merge_topk_peers(self._h, C.c_void_p(int(peer_ptrs_dev)), G, Q, k, self._ptr(q_floor),
+                                                     self._ptr(db_floor_all), max_floor_diff, self._ptr(keys),
+                                                     self._ptr(scores), self._ptr(idx), self._ptr(valid), self._ptr(count),
+                                                     self._stream()))
         return TopkResult(scores, idx, valid, count, keys)
 
     # ------------------------------------------------------------------ K4

@@ -3,12 +3,13 @@
 One process per GPU (`torch.distributed`, NCCL over NVLink/NVSwitch).  Every rank
 holds all queries and a contiguous slice of database rows; it runs the fused
 sweep on its slice with global column indices (`db_index_offset`), then the
-per-rank `[Q,k]` candidate-key lists are all-gathered (8*Q*k bytes per rank) and
-merged by the K3 kernel on every rank.  Top-k under a total order is an
-associative merge, so the result equals the single-GPU sweep exactly.
+per-rank `[Q,k]` candidate-key lists (8*Q*k bytes per rank) are exchanged and merged
+by the K3 kernel on every rank — either all-gathered first (NCCL) or read in place
+from the peers' memory over NVLink by the merge kernel itself.  Top-k under a total
+order is an associative merge, so the result equals the single-GPU sweep exactly.
 
-The path's only exchange step is that all-gather; there is no reduction over the
-descriptor dimension and no all-to-all.
+That exchange is the path's only one; there is no reduction over the descriptor
+dimension and no all-to-all.
 """
 from __future__ import annotations
 
@@ -23,16 +24,52 @@ def shard_bounds(n_total: int, world: int, rank: int) -> Tuple[int, int]:
 
 
 class ShardedRetrieval:
-    """Gated top-k over a database sharded by rows across the ranks of `group`."""
+    """Gated top-k over a database sharded by rows across the ranks of `group`.
 
-    def __init__(self, engine, group=None):
+    exchange = "allgather": the per-rank `[Q,k]` key lists are all-gathered (NCCL; gloo in the CPU
+    tests) and merged.  exchange = "peer": every rank writes its keys into a symmetric-memory buffer
+    that the other ranks have mapped, and after a cross-GPU barrier on the stream the merge kernel
+    reads the G lists IN PLACE over NVLink (`semgate_merge_topk_peers`) — one kernel does the
+    exchange and the merge, the gathered copy never exists.  "auto" = "peer" on NCCL groups when
+    symmetric memory can be set up, else "allgather"; both give bit-identical results."""
+
+    def __init__(self, engine, group=None, exchange: str = "auto"):
         import torch.distributed as dist
+        if exchange not in ("auto", "allgather", "peer"):
+            raise ValueError("exchange must be 'auto', 'allgather' or 'peer'")
         self.engine = engine
         self.group = group
         self.dist = dist
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._gather_buf = None
+        self.exchange = exchange
+        self._symm = None          # (shape, keys tensor, handle)
+        self.peer_error = None     # why "auto" fell back, if it did
+
+    # -- peer-memory exchange ----------------------------------------------------
+    def _symm_keys(self, Q: int, k: int, device):
+        """Symmetric `[Q,k]` int64 buffer + rendezvous handle, cached per shape."""
+        import torch
+        import torch.distributed._symmetric_memory as symm_mem
+        if self._symm is None or self._symm[0] != (Q, k):
+            t = symm_mem.empty((Q, k), dtype=torch.int64, device=device)
+            grp = self.group if self.group is not None else self.dist.group.WORLD
+            hdl = symm_mem.rendezvous(t, grp)
+            self._symm = ((Q, k), t, hdl)
+        return self._symm[1], self._symm[2]
+
+    def _use_peer(self) -> bool:
+        if self.exchange == "allgather" or self.world == 1:
+            return False
+        if self.exchange == "peer":
+            return True
+        if self.peer_error is not None:
+            return False
+        try:
+            return self.dist.get_backend(self.group) == "nccl"
+        except Exception:
+            return False
 
     def sweep(self, q_bf16, db_shard_bf16, make_params, shard_lo: int, q_ts=None, db_ts_shard=None, q_floor=None,
               db_floor_shard=None, db_floor_all=None, max_floor_diff: int = -1):
@@ -43,9 +80,23 @@ class ShardedRetrieval:
         if self.world == 1:
             return self.engine.gated_topk(q_bf16, db_shard_bf16, params, q_ts=q_ts, db_ts=db_ts_shard, q_floor=q_floor,
                                           db_floor=db_floor_shard)
+        Q, k = q_bf16.shape[0], params.k if hasattr(params, "k") else params["k"]
+        if self._use_peer():
+            try:
+                keys, hdl = self._symm_keys(Q, k, q_bf16.device)
+            except Exception as e:          # no P2P mapping on this system
+                if self.exchange == "peer":
+                    raise
+                self.peer_error = f"{type(e).__name__}: {e}"
+            else:
+                hdl.barrier(channel=0)      # every rank has finished reading the previous step's keys
+                self.engine.gated_topk(q_bf16, db_shard_bf16, params, q_ts=q_ts, db_ts=db_ts_shard, q_floor=q_floor,
+                                       db_floor=db_floor_shard, want_lists=False, keys=keys)
+                hdl.barrier(channel=1)      # every rank's keys are written
+                return self.engine.merge_topk_peers(hdl.buffer_ptrs_dev, self.world, Q, k, q_floor=q_floor,
+                                                    db_floor_all=db_floor_all, max_floor_diff=max_floor_diff)
         local = self.engine.gated_topk(q_bf16, db_shard_bf16, params, q_ts=q_ts, db_ts=db_ts_shard, q_floor=q_floor,
                                        db_floor=db_floor_shard, want_keys=True, want_lists=False)
-        Q, k = local.keys.shape
         buf = self._gather_buf
         if buf is None or buf.shape != (self.world * Q, k) or buf.device != local.keys.device:
             # concatenation along dim 0 is the layout every backend accepts; viewed as [G,Q,k] below

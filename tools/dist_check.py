@@ -23,7 +23,17 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     eng = _native.get_engine(local)
-    sr = ShardedRetrieval(eng)
+    ok = True
+    for exchange in ("allgather", "peer"):
+      sr = ShardedRetrieval(eng, exchange=exchange)
+      ok = check(sr, eng, dev, rank, world, exchange) and ok
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+def check(sr, eng, dev, rank, world, exchange):
     ok = True
     for (n_db, n_q, d, k, thr, gap) in [(3001, 700, 128, 25, 0.4, 5.0), (20000, 4000, 512, 10, 0.5, 10.0)]:
         desc, ts, fl = synthetic.make_case(n_db, d, 4, seed=11)
@@ -42,13 +52,16 @@ def main():
         torch.cuda.synchronize()
         same = (torch.equal(res.idx, whole.idx) and torch.equal(res.scores, whole.scores)
                 and torch.equal(res.valid, whole.valid) and torch.equal(res.count, whole.count))
-        print(f"rank {rank}/{world}: n_db={n_db} n_q={n_q} d={d} k={k}: sharded == whole: {same}; "
+        print(f"rank {rank}/{world} [{exchange}]: n_db={n_db} n_q={n_q} d={d} k={k}: sharded == whole: {same}; "
               f"candidates {int(whole.count.sum())}", flush=True)
         ok = ok and same
-    flag = torch.tensor([1 if ok else 0], device=dev)
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    dist.destroy_process_group()
-    sys.exit(0 if int(flag.item()) == 1 else 1)
+        # a second sweep through the same symmetric buffer (the barriers must keep steps apart)
+        res2 = sr.sweep(xb[:n_q], xb[lo:hi], mk, lo, q_ts=tts[:n_q].contiguous(), db_ts_shard=tts[lo:hi].contiguous(),
+                        q_floor=tfl[:n_q].contiguous(), db_floor_shard=tfl[lo:hi].contiguous(), db_floor_all=tfl,
+                        max_floor_diff=0)
+        torch.cuda.synchronize()
+        ok = ok and torch.equal(res2.idx, whole.idx) and torch.equal(res2.scores, whole.scores)
+    return ok
 
 
 if __name__ == "__main__":
