@@ -140,6 +140,22 @@ int semgate_compact(semgate_handle_t h, const float* scores, const int32_t* idx,
                     int64_t Q, int32_t k, int32_t* out_query_idx, int32_t* out_match_idx, float* out_similarity,
                     uint8_t* out_is_valid, int64_t* out_total, void* workspace, semgate_stream_t stream);
 
+/* Same, emitting only the floor-consistent candidates (is_valid != 0): the list handed on to geometric
+ * verification, which skips cross-floor pairs (geometric_verification.py:709). */
+int semgate_compact_valid(semgate_handle_t h, const float* scores, const int32_t* idx, const uint8_t* valid, const int32_t* count,
+                          int64_t Q, int32_t k, int32_t* out_query_idx, int32_t* out_match_idx, float* out_similarity,
+                          uint8_t* out_is_valid, int64_t* out_total, void* workspace, semgate_stream_t stream);
+
+/* ---- match statistics -------------------------------------------------------
+ * replaces SemanticPlaceRecognition.get_statistics (place_recognition.py:913-933) for a
+ * device-resident candidate list: out_stats (device, 4 doubles) = { total, valid, sum(similarity),
+ * sum(similarity of valid) }, accumulated in fp64 in a scheduling-independent order.  The number
+ * of candidates is *total_dev (device int64, e.g. semgate_compact's out_total) when given, else M.
+ * workspace >= semgate_stats_workspace_bytes(). */
+size_t semgate_stats_workspace_bytes(void);
+int semgate_candidate_stats(semgate_handle_t h, const float* similarity, const uint8_t* is_valid, const int64_t* total_dev,
+                            int64_t M, void* workspace, double* out_stats, semgate_stream_t stream);
+
 /* ---- floor gate over explicit candidate pairs --------------------------------
  * replaces SemanticLoopClosureGate.gate_candidates (loop_closure_gate.py:105-126).
  * max_floor_diff: 0 = strict_mode True, 1 = strict_mode False.

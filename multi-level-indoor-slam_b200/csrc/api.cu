@@ -360,17 +360,47 @@ int semgate_similarity_matrix(semgate_handle_t h, const void* q_bf16, int64_t Q,
 // ---------------------------------------------------------------- K4
 size_t semgate_compact_workspace_bytes(int64_t Q) { return align256(compact_workspace_bytes(Q < 0 ? 0 : Q)); }
 
-int semgate_compact(semgate_handle_t h, const float* scores, const int32_t* idx, const uint8_t* valid, const int32_t* count,
-                    int64_t Q, int32_t k, int32_t* out_query_idx, int32_t* out_match_idx, float* out_similarity,
-                    uint8_t* out_is_valid, int64_t* out_total, void* workspace, semgate_stream_t stream) {
+static int compact_impl(semgate_handle_t h, const float* scores, const int32_t* idx, const uint8_t* valid, const int32_t* count,
+                        int64_t Q, int32_t k, bool valid_only, int32_t* out_query_idx, int32_t* out_match_idx,
+                        float* out_similarity, uint8_t* out_is_valid, int64_t* out_total, void* workspace,
+                        semgate_stream_t stream) {
   if (!h) return fail(SEMGATE_EINVAL, "handle is NULL");
   if (Q < 0 || k < 1 || !out_total) return fail(SEMGATE_EINVAL, "compact: bad arguments");
   if (Q > 0 && (!scores || !idx || !valid || !count || !out_query_idx || !out_match_idx || !out_similarity || !out_is_valid || !workspace))
     return fail(SEMGATE_EINVAL, "compact: NULL pointer");
   DeviceGuard g(h->device);
-  RC_TRY(launch_compact(scores, idx, valid, count, Q, k, out_query_idx, out_match_idx, out_similarity, out_is_valid, out_total,
-                        workspace, static_cast<cudaStream_t>(stream)), "compact launch");
+  RC_TRY(launch_compact(scores, idx, valid, count, Q, k, valid_only, out_query_idx, out_match_idx, out_similarity, out_is_valid,
+                        out_total, workspace, static_cast<cudaStream_t>(stream)), "compact launch");
   h->launches += Q > 0 ? 3 : 0;
+  return 0;
+}
+
+int semgate_compact(semgate_handle_t h, const float* scores, const int32_t* idx, const uint8_t* valid, const int32_t* count,
+                    int64_t Q, int32_t k, int32_t* out_query_idx, int32_t* out_match_idx, float* out_similarity,
+                    uint8_t* out_is_valid, int64_t* out_total, void* workspace, semgate_stream_t stream) {
+  return compact_impl(h, scores, idx, valid, count, Q, k, false, out_query_idx, out_match_idx, out_similarity, out_is_valid,
+                      out_total, workspace, stream);
+}
+
+int semgate_compact_valid(semgate_handle_t h, const float* scores, const int32_t* idx, const uint8_t* valid, const int32_t* count,
+                          int64_t Q, int32_t k, int32_t* out_query_idx, int32_t* out_match_idx, float* out_similarity,
+                          uint8_t* out_is_valid, int64_t* out_total, void* workspace, semgate_stream_t stream) {
+  return compact_impl(h, scores, idx, valid, count, Q, k, true, out_query_idx, out_match_idx, out_similarity, out_is_valid,
+                      out_total, workspace, stream);
+}
+
+// ---------------------------------------------------------------- match statistics
+size_t semgate_stats_workspace_bytes(void) { return align256(stats_workspace_bytes()); }
+
+int semgate_candidate_stats(semgate_handle_t h, const float* similarity, const uint8_t* is_valid, const int64_t* total_dev,
+                            int64_t M, void* workspace, double* out_stats, semgate_stream_t stream) {
+  if (!h) return fail(SEMGATE_EINVAL, "handle is NULL");
+  if (M < 0 || !workspace || !out_stats) return fail(SEMGATE_EINVAL, "candidate_stats: bad arguments");
+  if ((M > 0 || total_dev) && (!similarity || !is_valid)) return fail(SEMGATE_EINVAL, "candidate_stats: NULL pointer");
+  DeviceGuard g(h->device);
+  RC_TRY(launch_candidate_stats(similarity, is_valid, total_dev, M, workspace, out_stats, static_cast<cudaStream_t>(stream)),
+         "candidate_stats launch");
+  h->launches += 1;
   return 0;
 }
 

@@ -358,19 +358,32 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* smem /*>=32*/, i
   return r;
 }
 
+// entries of a row that are emitted: all `count[row]` of them, or only the floor-consistent ones
+// (valid_only: the list handed to geometric verification, which skips cross-floor pairs anyway,
+// geometric_verification.py:709)
+__device__ __forceinline__ int row_emit_count(const int32_t* __restrict__ count, const uint8_t* __restrict__ valid, int64_t row,
+                                              int k, bool valid_only) {
+  const int c = count[row];
+  if (!valid_only) return c;
+  int n = 0;
+  for (int i = 0; i < c; ++i) n += valid[row * k + i] ? 1 : 0;
+  return n;
+}
+
 __global__ void __launch_bounds__(kScanBlock)
-compact_count_kernel(const int32_t* __restrict__ count, int64_t Q, int64_t* __restrict__ block_sums) {
+compact_count_kernel(const int32_t* __restrict__ count, const uint8_t* __restrict__ valid, int64_t Q, int k, bool valid_only,
+                     int64_t* __restrict__ block_sums) {
   __shared__ int sm[32];
   __shared__ int tot;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * kScanBlock + threadIdx.x;
-  const int v = row < Q ? count[row] : 0;
+  const int v = row < Q ? row_emit_count(count, valid, row, k, valid_only) : 0;
   block_exclusive_scan(v, sm, &tot);
   if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
 }
 
 __global__ void __launch_bounds__(kScanThreads)
 compact_scan_kernel(int64_t* __restrict__ block_sums, int64_t nblocks, int64_t* __restrict__ out_total) {
-  // serial-in-chunks exclusive scan; nblocks = ceil(Q/1024) is small
+  // serial-in-chunks exclusive scan; nblocks = ceil(Q / kScanBlock)
   __shared__ int sm[32];
   __shared__ int tot;
   int64_t carry = 0;
@@ -387,30 +400,39 @@ compact_scan_kernel(int64_t* __restrict__ block_sums, int64_t nblocks, int64_t* 
 
 __global__ void __launch_bounds__(kScanBlock)
 compact_scatter_kernel(const float* __restrict__ scores, const int32_t* __restrict__ idx, const uint8_t* __restrict__ valid,
-                       const int32_t* __restrict__ count, int64_t Q, int k, const int64_t* __restrict__ block_offsets,
-                       int32_t* __restrict__ out_q, int32_t* __restrict__ out_m, float* __restrict__ out_s,
-                       uint8_t* __restrict__ out_v) {
+                       const int32_t* __restrict__ count, int64_t Q, int k, bool valid_only,
+                       const int64_t* __restrict__ block_offsets, int32_t* __restrict__ out_q, int32_t* __restrict__ out_m,
+                       float* __restrict__ out_s, uint8_t* __restrict__ out_v) {
   __shared__ int sm[32];
   __shared__ int offs[kScanBlock];
   __shared__ int cnts[kScanBlock];
   const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kScanBlock;
   const int64_t row = row0 + threadIdx.x;
-  const int v = row < Q ? count[row] : 0;
+  const int v = row < Q ? row_emit_count(count, valid, row, k, valid_only) : 0;
   const int ex = block_exclusive_scan(v, sm, nullptr);
   offs[threadIdx.x] = ex;
-  cnts[threadIdx.x] = v;
+  cnts[threadIdx.x] = row < Q ? count[row] : 0;
   __syncthreads();
   const int64_t base = block_offsets[blockIdx.x];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int r = w; r < kScanBlock && row0 + r < Q; r += (kScanBlock >> 5)) {
     const int c = cnts[r];
-    const int64_t o = base + offs[r];
+    int64_t o = base + offs[r];
     const int64_t src = (row0 + r) * k;
-    for (int i = lane; i < c; i += 32) {
-      out_q[o + i] = static_cast<int32_t>(row0 + r);
-      out_m[o + i] = idx[src + i];
-      out_s[o + i] = scores[src + i];
-      out_v[o + i] = valid[src + i];
+    for (int i0 = 0; i0 < c; i0 += 32) {
+      const int i = i0 + lane;
+      const bool live = i < c;
+      const uint8_t vv = live ? valid[src + i] : 0;
+      const bool emit = live && (!valid_only || vv != 0);
+      const uint32_t ballot = __ballot_sync(0xffffffffu, emit);
+      if (emit) {
+        const int64_t d = o + __popc(ballot & ((1u << lane) - 1u));   // order inside the row is kept
+        out_q[d] = static_cast<int32_t>(row0 + r);
+        out_m[d] = idx[src + i];
+        out_s[d] = scores[src + i];
+        out_v[d] = vv;
+      }
+      o += __popc(ballot);
     }
   }
 }
@@ -420,15 +442,83 @@ size_t compact_workspace_bytes(int64_t Q) {
 }
 
 int launch_compact(const float* scores, const int32_t* idx, const uint8_t* valid, const int32_t* count, int64_t Q, int k,
-                   int32_t* out_q, int32_t* out_m, float* out_s, uint8_t* out_v, int64_t* out_total, void* workspace,
-                   cudaStream_t st) {
+                   bool valid_only, int32_t* out_q, int32_t* out_m, float* out_s, uint8_t* out_v, int64_t* out_total,
+                   void* workspace, cudaStream_t st) {
   if (Q <= 0) return static_cast<int>(cudaMemsetAsync(out_total, 0, sizeof(int64_t), st));
   const int64_t nb = (Q + kScanBlock - 1) / kScanBlock;
   int64_t* bs = static_cast<int64_t*>(workspace);
-  compact_count_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, st>>>(count, Q, bs);
+  compact_count_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, st>>>(count, valid, Q, k, valid_only, bs);
   compact_scan_kernel<<<1, kScanThreads, 0, st>>>(bs, nb, out_total);
-  compact_scatter_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, st>>>(scores, idx, valid, count, Q, k, bs, out_q, out_m,
-                                                                          out_s, out_v);
+  compact_scatter_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, st>>>(scores, idx, valid, count, Q, k, valid_only, bs,
+                                                                          out_q, out_m, out_s, out_v);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// =========================================================================== match statistics
+// get_statistics (place_recognition.py:913-933) over a device-resident candidate list: number of
+// valid candidates, sum of similarities, sum over the valid ones, in fp64.  Every block reduces a
+// grid-stride slice; the block that finishes last adds the per-block partials in index order, so
+// the result does not depend on scheduling.
+constexpr int kStatsBlocks = 296;
+constexpr int kStatsThreads = 256;
+
+__device__ __forceinline__ double block_sum_f64(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  double t = (l < (blockDim.x >> 5)) ? red[l] : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(kStatsThreads)
+candidate_stats_kernel(const float* __restrict__ sim, const uint8_t* __restrict__ valid, const int64_t* __restrict__ total_dev,
+                       int64_t M_host, double* __restrict__ partials /*[grid][3]*/, unsigned* __restrict__ done,
+                       double* __restrict__ out /*[4]: total, valid, sum, sum_valid*/) {
+  __shared__ double red[32];
+  __shared__ bool last;
+  const int64_t M = total_dev ? *total_dev : M_host;
+  double nv = 0.0, ss = 0.0, sv = 0.0;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < M;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const double s = static_cast<double>(sim[i]);
+    const bool v = valid[i] != 0;
+    ss += s;
+    if (v) { nv += 1.0; sv += s; }
+  }
+  nv = block_sum_f64(nv, red);
+  ss = block_sum_f64(ss, red);
+  sv = block_sum_f64(sv, red);
+  if (threadIdx.x == 0) {
+    partials[3 * blockIdx.x] = nv; partials[3 * blockIdx.x + 1] = ss; partials[3 * blockIdx.x + 2] = sv;
+    __threadfence();
+    last = atomicAdd(done, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (unsigned g = 0; g < gridDim.x; ++g) {
+      a += __ldcg(partials + 3 * g); b += __ldcg(partials + 3 * g + 1); c += __ldcg(partials + 3 * g + 2);
+    }
+    out[0] = static_cast<double>(M); out[1] = a; out[2] = b; out[3] = c;
+    *done = 0;   // ready for the next launch
+  }
+}
+
+size_t stats_workspace_bytes() { return static_cast<size_t>(kStatsBlocks) * 3 * sizeof(double) + 256; }
+
+int launch_candidate_stats(const float* sim, const uint8_t* valid, const int64_t* total_dev, int64_t M, void* workspace,
+                           double* out, cudaStream_t st) {
+  double* partials = static_cast<double*>(workspace);
+  unsigned* done = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + static_cast<size_t>(kStatsBlocks) * 3 * sizeof(double));
+  cudaError_t e = cudaMemsetAsync(done, 0, sizeof(unsigned), st);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  candidate_stats_kernel<<<kStatsBlocks, kStatsThreads, 0, st>>>(sim, valid, total_dev, M, partials, done, out);
   return static_cast<int>(cudaGetLastError());
 }
 

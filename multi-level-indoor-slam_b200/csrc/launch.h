@@ -57,8 +57,13 @@ int launch_merge_topk(const MergeLaunch& a, cudaStream_t st);
 // K4: padded [Q,k] lists -> flat candidate arrays (query asc, score desc)
 size_t compact_workspace_bytes(int64_t Q);
 int launch_compact(const float* scores, const int32_t* idx, const uint8_t* valid, const int32_t* count, int64_t Q, int k,
-                   int32_t* out_q, int32_t* out_m, float* out_s, uint8_t* out_v, int64_t* out_total, void* workspace,
-                   cudaStream_t st);
+                   bool valid_only, int32_t* out_q, int32_t* out_m, float* out_s, uint8_t* out_v, int64_t* out_total,
+                   void* workspace, cudaStream_t st);
+
+// get_statistics (place_recognition.py:913-933) on the device: out[4] = total, valid, sum(sim), sum(valid sim), fp64
+size_t stats_workspace_bytes();
+int launch_candidate_stats(const float* sim, const uint8_t* valid, const int64_t* total_dev, int64_t M, void* workspace,
+                           double* out, cudaStream_t st);
 
 // floor gate over explicit candidate pairs (loop_closure_gate.py:105-126)
 int launch_gate_candidates(const int32_t* floors, int64_t n_floors, const int32_t* q_idx, const int32_t* m_idx, int64_t M,

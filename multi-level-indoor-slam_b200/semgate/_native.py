@@ -28,7 +28,7 @@ SYMBOLS = [
     "semgate_compact", "semgate_gate_candidates", "semgate_find_loop_closures_host", "semgate_query_host",
     "semgate_gate_candidates_host", "semgate_spatial_workspace_bytes", "semgate_spatial_count", "semgate_spatial_fill",
     "semgate_spatial_candidates_host", "semgate_rerank_scores", "semgate_rerank_select", "semgate_similarity_matrix",
-    "semgate_merge_topk_peers",
+    "semgate_merge_topk_peers", "semgate_compact_valid", "semgate_stats_workspace_bytes", "semgate_candidate_stats",
 ]
 
 
@@ -98,6 +98,10 @@ def load_library():
     lib.semgate_rerank_select.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, vp, vp, vp]
     lib.semgate_similarity_matrix.argtypes = [vp, vp, i64, vp, i64, i32, vp, i64, vp]
     lib.semgate_merge_topk_peers.argtypes = [vp, vp, i32, i64, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp]
+    lib.semgate_compact_valid.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.semgate_stats_workspace_bytes.argtypes = []
+    lib.semgate_stats_workspace_bytes.restype = sz
+    lib.semgate_candidate_stats.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp]
     for name in SYMBOLS:
         getattr(lib, name)   # AttributeError here = the library is older than the header
     _lib = lib
@@ -331,9 +335,10 @@ class Engine:
         return TopkResult(scores, idx, valid, count, keys)
 
     # ------------------------------------------------------------------ K4
-    def compact(self, res: TopkResult):
+    def compact(self, res: TopkResult, valid_only: bool = False):
         """Padded lists -> (query_idx, match_idx, similarity, is_valid, total) CUDA tensors;
-        the arrays have capacity Q*k, the first `total` entries are meaningful."""
+        the arrays have capacity Q*k, the first `total` entries are meaningful.
+        `valid_only`: emit only the floor-consistent candidates (the verifier hand-off list)."""
         torch = self._torch()
         Q, k = res.scores.shape
         dev = res.scores.device
@@ -345,10 +350,29 @@ class Engine:
         total = torch.zeros((1,), dtype=torch.int64, device=dev)
         wsb = int(self.lib.semgate_compact_workspace_bytes(Q))
         ws = torch.empty((max(wsb, 256),), dtype=torch.uint8, device=dev)
-        _check(self.lib.semgate_compact(self._h, self._ptr(res.scores), self._ptr(res.idx), self._ptr(res.valid),
-                                        self._ptr(res.count), Q, k, self._ptr(oq), self._ptr(om), self._ptr(os_),
-                                        self._ptr(ov), self._ptr(total), self._ptr(ws), self._stream()))
+        fn = self.lib.semgate_compact_valid if valid_only else self.lib.semgate_compact
+        _check(fn(self._h, self._ptr(res.scores), self._ptr(res.idx), self._ptr(res.valid),
+                  self._ptr(res.count), Q, k, self._ptr(oq), self._ptr(om), self._ptr(os_),
+                  self._ptr(ov), self._ptr(total), self._ptr(ws), self._stream()))
         return oq, om, os_, ov, total
+
+    def candidate_stats(self, similarity, is_valid, total):
+        """Device-side get_statistics: float64[4] CUDA tensor = (total, valid, sum(sim), sum(valid sim)).
+        `total`: the device int64 tensor `compact` returned, or a Python int."""
+        torch = self._torch()
+        self._expect(similarity, torch.float32, "similarity", 1)
+        self._expect(is_valid, torch.uint8, "is_valid", 1)
+        dev = similarity.device
+        out = torch.empty((4,), dtype=torch.float64, device=dev)
+        ws = torch.empty((int(self.lib.semgate_stats_workspace_bytes()),), dtype=torch.uint8, device=dev)
+        if isinstance(total, int):
+            tptr, m = None, total
+        else:
+            self._expect(total, torch.int64, "total", 1)
+            tptr, m = self._ptr(total), 0
+        _check(self.lib.semgate_candidate_stats(self._h, self._ptr(similarity), self._ptr(is_valid), tptr, m, self._ptr(ws),
+                                                self._ptr(out), self._stream()))
+        return out
 
     # ------------------------------------------------------------------ gate
     def gate_candidates(self, floor_labels, query_idx, match_idx, max_floor_diff: int):

@@ -455,11 +455,16 @@ class SemanticPlaceRecognition:
         return self.find_loop_closures_arrays(enable_floor_gating, k, gate_mode).to_matches()
 
     def find_loop_closures_arrays(self, enable_floor_gating: bool = True, k: int = 10,
-                                  gate_mode: str = "flag") -> MatchArrays:
-        """Same result as struct-of-arrays (no per-match Python objects)."""
+                                  gate_mode: str = "flag", valid_only: bool = False,
+                                  with_statistics: bool = False):
+        """Same result as struct-of-arrays (no per-match Python objects).
+        `valid_only`: only the floor-consistent candidates (what geometric verification would keep,
+        geometric_verification.py:709).  `with_statistics`: also return `get_statistics` of the full
+        candidate list, reduced on the device (returns `(arrays, stats)`)."""
         e = np.zeros(0, dtype=np.int32)
+        empty = MatchArrays(e, e.copy(), np.zeros(0, np.float32), np.zeros(0, bool), np.zeros(0), np.zeros(0))
         if len(self.vpr.descriptors) < 2:
-            return MatchArrays(e, e.copy(), np.zeros(0, np.float32), np.zeros(0, bool), np.zeros(0), np.zeros(0))
+            return (empty, self.get_statistics([])) if with_statistics else empty
         if gate_mode not in GATE_MODES:
             raise ValueError(f"gate_mode must be one of {sorted(GATE_MODES)}")
         if not (1 <= int(k) <= _native.MAX_K):
@@ -472,12 +477,29 @@ class SemanticPlaceRecognition:
                                      max_floor_diff=0 if enable_floor_gating else -1, gate_mode=GATE_MODES[gate_mode])
         ts, fl = db.ts[:n], db.floor[:n]
         r = eng.gated_topk(db.bf16[:n], db.bf16[:n], params, q_ts=ts, db_ts=ts, q_floor=fl, db_floor=fl)
-        oq, om, os_, ov, total = eng.compact(r)
+        stats = None
+        if with_statistics:
+            aq, am, as_, av, atot = eng.compact(r)
+            stats = self._stats_dict(eng.candidate_stats(as_, av, atot).cpu().numpy())
+            if not valid_only:
+                oq, om, os_, ov, total = aq, am, as_, av, atot
+        if valid_only or not with_statistics:
+            oq, om, os_, ov, total = eng.compact(r, valid_only=valid_only)
         t = int(total.item())
         q = oq[:t].cpu().numpy()
         m = om[:t].cpu().numpy()
         tsh = ts.cpu().numpy()
-        return MatchArrays(q, m, os_[:t].cpu().numpy(), ov[:t].cpu().numpy().astype(bool), tsh[q], tsh[m])
+        arrays = MatchArrays(q, m, os_[:t].cpu().numpy(), ov[:t].cpu().numpy().astype(bool), tsh[q], tsh[m])
+        return (arrays, stats) if with_statistics else arrays
+
+    @staticmethod
+    def _stats_dict(v) -> Dict:
+        """(total, valid, sum, sum_valid) -> the reference's statistics dict (:913-933)."""
+        n, valid = int(v[0]), int(v[1])
+        if n == 0:
+            return {'total_matches': 0, 'valid_matches': 0, 'rejected_matches': 0, 'rejection_rate': 0.0}
+        return {'total_matches': n, 'valid_matches': valid, 'rejected_matches': n - valid, 'rejection_rate': (n - valid) / n,
+                'mean_similarity': float(v[2]) / n, 'mean_valid_similarity': float(v[3]) / valid if valid > 0 else 0.0}
 
     def get_statistics(self, matches) -> Dict:
         """Statistics of a match list (reference :913-933).  Accepts List[PlaceMatch] or MatchArrays."""

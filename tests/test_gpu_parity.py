@@ -300,6 +300,58 @@ def test_merge_topk_kernel_exact(eng, G, k, fill):
     assert m.count.cpu().numpy()[5] == 0 and np.all(m.idx.cpu().numpy()[5] == -1)
 
 
+def test_valid_only_compaction_and_device_statistics(eng):
+    """§8f rank 4: the floor-consistent hand-off list (geometric_verification.py:709 skips cross-floor pairs) and
+    get_statistics (place_recognition.py:913-933) reduced on the device, against the host path and the oracle."""
+    from semgate import SemanticPlaceRecognition, PlaceDescriptor, synthetic
+    n, d, k = 3000, 256, 25
+    desc, ts, fl = synthetic.make_case(n, d, 3, seed=77)
+    spr = SemanticPlaceRecognition('mixvpr', 'cuda', similarity_threshold=0.5, min_time_gap=10.0, descriptor_dim=d)
+    for i in range(n):
+        spr.vpr.descriptors.append(PlaceDescriptor(float(ts[i]), desc[i], floor_label=int(fl[i]) if i % 97 else None))
+    full = spr.find_loop_closures_arrays(k=k)
+    only, stats = spr.find_loop_closures_arrays(k=k, valid_only=True, with_statistics=True)
+    keep = full.is_valid
+    assert keep.sum() > 100 and (~keep).sum() > 100
+    assert np.array_equal(only.query_idx, full.query_idx[keep]) and np.array_equal(only.match_idx, full.match_idx[keep])
+    assert np.array_equal(only.similarity, full.similarity[keep]) and only.is_valid.all()
+    host = spr.get_statistics(full)
+    for key in ("total_matches", "valid_matches", "rejected_matches"):
+        assert stats[key] == host[key]
+    for key in ("rejection_rate", "mean_similarity", "mean_valid_similarity"):
+        assert abs(stats[key] - host[key]) <= 1e-12 * max(1.0, abs(host[key]))
+    full2, stats2 = spr.find_loop_closures_arrays(k=k, with_statistics=True)
+    assert np.array_equal(full2.match_idx, full.match_idx) and stats2 == stats      # order-independent reduction
+    # nothing valid / nothing at all
+    spr2 = SemanticPlaceRecognition('mixvpr', 'cuda', similarity_threshold=2.0, descriptor_dim=d)
+    for i in range(300):
+        spr2.vpr.descriptors.append(PlaceDescriptor(float(ts[i]), desc[i], floor_label=int(fl[i])))
+    e, st = spr2.find_loop_closures_arrays(k=k, valid_only=True, with_statistics=True)
+    assert len(e) == 0 and st == {'total_matches': 0, 'valid_matches': 0, 'rejected_matches': 0, 'rejection_rate': 0.0}
+
+
+def test_merge_topk_peers_pointer_table(eng):
+    """The peer-memory form of K3 (lists addressed through a device pointer table, as over NVLink)
+    equals the gathered form on the same keys; here all "peers" live on this GPU."""
+    import torch
+    rng = np.random.default_rng(5)
+    for G, Q, k in ((2, 1000, 25), (8, 333, 25), (5, 64, 64), (148, 3, 25)):
+        sc = rng.uniform(-1, 1, size=(G, Q, k)).astype(np.float32)
+        ix = (rng.permutation(G * Q * k).reshape(G, Q, k) % (2 ** 31 - 1)).astype(np.int64)
+        ix[rng.uniform(size=ix.shape) > 0.8] = -1
+        keys = torch.from_numpy(O.pack_keys(sc, ix)).cuda()
+        parts = [keys[g].clone() for g in range(G)]                      # separately allocated buffers
+        table = torch.tensor([p.data_ptr() for p in parts], dtype=torch.int64, device="cuda")
+        fl = torch.from_numpy(rng.integers(1, 5, size=2 ** 20).astype(np.int32)).cuda()
+        qf = torch.from_numpy(rng.integers(1, 5, size=Q).astype(np.int32)).cuda()
+        a = eng.merge_topk(keys, k, q_floor=qf, db_floor_all=None, max_floor_diff=-1, want_keys=True)
+        b = eng.merge_topk_peers(table.data_ptr(), G, Q, k, q_floor=qf, db_floor_all=None, max_floor_diff=-1, want_keys=True)
+        torch.cuda.synchronize()
+        assert torch.equal(a.keys, b.keys) and torch.equal(a.idx, b.idx) and torch.equal(a.scores, b.scores)
+        assert torch.equal(a.count, b.count) and torch.equal(a.valid, b.valid)
+        del fl
+
+
 def test_similarity_matrix_dense(eng):
     """Dense-output mode of the fused kernel vs numpy (place_recognition.py:171, :190), ragged shapes,
     and the mirrored _compute_similarity / compute_all_pairwise_similarities."""
