@@ -103,7 +103,9 @@ Schedule make_schedule(int64_t Q, int64_t N, int d_pad, int cta_group, int sm_co
   const int64_t chunk_bytes = stream_rows * sc.pace_kb * BK * 2;
   int window = static_cast<int>(std::min<int64_t>(64, std::max<int64_t>(2, window_bytes / std::max<int64_t>(chunk_bytes, 1))));
   const int64_t run_chunks = static_cast<int64_t>(std::max(sc.len_main, sc.len_last)) * sc.cpt;
-  sc.sync_window = (window_bytes > 0 && run_chunks > 4 * window) ? window : 0;
+  // one query block per super-row that stays in L2: the units share nothing that streams, nothing to pace
+  const bool shares = sc.rm > 1 || !sc.a_resident;
+  sc.sync_window = (window_bytes > 0 && shares && run_chunks > 4 * window) ? window : 0;
   // test knob: force a window of that many chunks wherever a run is longer than the window
   const int forced = static_cast<int>(env_long("SEMGATE_WINDOW_CHUNKS", 0));
   if (forced > 0) sc.sync_window = run_chunks > forced ? forced : 0;

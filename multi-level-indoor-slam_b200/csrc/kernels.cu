@@ -419,6 +419,15 @@ compact_scatter_kernel(const float* __restrict__ scores, const int32_t* __restri
     const int c = cnts[r];
     int64_t o = base + offs[r];
     const int64_t src = (row0 + r) * k;
+    if (!valid_only) {                        // everything is emitted: straight coalesced copy
+      for (int i = lane; i < c; i += 32) {
+        out_q[o + i] = static_cast<int32_t>(row0 + r);
+        out_m[o + i] = idx[src + i];
+        out_s[o + i] = scores[src + i];
+        out_v[o + i] = valid[src + i];
+      }
+      continue;
+    }
     for (int i0 = 0; i0 < c; i0 += 32) {
       const int i = i0 + lane;
       const bool live = i < c;
