@@ -145,6 +145,46 @@ def test_gated_topk_vs_oracle(eng, shape, cg):
     parity.check_decisions_exact(c, ts[:N], fl32[:N], gap, 0, q_ts=ts[:Q], q_floors=fl32[:Q])
 
 
+@pytest.mark.parametrize("seed", list(range(16)))
+def test_randomised_configurations_vs_oracle(eng, seed):
+    """Seeded random draws over everything the interface lets a caller vary (shapes incl. ragged and tiny,
+    k, threshold incl. none, window incl. 0 / none, strict / non-strict / no gate, flag / mask mode, None
+    labels, unsorted timestamps, tile shape 1 / 2 / 4 CTAs): exact candidate sets against the oracle's
+    model of the GPU arithmetic, bit-exact decisions on every returned pair."""
+    from semgate import synthetic
+    rng = np.random.default_rng(1000 + seed)
+    Q = int(rng.choice([1, 3, 127, 129, 300, 641, 1100]))
+    N = int(rng.choice([1, 2, 255, 257, 900, 2500, 6000]))
+    D = int(rng.choice([17, 64, 100, 192, 500, 1031]))
+    k = int(rng.choice([1, 5, 10, 25, 33, 64]))
+    thr = float(rng.choice([-np.inf, 0.2, 0.45, 0.6]))
+    gap = float(rng.choice([0.0, 2.5, 10.0]))
+    use_ts = bool(rng.integers(0, 4))           # 1 in 4: no timestamps at all (query(timestamp=None))
+    mfd = int(rng.choice([-1, 0, 1]))
+    mode = int(rng.integers(0, 2))
+    cg = int(rng.choice([1, 2, 4]))
+    n = max(Q, N)
+    desc, ts, fl = synthetic.make_case(n, D, int(rng.integers(2, 6)), seed=seed)
+    fl32 = fl.astype(np.int32)
+    fl32[rng.uniform(size=n) < 0.05] = O.FLOOR_NONE
+    if rng.integers(0, 2):
+        ts = ts[rng.permutation(n)]             # arbitrary (unsorted) stamps
+    qts, dts = (ts[:Q], ts[:N]) if use_ts else (None, None)
+    got = run_gpu(eng, desc[:Q], desc[:N], k, thr, gap, qts, dts, fl32[:Q], fl32[:N], mfd=mfd, mode=mode, cg=cg)
+    check_padded(got, k)
+    ref = O.gated_topk(desc[:Q], desc[:N], qts, dts, fl32[:Q], fl32[:N], k=k, threshold=thr, min_time_gap=gap,
+                       max_floor_diff=mfd, gate_mode=O.GATE_MASK if mode else O.GATE_FLAG, bf16=True)
+    # one bf16 rounding flip of a normalised element (row norm summed in a different order) moves a score by up
+    # to ~ 2^-9 * x_i * y_i, which grows as the descriptor gets shorter: 4.9e-4 at d = 17
+    parity.compare_candidates(O.compact(ref), O.compact(got), k, thr, tol=max(BF16_MODEL_TOL, 8e-3 / D))
+    c = O.compact(got)
+    if len(c["query_idx"]):
+        if use_ts:
+            parity.check_decisions_exact(c, ts[:N], fl32[:N], gap, mfd, q_ts=ts[:Q], q_floors=fl32[:Q])
+        if mode == 1 and mfd >= 0:
+            assert c["is_valid"].all()
+
+
 @pytest.mark.parametrize("cg", [1, 2, 4])
 def test_mask_mode_and_nonstrict(eng, cg):
     from semgate import synthetic
