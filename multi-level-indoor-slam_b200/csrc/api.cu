@@ -3,6 +3,7 @@
 #include "launch.h"
 
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -100,6 +101,12 @@ int check_params(const semgate_topk_params* p) {
 
 // CTA-pair tiles (cta_group::2) halve the database-tile traffic per SM and win a few percent on
 // large sweeps; with few query rows half of every 256-row pair tile would be padding.
+// A few query rows against a whole database is a GEMV: the bandwidth-built streaming kernel (K6) takes it
+// unless the caller pinned a tensor-core tile shape.
+bool use_stream_path(semgate_handle_t h, const semgate_topk_params* p, int64_t Q, int32_t d_pad) {
+  return p->cta_group == 0 && h->cta_group == 0 && stream_query_fits(Q, d_pad, p->k);
+}
+
 int resolve_cg(semgate_handle_t h, const semgate_topk_params* p, int64_t Q) {
   const int want = p->cta_group ? p->cta_group : h->cta_group;
   if (want == 1 || want == 2 || want == 4) return want;
@@ -212,7 +219,9 @@ size_t semgate_topk_workspace_bytes(semgate_handle_t h, int64_t Q, int64_t N, in
   if (!h || !p || Q <= 0 || N <= 0 || p->k < 1 || p->k > SEMGATE_MAX_K) return 256;
   const int cg = resolve_cg(h, p, Q);
   Schedule sc = make_schedule(Q, N, d_pad, cg, h->sm_count);
-  return align256(topk_workspace_bytes(sc, cg, p->k));
+  size_t need = topk_workspace_bytes(sc, cg, p->k);
+  if (use_stream_path(h, p, Q, d_pad)) need = std::max(need, stream_query_workspace_bytes(Q, p->k, h->sm_count));
+  return align256(need);
 }
 
 int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const void* db_bf16, int64_t N, int32_t d_pad,
@@ -251,8 +260,9 @@ int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const 
   if ((reinterpret_cast<uintptr_t>(q_bf16) & 15) || (reinterpret_cast<uintptr_t>(db_bf16) & 15))
     return fail(SEMGATE_EINVAL, "gated_topk: descriptor matrices must be 16-byte aligned");
 
+  const bool gemv = use_stream_path(h, p, Q, d_pad);
   Schedule sc = make_schedule(Q, N, d_pad, cg, h->sm_count);
-  const size_t need = topk_workspace_bytes(sc, cg, k);
+  const size_t need = gemv ? stream_query_workspace_bytes(Q, k, h->sm_count) : topk_workspace_bytes(sc, cg, k);
   if (!workspace || workspace_bytes < need)
     return fail(SEMGATE_ENOMEM, "gated_topk: workspace %zu < required %zu bytes", workspace_bytes, need);
 
@@ -279,14 +289,24 @@ int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const 
     h->prof_used += 2;
     CUDA_TRY(cudaEventRecord(ev0, st));
   }
-  RC_TRY(launch_gated_topk(a, sc, static_cast<uint64_t*>(workspace), st, &launches), "gated_topk launch");
+  if (gemv) {
+    RC_TRY(launch_stream_query(a, static_cast<uint64_t*>(workspace), st), "stream_query launch");
+    launches = 1;
+  } else {
+    RC_TRY(launch_gated_topk(a, sc, static_cast<uint64_t*>(workspace), st, &launches), "gated_topk launch");
+  }
   if (ev1) CUDA_TRY(cudaEventRecord(ev1, st));
   h->launches += launches;
 
   m.keys_in = static_cast<const uint64_t*>(workspace);
-  m.row_stride = 0;   // per-row offsets follow the schedule (n_lists < 0)
   m.list_stride = k;
-  m.n_lists = -1; m.sc = sc; m.rows_per_mblock = 128 * cg;   // cg = CTAs (128-row query blocks) per schedule unit
+  if (gemv) {            // [Q][blocks][k]
+    m.n_lists = stream_query_lists(h->sm_count);
+    m.row_stride = static_cast<int64_t>(m.n_lists) * k;
+  } else {               // per-row offsets follow the schedule
+    m.row_stride = 0;
+    m.n_lists = -1; m.sc = sc; m.rows_per_mblock = 128 * cg;   // cg = CTAs (128-row query blocks) per schedule unit
+  }
   RC_TRY(launch_merge_topk(m, st), "merge_topk launch");
   h->launches += 1;
   return 0;

@@ -51,6 +51,38 @@ __host__ __device__ __forceinline__ bool time_excluded(double t_db, double t_q, 
   return d < gap;
 }
 
+// ---- running top-k list of one query row: k unsorted keys (shared memory), admission bound = threshold
+// until the list is full, then its smallest key's score; insertion replaces the minimum and rescans.
+struct RowList {
+  uint64_t* keys;     // this thread's row in shared memory
+  int cnt;
+  int min_pos;
+  uint64_t min_key;
+  float f;            // current admission bound on the score
+
+  __device__ __forceinline__ void reset(float thr) { cnt = 0; min_pos = 0; min_key = 0; f = thr; }
+
+  __device__ __forceinline__ void rescan(int k) {
+    uint64_t mk = keys[0];
+    int mp = 0;
+    for (int i = 1; i < k; ++i) {
+      uint64_t v = keys[i];
+      if (v < mk) { mk = v; mp = i; }
+    }
+    min_key = mk; min_pos = mp; f = key_score(mk);
+  }
+
+  __device__ __forceinline__ void insert(uint64_t key, int k) {
+    if (cnt < k) {
+      keys[cnt++] = key;
+      if (cnt == k) rescan(k);
+    } else if (key > min_key) {
+      keys[min_pos] = key;
+      rescan(k);
+    }
+  }
+};
+
 // ---- tile schedule of the fused kernel.
 // The output is tiled BM x BN.  Query blocks ("m-blocks") are processed in
 // super-rows of `rm` consecutive m-blocks; inside a super-row every m-block's

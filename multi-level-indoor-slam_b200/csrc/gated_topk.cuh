@@ -63,36 +63,6 @@ struct TopkParams {
   Schedule sc;
 };
 
-struct RowList {
-  uint64_t* keys;     // this thread's row in shared memory
-  int cnt;
-  int min_pos;
-  uint64_t min_key;
-  float f;            // current admission bound on the score
-
-  __device__ __forceinline__ void reset(float thr) { cnt = 0; min_pos = 0; min_key = 0; f = thr; }
-
-  __device__ __forceinline__ void rescan(int k) {
-    uint64_t mk = keys[0];
-    int mp = 0;
-    for (int i = 1; i < k; ++i) {
-      uint64_t v = keys[i];
-      if (v < mk) { mk = v; mp = i; }
-    }
-    min_key = mk; min_pos = mp; f = key_score(mk);
-  }
-
-  __device__ __forceinline__ void insert(uint64_t key, int k) {
-    if (cnt < k) {
-      keys[cnt++] = key;
-      if (cnt == k) rescan(k);
-    } else if (key > min_key) {
-      keys[min_pos] = key;
-      rescan(k);
-    }
-  }
-};
-
 // v[i] for a lane-varying i without a local-memory array: five levels of selects
 __device__ __forceinline__ uint32_t pick32(const uint32_t (&v)[32], int i) {
   uint32_t a[16], b[8], c[4], d[2];

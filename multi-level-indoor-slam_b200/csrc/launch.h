@@ -33,6 +33,13 @@ size_t topk_workspace_bytes(const Schedule& sc, int cta_group, int k);    // lis
 int launch_gated_topk(const TopkLaunch& a, const Schedule& sc, uint64_t* partial, cudaStream_t st,
                       int* launches);
 
+// K6: streaming query (<= kStreamMaxQ query rows): bandwidth-built GEMV form of K2, one k-list per (query, block)
+constexpr int kStreamMaxQ = 4;
+bool stream_query_fits(int64_t Q, int d_pad, int k);
+size_t stream_query_workspace_bytes(int64_t Q, int k, int sm_count);
+int stream_query_lists(int sm_count);
+int launch_stream_query(const TopkLaunch& a, uint64_t* partial /*[Q][lists][k]*/, cudaStream_t st);
+
 // K1
 int launch_normalize_cast(const float* x, int64_t n, int d, int64_t ld, void* out_bf16, int d_pad, cudaStream_t st);
 

@@ -185,6 +185,37 @@ def test_randomised_configurations_vs_oracle(eng, seed):
             assert c["is_valid"].all()
 
 
+@pytest.mark.parametrize("Q", [1, 2, 3, 4])
+def test_streaming_query_kernel(eng, Q):
+    """K6 (<= 4 query rows, cta_group auto): the bandwidth-built GEMV form must give what the fused
+    tensor-core kernel and the oracle give — every gate / window / threshold / top-k rule, ragged row
+    splits, shard offsets, k up to 64."""
+    import torch
+    from semgate import _native, synthetic
+    for N, D, k, thr, gap, mode, mfd in ((1, 64, 5, -np.inf, 10.0, 0, 0), (37, 100, 25, 0.2, 0.0, 0, -1),
+                                         (5000, 512, 25, 0.45, 10.0, 0, 0), (20011, 4096, 64, 0.3, 3.0, 1, 1),
+                                         (3000, 8448, 10, 0.4, 10.0, 1, 0)):
+        n = max(N, Q)
+        desc, ts, fl = synthetic.make_case(n, D, 4, seed=N + Q)
+        fl32 = fl.astype(np.int32)
+        fl32[::11] = O.FLOOR_NONE
+        # queries: perturbed copies of database rows spread over the database (so every block range has hits)
+        qrows = (np.arange(Q) * max(1, N // max(Q, 1)) + N // 3) % N
+        qd = desc[qrows] + 0.05 * np.random.default_rng(Q).standard_normal((Q, D)).astype(np.float32)
+        qts = ts[qrows] + 1.0
+        qfl = fl32[qrows]
+        args = (qd, desc[:N], k, thr, gap, qts, ts[:N], qfl, fl32[:N])
+        got = run_gpu(eng, *args, mfd=mfd, mode=mode, cg=0, offset=7)          # auto -> K6
+        check_padded(got, k)
+        k2 = run_gpu(eng, *args, mfd=mfd, mode=mode, cg=1, offset=7)           # pinned tile shape -> K2
+        ref = O.gated_topk(qd, desc[:N], qts, ts[:N], qfl, fl32[:N], k=k, threshold=thr, min_time_gap=gap,
+                           max_floor_diff=mfd, gate_mode=O.GATE_MASK if mode else O.GATE_FLAG, bf16=True, db_index_offset=7)
+        tol = max(BF16_MODEL_TOL, 8e-3 / D)
+        parity.compare_candidates(O.compact(ref), O.compact(got), k, thr, tol=tol)
+        parity.compare_candidates(O.compact(k2), O.compact(got), k, thr, tol=5e-5)   # same operands; CUDA-core fp32 FMA chain vs tensor-core accumulation
+        assert np.array_equal(got["keys"], O.pack_keys(got["scores"], got["idx"]))
+
+
 @pytest.mark.parametrize("cg", [1, 2, 4])
 def test_mask_mode_and_nonstrict(eng, cg):
     from semgate import synthetic

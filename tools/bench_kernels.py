@@ -53,7 +53,7 @@ def main():
         prm = _native.make_params(k=25)
         best, med = timeit(lambda: eng.gated_topk(q, db, prm), iters=20)
         byts = 2 * n * dp
-        out["kernels"].append({"kernel": "K2+K3, single query (query())", "shape": [1, n, d], "ms": med,
+        out["kernels"].append({"kernel": "K6+K3, streaming single query (query())", "shape": [1, n, d], "ms": med,
                                "algorithmic_bytes": byts, "gbs": byts / med / 1e6, "frac_of_hbm_peak": byts / med / 1e6 / peak,
                                "queries_per_s": 1e3 / med})
         del db
@@ -67,6 +67,12 @@ def main():
     byts = 9 * M
     out["kernels"].append({"kernel": "gate_candidates", "shape": [M], "ms": med, "algorithmic_bytes": byts,
                            "gbs": byts / med / 1e6, "frac_of_hbm_peak": byts / med / 1e6 / peak, "candidates_per_s": M / med * 1e3})
+    # the order K4 emits: query index ascending, k = 25 matches each (label gathers of the query side coalesce)
+    qi = torch.arange(M // 25, device="cuda", dtype=torch.int32).repeat_interleave(25) % nl
+    best, med = timeit(lambda: eng.gate_candidates(fl, qi, mi, 0))
+    out["kernels"].append({"kernel": "gate_candidates (query-sorted pairs, as compacted)", "shape": [M], "ms": med,
+                           "algorithmic_bytes": byts, "gbs": byts / med / 1e6, "frac_of_hbm_peak": byts / med / 1e6 / peak,
+                           "candidates_per_s": M / med * 1e3})
     del fl, qi, mi
 
     # K3 + K4 on a 1M-row result
