@@ -215,6 +215,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit_cg1(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// cta_group::1 commit that arrives on the barrier at this offset in every CTA of `mask`
+// (a stage that peers multicast into is free only when every consumer is done with it).
+__device__ __forceinline__ void umma_commit_cg1_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(mask) : "memory");
+}
 // cta_group::2: arrive on the barrier at this offset in every CTA of `mask`.
 __device__ __forceinline__ void umma_commit_cg2_mc(uint32_t bar, uint16_t mask) {
   asm volatile(

@@ -779,6 +779,43 @@ def test_rerank_golden(path):
     assert vpr.rerank_candidates(0, [(1, 0.5), (2, 0.9)], top_k=5) == [(1, 0.5), (2, 0.9)]
 
 
+def test_rerank_cluster_lockstep_cases(eng, monkeypatch):
+    """K5 runs two consecutive pairs per 2-CTA cluster in lock-step: same query (multicast operand),
+    different queries (private operands), one or both pairs without cached features (the idle CTA only
+    keeps the stage ring turning), an odd tail; results equal the single-CTA form bit for bit and the oracle."""
+    import torch
+    from semgate import synthetic
+    n, P, D = 12, 200, 128
+    feats, _ = synthetic.make_local_features(n, P, D, seed=4)
+    fb = eng.normalize_cast(_t(feats.reshape(n * P, D))).view(n, P, -1)
+    pairs = [(0, 1), (0, 2),        # shared query
+             (1, 3), (2, 3),        # different queries
+             (5, -1), (5, 6),       # first pair of the group invalid
+             (4, 7), (99, 7),       # second invalid (index beyond the store)
+             (-1, 2), (-1, 3),      # both invalid: the group is skipped
+             (8, 9), (8, 10), (8, 11),   # odd tail: last group has one pair
+             ]
+    q = np.array([a for a, _ in pairs], np.int32)
+    m = np.array([b for _, b in pairs], np.int32)
+    g = np.linspace(0.1, 0.9, len(pairs)).astype(np.float32)
+    outs = {}
+    for cl in ("2", "1"):
+        monkeypatch.setenv("SEMGATE_RERANK_CLUSTER", cl)
+        cross, comb = eng.rerank_scores(fb, _t(q), _t(m), _t(g))
+        torch.cuda.synchronize()
+        outs[cl] = (cross.cpu().numpy(), comb.cpu().numpy())
+    monkeypatch.delenv("SEMGATE_RERANK_CLUSTER")
+    assert np.array_equal(outs["2"][0], outs["1"][0], equal_nan=True) and np.array_equal(outs["2"][1], outs["1"][1])
+    cross, comb = outs["2"]
+    for i, (a, b) in enumerate(pairs):
+        if 0 <= a < n and 0 <= b < n:
+            want = float(O.cross_correlation_score(feats[a], feats[b], bf16=True))
+            assert abs(cross[i] - want) <= BF16_MODEL_TOL, (i, a, b, cross[i], want)
+            assert abs(comb[i] - (0.5 * g[i] + 0.5 * want)) <= BF16_MODEL_TOL
+        else:
+            assert np.isnan(cross[i]) and comb[i] == g[i]
+
+
 def test_rerank_batch_dinov2_shape(eng):
     """529 patches x 768-d (DINOv2 at 322x322): a batch of pairs against the oracle, and the batched
     per-query selection against per-query Python sorting."""
