@@ -155,7 +155,8 @@ static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int d_pad, 
 
 static size_t smem_bytes_for(int cg, int stages, int kstride) {
   const size_t stage = A_STAGE_BYTES + static_cast<size_t>(BN / std::min(cg, 2)) * BK * 2;
-  return 1024 /*realign slack*/ + stages * stage + static_cast<size_t>(BM) * kstride * 8 + 256 /*barriers + tmem slot*/;
+  return 1024 /*realign slack*/ + stages * stage + static_cast<size_t>(BM) * kstride * 8 +
+         2 * BN * (sizeof(double) + sizeof(int32_t)) /*per-tile timestamps + labels*/ + 256 /*barriers + tmem slot*/;
 }
 
 int launch_gated_topk(const TopkLaunch& a, const Schedule& sc, uint64_t* partial, cudaStream_t st, int* launches) {

@@ -97,7 +97,11 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + static_cast<size_t>(stages) * A_STAGE_BYTES;
   uint64_t* lists = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * STAGE_BYTES);
-  uint64_t* bars = lists + static_cast<size_t>(BM) * p.kstride;
+  // per-tile copies of the database timestamps / floor labels (one buffer per accumulator): a hit reads
+  // them from shared memory instead of paying a dependent global load per hit column
+  double* ts_s = reinterpret_cast<double*>(lists + static_cast<size_t>(BM) * p.kstride);
+  int32_t* fl_s = reinterpret_cast<int32_t*>(ts_s + 2 * BN);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(fl_s + 2 * BN);
   // barrier slots: full[kMaxStages] empty[kMaxStages] tmem_full[2] tmem_empty[2]
   const uint32_t bar_full = ptx::smem_u32(bars);
   const uint32_t bar_empty = bar_full + 8 * kMaxStages;
@@ -268,6 +272,7 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     // ===================================================== epilogue: gate + threshold + running top-k
     const int quad = warp & 3;
     const int row_in_tile = quad * 32 + lane;
+    const int et = (warp - 2) * 32 + lane;            // 0..127 among the epilogue threads
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     RowList L;
     L.keys = lists + static_cast<size_t>(row_in_tile) * p.kstride;
@@ -290,10 +295,22 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 
       for (int nt = run.nt0; nt < run.nt1; ++nt, ++it) {
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        const int col_base = nt * BN;
+        if (use_time || mask_mode) {
+          // stage this tile's timestamps / labels while its MMAs run.  One barrier per tile is enough:
+          // whoever overwrites buffer `acc` here has passed the previous tile's barrier, which every
+          // epilogue warp only reaches after it finished the tile before that (the buffer's last reader).
+#pragma unroll
+          for (int j = et; j < BN; j += 128) {
+            const int col = col_base + j;
+            if (use_time) ts_s[acc * BN + j] = col < p.N ? __ldg(p.db_ts + col) : 0.0;
+            if (mask_mode) fl_s[acc * BN + j] = col < p.N ? __ldg(p.db_floor + col) : kFloorNone;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
         ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase);
         ptx::tc_fence_after();
         const uint32_t t_acc = t_lane + acc * BN;
-        const int col_base = nt * BN;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t v[32];
@@ -337,8 +354,8 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 const int col = col_base + c * 32 + i;      // local database row
                 if (col < p.N) {                            // TMA zero-fill beyond N must not score
                   bool ok = true;
-                  if (use_time) ok = !time_excluded(__ldg(p.db_ts + col), tq, p.gap);
-                  if (ok && mask_mode) ok = floor_ok(qf, __ldg(p.db_floor + col), p.max_floor_diff);
+                  if (use_time) ok = !time_excluded(ts_s[acc * BN + c * 32 + i], tq, p.gap);
+                  if (ok && mask_mode) ok = floor_ok(qf, fl_s[acc * BN + c * 32 + i], p.max_floor_diff);
                   if (ok) L.insert(pack_key(s, static_cast<uint32_t>(col) + p.db_index_offset), k);
                 }
               }

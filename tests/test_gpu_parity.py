@@ -736,6 +736,87 @@ def test_full_size_properties_c2(eng, cg):
     assert np.array_equal(flat["match_idx"], c["match_idx"]) and np.array_equal(flat["is_valid"], c["is_valid"])
 
 
+def _sampled_rows_reference(xq_bf16, xdb_bf16, rows, ts_q, ts_db, fl_q, fl_db, k, thr, gap):
+    """fp32 torch reference of the same op on a sample of query rows (the full Q x N matrix of the
+    large configs cannot exist): similarities of the bf16 operands accumulated in fp32, window in fp64,
+    top-k, threshold, floor flag — the order of place_recognition.py:882-899."""
+    import torch
+    out = {"query_idx": [], "match_idx": [], "similarity": [], "is_valid": []}
+    r = torch.from_numpy(rows).cuda()
+    q = xq_bf16[r].float()
+    sims = torch.empty((len(rows), xdb_bf16.shape[0]), dtype=torch.float32, device="cuda")
+    step = 65536
+    for s0 in range(0, xdb_bf16.shape[0], step):
+        sims[:, s0:s0 + step] = q @ xdb_bf16[s0:s0 + step].float().T
+    tq = torch.from_numpy(ts_q[rows]).cuda()
+    tdb = torch.from_numpy(ts_db).cuda()
+    sims[(tdb[None, :] - tq[:, None]).abs() < gap] = -float("inf")
+    top_s, top_i = torch.topk(sims, k, dim=1)
+    top_s, top_i = top_s.cpu().numpy(), top_i.cpu().numpy()
+    for a, row in enumerate(rows):
+        for s, j in zip(top_s[a], top_i[a]):
+            if np.isfinite(s) and s >= np.float32(thr):
+                out["query_idx"].append(int(row)); out["match_idx"].append(int(j)); out["similarity"].append(float(s))
+                out["is_valid"].append(bool(O.floor_ok(fl_q[row], fl_db[j], 0)))
+    return {key: np.asarray(v) for key, v in out.items()}
+
+
+@pytest.mark.parametrize("cfg", ["c3", "c5"])
+def test_full_size_properties_large_configs(eng, cfg):
+    """BASELINE configs 3 (10k x 100k x 8448-d) and 5 (1M x 1M x 4096-d, 16 floors) at full size: structural
+    invariants of every list, bit-exact decisions on every returned pair, determinism, and 64 sampled query
+    rows against an fp32 torch reference of the same op (scores within the bf16-model tolerance, sets equal up
+    to the boundary rule)."""
+    import torch
+    from semgate import _native, synthetic
+    Q, N, D, F = (10_000, 100_000, 8448, 4) if cfg == "c3" else (1_000_000, 1_000_000, 4096, 16)
+    k, thr, gap = 25, 0.5, 10.0
+    dp = _native.pad_dim(D)
+    xb = torch.empty((N, dp), dtype=torch.bfloat16, device="cuda")
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    places = max(8, N // 20)
+    anchors = torch.randn((places, D), generator=g, device="cuda")
+    step = max(1024, (1 << 27) // D)
+    for s0 in range(0, N, step):
+        e0 = min(N, s0 + step)
+        pid = torch.randint(0, places, (e0 - s0,), generator=g, device="cuda")
+        eng.normalize_cast(anchors[pid] + 0.6 * torch.randn((e0 - s0, D), generator=g, device="cuda"), out=xb[s0:e0])
+    del anchors
+    ts = synthetic.make_timestamps(N)
+    fl = synthetic.make_floors(N, F).astype(np.int32)
+    tts, tfl = _t(ts), _t(fl)
+    p = _native.make_params(k=k, similarity_threshold=thr, min_time_gap=gap, max_floor_diff=0)
+    qb, qts, qfl = xb[:Q], tts[:Q].contiguous(), tfl[:Q].contiguous()
+    r = eng.gated_topk(qb, xb, p, q_ts=qts, db_ts=tts, q_floor=qfl, db_floor=tfl, want_keys=True)
+    torch.cuda.synchronize()
+    if cfg == "c3":
+        r2 = eng.gated_topk(qb, xb, p, q_ts=qts, db_ts=tts, q_floor=qfl, db_floor=tfl, want_keys=True)
+        assert torch.equal(r.keys, r2.keys), "sweep must be deterministic"
+    # structure, on the device (1M x 25 lists)
+    pos = torch.arange(k, device="cuda")[None, :]
+    filled = pos < r.count[:, None]
+    assert bool(((r.idx >= 0) == filled).all()) and bool((r.scores[filled] >= thr).all())
+    assert bool((r.scores[:, 1:][filled[:, 1:]] <= r.scores[:, :-1][filled[:, 1:]]).all()), "scores not descending"
+    assert bool((r.idx[filled] < N).all()) and bool((r.valid[~filled] == 0).all())
+    # decisions, bit-exact, on every returned pair
+    qi = torch.arange(Q, device="cuda")[:, None].expand(Q, k)[filled]
+    mi = r.idx[filled].long()
+    assert not bool(((tts[mi] - tts[qi]).abs() < gap).any()), "a returned pair lies inside the exclusion window"
+    assert bool(((tfl[qi] == tfl[mi]) == (r.valid[filled] != 0)).all()), "floor-gate bits differ"
+    total = int(r.count.sum().item())
+    assert total > Q                                   # the synthetic places give every keyframe revisits
+    # sampled rows against the fp32 torch reference
+    rows = np.sort(np.random.default_rng(3).choice(Q, 64, replace=False))
+    ref = _sampled_rows_reference(qb, xb, rows, ts[:Q], ts, fl[:Q], fl, k, thr, gap)
+    rr = torch.from_numpy(rows).cuda()
+    sub = dict(scores=r.scores[rr].cpu().numpy(), idx=r.idx[rr].cpu().numpy().astype(np.int64),
+               valid=r.valid[rr].cpu().numpy().astype(bool), count=r.count[rr].cpu().numpy())
+    got = O.compact(sub)
+    got["query_idx"] = rows[got["query_idx"]]
+    rep = parity.compare_candidates(ref, got, k, thr, tol=BF16_MODEL_TOL)
+    assert rep["max_score_err"] <= BF16_MODEL_TOL
+
+
 # --------------------------------------------------------------------------- K5: CricaVPR cross-correlation re-rank
 RER = sorted(glob.glob(os.path.join(GOLDEN, "rerank_*.npz")))
 
