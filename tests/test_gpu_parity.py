@@ -502,6 +502,28 @@ def test_accumulate_over_database_slices(eng):
     assert torch.equal(m.idx, whole.idx) and torch.equal(m.scores, whole.scores) and torch.equal(m.valid, whole.valid)
 
 
+def test_accumulate_streaming_queries(eng):
+    """`accumulate` through the streaming kernel (2 query rows) and the block-per-row merge with a seeded list."""
+    import torch
+    from semgate import _native, synthetic
+    desc, ts, fl = synthetic.make_case(9000, 256, 3, seed=21)
+    fl32 = fl.astype(np.int32)
+    xb = eng.normalize_cast(_t(desc))
+    tts, tfl = _t(ts), _t(fl32)
+    q, qts, qfl = xb[100:102].contiguous(), tts[100:102].contiguous(), tfl[100:102].contiguous()
+    kw = dict(k=25, similarity_threshold=0.2, min_time_gap=5.0, max_floor_diff=0)
+    whole = eng.gated_topk(q, xb, _native.make_params(**kw), q_ts=qts, db_ts=tts, q_floor=qfl, db_floor=tfl, want_keys=True)
+    keys = None
+    for lo, hi in ((0, 4000), (4000, 4001), (4001, 9000)):
+        p = _native.make_params(db_index_offset=lo, accumulate=keys is not None, **kw)
+        r = eng.gated_topk(q, xb[lo:hi], p, q_ts=qts, db_ts=tts[lo:hi].contiguous(), q_floor=qfl,
+                           db_floor=tfl[lo:hi].contiguous(), want_keys=True, want_lists=False, keys=keys)
+        keys = r.keys
+    torch.cuda.synchronize()
+    assert int(whole.count.sum()) > 10
+    assert torch.equal(keys, whole.keys)
+
+
 def test_host_abi_chunked_pipeline(eng):
     """Large enough that semgate_find_loop_closures_host pipelines H2D chunks against partial sweeps."""
     from semgate import _native, synthetic
