@@ -153,6 +153,17 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU arm
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its ranks; the CPU arm is meant to use every host core."""
+    n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)          # process-wide, stays in effect
+    except Exception:
+        pass
+    return n
+
+
 def cpu_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -194,6 +205,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_all_host_threads()
     desc, ts, fl = cpu_inputs(N_DB_PER_GPU)
     budget = 150.0 / max(args.steps + args.warmup, 1)
     rows, _ = calibrate_rows(desc, ts, fl, min(8.0, budget))
@@ -436,6 +448,7 @@ def run_ours(args):
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample)
     cpu = None
     if world == 1 and not args.no_cpu:
+        use_all_host_threads()
         desc = q_host.numpy()
         rows, _ = calibrate_rows(desc, ts_host, fl_host, 10.0)
         dt = cpu_sweep(desc, ts_host, fl_host, rows)
