@@ -56,7 +56,9 @@ typedef struct semgate_topk_params {
   int32_t max_floor_diff;       /* -1 gating off; 0 strict; 1 non-strict */
   int32_t gate_mode;            /* SEMGATE_GATE_FLAG | SEMGATE_GATE_MASK */
   uint32_t db_index_offset;     /* global index of database row 0 (row-sharded multi-GPU) */
-  int32_t cta_group;            /* 0 = handle default (auto by size); 1 = single-CTA tiles; 2 = CTA-pair tiles */
+  int32_t cta_group;            /* 0 = handle default (auto: <= 4 query rows -> streaming kernel, Q >= 4096 -> CTA
+                                   pairs, else single CTAs); 1 = single-CTA tiles; 2 = CTA-pair tiles (cta_group::2);
+                                   4 = clusters of two pairs sharing a multicast database tile */
   int32_t accumulate;           /* 1: out_keys already holds each query's list over OTHER database rows (earlier
                                    sweeps of disjoint slices); merge this sweep into it in place */
 } semgate_topk_params;
@@ -68,7 +70,7 @@ const char* semgate_last_error(void);
 int semgate_create(semgate_handle_t* out, int device);
 int semgate_destroy(semgate_handle_t h);
 int semgate_device_info(semgate_handle_t h, int* sm_count, int* cc_major, int* cc_minor);
-/* options: "cta_group" (0 auto | 1 | 2); "profile" (0|1): bracket every fused-kernel launch with CUDA
+/* options: "cta_group" (0 auto | 1 | 2 | 4); "profile" (0|1): bracket every fused-kernel launch with CUDA
  * events on its own stream */
 int semgate_set_option(semgate_handle_t h, const char* name, int64_t value);
 /* sum of the fused kernel's (K2) device durations since the last read, and how many
