@@ -179,14 +179,18 @@ int launch_normalize_cast(const float* x, int64_t n, int d, int64_t ld, void* ou
 // (distinct database rows), 0 = empty.
 constexpr int kMergeWarps = 8;
 
-// ROWBLOCK = false: one warp per row.  ROWBLOCK = true (few rows, many lists: a single streaming
-// query leaves one list per SM): one block per row, every warp merges a slice of the row's keys and
-// warp 0 merges the eight intermediate lists from shared memory.
+// ROWBLOCK = false: one warp per row (8 rows per block).  ROWBLOCK = true (few rows, many lists: a
+// streaming query leaves one list per block of K6): one 32-warp block per row, a three-level tree —
+// every warp merges a slice of the row's keys, warps 0-3 merge eight of those lists each, warp 0
+// merges the last four — so the dependent chain is 2 + 1 + 1 batches instead of one warp's dozens.
+constexpr int kRowBlockWarps = 32;
+
 template <int P, bool ROWBLOCK>
-__global__ void __launch_bounds__(kMergeWarps * 32)
+__global__ void __launch_bounds__(ROWBLOCK ? kRowBlockWarps * 32 : kMergeWarps * 32)
 merge_topk_kernel(const MergeLaunch a) {
   static_assert(P == 4 || P == 8, "keys per lane");
-  __shared__ uint64_t stage[ROWBLOCK ? kMergeWarps * 64 : 1];
+  __shared__ uint64_t stage[ROWBLOCK ? kRowBlockWarps * kMaxK : 1];
+  __shared__ uint64_t stage2[ROWBLOCK ? 4 * kMaxK : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t row = ROWBLOCK ? static_cast<int64_t>(blockIdx.x) : static_cast<int64_t>(blockIdx.x) * kMergeWarps + warp;
   if (row >= a.Q) return;
@@ -215,15 +219,22 @@ merge_topk_kernel(const MergeLaunch a) {
     else
       merge_range<P>(base, 0, total, k, a.list_stride, k, lane, run, have_run, a.list_ptrs, row * k);
   } else {
-    const int per = (total + kMergeWarps - 1) / kMergeWarps;
+    const int per = (total + kRowBlockWarps - 1) / kRowBlockWarps;
     const int e0 = min(total, warp * per), e1 = min(total, e0 + per);
     merge_range<P>(base, e0, e1, k, a.list_stride, k, lane, run, have_run, a.list_ptrs, row * k);
-    stage[warp * 64 + lane] = run[0];
-    stage[warp * 64 + 32 + lane] = run[1];
+    if (lane < k) stage[warp * k + lane] = run[0];              // k keys per warp, packed
+    if (lane + 32 < k) stage[warp * k + 32 + lane] = run[1];
     __syncthreads();
+    if (warp >= 4) return;
+    run[0] = run[1] = 0ull;
+    merge_range<P>(stage + warp * 8 * k, 0, 8 * k, k, k, k, lane, run, false);
+    if (lane < k) stage2[warp * k + lane] = run[0];
+    if (lane + 32 < k) stage2[warp * k + 32 + lane] = run[1];
+    // only warps 0-3 are left: a named barrier over 128 threads
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     if (warp != 0) return;
     run[0] = run[1] = 0ull;
-    merge_range<P>(stage, 0, kMergeWarps * 64, 64, 64, k, lane, run, false);
+    merge_range<P>(stage2, 0, 4 * k, k, k, k, lane, run, false);
   }
 
   int cnt = 0;
@@ -261,7 +272,7 @@ int launch_merge_topk(const MergeLaunch& a, cudaStream_t st) {
   const int lists = a.n_lists >= 0 ? a.n_lists : std::max(a.sc.s_main, a.sc.s_last);
   const int64_t keys = static_cast<int64_t>(lists) * a.k;
   if (a.Q <= 2048 && keys >= 1024)
-    merge_topk_kernel<8, true><<<static_cast<unsigned>(a.Q), kMergeWarps * 32, 0, st>>>(a);
+    merge_topk_kernel<8, true><<<static_cast<unsigned>(a.Q), kRowBlockWarps * 32, 0, st>>>(a);
   else if (keys <= (a.seed_keys ? 64 : 128))
     merge_topk_kernel<4, false><<<grid, kMergeWarps * 32, 0, st>>>(a);
   else
