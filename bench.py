@@ -261,6 +261,8 @@ def run_ours(args):
     if args.cta_group:
         eng.set_option("cta_group", args.cta_group)
     eng.set_option("profile", 1)
+    if args.symmetric == "off":
+        eng.set_option("symmetric", -1)
     sr = ShardedRetrieval(eng, exchange=args.exchange)
 
     n_db_total = db_total(world)
@@ -313,9 +315,15 @@ def run_ours(args):
         return _native.make_params(k=TOPK, similarity_threshold=THRESHOLD, min_time_gap=MIN_TIME_GAP, max_floor_diff=0,
                                    gate_mode=_native.GATE_FLAG, db_index_offset=offset)
 
+    # an all-pairs sweep over a database every rank holds in full: the ranks split the triangle of tiles
+    triangle = STRONG and world > 1 and N_Q == n_db_total and args.symmetric == "auto"
+
     def step():
-        res = sr.sweep(q_bf16, db_bf16, mk, lo, q_ts=q_ts, db_ts_shard=db_ts, q_floor=q_fl, db_floor_shard=db_fl,
-                       db_floor_all=fl_all, max_floor_diff=0)
+        if triangle:
+            res = sr.sweep_all_pairs(full, mk, ts=ts_all, floor=fl_all, max_floor_diff=0)
+        else:
+            res = sr.sweep(q_bf16, db_bf16, mk, lo, q_ts=q_ts, db_ts_shard=db_ts, q_floor=q_fl, db_floor_shard=db_fl,
+                           db_floor_all=fl_all, max_floor_diff=0)
         return eng.compact(res)
 
     def barrier():
@@ -343,6 +351,7 @@ def run_ours(args):
     k2_ms, k2_n = eng.profile_read()
     clocks = sampler.stop() if rank == 0 else None
     total_candidates = int(out[4].item())
+    sweep_mode, sweep_tiles = eng.last_sweep_mode()   # 0 full, 1 symmetric (every similarity computed once), 2 overflowed
     if world > 1:
         t = torch.tensor([ms, k2_ms / max(k2_n, 1)], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -357,13 +366,25 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (K2): algorithmic FLOPs = 2*Q*N_local*Dpad per launch
     peak_tf, peak_hbm, peak_src = measured_peaks()
-    flops_per_launch = 2.0 * N_Q * (hi - lo) * dp
+    # A symmetric sweep (queries == database) computes only the tiles on or above the block diagonal: the
+    # roofline counts the FLOPs the tensor cores EXECUTED, the full-matrix figure is given beside it.
+    flops_full = 2.0 * N_Q * (hi - lo) * dp
+    flops_per_launch = flops_full
+    if sweep_mode == 1:
+        nb = (N_Q + 255) // 256            # sweep_tiles: this rank's share of the nb*(nb+1)/2 tiles
+        flops_per_launch = 2.0 * N_Q * n_db_total * dp * sweep_tiles / float(nb * nb)
     achieved_tf = flops_per_launch / (k2_avg * 1e-3) / 1e12 if k2_avg > 0 else 0.0
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf, "traffic": None, "kernel": "gated_topk_kernel (K2)",
                 "kernel_ms": k2_avg, "kernel_share_of_step": k2_avg / (ms / args.steps), "peak_source": peak_src,
-                "flops_per_launch": flops_per_launch}
+                "flops_per_launch": flops_per_launch, "flops_counted": "executed by the tensor cores",
+                "sweep": {0: "full matrix", 1: "symmetric: S_ij = S_ji computed once, gated in both directions",
+                          2: "symmetric attempt overflowed, full sweep redone"}[sweep_mode],
+                "full_matrix_flops": flops_full,
+                "full_matrix_equivalent_tflops": flops_full / (k2_avg * 1e-3) / 1e12 if k2_avg > 0 else 0.0}
     prof = os.path.join(ROOT, "profiles", "k2_traffic.json")
+    if sweep_mode == 1:
+        prof = os.path.join(ROOT, "profiles", "k2_sym_traffic.json")
     if os.path.isfile(prof) and args.workload == "c2" and world == 1:   # the ncu capture is of this workload
         try:
             roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
@@ -480,6 +501,8 @@ def main():
     ap.add_argument("--cta-group", type=int, default=0, choices=[0, 1, 2, 4])
     ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "peer"],
                     help="N>1: how the per-GPU candidate lists meet (NCCL all-gather, or read in place over NVLink by the merge kernel)")
+    ap.add_argument("--symmetric", default="auto", choices=["auto", "off"],
+                    help="auto: all-pairs sweeps (queries == database) compute every similarity once; off: always the full matrix")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg")
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"],

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SEMGATE_VERSION 100
+#define SEMGATE_VERSION 101
 #define SEMGATE_MAX_K 64
 #define SEMGATE_FLOOR_NONE INT32_MIN
 
@@ -61,6 +61,18 @@ typedef struct semgate_topk_params {
                                    4 = clusters of two pairs sharing a multicast database tile */
   int32_t accumulate;           /* 1: out_keys already holds each query's list over OTHER database rows (earlier
                                    sweeps of disjoint slices); merge this sweep into it in place */
+  int32_t symmetric;            /* all-pairs sweeps (queries == database, place_recognition.py:190 computes X X^T):
+                                   0 = auto: when q_bf16 == db_bf16, q_ts == db_ts, q_floor == db_floor, Q == N,
+                                   db_index_offset == 0 and the tiles are CTA pairs, every similarity is computed once
+                                   and gated in both directions (half the tensor work, same lists);
+                                   1 = require it (SEMGATE_EINVAL if the arguments do not allow it); -1 = never */
+  int32_t part_index;           /* a symmetric sweep split over the GPUs of a box: with part_count = G > 1 (needs  */
+  int32_t part_count;           /* symmetric = 1) this call computes part part_index of the tile triangle -- every G-th
+                                   group of query blocks, dealt out boustrophedon so the parts are equal -- and its
+                                   lists hold each query's best candidates among the pairs of THAT part; merging the G
+                                   parts' out_keys (semgate_merge_topk / _peers) gives the sweep's lists.  No full
+                                   sweep stands behind a part: if semgate_last_sweep_mode reports 2 on ANY part, the
+                                   caller redoes the sweep row-sharded (semgate/dist.py does).  0 or 1: whole sweep */
 } semgate_topk_params;
 
 int semgate_version(void);
@@ -70,7 +82,8 @@ const char* semgate_last_error(void);
 int semgate_create(semgate_handle_t* out, int device);
 int semgate_destroy(semgate_handle_t h);
 int semgate_device_info(semgate_handle_t h, int* sm_count, int* cc_major, int* cc_minor);
-/* options: "cta_group" (0 auto | 1 | 2 | 4); "profile" (0|1): bracket every fused-kernel launch with CUDA
+/* options: "cta_group" (0 auto | 1 | 2 | 4); "symmetric" (0 auto | -1 never: handle default for
+ * semgate_topk_params.symmetric == 0); "profile" (0|1): bracket every fused-kernel launch with CUDA
  * events on its own stream */
 int semgate_set_option(semgate_handle_t h, const char* name, int64_t value);
 /* sum of the fused kernel's (K2) device durations since the last read, and how many
@@ -78,6 +91,20 @@ int semgate_set_option(semgate_handle_t h, const char* name, int64_t value);
 int semgate_profile_read(semgate_handle_t h, double* total_ms, int64_t* n_launches);
 /* kernels launched through this handle since creation (bench.py's gpu_launches) */
 int64_t semgate_launch_count(semgate_handle_t h);
+
+/* How the last semgate_gated_topk on this handle ran: *out_mode = 0 full sweep, 1 symmetric sweep,
+ * 2 symmetric sweep whose candidate buffers overflowed, so that the full sweep behind it produced the
+ * result (reads a device flag: synchronises the stream of that call).  *out_tiles (may be NULL) = 256-row x
+ * 256-column (CTA pairs; 128 x 256 for single-CTA tiles) similarity tiles its schedule computes; mode 2 ran both. */
+int semgate_last_sweep_mode(semgate_handle_t h, int32_t* out_mode, int64_t* out_tiles);
+
+/* Testing aid, needs no device: walks the fused kernel's tile schedule for a Q x N sweep on the host exactly as
+ * the kernel's warp roles do and checks its invariants (every tile computed once -- in a symmetric sweep every
+ * tile on or above the block diagonal and nothing else --, list slots, pacing counters).
+ * out_shape[8] = blocks, tiles, rm, s_main, r_last, s_last, pacing window, query blocks L2-resident;
+ * out_tiles[2] = tiles computed, longest unit's tile count (the makespan in tile-times). */
+int semgate_schedule_check(int64_t Q, int64_t N, int32_t d_pad, int32_t cta_group, int32_t sm_count, int32_t symmetric,
+                           int32_t part_index, int32_t part_count, int32_t* out_shape, int64_t* out_tiles);
 
 /* descriptor length padded to the kernel's K granule (64) */
 int semgate_pad_dim(int d);

@@ -54,6 +54,11 @@ struct semgate_ctx {
   int sm_count = 0;
   int cc_major = 0, cc_minor = 0;
   int cta_group = 0;               // 0 = auto (by problem size), 1, 2
+  int symmetric = 0;               // 0 = auto (symmetric sweep when queries and database alias), -1 = never
+  int last_mode = 0;               // last fused sweep: 0 full, 1 symmetric
+  const uint32_t* last_sym_flag = nullptr;   // ... and its overflow flag (device)
+  cudaStream_t last_stream = nullptr;
+  int64_t last_tiles = 0;          // tiles the last fused sweep computed (its schedule's count)
   int64_t launches = 0;
   cudaStream_t stream = nullptr;   // used by the *_host entry points (compute)
   cudaStream_t copy_stream = nullptr;   // H2D + normalisation of the next chunk, overlapped with the sweep
@@ -95,6 +100,10 @@ int check_params(const semgate_topk_params* p) {
   if (p->gate_mode != SEMGATE_GATE_FLAG && p->gate_mode != SEMGATE_GATE_MASK) return fail(SEMGATE_EINVAL, "gate_mode=%d", p->gate_mode);
   if (p->cta_group != 0 && p->cta_group != 1 && p->cta_group != 2 && p->cta_group != 4) return fail(SEMGATE_EINVAL, "cta_group=%d", p->cta_group);
   if (p->accumulate != 0 && p->accumulate != 1) return fail(SEMGATE_EINVAL, "accumulate=%d", p->accumulate);
+  if (p->symmetric < -1 || p->symmetric > 1) return fail(SEMGATE_EINVAL, "symmetric=%d", p->symmetric);
+  if (p->part_count < 0 || p->part_index < 0 || p->part_index >= std::max(p->part_count, 1))
+    return fail(SEMGATE_EINVAL, "part %d of %d", p->part_index, p->part_count);
+  if (p->part_count > 1 && p->symmetric != 1) return fail(SEMGATE_EINVAL, "part_count > 1 splits a symmetric sweep: set symmetric = 1");
   if (std::isnan(p->similarity_threshold)) return fail(SEMGATE_EINVAL, "similarity_threshold is NaN");
   return 0;
 }
@@ -111,6 +120,27 @@ int resolve_cg(semgate_handle_t h, const semgate_topk_params* p, int64_t Q) {
   const int want = p->cta_group ? p->cta_group : h->cta_group;
   if (want == 1 || want == 2 || want == 4) return want;
   return Q >= 4096 ? 2 : 1;
+}
+
+// Symmetric sweep: possible when the shapes allow it (square problem on CTA-pair tiles, one index space,
+// nothing to accumulate into) and wanted unless the caller or the handle said never.
+bool sym_shape_ok(semgate_handle_t h, const semgate_topk_params* p, int64_t Q, int64_t N, int32_t d_pad) {
+  return Q == N && Q > 256 && resolve_cg(h, p, Q) == 2 && !use_stream_path(h, p, Q, d_pad) && p->accumulate == 0;
+}
+bool sym_wanted(semgate_handle_t h, const semgate_topk_params* p) {
+  return p->symmetric == 1 || (p->symmetric == 0 && h->symmetric == 0);
+}
+
+// workspace of a symmetric sweep: [partial lists of either schedule | pacing counters of the full schedule |
+// symmetric state: its pacing counters, bounds, counts, flag, candidate buffers]
+struct SymLayout { size_t partial, sync_full, state, total; };
+SymLayout sym_layout(const Schedule& sc_full, const Schedule& sc_sym, int64_t N, int k) {
+  SymLayout l;
+  l.partial = std::max(topk_partial_bytes(sc_full, 2, k), topk_partial_bytes(sc_sym, 2, k));
+  l.sync_full = align256(topk_sync_bytes(sc_full));
+  l.state = sym_state_bytes(N, k, topk_sync_bytes(sc_sym));
+  l.total = l.partial + l.sync_full + l.state;
+  return l;
 }
 
 }  // namespace
@@ -140,6 +170,8 @@ int semgate_create(semgate_handle_t* out, int device) {
   h->cc_minor = prop.minor;
   const char* env = getenv("SEMGATE_CTA_GROUP");
   if (env && (env[0] == '1' || env[0] == '2' || env[0] == '4')) h->cta_group = env[0] - '0';
+  env = getenv("SEMGATE_SYMMETRIC");
+  if (env && env[0] == '0') h->symmetric = -1;
   DeviceGuard g(device);
   cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate"); }
@@ -176,6 +208,11 @@ int semgate_set_option(semgate_handle_t h, const char* name, int64_t value) {
     h->cta_group = static_cast<int>(value);
     return 0;
   }
+  if (strcmp(name, "symmetric") == 0) {
+    if (value != 0 && value != -1) return fail(SEMGATE_EINVAL, "symmetric must be 0 (auto) or -1 (never)");
+    h->symmetric = static_cast<int>(value);
+    return 0;
+  }
   if (strcmp(name, "profile") == 0) {
     h->profile = value != 0;
     return 0;
@@ -184,6 +221,20 @@ int semgate_set_option(semgate_handle_t h, const char* name, int64_t value) {
 }
 
 int64_t semgate_launch_count(semgate_handle_t h) { return h ? h->launches : 0; }
+
+int semgate_last_sweep_mode(semgate_handle_t h, int32_t* out_mode, int64_t* out_tiles) {
+  if (!h || !out_mode) return fail(SEMGATE_EINVAL, "NULL argument");
+  *out_mode = h->last_mode;
+  if (out_tiles) *out_tiles = h->last_tiles;
+  if (h->last_mode == 1 && h->last_sym_flag) {
+    DeviceGuard g(h->device);
+    uint32_t flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, h->last_sym_flag, sizeof(flag), cudaMemcpyDeviceToHost, h->last_stream));
+    CUDA_TRY(cudaStreamSynchronize(h->last_stream));
+    if (flag != 0) *out_mode = 2;
+  }
+  return 0;
+}
 
 int semgate_profile_read(semgate_handle_t h, double* total_ms, int64_t* n_launches) {
   if (!h || !total_ms || !n_launches) return fail(SEMGATE_EINVAL, "NULL argument");
@@ -198,6 +249,27 @@ int semgate_profile_read(semgate_handle_t h, double* total_ms, int64_t* n_launch
   *total_ms = sum;
   *n_launches = static_cast<int64_t>(h->prof_used / 2);
   h->prof_used = 0;
+  return 0;
+}
+
+// ---------------------------------------------------------------- schedule self-check (no device needed)
+int semgate_schedule_check(int64_t Q, int64_t N, int32_t d_pad, int32_t cta_group, int32_t sm_count, int32_t symmetric,
+                           int32_t part_index, int32_t part_count, int32_t* out_shape, int64_t* out_tiles) {
+  if (Q <= 0 || N <= 0 || d_pad <= 0 || d_pad % 64 != 0 || sm_count < 4 || (cta_group != 1 && cta_group != 2))
+    return fail(SEMGATE_EINVAL, "schedule_check: bad arguments");
+  if (symmetric && (cta_group != 2 || Q != N)) return fail(SEMGATE_EINVAL, "schedule_check: a symmetric sweep needs Q == N and CTA pairs");
+  if (part_count < 0 || part_index < 0 || part_index >= std::max(part_count, 1) || (part_count > 1 && !symmetric))
+    return fail(SEMGATE_EINVAL, "schedule_check: bad part %d of %d", part_index, part_count);
+  const Schedule sc = make_schedule(Q, N, d_pad, cta_group, sm_count, symmetric != 0, part_index, part_count);
+  int64_t computed = 0, makespan = 0;
+  const int err = schedule_selfcheck(sc, topk_units(cta_group, sm_count), &computed, &makespan);
+  if (out_shape) {
+    out_shape[0] = sc.mblocks; out_shape[1] = sc.ntiles; out_shape[2] = sc.rm; out_shape[3] = sc.s_main;
+    out_shape[4] = sc.r_last; out_shape[5] = sc.s_last; out_shape[6] = sc.sync_window; out_shape[7] = sc.a_resident;
+  }
+  if (out_tiles) { out_tiles[0] = computed; out_tiles[1] = makespan; }
+  if (err) return fail(SEMGATE_EINVAL, "schedule_check: invariant %d broken (Q=%lld N=%lld d_pad=%d cta_group=%d sym=%d)", err,
+                       (long long)Q, (long long)N, d_pad, cta_group, symmetric);
   return 0;
 }
 
@@ -221,6 +293,8 @@ size_t semgate_topk_workspace_bytes(semgate_handle_t h, int64_t Q, int64_t N, in
   Schedule sc = make_schedule(Q, N, d_pad, cg, h->sm_count);
   size_t need = topk_workspace_bytes(sc, cg, p->k);
   if (use_stream_path(h, p, Q, d_pad)) need = std::max(need, stream_query_workspace_bytes(Q, p->k, h->sm_count));
+  if (sym_wanted(h, p) && sym_shape_ok(h, p, Q, N, d_pad))
+    need = std::max(need, sym_layout(sc, make_schedule(Q, N, d_pad, 2, h->sm_count, true, p->part_index, p->part_count), N, p->k).total);
   return align256(need);
 }
 
@@ -266,6 +340,21 @@ int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const 
   if (!workspace || workspace_bytes < need)
     return fail(SEMGATE_ENOMEM, "gated_topk: workspace %zu < required %zu bytes", workspace_bytes, need);
 
+  // Symmetric sweep: the queries are the database itself (same rows, stamps and labels), so S = S^T and only
+  // the tiles on or above the block diagonal are computed.  Automatic when the arguments alias.
+  const bool aliased = q_bf16 == db_bf16 && q_ts == db_ts && q_floor == db_floor && p->db_index_offset == 0;
+  bool sym = sym_wanted(h, p) && sym_shape_ok(h, p, Q, N, d_pad) && aliased;
+  Schedule sc_sym{};
+  SymLayout lay{};
+  if (sym) {
+    sc_sym = make_schedule(Q, N, d_pad, 2, h->sm_count, true, p->part_index, p->part_count);
+    lay = sym_layout(sc, sc_sym, N, k);
+    if (workspace_bytes < lay.total) sym = false;     // a caller that sized its workspace for the full sweep only
+  }
+  if (p->symmetric == 1 && !sym)
+    return fail(SEMGATE_EINVAL, "gated_topk: symmetric=1 needs aliased query/database arguments, Q == N > 256, CTA-pair tiles, "
+                "no accumulate, and a workspace of semgate_topk_workspace_bytes()");
+
   TopkLaunch a{};
   a.q_bf16 = q_bf16; a.Q = Q; a.db_bf16 = db_bf16; a.N = N; a.d_pad = d_pad;
   a.q_ts = q_ts; a.db_ts = db_ts;
@@ -289,9 +378,22 @@ int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const 
     h->prof_used += 2;
     CUDA_TRY(cudaEventRecord(ev0, st));
   }
+  uint32_t* sym_flag = nullptr;
   if (gemv) {
     RC_TRY(launch_stream_query(a, static_cast<uint64_t*>(workspace), st), "stream_query launch");
     launches = 1;
+  } else if (sym) {
+    char* ws = static_cast<char*>(workspace);
+    TopkLaunch b = a;
+    b.state = ws + lay.partial + lay.sync_full;
+    RC_TRY(launch_gated_topk(b, sc_sym, static_cast<uint64_t*>(workspace), st, &launches), "gated_topk (symmetric) launch");
+    sym_flag = reinterpret_cast<uint32_t*>(ws + lay.partial + lay.sync_full + topk_sync_bytes(sc_sym)) + 2 * N;
+    if (p->part_count <= 1) {
+      // the full sweep, armed by the overflow flag: a no-op unless some keyframe's candidate buffer ran over
+      a.state = ws + lay.partial;
+      a.run_if = sym_flag;
+      RC_TRY(launch_gated_topk(a, sc, static_cast<uint64_t*>(workspace), st, &launches), "gated_topk launch");
+    }   // one part of a multi-GPU sweep: the caller reads the flag (semgate_last_sweep_mode) and decides with its peers
   } else {
     RC_TRY(launch_gated_topk(a, sc, static_cast<uint64_t*>(workspace), st, &launches), "gated_topk launch");
   }
@@ -306,9 +408,21 @@ int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const 
   } else {               // per-row offsets follow the schedule
     m.row_stride = 0;
     m.n_lists = -1; m.sc = sc; m.rows_per_mblock = 128 * cg;   // cg = CTAs (128-row query blocks) per schedule unit
+    if (sym) {
+      m.sc_sym = sc_sym; m.sym_flag = sym_flag; m.sym_cnt = sym_flag - N;
+      m.sym_force = p->part_count > 1 ? 1 : 0;
+      m.sym_cap = sym_capacity(k, N);
+      m.sym_ovf = reinterpret_cast<const uint64_t*>(static_cast<char*>(workspace) + lay.partial + lay.sync_full +
+                                                    sym_zeroed_bytes(N, topk_sync_bytes(sc_sym)));
+    }
   }
   RC_TRY(launch_merge_topk(m, st), "merge_topk launch");
   h->launches += 1;
+  h->last_mode = sym ? 1 : 0;
+  h->last_sym_flag = sym_flag;
+  h->last_stream = st;
+  h->last_tiles = gemv ? 0 : static_cast<int64_t>(sc.mblocks) * sc.ntiles;
+  if (sym) schedule_selfcheck(sc_sym, topk_units(2, h->sm_count), &h->last_tiles, nullptr);   // host-side count of this part's tiles
   return 0;
 }
 

@@ -117,13 +117,37 @@ struct Schedule {
   int cpt;          // chunks per tile = ceil(kblocks / pace_kb)
   int len_main;     // ceil(ntiles / s_main): longest run of a full super-row, in tiles
   int len_last;     // ceil(ntiles / s_last)
+  int sym;          // 1: the queries ARE the database (all-pairs sweep, S = S^T): only tiles on or above the
+                    //    block diagonal are computed, see "Symmetric sweep" below
+  int part_index;   // symmetric sweep split over `part_count` GPUs: this launch computes the super-rows that
+  int part_count;   //    sched_owned() gives part_index (0 / 0 or 1: everything)
 };
+
+// Super-rows get shorter towards the end of a symmetric sweep; dealing them out boustrophedon
+// (0 1 .. G-1 G-1 .. 1 0 0 1 ..) keeps the parts' tile counts within a fraction of a percent.
+__host__ __device__ __forceinline__ bool sched_owned(const Schedule& sc, int sr) {
+  if (sc.part_count <= 1) return true;
+  const int g = sr % (2 * sc.part_count);
+  return (g < sc.part_count ? g : 2 * sc.part_count - 1 - g) == sc.part_index;
+}
+
+// Symmetric sweep (sym = 1, CTA-pair tiles only, so that a query block and a database tile are both 256
+// rows and share one numbering).  Super-row sr holds the blocks [sr*rm, sr*rm + r) and sweeps the tiles
+// [sr*rm, ntiles) as a rectangle, split into min(S, length) runs; block b skips the tiles left of its
+// diagonal tile (nt < b), which only shortens the first run(s).  A tile right of the diagonal feeds two
+// sets of lists: the rows' (as always) and, transposed, the columns' (gated_topk.cuh, "column direction").
+__host__ __device__ __forceinline__ int sched_sym_splits(const Schedule& sc, int sr) {
+  const int len = sc.ntiles - sr * sc.rm;
+  const int S = sr < sc.n_full ? sc.s_main : sc.s_last;
+  return S < len ? S : len;
+}
 
 __host__ __device__ __forceinline__ int64_t sched_sync_counters(const Schedule& sc) {
   return (static_cast<int64_t>(sc.n_full) * sc.len_main + sc.len_last) * sc.cpt;
 }
 
 __host__ __device__ __forceinline__ int sched_slots(const Schedule& sc, int mb) {
+  if (sc.sym) return sched_owned(sc, mb / sc.rm) ? sched_sym_splits(sc, mb / sc.rm) : 0;   // other parts' rows: no lists here
   return mb < sc.n_full * sc.rm ? sc.s_main : sc.s_last;
 }
 
@@ -146,7 +170,8 @@ __host__ __device__ __forceinline__ int split_begin(int n, int s, int j) {
 struct Run {
   int mb;      // m-block (pair-row for CG = 2)
   int slot;    // which of the m-block's runs (partial-list slot)
-  int nt0;     // first n-tile
+  int nt0;     // first n-tile of the run (its position in the pacing counters)
+  int nt_first;  // first n-tile actually computed (symmetric sweep: max(nt0, mb); else nt0)
   int nt1;     // one past the last n-tile
   // pacing: counters of this super-row; all `units_all` units reach tile ordinal < short_len,
   // only the `units_long` units with the longer runs reach ordinal == short_len
@@ -157,22 +182,27 @@ struct Run {
 };
 
 template <typename F>
-__device__ __forceinline__ void for_each_run(const Schedule& sc, int unit, F&& f) {
+__host__ __device__ __forceinline__ void for_each_run(const Schedule& sc, int unit, F&& f) {
   const int n_sr = sc.n_full + (sc.r_last > 0 ? 1 : 0);
   for (int sr = 0; sr < n_sr; ++sr) {
+    if (!sched_owned(sc, sr)) continue;
     const bool full_sr = sr < sc.n_full;
     const int r = full_sr ? sc.rm : sc.r_last;
-    const int S = full_sr ? sc.s_main : sc.s_last;
+    const int lo = sc.sym ? sr * sc.rm : 0;          // first tile the super-row sweeps
+    const int len = sc.ntiles - lo;
+    const int S = sc.sym ? sched_sym_splits(sc, sr) : (full_sr ? sc.s_main : sc.s_last);
     if (unit >= r * S) continue;
     Run run;
     run.mb = sr * sc.rm + unit % r;
     run.slot = unit / r;
-    run.nt0 = split_begin(sc.ntiles, S, run.slot);
-    run.nt1 = split_begin(sc.ntiles, S, run.slot + 1);
+    run.nt0 = lo + split_begin(len, S, run.slot);
+    run.nt1 = lo + split_begin(len, S, run.slot + 1);
+    run.nt_first = (sc.sym && run.mb > run.nt0) ? (run.mb < run.nt1 ? run.mb : run.nt1) : run.nt0;
     run.sync_base = (full_sr ? static_cast<int64_t>(sr) * sc.len_main : static_cast<int64_t>(sc.n_full) * sc.len_main) * sc.cpt;
-    run.short_len = sc.ntiles / S;
+    run.short_len = len / S;
     run.units_all = r * S;
-    run.units_long = r * (sc.ntiles % S);
+    run.units_long = r * (len % S);
+    // a symmetric run may be empty (all of it left of the diagonal): it still flushes an empty list
     if (run.nt0 < run.nt1) f(run);
   }
 }

@@ -16,7 +16,7 @@ static long env_long(const char* name, long dflt) {
   return (e && *e) ? atol(e) : dflt;
 }
 
-static size_t smem_bytes_for(int cg, int stages, int kstride);
+static size_t smem_bytes_for(int cg, int stages, int kstride, bool sym = false);
 constexpr size_t kSmemLimit = 232448;   // 227 KB per CTA
 
 // Schedule units (CTAs, CTA pairs, or 4-CTA clusters of two pairs) that are co-resident.  A cluster
@@ -45,8 +45,22 @@ int topk_units(int cta_group, int sm_count) {
   return std::max(1, cached > 0 ? cached : sm_count / 4 - 5);   // conservative if the query failed
 }
 
-Schedule make_schedule(int64_t Q, int64_t N, int d_pad, int cta_group, int sm_count) {
+// makespan of a symmetric sweep in tile-times: super-row sr sweeps the tiles [sr*rm, nb) in min(S, length) runs
+static int64_t sym_cost(int nb, int rm, int units) {
+  int64_t c = 0;
+  for (int lo = 0; lo < nb; lo += rm) {
+    const int r = std::min(rm, nb - lo), len = nb - lo;
+    const int S = std::min(len, std::max(1, units / r));
+    c += (len + S - 1) / S;
+  }
+  return c;
+}
+
+Schedule make_schedule(int64_t Q, int64_t N, int d_pad, int cta_group, int sm_count, bool sym, int part_index, int part_count) {
   Schedule sc{};
+  sc.sym = sym ? 1 : 0;
+  sc.part_index = sym ? part_index : 0;
+  sc.part_count = sym ? std::max(part_count, 1) : 1;
   const int units = topk_units(cta_group, sm_count);
   const int bm_unit = BM * cta_group;
   sc.mblocks = static_cast<int>((Q + bm_unit - 1) / bm_unit);
@@ -71,6 +85,7 @@ Schedule make_schedule(int64_t Q, int64_t N, int d_pad, int cta_group, int sm_co
       const int s_last = std::min(sc.ntiles, units / r_last);
       c += (sc.ntiles + s_last - 1) / s_last;
     }
+    if (sym) c = sym_cost(sc.ntiles, rm, units);
     cost[rm] = c;
     if (best_cost < 0 || c < best_cost) best_cost = c;
   }
@@ -92,6 +107,10 @@ Schedule make_schedule(int64_t Q, int64_t N, int d_pad, int cta_group, int sm_co
   sc.s_max = std::max(sc.n_full > 0 ? sc.s_main : 0, sc.s_last);
   sc.len_main = sc.n_full > 0 ? (sc.ntiles + sc.s_main - 1) / sc.s_main : 0;
   sc.len_last = sc.r_last > 0 ? (sc.ntiles + sc.s_last - 1) / sc.s_last : 0;
+  if (sym && sc.r_last > 0) {   // the tail super-row only sweeps its own r_last tiles
+    const int S = std::min(sc.s_last, sc.r_last);
+    sc.len_last = (sc.r_last + S - 1) / S;
+  }
 
   // Pacing: chunks of 16 k-blocks; the window holds `SEMGATE_WINDOW_MB` of streamed operands of the
   // whole grid.  Off for short runs (nothing to drift) and with SEMGATE_WINDOW_MB=0.
@@ -125,6 +144,60 @@ size_t topk_workspace_bytes(const Schedule& sc, int cta_group, int k) {
   return topk_partial_bytes(sc, cta_group, k) + topk_sync_bytes(sc);
 }
 
+// Host-side walk of the schedule the kernel's warp roles follow (tests/test_abi.py, no GPU needed).
+// Returns 0 if it is consistent, else a code naming the first broken invariant:
+//   1 a tile computed twice or not at all (full: every (block, tile); symmetric: tile >= block, nothing else)
+//   2 a run's list slot outside sched_slots(block)      3 two runs of a block share a list slot
+//   4 a pacing counter outside the allocated array      5 arrivals on a counter differ from what waiters expect
+//   6 a block without a flushed list for one of its slots
+int schedule_selfcheck(const Schedule& sc, int units, int64_t* tiles_computed, int64_t* makespan_tiles) {
+  const int nb = sc.mblocks, nt = sc.ntiles;
+  std::vector<uint8_t> seen(static_cast<size_t>(nb) * nt, 0);
+  std::vector<uint32_t> slot_used(static_cast<size_t>(nb) * std::max(sc.s_max, 1), 0);
+  const int64_t n_counters = sched_sync_counters(sc);
+  std::vector<int32_t> arrivals(static_cast<size_t>(std::max<int64_t>(n_counters, 1)), 0), expect(arrivals.size(), -1);
+  int err = 0;
+  int64_t computed = 0, makespan = 0;
+  for (int u = 0; u < units && !err; ++u) {
+    int64_t mine = 0;
+    for_each_run(sc, u, [&](const Run& run) {
+      if (err) return;
+      if (run.mb >= nb || run.slot >= sched_slots(sc, run.mb) || run.slot >= sc.s_max) { err = 2; return; }
+      if (slot_used[static_cast<size_t>(run.mb) * sc.s_max + run.slot]++) { err = 3; return; }
+      if (run.nt_first < run.nt0 || run.nt_first > run.nt1) { err = 1; return; }
+      for (int t = run.nt_first; t < run.nt1; ++t) {
+        if (t >= nt || seen[static_cast<size_t>(run.mb) * nt + t]++) { err = 1; return; }
+        ++computed; ++mine;
+      }
+      // every chunk ordinal of the run (computed or skipped) arrives once on the super-row's counters
+      for (int64_t c = 0; c < static_cast<int64_t>(run.nt1 - run.nt0) * sc.cpt; ++c) {
+        const int64_t at = run.sync_base + c;
+        if (at < 0 || at >= n_counters) { err = 4; return; }
+        ++arrivals[at];
+        const int need = (c / sc.cpt) < run.short_len ? run.units_all : run.units_long;
+        if (expect[at] >= 0 && expect[at] != need) { err = 5; return; }
+        expect[at] = need;
+      }
+    });
+    makespan = std::max(makespan, mine);
+  }
+  if (!err)
+    for (size_t i = 0; i < arrivals.size() && !err; ++i)
+      if (expect[i] >= 0 && arrivals[i] != expect[i]) err = 5;
+  if (!err)
+    for (int b = 0; b < nb && !err; ++b) {
+      for (int t = 0; t < nt; ++t) {
+        const bool want = sc.sym ? (t >= b && sched_owned(sc, b / sc.rm)) : true;
+        if ((seen[static_cast<size_t>(b) * nt + t] != 0) != want) { err = 1; break; }
+      }
+      for (int sl = 0; sl < sched_slots(sc, b) && !err; ++sl)
+        if (slot_used[static_cast<size_t>(b) * sc.s_max + sl] != 1) err = 6;
+    }
+  if (tiles_computed) *tiles_computed = computed;
+  if (makespan_tiles) *makespan_tiles = makespan;
+  return err;
+}
+
 // ------------------------------------------------------------------ tensor maps
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -153,10 +226,24 @@ static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int d_pad, 
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
 }
 
-static size_t smem_bytes_for(int cg, int stages, int kstride) {
+static size_t smem_bytes_for(int cg, int stages, int kstride, bool sym) {
   const size_t stage = A_STAGE_BYTES + static_cast<size_t>(BN / std::min(cg, 2)) * BK * 2;
   return 1024 /*realign slack*/ + stages * stage + static_cast<size_t>(BM) * kstride * 8 +
-         2 * BN * (sizeof(double) + sizeof(int32_t)) /*per-tile timestamps + labels*/ + 256 /*barriers + tmem slot*/;
+         2 * BN * (sizeof(double) + sizeof(int32_t)) /*per-tile timestamps + labels*/ +
+         (sym ? 2 * BN * sizeof(float) + 64 : 0) /*column bounds + chunk minima*/ + 256 /*barriers + tmem slot*/;
+}
+
+// Symmetric sweep: candidate-buffer depth per keyframe and the layout of its state behind the pacing counters:
+// [pacing counters | bound u32[N] | count u32[N] | flag (64 B)] (zeroed per launch, one memset) [buffers u64[N][cap]]
+// depth: at least 4 k-lists; up to 1024 while the buffers of all keyframes stay within 1 GiB
+int sym_capacity(int k, int64_t N) {
+  int cap = k <= 32 ? 128 : 256;
+  while (cap < 1024 && static_cast<int64_t>(2 * cap) * N * 8 <= (1ll << 30)) cap *= 2;
+  return cap;
+}
+size_t sym_zeroed_bytes(int64_t N, size_t sync_bytes) { return ((sync_bytes + 8 * static_cast<size_t>(N) + 64) + 255) & ~static_cast<size_t>(255); }
+size_t sym_state_bytes(int64_t N, int k, size_t sync_bytes) {
+  return sym_zeroed_bytes(N, sync_bytes) + static_cast<size_t>(N) * sym_capacity(k, N) * sizeof(uint64_t);
 }
 
 int launch_gated_topk(const TopkLaunch& a, const Schedule& sc, uint64_t* partial, cudaStream_t st, int* launches) {
@@ -186,9 +273,26 @@ int launch_gated_topk(const TopkLaunch& a, const Schedule& sc, uint64_t* partial
   p.dense = a.dense; p.dense_ld = a.dense_ld;
   if (a.dense != nullptr) p.sc.sync_window = 0;   // no workspace in dense mode
   p.sync = nullptr;
-  if (p.sc.sync_window > 0) {
-    // the pacing counters live behind the partial lists in the caller's workspace
-    p.sync = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(partial) + topk_partial_bytes(sc, cg, a.k));
+  p.run_if = a.run_if;
+  const bool sym = sc.sym != 0;
+  if (sym) {
+    if (cg != 2 || a.Q != a.N || a.q_bf16 != a.db_bf16 || a.dense != nullptr || a.state == nullptr) return static_cast<int>(cudaErrorInvalidValue);
+    // [pacing counters | bounds | counts | flag] zeroed together, candidate buffers behind
+    char* z = static_cast<char*>(a.state);
+    const size_t sync_bytes = topk_sync_bytes(sc);
+    p.sync = sync_bytes ? reinterpret_cast<uint32_t*>(z) : nullptr;
+    p.sym_bound = reinterpret_cast<uint32_t*>(z + sync_bytes);
+    p.sym_cnt = p.sym_bound + a.N;
+    p.sym_flag = p.sym_cnt + a.N;
+    p.sym_cap = sym_capacity(a.k, a.N);
+    p.sym_ovf = reinterpret_cast<uint64_t*>(z + sym_zeroed_bytes(a.N, sync_bytes));
+    cudaError_t me = cudaMemsetAsync(z, 0, sym_zeroed_bytes(a.N, sync_bytes), st);
+    if (me != cudaSuccess) return static_cast<int>(me);
+    if (launches) ++*launches;
+  } else if (p.sc.sync_window > 0) {
+    // the pacing counters live behind the partial lists in the caller's workspace (or where the caller says)
+    p.sync = a.state ? static_cast<uint32_t*>(a.state)
+                     : reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(partial) + topk_partial_bytes(sc, cg, a.k));
     cudaError_t me = cudaMemsetAsync(p.sync, 0, topk_sync_bytes(sc), st);
     if (me != cudaSuccess) return static_cast<int>(me);
     if (launches) ++*launches;
@@ -200,16 +304,16 @@ int launch_gated_topk(const TopkLaunch& a, const Schedule& sc, uint64_t* partial
 
   // deepest ring that fits the 227 KB per-CTA limit
   int stages = kMaxStages;
-  while (stages > 2 && smem_bytes_for(cg, stages, p.kstride) > kSmemLimit) --stages;
+  while (stages > 2 && smem_bytes_for(cg, stages, p.kstride, sym) > kSmemLimit) --stages;
   stages = std::min(stages, std::max(2, p.kblocks));
   p.stages = stages;
-  const size_t smem = smem_bytes_for(cg, stages, p.kstride);
+  const size_t smem = smem_bytes_for(cg, stages, p.kstride, sym);
 
   const int units = topk_units(cg, a.sm_count);
   // only units that receive work in some super-row need to exist
   int used = 0;
-  if (sc.n_full > 0) used = std::max(used, sc.rm * sc.s_main);
-  if (sc.r_last > 0) used = std::max(used, sc.r_last * sc.s_last);
+  if (sc.n_full > 0) used = std::max(used, sc.rm * std::min(sc.s_main, sc.ntiles));
+  if (sc.r_last > 0) used = std::max(used, sc.r_last * std::min(sc.s_last, sym ? sc.r_last : sc.ntiles));
   used = std::min(std::max(used, 1), units);
 
   cudaLaunchConfig_t cfg{};
@@ -227,7 +331,8 @@ int launch_gated_topk(const TopkLaunch& a, const Schedule& sc, uint64_t* partial
     if (ee != cudaSuccess) return ee;
     return cudaLaunchKernelEx(&cfg, kernel, tq, tdb, p);
   };
-  if (cg == 4) e = launch(gated_topk_kernel<2, 2>);
+  if (sym) e = launch(gated_topk_kernel<2, 1, true>);
+  else if (cg == 4) e = launch(gated_topk_kernel<2, 2>);
   else if (cg == 2) e = launch(gated_topk_kernel<2, 1>);
   else e = launch(gated_topk_kernel<1, 1>);
   if (e != cudaSuccess) return static_cast<int>(e);

@@ -60,6 +60,13 @@ struct TopkParams {
   uint32_t* sync;        // pacing counters (zeroed per launch) or null: see Schedule::sync_window
   uint64_t policy_q;     // L2 eviction priority of the query-block loads (re-read once per database tile)
   uint64_t policy_db;    // ... of the streamed database tiles
+  // symmetric sweep (SYM kernel): column-direction state, see the kernel's epilogue
+  uint32_t* sym_bound;   // [N] admission bound of every keyframe as a query, ordered-score image; 0 = none published yet
+  uint32_t* sym_cnt;     // [N] column-direction candidates appended so far
+  uint32_t* sym_flag;    // != 0: some keyframe overflowed its candidate buffer -> the full sweep takes over
+  uint64_t* sym_ovf;     // [N][sym_cap] appended candidate keys
+  int sym_cap;
+  const uint32_t* run_if;   // non-null: the whole launch is a no-op unless *run_if != 0 (the full sweep behind a symmetric one)
   Schedule sc;
 };
 
@@ -77,11 +84,25 @@ __device__ __forceinline__ uint32_t pick32(const uint32_t (&v)[32], int i) {
   return (i & 16) ? d[1] : d[0];
 }
 
-template <int CG, int MC>
+// SYM (CTA pairs only): the queries are the database.  Only tiles on or above the block diagonal are
+// computed; a tile right of the diagonal is read twice by the epilogue:
+//   row direction     (as always) rows = queries, columns = candidates -> the thread's shared-memory list;
+//   column direction  columns = queries, rows = candidates.  The owner of a query block publishes each
+//     row's admission bound (k-th score once its list is full, monotone, atomicMax on the ordered image) in
+//     sym_bound; whoever computes a tile stages the 256 column bounds (threshold if none yet) in shared
+//     memory, compares every score of a column with that column's bound and appends the few that pass
+//     to the keyframe's candidate buffer in HBM (sym_ovf, one atomic slot counter per keyframe).  A stale
+//     bound only lets more candidates through: a bound is the k-th score of a subset of a keyframe's
+//     admissible candidates, hence never above its final k-th score.  K3 merges buffer and lists.
+//     A buffer that overflows (thresholds that admit most of the database) raises sym_flag, and the
+//     full sweep launched right behind (run_if) redoes the job; nothing is lost, only time.
+template <int CG, int MC, bool SYM = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
                   const TopkParams p) {
   static_assert(MC == 1 || (MC == 2 && CG == 2), "multicast needs CTA pairs");
+  static_assert(!SYM || (CG == 2 && MC == 1), "symmetric sweep: a query block must be one database tile");
+  if (p.run_if != nullptr && ptx::ld_relaxed_gpu(p.run_if) == 0u) return;   // grid-uniform, before any barrier
   constexpr int CSIZE = CG * MC;                 // CTAs per cluster = per schedule unit
   constexpr uint32_t B_ROWS = BN / CG;           // database rows held by one CTA
   constexpr uint32_t B_LOAD_ROWS = B_ROWS / MC;  // ... of which it fetches this many itself
@@ -101,7 +122,10 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   // them from shared memory instead of paying a dependent global load per hit column
   double* ts_s = reinterpret_cast<double*>(lists + static_cast<size_t>(BM) * p.kstride);
   int32_t* fl_s = reinterpret_cast<int32_t*>(ts_s + 2 * BN);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(fl_s + 2 * BN);
+  // symmetric sweep: the tile's column bounds and their minimum per 32-column chunk (one set per accumulator)
+  float* bd_s = reinterpret_cast<float*>(fl_s + 2 * BN);
+  float* bmin_s = bd_s + (SYM ? 2 * BN : 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bmin_s + (SYM ? 16 : 0));
   // barrier slots: full[kMaxStages] empty[kMaxStages] tmem_full[2] tmem_empty[2]
   const uint32_t bar_full = ptx::smem_u32(bars);
   const uint32_t bar_empty = bar_full + 8 * kMaxStages;
@@ -156,7 +180,13 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       // (e.g. one that idles through the full super-rows and reaches the tail super-row seconds
       // before anybody else) stops pacing for the rest of the run and just streams.
       bool paced = window > 0;
-      for (int nt = run.nt0; nt < run.nt1; ++nt) {
+      if (window > 0 && ptx::elect_one()) {
+        // tiles left of the diagonal (symmetric sweep) are not computed; the other units of the
+        // super-row still count on this one's chunk arrivals
+        for (int c = 0; c < (run.nt_first - run.nt0) * cpt; ++c) ptx::red_add_relaxed_gpu(pace + c, 1u);
+      }
+      __syncwarp();
+      for (int nt = run.nt_first; nt < run.nt1; ++nt) {
         // rows of the database tile this CTA fetches: its half of the tile, and with MC = 2 the
         // quarter of that half that its pair is responsible for
         const int n0 = nt * BN + static_cast<int>(half * B_ROWS + (MC == 2 ? pair * B_LOAD_ROWS : 0u));
@@ -227,7 +257,7 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       const uint64_t adesc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a));
       const uint64_t bdesc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b));
       for_each_run(sc, unit, [&](const Run& run) {
-        for (int nt = run.nt0; nt < run.nt1; ++nt, ++it) {
+        for (int nt = run.nt_first; nt < run.nt1; ++nt, ++it) {
           const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
           ptx::mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
           ptx::tc_fence_after();
@@ -292,11 +322,13 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         if (mask_mode) qf = p.q_floor[grow];
       }
       L.reset(row_live ? p.threshold : pos_inf);
+      float published = __int_as_float(0xff800000);   // SYM: last bound this thread published for its row
 
-      for (int nt = run.nt0; nt < run.nt1; ++nt, ++it) {
+      for (int nt = run.nt_first; nt < run.nt1; ++nt, ++it) {
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         const int col_base = nt * BN;
-        if (use_time || mask_mode) {
+        const bool do_cols = SYM && nt != run.mb;   // the diagonal tile holds both orientations of its pairs
+        if (use_time || mask_mode || SYM) {
           // stage this tile's timestamps / labels while its MMAs run.  One barrier per tile is enough:
           // whoever overwrites buffer `acc` here has passed the previous tile's barrier, which every
           // epilogue warp only reaches after it finished the tile before that (the buffer's last reader).
@@ -305,6 +337,17 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             const int col = col_base + j;
             if (use_time) ts_s[acc * BN + j] = col < p.N ? __ldg(p.db_ts + col) : 0.0;
             if (mask_mode) fl_s[acc * BN + j] = col < p.N ? __ldg(p.db_floor + col) : kFloorNone;
+            if constexpr (SYM) {
+              float b = pos_inf;                      // beyond N (TMA zero fill) and on the diagonal: nothing passes
+              if (do_cols && col < p.N) {
+                const uint32_t g = ptx::ld_relaxed_gpu(p.sym_bound + col);
+                b = g != 0u ? ordered_to_score(g) : p.threshold;
+              }
+              bd_s[acc * BN + j] = b;
+              // columns j of this warp in this pass are exactly chunk j / 32
+              const uint32_t mn = __reduce_min_sync(0xffffffffu, score_to_ordered(b));
+              if (lane == 0) bmin_s[acc * 8 + (j >> 5)] = ordered_to_score(mn);
+            }
           }
           asm volatile("bar.sync 1, 128;" ::: "memory");
         }
@@ -361,6 +404,49 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
               }
             }
             __syncwarp();
+          }
+          if constexpr (SYM) {
+            // column direction: this thread's row is a candidate of the 32 keyframes that head the columns
+            const bool maybe = do_cols && row_live && mx >= bmin_s[acc * 8 + c];
+            if (__any_sync(0xffffffffu, maybe)) {
+              uint32_t cm = 0;
+              if (maybe) {
+                const float4* bd4 = reinterpret_cast<const float4*>(bd_s + acc * BN + c * 32);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 b = bd4[i];
+                  cm |= (__uint_as_float(v[4 * i + 0]) >= b.x ? 1u : 0u) << (4 * i + 0);
+                  cm |= (__uint_as_float(v[4 * i + 1]) >= b.y ? 1u : 0u) << (4 * i + 1);
+                  cm |= (__uint_as_float(v[4 * i + 2]) >= b.z ? 1u : 0u) << (4 * i + 2);
+                  cm |= (__uint_as_float(v[4 * i + 3]) >= b.w ? 1u : 0u) << (4 * i + 3);
+                }
+              }
+              while (cm) {
+                const int i = __ffs(cm) - 1;
+                cm &= cm - 1;
+                const float s = __uint_as_float(pick32(v, i));
+                const int j = acc * BN + c * 32 + i;
+                bool ok = true;
+                if (use_time) ok = !time_excluded(tq, ts_s[j], p.gap);     // |a - b| is symmetric in fp64
+                if (ok && mask_mode) ok = floor_ok(fl_s[j], qf, p.max_floor_diff);
+                if (ok) {
+                  const int col = col_base + c * 32 + i;                   // < N: columns beyond carry +inf bounds
+                  const uint32_t at = atomicAdd(p.sym_cnt + col, 1u);
+                  if (at < static_cast<uint32_t>(p.sym_cap))
+                    p.sym_ovf[static_cast<int64_t>(col) * p.sym_cap + at] = pack_key(s, static_cast<uint32_t>(grow) + p.db_index_offset);
+                  else
+                    *reinterpret_cast<volatile uint32_t*>(p.sym_flag) = 1u;
+                }
+              }
+              __syncwarp();
+            }
+          }
+        }
+        if constexpr (SYM) {
+          // publish this row's admission bound once it is a real k-th score (monotone)
+          if (row_live && L.cnt == k && L.f > published) {
+            atomicMax(p.sym_bound + grow, score_to_ordered(L.f));
+            published = L.f;
           }
         }
         // accumulator drained: hand it back to the MMA issuer

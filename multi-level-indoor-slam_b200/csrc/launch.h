@@ -20,11 +20,22 @@ struct TopkLaunch {
   int cta_group;                                  // CTAs per schedule unit: 1, 2 (cta_group::2 pair) or 4 (two pairs, multicast)
   int sm_count;
   float* dense; int64_t dense_ld;                 // non-null: dense fp32 similarity output instead of lists
+  void* state;                                    // symmetric schedule: sym_state_bytes() of device memory (pacing counters,
+                                                  // bounds, counts, flag, candidate buffers); else optional home of the
+                                                  // pacing counters (null: behind the partial lists)
+  const uint32_t* run_if;                         // non-null: device flag, the launch is a no-op unless it is non-zero
 };
 
 // Tile schedule for a Q x N problem on `units` CTAs (1), CTA pairs (2) or two-pair clusters (4).
 int topk_units(int cta_group, int sm_count);
-Schedule make_schedule(int64_t Q, int64_t N, int d_pad, int cta_group, int sm_count);
+Schedule make_schedule(int64_t Q, int64_t N, int d_pad, int cta_group, int sm_count, bool sym = false, int part_index = 0,
+                       int part_count = 1);
+// symmetric sweep (queries == database): state behind the partial lists, see gated_topk.cu
+int sym_capacity(int k, int64_t N);
+size_t topk_sync_bytes(const Schedule& sc);
+size_t sym_zeroed_bytes(int64_t N, size_t sync_bytes);
+size_t sym_state_bytes(int64_t N, int k, size_t sync_bytes);
+int schedule_selfcheck(const Schedule& sc, int units, int64_t* tiles_computed, int64_t* makespan_tiles);
 size_t topk_partial_bytes(const Schedule& sc, int cta_group, int k);      // candidate-key lists (256-byte multiple)
 size_t topk_workspace_bytes(const Schedule& sc, int cta_group, int k);    // lists + pacing counters
 
@@ -53,6 +64,11 @@ struct MergeLaunch {
   const uint64_t* const* list_ptrs;  // optional device array of n_lists pointers: list g of row r = list_ptrs[g] + r*k
                                      // (per-GPU lists read in place over NVLink peer memory; keys_in unused)
   const uint64_t* seed_keys;         // optional [Q,k]: one more list per row (may alias keys_out)
+  // symmetric sweep: while *sym_flag == 0 the lists follow `sc_sym` and row r also owns the first
+  // min(sym_cnt[r], sym_cap) keys of sym_ovf + r * sym_cap; otherwise (overflow: the full sweep ran) `sc` holds
+  const uint32_t* sym_flag; const uint32_t* sym_cnt; const uint64_t* sym_ovf; int sym_cap;
+  int sym_force;                     // 1: no full sweep stands behind (one part of a multi-GPU sweep): `sc_sym` always holds
+  Schedule sc_sym;
   // outputs (any may be null)
   uint64_t* keys_out;                // [Q,k] sorted descending, 0 padded
   float* scores; int32_t* idx; uint8_t* valid; int32_t* count;

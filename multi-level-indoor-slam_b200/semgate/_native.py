@@ -29,6 +29,7 @@ SYMBOLS = [
     "semgate_gate_candidates_host", "semgate_spatial_workspace_bytes", "semgate_spatial_count", "semgate_spatial_fill",
     "semgate_spatial_candidates_host", "semgate_rerank_scores", "semgate_rerank_select", "semgate_similarity_matrix",
     "semgate_merge_topk_peers", "semgate_compact_valid", "semgate_stats_workspace_bytes", "semgate_candidate_stats",
+    "semgate_last_sweep_mode", "semgate_schedule_check",
 ]
 
 
@@ -48,6 +49,9 @@ class TopkParams(C.Structure):
         ("db_index_offset", C.c_uint32),
         ("cta_group", C.c_int32),
         ("accumulate", C.c_int32),
+        ("symmetric", C.c_int32),
+        ("part_index", C.c_int32),
+        ("part_count", C.c_int32),
     ]
 
 
@@ -102,6 +106,8 @@ def load_library():
     lib.semgate_stats_workspace_bytes.argtypes = []
     lib.semgate_stats_workspace_bytes.restype = sz
     lib.semgate_candidate_stats.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp]
+    lib.semgate_last_sweep_mode.argtypes = [vp, P(i32), P(i64)]
+    lib.semgate_schedule_check.argtypes = [i64, i64, i32, i32, i32, i32, i32, i32, P(i32), P(i64)]
     for name in SYMBOLS:
         getattr(lib, name)   # AttributeError here = the library is older than the header
     _lib = lib
@@ -119,13 +125,26 @@ def pad_dim(d: int) -> int:
 
 def make_params(k: int, similarity_threshold: float = -np.inf, min_time_gap: float = 10.0, max_floor_diff: int = -1,
                 gate_mode: int = GATE_FLAG, db_index_offset: int = 0, cta_group: int = 0,
-                accumulate: bool = False) -> TopkParams:
+                accumulate: bool = False, symmetric: int = 0, part_index: int = 0, part_count: int = 0) -> TopkParams:
     if not (1 <= int(k) <= MAX_K):
         raise ValueError(f"k={k} outside 1..{MAX_K}")
     # the reference compares `sim < threshold` in the similarity dtype (fp32): same rounding here
     thr = float(np.float32(similarity_threshold))
     return TopkParams(thr, float(min_time_gap), int(k), int(max_floor_diff), int(gate_mode), int(db_index_offset),
-                      int(cta_group), 1 if accumulate else 0)
+                      int(cta_group), 1 if accumulate else 0, int(symmetric), int(part_index), int(part_count))
+
+
+def schedule_check(Q: int, N: int, d_pad: int, cta_group: int = 2, sm_count: int = 148, symmetric: bool = False,
+                   part_index: int = 0, part_count: int = 1):
+    """Host-side walk of the fused kernel's tile schedule (no device needed); raises if an invariant breaks.
+    Returns dict(blocks, tiles, rm, s_main, r_last, s_last, window, resident, computed, makespan)."""
+    shape, tiles = (C.c_int32 * 8)(), (C.c_int64 * 2)()
+    _check(load_library().semgate_schedule_check(int(Q), int(N), int(d_pad), int(cta_group), int(sm_count),
+                                                 1 if symmetric else 0, int(part_index), int(part_count), shape, tiles))
+    names = ("blocks", "tiles", "rm", "s_main", "r_last", "s_last", "window", "resident")
+    out = dict(zip(names, list(shape)))
+    out["computed"], out["makespan"] = int(tiles[0]), int(tiles[1])
+    return out
 
 
 def _np_ptr(a: Optional[np.ndarray]):
@@ -176,6 +195,12 @@ class Engine:
         ms, n = C.c_double(0.0), C.c_int64(0)
         _check(self.lib.semgate_profile_read(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def last_sweep_mode(self):
+        """(mode, tiles) of the last gated_topk: 0 full sweep, 1 symmetric, 2 symmetric overflowed -> full redone."""
+        mode, tiles = C.c_int32(0), C.c_int64(0)
+        _check(self.lib.semgate_last_sweep_mode(self._h, C.byref(mode), C.byref(tiles)))
+        return mode.value, tiles.value
 
     @property
     def launch_count(self) -> int:

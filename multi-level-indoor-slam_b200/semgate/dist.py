@@ -10,6 +10,10 @@ order is an associative merge, so the result equals the single-GPU sweep exactly
 
 That exchange is the path's only one; there is no reduction over the descriptor
 dimension and no all-to-all.
+
+All-pairs sweeps (`sweep_all_pairs`: the queries are the whole database, held by every
+rank) split the triangle of similarity tiles instead of the rows, because S = S^T:
+half the tensor work, the same exchange.
 """
 from __future__ import annotations
 
@@ -46,6 +50,7 @@ class ShardedRetrieval:
         self.exchange = exchange
         self._symm = None          # (shape, keys tensor, handle)
         self.peer_error = None     # why "auto" fell back, if it did
+        self.last_all_pairs = None # how the last sweep_all_pairs ran
 
     # -- peer-memory exchange ----------------------------------------------------
     def _symm_keys(self, Q: int, k: int, device):
@@ -71,32 +76,31 @@ class ShardedRetrieval:
         except Exception:
             return False
 
-    def sweep(self, q_bf16, db_shard_bf16, make_params, shard_lo: int, q_ts=None, db_ts_shard=None, q_floor=None,
-              db_floor_shard=None, db_floor_all=None, max_floor_diff: int = -1):
-        """`make_params(db_index_offset)` builds the sweep parameters for this shard.
-        Returns the merged TopkResult (identical on every rank)."""
+    def _exchange_and_merge(self, local_fn, Q: int, k: int, device, q_floor, db_floor_all, max_floor_diff: int,
+                            agree=None):
+        """`local_fn(keys)` runs this rank's sweep, writing its `[Q,k]` key lists into `keys` when given
+        (the symmetric-memory buffer) or returning them in `.keys`; the lists of all ranks are then merged
+        on every rank.  `agree()`, if given, is called by every rank after its sweep and before anybody
+        reads a peer's lists; a false answer (collective: the same on all ranks) abandons the merge."""
         import torch
-        params = make_params(shard_lo)
-        if self.world == 1:
-            return self.engine.gated_topk(q_bf16, db_shard_bf16, params, q_ts=q_ts, db_ts=db_ts_shard, q_floor=q_floor,
-                                          db_floor=db_floor_shard)
-        Q, k = q_bf16.shape[0], params.k if hasattr(params, "k") else params["k"]
         if self._use_peer():
             try:
-                keys, hdl = self._symm_keys(Q, k, q_bf16.device)
+                keys, hdl = self._symm_keys(Q, k, device)
             except Exception as e:          # no P2P mapping on this system
                 if self.exchange == "peer":
                     raise
                 self.peer_error = f"{type(e).__name__}: {e}"
             else:
                 hdl.barrier(channel=0)      # every rank has finished reading the previous step's keys
-                self.engine.gated_topk(q_bf16, db_shard_bf16, params, q_ts=q_ts, db_ts=db_ts_shard, q_floor=q_floor,
-                                       db_floor=db_floor_shard, want_lists=False, keys=keys)
+                local_fn(keys)
+                if agree is not None and not agree():
+                    return None
                 hdl.barrier(channel=1)      # every rank's keys are written
                 return self.engine.merge_topk_peers(hdl.buffer_ptrs_dev, self.world, Q, k, q_floor=q_floor,
                                                     db_floor_all=db_floor_all, max_floor_diff=max_floor_diff)
-        local = self.engine.gated_topk(q_bf16, db_shard_bf16, params, q_ts=q_ts, db_ts=db_ts_shard, q_floor=q_floor,
-                                       db_floor=db_floor_shard, want_keys=True, want_lists=False)
+        local = local_fn(None)
+        if agree is not None and not agree():
+            return None
         buf = self._gather_buf
         if buf is None or buf.shape != (self.world * Q, k) or buf.device != local.keys.device:
             # concatenation along dim 0 is the layout every backend accepts; viewed as [G,Q,k] below
@@ -105,6 +109,72 @@ class ShardedRetrieval:
         self.dist.all_gather_into_tensor(buf, local.keys, group=self.group)
         return self.engine.merge_topk(buf.view(self.world, Q, k), k, q_floor=q_floor, db_floor_all=db_floor_all,
                                       max_floor_diff=max_floor_diff)
+
+    def sweep(self, q_bf16, db_shard_bf16, make_params, shard_lo: int, q_ts=None, db_ts_shard=None, q_floor=None,
+              db_floor_shard=None, db_floor_all=None, max_floor_diff: int = -1):
+        """`make_params(db_index_offset)` builds the sweep parameters for this shard.
+        Returns the merged TopkResult (identical on every rank)."""
+        params = make_params(shard_lo)
+        eng = self.engine
+        if self.world == 1:
+            return eng.gated_topk(q_bf16, db_shard_bf16, params, q_ts=q_ts, db_ts=db_ts_shard, q_floor=q_floor,
+                                  db_floor=db_floor_shard)
+        Q, k = q_bf16.shape[0], params.k if hasattr(params, "k") else params["k"]
+
+        def local_fn(keys):
+            if keys is not None:
+                return eng.gated_topk(q_bf16, db_shard_bf16, params, q_ts=q_ts, db_ts=db_ts_shard, q_floor=q_floor,
+                                      db_floor=db_floor_shard, want_lists=False, keys=keys)
+            return eng.gated_topk(q_bf16, db_shard_bf16, params, q_ts=q_ts, db_ts=db_ts_shard, q_floor=q_floor,
+                                  db_floor=db_floor_shard, want_keys=True, want_lists=False)
+        return self._exchange_and_merge(local_fn, Q, k, q_bf16.device, q_floor, db_floor_all, max_floor_diff)
+
+    def sweep_all_pairs(self, x_bf16, make_params, ts=None, floor=None, max_floor_diff: int = -1):
+        """All-pairs sweep of a database every rank holds in full (`find_loop_closures` over the whole map:
+        the queries ARE the database, place_recognition.py:190 computes X X^T).  Similarity is symmetric, so
+        the ranks split the TRIANGLE of tiles instead of the rows: every rank computes its share of the
+        tiles on or above the block diagonal once and gates each of them in both directions
+        (`semgate_topk_params.part_index / part_count`), then the per-rank lists are merged as in `sweep`.
+        Half the tensor work of the row-sharded sweep, same lists.  If any rank's candidate buffers overflow
+        (thresholds that admit most of the database) all ranks agree on it and redo the sweep row-sharded.
+        Returns the merged TopkResult (identical on every rank)."""
+        import torch
+        eng = self.engine
+        n = x_bf16.shape[0]
+        params = make_params(0)
+        if self.world == 1:
+            return eng.gated_topk(x_bf16, x_bf16, params, q_ts=ts, db_ts=ts, q_floor=floor, db_floor=floor)
+        k = params.k if hasattr(params, "k") else params["k"]
+        wanted = (params.symmetric if hasattr(params, "symmetric") else params.get("symmetric", 0)) >= 0
+
+        def rows():
+            lo, hi = shard_bounds(n, self.world, self.rank)
+            return self.sweep(x_bf16, x_bf16[lo:hi], make_params, lo, q_ts=ts, db_ts_shard=None if ts is None else ts[lo:hi],
+                              q_floor=floor, db_floor_shard=None if floor is None else floor[lo:hi], db_floor_all=floor,
+                              max_floor_diff=max_floor_diff)
+        if not wanted or n <= 256:
+            return rows()
+        if hasattr(params, "part_count"):
+            params.symmetric, params.part_index, params.part_count = 1, self.rank, self.world
+            if params.cta_group == 0:
+                params.cta_group = 2          # a query block must be one database tile
+        else:
+            params.update(symmetric=1, part_index=self.rank, part_count=self.world)
+
+        def local_fn(keys):
+            if keys is not None:
+                return eng.gated_topk(x_bf16, x_bf16, params, q_ts=ts, db_ts=ts, q_floor=floor, db_floor=floor,
+                                      want_lists=False, keys=keys)
+            return eng.gated_topk(x_bf16, x_bf16, params, q_ts=ts, db_ts=ts, q_floor=floor, db_floor=floor,
+                                  want_keys=True, want_lists=False)
+
+        def agree():
+            over = torch.tensor([1 if eng.last_sweep_mode()[0] == 2 else 0], dtype=torch.int32, device=x_bf16.device)
+            self.dist.all_reduce(over, op=self.dist.ReduceOp.MAX, group=self.group)
+            return int(over.item()) == 0
+        res = self._exchange_and_merge(local_fn, n, k, x_bf16.device, floor, floor, max_floor_diff, agree=agree)
+        self.last_all_pairs = "triangle" if res is not None else "rows (candidate buffers overflowed)"
+        return res if res is not None else rows()
 
     def sweep_from_host(self, q_host, db_shard_host, ts_all_host, floor_all_host, make_params, shard_lo: int,
                         shard_hi: int, n_q: int, max_floor_diff: int = -1, src: int = 0):

@@ -30,17 +30,60 @@ def test_library_builds_and_exports_header_symbols():
     from semgate import _native
     assert sorted(_native.SYMBOLS) == declared, "ctypes binding and header disagree"
     lib.semgate_version.restype = ctypes.c_int
-    assert lib.semgate_version() == 100
+    assert lib.semgate_version() == 101
     assert lib.semgate_pad_dim(4096) == 4096 and lib.semgate_pad_dim(100) == 128 and lib.semgate_pad_dim(8448) == 8448
 
 
 def test_params_struct_layout():
     from semgate import _native
-    # float, (pad), double, 5 x 32-bit -> 40 bytes with natural alignment
-    assert ctypes.sizeof(_native.TopkParams) == 40
+    # float, (pad), double, 9 x 32-bit -> 52, rounded to the double's alignment
+    assert ctypes.sizeof(_native.TopkParams) == 56
+    assert _native.TopkParams.symmetric.offset == 40 and _native.TopkParams.part_count.offset == 48
     assert _native.TopkParams.min_time_gap.offset == 8 and _native.TopkParams.k.offset == 16
     p = _native.make_params(k=25, similarity_threshold=0.5, min_time_gap=10.0, max_floor_diff=0)
     assert p.k == 25 and p.similarity_threshold == 0.5 and p.gate_mode == 0
+
+
+@pytest.mark.parametrize("sym", [False, True])
+def test_tile_schedule_invariants(sym):
+    """The schedule every warp role of the fused kernel walks, checked on the host: each tile computed exactly
+    once (symmetric sweep: exactly the tiles on or above the block diagonal), list slots unique per block,
+    pacing counters in range and arrivals equal to what the waiters expect."""
+    import numpy as np
+    from semgate import _native
+    rng = np.random.default_rng(7)
+    sizes = [257, 300, 512, 513, 1000, 4096, 5000, 18945, 20000, 100000, 300000, 1000000]
+    sizes += [int(v) for v in rng.integers(257, 60000, size=24)]
+    for n in sizes:
+        for d_pad in (64, 512, 4096, 8448, 49152):
+            if n > 100000 and d_pad != 4096:
+                continue
+            for sms in (148, 132, 16):
+                if n > 100000 and sms != 148:
+                    continue
+                r = _native.schedule_check(n, n, d_pad, 2, sms, sym)
+                nb = (n + 255) // 256
+                assert r["blocks"] == nb and r["tiles"] == nb
+                assert r["computed"] == (nb * (nb + 1) // 2 if sym else nb * nb)
+    if not sym:   # rectangular problems, single-CTA tiles
+        for Q, N, cg in [(1, 1, 1), (100, 5000, 1), (10000, 100000, 2), (8192, 250000, 2), (1500, 300, 1), (129, 257, 2)]:
+            r = _native.schedule_check(Q, N, 4096, cg)
+            assert r["computed"] == r["blocks"] * r["tiles"]
+    else:
+        full = _native.schedule_check(1000000, 1000000, 4096, 2, 148, False)
+        half = _native.schedule_check(1000000, 1000000, 4096, 2, 148, True)
+        assert half["makespan"] < 0.51 * full["makespan"]
+        with pytest.raises(_native.SemgateError):
+            _native.schedule_check(1000, 2000, 4096, 2, 148, True)
+        # split over G GPUs: the parts tile the triangle exactly once and are balanced
+        for n, G in [(20000, 2), (56568, 8), (300000, 4), (1000000, 8), (5000, 3)]:
+            parts = [_native.schedule_check(n, n, 4096, 2, 148, True, g, G) for g in range(G)]
+            nb = (n + 255) // 256
+            assert sum(p["computed"] for p in parts) == nb * (nb + 1) // 2
+            if n >= 300000:
+                assert max(p["makespan"] for p in parts) <= 1.03 * sum(p["makespan"] for p in parts) / G
+        with pytest.raises(_native.SemgateError):
+            _native.schedule_check(5000, 5000, 4096, 2, 148, False, 1, 2)      # only symmetric sweeps split this way
 
 
 def test_no_gpu_fails_loudly():

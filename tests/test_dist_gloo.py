@@ -36,8 +36,35 @@ class OracleEngine:
     def normalize_cast(self, x, out=None):
         return x          # the stand-in sweep normalises inside the oracle call
 
+    overflow_on_rank = None       # test knob: this rank reports an overflowed symmetric part
+    _mode = 0
+
+    def last_sweep_mode(self):
+        return self._mode, 0
+
+    def _triangle_part(self, x, params, ts):
+        """One part of a symmetric all-pairs sweep: every unordered pair {i, j} belongs to exactly one part
+        (here: by the 64-row block of min(i, j), dealt out round-robin -- the kernel's own deal differs, any
+        exact partition merges to the same lists) and feeds the lists of both i and j."""
+        part, parts = params["part_index"], params["part_count"]
+        n = x.shape[0]
+        xn = O.l2_normalize(x)
+        S = xn @ xn.T
+        if ts is not None:
+            S[O.time_excluded(ts, ts, params["gap"])] = -np.inf
+        i, j = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+        S[((np.minimum(i, j) // 64) % parts) != part] = -np.inf
+        S[S < np.float32(params["thr"])] = -np.inf
+        sc, ix, ct = O._topk_rows(S, params["k"])
+        self._mode = 2 if self.overflow_on_rank == part else 1
+        return _Res(keys=torch.from_numpy(O.pack_keys(sc, ix)))
+
     def gated_topk(self, q_bf16, db_bf16, params, q_ts=None, db_ts=None, q_floor=None, db_floor=None,
                    want_keys=False, want_lists=True):
+        if params.get("part_count", 0) > 1:
+            assert q_bf16 is db_bf16 and q_ts is db_ts and q_floor is db_floor and params["symmetric"] == 1
+            return self._triangle_part(q_bf16.numpy(), params, None if q_ts is None else q_ts.numpy())
+        self._mode = 0
         lo, n = params["offset"], db_bf16.shape[0]
         r = O.gated_topk(q_bf16.numpy(), db_bf16.numpy(), None if q_ts is None else q_ts.numpy(),
                          None if db_ts is None else db_ts.numpy(), None if q_floor is None else q_floor.numpy(),
@@ -89,6 +116,16 @@ def _worker(rank, world, port, out_dir):
                                   n_q, max_floor_diff=0)
         for a, b in ((res.scores, res2.scores), (res.idx, res2.idx), (res.valid, res2.valid), (res.count, res2.count)):
             assert torch.equal(a, b), "sweep_from_host differs from sweep"
+        # all-pairs sweep: the ranks split the triangle of pairs; then the same with one rank reporting an
+        # overflowed part, which must send every rank down the row-sharded path
+        n_ap = 700
+        x, tts, tfl = t(desc[:n_ap]), t(ts[:n_ap]), t(fl[:n_ap])
+        for knob, how in ((None, "triangle"), (1, "rows (candidate buffers overflowed)")):
+            sr.engine.overflow_on_rank = knob
+            ap = sr.sweep_all_pairs(x, mk, ts=tts, floor=tfl, max_floor_diff=0)
+            assert sr.last_all_pairs == how
+            np.savez(os.path.join(out_dir, f"ap{0 if knob is None else 1}_rank{rank}.npz"), scores=ap.scores.numpy(),
+                     idx=ap.idx.numpy(), valid=ap.valid.numpy(), count=ap.count.numpy())
     finally:
         dist.destroy_process_group()
 
@@ -139,3 +176,11 @@ def test_sharded_sweep_world2_gloo(tmp_path):
     assert np.array_equal(r0["scores"], whole["scores"])
     assert np.array_equal(r0["valid"], whole["valid"])
     assert np.array_equal(r0["count"], whole["count"])
+    # all-pairs over the first 700 keyframes, triangle split and its row-sharded fallback
+    ap = O.gated_topk(desc[:700], desc[:700], ts[:700], ts[:700], fl[:700], fl[:700], k=k, threshold=0.3, min_time_gap=5.0,
+                      max_floor_diff=0)
+    for tag in ("ap0", "ap1"):
+        for rank in (0, 1):
+            r = np.load(tmp_path / f"{tag}_rank{rank}.npz")
+            assert np.array_equal(r["idx"], ap["idx"]) and np.array_equal(r["valid"], ap["valid"]), (tag, rank)
+            assert np.allclose(r["scores"], ap["scores"], atol=1e-6) and np.array_equal(r["count"], ap["count"])

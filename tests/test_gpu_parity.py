@@ -40,22 +40,24 @@ def _t(a, dtype=None):
 
 
 def run_gpu(eng, q, db, k, thr=-np.inf, gap=10.0, q_ts=None, db_ts=None, q_fl=None, db_fl=None, mfd=-1,
-            mode=0, cg=1, offset=0):
-    """normalise + gated_topk on the GPU; returns the padded result as numpy."""
+            mode=0, cg=1, offset=0, sym=0):
+    """normalise + gated_topk on the GPU; returns the padded result as numpy.  Arguments that are the same
+    object on the host are the same tensor on the device (what the symmetric sweep keys on)."""
     import torch
     from semgate import _native
     qb = eng.normalize_cast(_t(q, torch.float32))
     dbb = qb if db is q else eng.normalize_cast(_t(db, torch.float32))
     p = _native.make_params(k=k, similarity_threshold=thr, min_time_gap=gap, max_floor_diff=mfd, gate_mode=mode,
-                            db_index_offset=offset, cta_group=cg)
-    r = eng.gated_topk(qb, dbb, p,
-                       q_ts=None if q_ts is None else _t(q_ts, torch.float64),
-                       db_ts=None if db_ts is None else _t(db_ts, torch.float64),
-                       q_floor=None if q_fl is None else _t(q_fl, torch.int32),
-                       db_floor=None if db_fl is None else _t(db_fl, torch.int32), want_keys=True)
+                            db_index_offset=offset, cta_group=cg, symmetric=sym)
+    tq = None if q_ts is None else _t(q_ts, torch.float64)
+    td = tq if db_ts is q_ts else (None if db_ts is None else _t(db_ts, torch.float64))
+    fq = None if q_fl is None else _t(q_fl, torch.int32)
+    fd = fq if db_fl is q_fl else (None if db_fl is None else _t(db_fl, torch.int32))
+    r = eng.gated_topk(qb, dbb, p, q_ts=tq, db_ts=td, q_floor=fq, db_floor=fd, want_keys=True)
     torch.cuda.synchronize()
     return dict(scores=r.scores.cpu().numpy(), idx=r.idx.cpu().numpy().astype(np.int64),
-                valid=r.valid.cpu().numpy().astype(bool), count=r.count.cpu().numpy(), keys=r.keys.cpu().numpy())
+                valid=r.valid.cpu().numpy().astype(bool), count=r.count.cpu().numpy(), keys=r.keys.cpu().numpy(),
+                mode=eng.last_sweep_mode()[0])
 
 
 def check_padded(res, k):
@@ -716,6 +718,151 @@ def test_errors(eng):
     with pytest.raises(IndexError):
         SemanticLoopClosureGate(np.array([1, 2, 3])).gate_arrays([0], [7])
     assert SemanticPlaceRecognition('mixvpr').find_loop_closures() == []
+
+
+# --------------------------------------------------------------------------- symmetric all-pairs sweep
+def _same_lists(a, b, k, thr):
+    """Two sweeps of the same data: identical lists.  (S_ij comes out of a different tile position in the two
+    forms; if the tensor core's summation were not symmetric in its operands the scores could differ in the
+    last bit, so fall back to the parity rule with a last-bit tolerance before failing.)"""
+    if np.array_equal(a["keys"], b["keys"]):
+        assert np.array_equal(a["idx"], b["idx"]) and np.array_equal(a["valid"], b["valid"])
+        assert np.array_equal(a["count"], b["count"])
+        return
+    rep = parity.compare_candidates(O.compact(a), O.compact(b), k, thr, tol=2e-6)
+    assert rep["max_score_err"] <= 2e-6
+
+
+SYM_CASES = [
+    # n,    d,   k,  thr,   gap,  floors, mode, mfd
+    (300,   64,  5,  0.3,   2.0,  3, 0, 0),      # two blocks: diagonal tiles + one off-diagonal tile
+    (513,   96,  7,  0.2,   3.0,  4, 0, 0),      # ragged third block, D not a multiple of 64
+    (777,   128, 25, 0.5,   10.0, 3, 1, 0),      # mask mode
+    (1500,  64,  64, 0.3,   1.0,  3, 0, 1),      # k = 64, non-strict gate
+    (2500,  192, 25, 0.45,  10.0, 3, 1, 1),      # mask mode, non-strict
+    (5000,  512, 25, 0.5,   10.0, 3, 0, 0),      # C1
+    (9001,  64,  10, 0.35,  0.0,  5, 0, -1),     # gap = 0 (self pairs stay), gating off, several super-rows
+]
+
+
+@pytest.mark.parametrize("case", SYM_CASES, ids=[f"{c[0]}x{c[1]}k{c[2]}m{c[6]}" for c in SYM_CASES])
+def test_symmetric_sweep_equals_full_sweep(eng, case):
+    """Queries == database: every similarity computed once and gated in both directions gives the lists of the
+    full sweep, and the oracle's."""
+    from semgate import synthetic
+    n, d, k, thr, gap, nf, mode, mfd = case
+    desc, ts, fl = synthetic.make_case(n, d, nf, seed=n + d)
+    fl = fl.astype(np.int32)
+    if n == 777:
+        fl[::7] = O.FLOOR_NONE                          # unlabelled keyframes pass every gate
+    if n == 2500:
+        ts = ts[np.random.default_rng(3).permutation(n)].copy()   # unsorted stamps
+    kw = dict(k=k, thr=thr, gap=gap, q_ts=ts, db_ts=ts, mfd=mfd, mode=mode, cg=2)
+    if mfd >= 0:
+        kw.update(q_fl=fl, db_fl=fl)
+    full = run_gpu(eng, desc, desc, sym=-1, **kw)
+    half = run_gpu(eng, desc, desc, sym=1, **kw)
+    assert full["mode"] == 0 and half["mode"] == 1, "the symmetric sweep must have run (and not overflowed)"
+    check_padded(half, k)
+    _same_lists(full, half, k, thr)
+    ref = O.gated_topk(desc, desc, ts, ts, fl if mfd >= 0 else None, fl if mfd >= 0 else None, k=k, threshold=thr,
+                       min_time_gap=gap, max_floor_diff=mfd, gate_mode=mode, bf16=True)
+    parity.compare_candidates(O.compact(ref), O.compact(half), k, thr, tol=BF16_MODEL_TOL, exact_sets=False)
+    parity.check_decisions_exact(O.compact(half), ts, fl if mfd >= 0 else None, gap, mfd)
+
+
+def test_symmetric_sweep_overflow_falls_back_to_full_sweep(eng):
+    """A threshold that admits everything floods the per-keyframe candidate buffers: the overflow flag arms the
+    full sweep launched behind the symmetric one, and the lists are still the full sweep's."""
+    from semgate import synthetic
+    n, d, k = 3000, 64, 25
+    desc, ts, fl = synthetic.make_case(n, d, 3, seed=5)
+    fl = fl.astype(np.int32)
+    kw = dict(k=k, thr=-np.inf, gap=10.0, q_ts=ts, db_ts=ts, q_fl=fl, db_fl=fl, mfd=0, cg=2)
+    full = run_gpu(eng, desc, desc, sym=-1, **kw)
+    half = run_gpu(eng, desc, desc, sym=0, **kw)
+    assert half["mode"] == 2, "the buffers must have overflowed"
+    _same_lists(full, half, k, -np.inf)
+    # a threshold that lets a few dozen candidates per keyframe through stays inside the buffers
+    some = run_gpu(eng, desc, desc, sym=0, **dict(kw, thr=0.3))
+    assert some["mode"] == 1
+    _same_lists(run_gpu(eng, desc, desc, sym=-1, **dict(kw, thr=0.3)), some, k, 0.3)
+
+
+@pytest.mark.parametrize("chunks", ["1", "3"])
+def test_symmetric_sweep_paced(eng, chunks, monkeypatch):
+    """Forced pacing windows: units whose first tiles lie left of the diagonal still arrive on the counters."""
+    from semgate import synthetic
+    n, d, k = 6000, 256, 25
+    desc, ts, fl = synthetic.make_case(n, d, 3, seed=21)
+    fl = fl.astype(np.int32)
+    kw = dict(k=k, thr=0.5, gap=10.0, q_ts=ts, db_ts=ts, q_fl=fl, db_fl=fl, mfd=0, cg=2)
+    full = run_gpu(eng, desc, desc, sym=-1, **kw)
+    monkeypatch.setenv("SEMGATE_WINDOW_CHUNKS", chunks)
+    half = run_gpu(eng, desc, desc, sym=1, **kw)
+    assert half["mode"] == 1
+    _same_lists(full, half, k, 0.5)
+
+
+def test_symmetric_sweep_argument_rules(eng):
+    import torch
+    from semgate import _native
+    x = eng.normalize_cast(torch.randn(600, 64, device="cuda"))
+    y = x.clone()
+    ts = torch.arange(600, device="cuda", dtype=torch.float64)
+    with pytest.raises(_native.SemgateError):           # different matrices
+        eng.gated_topk(x, y, _native.make_params(k=5, cta_group=2, symmetric=1), q_ts=ts, db_ts=ts)
+    with pytest.raises(_native.SemgateError):           # single-CTA tiles
+        eng.gated_topk(x, x, _native.make_params(k=5, cta_group=1, symmetric=1), q_ts=ts, db_ts=ts)
+    with pytest.raises(_native.SemgateError):           # different stamps
+        eng.gated_topk(x, x, _native.make_params(k=5, cta_group=2, symmetric=1), q_ts=ts, db_ts=ts.clone())
+    with pytest.raises(_native.SemgateError):           # parts only split a symmetric sweep
+        eng.gated_topk(x, x, _native.make_params(k=5, cta_group=2, part_index=0, part_count=2), q_ts=ts, db_ts=ts)
+    with pytest.raises(_native.SemgateError):
+        eng.gated_topk(x, x, _native.make_params(k=5, cta_group=2, symmetric=1, part_index=2, part_count=2), q_ts=ts, db_ts=ts)
+    auto = dict(k=5, cta_group=2, similarity_threshold=0.3)
+    eng.gated_topk(x, y, _native.make_params(**auto), q_ts=ts, db_ts=ts)          # auto: full sweep
+    assert eng.last_sweep_mode()[0] == 0
+    eng.gated_topk(x, x, _native.make_params(**auto), q_ts=ts, db_ts=ts)          # auto: symmetric
+    assert eng.last_sweep_mode() == (1, 6)                                        # 3 blocks: 6 tiles of the 9
+    eng.set_option("symmetric", -1)
+    try:
+        eng.gated_topk(x, x, _native.make_params(**auto), q_ts=ts, db_ts=ts)
+        assert eng.last_sweep_mode() == (0, 9)
+    finally:
+        eng.set_option("symmetric", 0)
+
+
+@pytest.mark.parametrize("G", [2, 3, 8])
+def test_symmetric_sweep_parts_merge_to_full_sweep(eng, G):
+    """The multi-GPU form on one GPU: the G parts of the tile triangle, swept one after the other and merged by
+    K3, give the lists of the full sweep."""
+    import torch
+    from semgate import _native, synthetic
+    n, d, k = 12000, 128, 25
+    desc, ts, fl = synthetic.make_case(n, d, 4, seed=77)
+    xb = eng.normalize_cast(_t(desc, torch.float32))
+    tts, tfl = _t(ts, torch.float64), _t(fl.astype(np.int32), torch.int32)
+    common = dict(k=k, similarity_threshold=0.5, min_time_gap=10.0, max_floor_diff=0, cta_group=2)
+    full = eng.gated_topk(xb, xb, _native.make_params(symmetric=-1, **common), q_ts=tts, db_ts=tts, q_floor=tfl, db_floor=tfl,
+                          want_keys=True)
+    keys, tiles = [], 0
+    for g in range(G):
+        p = _native.make_params(symmetric=1, part_index=g, part_count=G, **common)
+        r = eng.gated_topk(xb, xb, p, q_ts=tts, db_ts=tts, q_floor=tfl, db_floor=tfl, want_lists=False, want_keys=True)
+        mode, t = eng.last_sweep_mode()
+        assert mode == 1
+        tiles += t
+        keys.append(r.keys.clone())
+    nb = (n + 255) // 256
+    assert tiles == nb * (nb + 1) // 2, "the parts must tile the triangle exactly once"
+    merged = eng.merge_topk(torch.stack(keys), k, q_floor=tfl, db_floor_all=tfl, max_floor_diff=0, want_keys=True)
+    torch.cuda.synchronize()
+    a = dict(keys=full.keys.cpu().numpy(), idx=full.idx.cpu().numpy().astype(np.int64), valid=full.valid.cpu().numpy().astype(bool),
+             count=full.count.cpu().numpy(), scores=full.scores.cpu().numpy())
+    b = dict(keys=merged.keys.cpu().numpy(), idx=merged.idx.cpu().numpy().astype(np.int64),
+             valid=merged.valid.cpu().numpy().astype(bool), count=merged.count.cpu().numpy(), scores=merged.scores.cpu().numpy())
+    _same_lists(a, b, k, 0.5)
 
 
 # --------------------------------------------------------------------------- full-size properties (BASELINE config 2)

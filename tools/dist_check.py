@@ -61,6 +61,22 @@ def check(sr, eng, dev, rank, world, exchange):
                         max_floor_diff=0)
         torch.cuda.synchronize()
         ok = ok and torch.equal(res2.idx, whole.idx) and torch.equal(res2.scores, whole.scores)
+        # all-pairs: the ranks split the triangle of tiles (every similarity computed once, on one GPU);
+        # with a threshold that admits everything the candidate buffers may overflow -> row-sharded redo
+        for thr_ap in (thr, -np.inf):
+            mk_ap = lambda off: _native.make_params(k=k, similarity_threshold=thr_ap, min_time_gap=gap, max_floor_diff=0,
+                                                    db_index_offset=off)
+            p_full = mk_ap(0)
+            p_full.symmetric = -1
+            full = eng.gated_topk(xb, xb, p_full, q_ts=tts, db_ts=tts, q_floor=tfl, db_floor=tfl)
+            ap = sr.sweep_all_pairs(xb, mk_ap, ts=tts, floor=tfl, max_floor_diff=0)
+            torch.cuda.synchronize()
+            good = (torch.equal(ap.idx, full.idx) and torch.equal(ap.scores, full.scores)
+                    and torch.equal(ap.valid, full.valid) and torch.equal(ap.count, full.count))
+            if thr_ap == thr:
+                good = good and sr.last_all_pairs == "triangle"
+            print(f"rank {rank}/{world} [{exchange}]: all-pairs n={n_db} thr={thr_ap}: {sr.last_all_pairs}: ok={good}", flush=True)
+            ok = ok and good
     return ok
 
 
