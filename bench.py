@@ -4,12 +4,14 @@ gated similarity pairs/s + queries/s at top-25; % of bf16 tensor peak).
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE config 2, MixVPR shape): 20 000 query keyframes x 4096-d against a
-database of 20 000 keyframes PER GPU (N=1: the 20k all-pairs loop-closure sweep with floor
-gate; N>1: the database grows with N and is sharded by rows, per-GPU work is fixed ->
-"weak").  A step = one pass of the hot path over resident, already normalised bf16
-descriptors: fused tcgen05 sweep (K2) + list merge (K3) [+ NCCL all-gather + merge at N>1]
-+ candidate compaction (K4).  `value` = query-database pairs scored per second, whole job.
+Workload (BASELINE config 2, MixVPR shape): the all-pairs loop-closure sweep with floor gate over
+n keyframes x 4096-d, 20 000^2 gated pairs PER GPU: n = 20 000 on one GPU (the configuration the
+metric is quoted on), n ~ 20 000 * sqrt(N) on N GPUs (28 160 / 39 936 / 56 320 at N = 2 / 4 / 8),
+where the GPUs split the triangle of similarity tiles -> per-GPU work is fixed, "weak".
+(`--symmetric off`: the full-matrix form; at N>1 then 20 000 queries against 20 000 database rows
+per GPU, sharded by rows.)  A step = one pass of the hot path over resident, already normalised bf16
+descriptors: fused tcgen05 sweep (K2) + list merge (K3) [+ exchange of the per-GPU lists over NVLink
++ merge at N>1] + candidate compaction (K4).  `value` = query-database pairs gated per second, whole job.
 `e2e` = the same metric through the host-buffer C-ABI call (fp32 descriptors in pinned host
 memory -> candidates back in host memory: H2D, normalise, sweep, compaction, D2H all timed).
 """
@@ -39,6 +41,7 @@ NUM_FLOORS = 3
 METRIC = "gated_similarity_pairs_per_s_top25"
 UNIT = "pairs/s"
 STRONG = False       # --workload c5: fixed 1M x 1M sweep, database rows split over the ranks
+ALLPAIRS = False     # default workload at N>1: all-pairs sweep, the ranks split the triangle of tiles (weak scaling)
 WORKLOAD_NAME = "BASELINE configs[1]: MixVPR-shape 4096-d, 20k-keyframe all-pairs loop-closure sweep with floor gate"
 
 
@@ -63,6 +66,22 @@ def set_workload(name: str):
         raise SystemExit(f"unknown workload {name}")
 
 
+def allpairs_keyframes(n_gpus: int) -> int:
+    """Keyframes of the all-pairs sweep whose pair count is 20 000^2 per GPU (equal row shards of whole
+    128-row blocks, so the e2e leg's all-gather of normalised rows is regular)."""
+    if n_gpus <= 1:
+        return 20000
+    g = 128 * n_gpus
+    return int(round(20000.0 * (n_gpus ** 0.5) / g)) * g
+
+
+def enable_allpairs(n_gpus: int):
+    global N_Q, N_DB_PER_GPU, STRONG, ALLPAIRS, WORKLOAD_NAME
+    N_Q = N_DB_PER_GPU = allpairs_keyframes(n_gpus)
+    STRONG = ALLPAIRS = True        # every rank holds the whole matrix; the work (not the rows) is split
+    WORKLOAD_NAME += f" -- {n_gpus} GPUs: all-pairs sweep over {N_Q} keyframes (20000^2 pairs per GPU)"
+
+
 def db_total(n_gpus: int) -> int:
     return N_DB_PER_GPU if STRONG else N_DB_PER_GPU * n_gpus
 
@@ -72,7 +91,11 @@ def workload_config(n_gpus: int):
         "workload": WORKLOAD_NAME,
         "queries": N_Q, "database_per_gpu": db_total(n_gpus) // n_gpus, "database_total": db_total(n_gpus), "dim": DIM,
         "top_k": TOPK, "similarity_threshold": THRESHOLD, "min_time_gap_s": MIN_TIME_GAP, "floors": NUM_FLOORS,
-        "gate": "strict floor gate, flag mode (reference order)", "sharding": f"db-rows x{n_gpus}" if n_gpus > 1 else "none",
+        "gate": "strict floor gate, flag mode (reference order)",
+        "sharding": ("none" if n_gpus == 1 else
+                     f"triangle of similarity tiles x{n_gpus} (every rank holds all rows; each similarity is computed once, on one GPU)"
+                     if ALLPAIRS else f"db-rows x{n_gpus}"),
+        "pairs_per_gpu": float(N_Q) * db_total(n_gpus) / n_gpus,
         "l2": f"inputs larger than L2 ({2 * db_total(n_gpus) // n_gpus * DIM / 1e6:.0f} MB bf16 database per GPU vs 126 MB L2); no explicit flush",
     }
 
@@ -220,7 +243,7 @@ def run_reference(args):
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(1),
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus if ALLPAIRS else 1),
         "queries_per_s": rows * args.steps / dt,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -391,12 +414,12 @@ def run_ours(args):
         except Exception:
             pass
 
-    if STRONG or args.no_e2e or args.workload != "c2":
+    if (STRONG and not ALLPAIRS) or args.no_e2e or args.workload != "c2":
         if rank == 0:
             out_json = {
                 "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "strong" if STRONG else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "scaling": "strong" if (STRONG and not ALLPAIRS) else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": workload_config(world), "queries_per_s": N_Q * args.steps / (ms * 1e-3),
                 "candidates_per_step": total_candidates, "roofline": roofline, "cpu_baseline": None, "e2e": None,
                 "gpu_launches": int(launches), "clocks": clocks,
@@ -410,8 +433,12 @@ def run_ours(args):
 
     # ---- end to end through the public host-buffer API (pinned host memory in, host memory out)
     e2e_steps = max(3, min(args.steps, 10))
-    q_host = torch.empty((N_Q, DIM), dtype=torch.float32, pin_memory=True)
-    q_host.copy_(q_f32)
+    if ALLPAIRS:
+        q_host = torch.empty((hi - lo, DIM), dtype=torch.float32, pin_memory=True)   # this rank's rows of the database
+        q_host.copy_(make_rows(hi - lo, 5000 + rank))
+    else:
+        q_host = torch.empty((N_Q, DIM), dtype=torch.float32, pin_memory=True)
+        q_host.copy_(q_f32)
     ts_host = synthetic.make_timestamps(n_db_total)
     fl_host = synthetic.make_floors(n_db_total, NUM_FLOORS).astype(np.int32)
     cap = N_Q * TOPK
@@ -425,6 +452,22 @@ def run_ours(args):
             r = eng.find_loop_closures_host(qh, ts_host, fl_host, p, out=outs)   # semgate_find_loop_closures_host
             return len(r[0])
         h2d = qh.nbytes + ts_host.nbytes + fl_host.nbytes
+    elif ALLPAIRS:
+        tsh = torch.from_numpy(ts_host).pin_memory()
+        flh = torch.from_numpy(fl_host).pin_memory()
+        ho = [torch.empty((cap,), dtype=dt, pin_memory=True) for dt in (torch.int32, torch.int32, torch.float32, torch.uint8)]
+
+        def e2e_step():
+            # every rank uploads and normalises its rows; the bf16 rows meet over NVLink (all-gather); triangle sweep
+            res = sr.sweep_all_pairs_from_host(q_host, tsh, flh, mk, lo, hi, N_Q, max_floor_diff=0)
+            oq, om, os_, ov, tot = eng.compact(res)
+            t = int(tot.item())
+            if rank == 0:
+                for h, d in zip(ho, (oq, om, os_, ov)):
+                    h[:t].copy_(d[:t], non_blocking=True)
+                torch.cuda.synchronize()
+            return t
+        h2d = N_Q * DIM * 4 + (ts_host.nbytes + fl_host.nbytes) * world   # one fp32 row shard per rank
     else:
         db_host = q_host if rank == 0 else torch.empty((hi - lo, DIM), dtype=torch.float32, pin_memory=True)
         if rank != 0:
@@ -459,6 +502,7 @@ def run_ours(args):
     e2e = {"value": pairs_per_step * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(n_e2e * 13 + 8), "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
            "api": "semgate_find_loop_closures_host (C ABI, pinned host buffers)" if world == 1 else
+                  "semgate python API (ShardedRetrieval.sweep_all_pairs_from_host): pinned host row shard -> device per rank, normalise, NCCL all-gather of the bf16 rows over NVLink, triangle sweep, list merge over NVLink, compaction, D2H" if ALLPAIRS else
                   "semgate python API (ShardedRetrieval.sweep_from_host): pinned host shard -> device per rank, normalise, NVLink broadcast of the bf16 queries, sharded sweep, NCCL merge, compaction, D2H"}
 
     if rank != 0:
@@ -482,6 +526,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
+        "all_pairs_split": sr.last_all_pairs,
         "queries_per_s": N_Q * args.steps / (ms * 1e-3), "candidates_per_step": total_candidates,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "cta_group": args.cta_group or os.environ.get("SEMGATE_CTA_GROUP", "auto (2 for Q >= 4096)"),
@@ -509,6 +554,8 @@ def main():
                     help="c2 (default) is the configuration the metric is quoted on")
     args = ap.parse_args()
     set_workload(args.workload)
+    if args.workload == "c2" and args.gpus > 1 and args.symmetric == "auto":
+        enable_allpairs(args.gpus)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "ours" and args.gpus != world:
         if args.gpus > 1:

@@ -45,15 +45,22 @@ int topk_units(int cta_group, int sm_count) {
   return std::max(1, cached > 0 ? cached : sm_count / 4 - 5);   // conservative if the query failed
 }
 
-// makespan of a symmetric sweep in tile-times: super-row sr sweeps the tiles [sr*rm, nb) in min(S, length) runs
-static int64_t sym_cost(int nb, int rm, int units) {
-  int64_t c = 0;
-  for (int lo = 0; lo < nb; lo += rm) {
+// makespan of a symmetric sweep in tile-times: super-row sr sweeps the tiles [sr*rm, nb) in min(S, length) runs;
+// split over `parts` GPUs (sched_owned's deal) it is the busiest part's
+static int64_t sym_cost(int nb, int rm, int units, int parts) {
+  std::vector<int64_t> c(static_cast<size_t>(std::max(parts, 1)), 0);
+  Schedule deal{};
+  deal.part_count = parts;
+  int sr = 0;
+  for (int lo = 0; lo < nb; lo += rm, ++sr) {
     const int r = std::min(rm, nb - lo), len = nb - lo;
     const int S = std::min(len, std::max(1, units / r));
-    c += (len + S - 1) / S;
+    for (int g = 0; g < std::max(parts, 1); ++g) {
+      deal.part_index = g;
+      if (sched_owned(deal, sr)) c[g] += (len + S - 1) / S;
+    }
   }
-  return c;
+  return *std::max_element(c.begin(), c.end());
 }
 
 Schedule make_schedule(int64_t Q, int64_t N, int d_pad, int cta_group, int sm_count, bool sym, int part_index, int part_count) {
@@ -85,7 +92,7 @@ Schedule make_schedule(int64_t Q, int64_t N, int d_pad, int cta_group, int sm_co
       const int s_last = std::min(sc.ntiles, units / r_last);
       c += (sc.ntiles + s_last - 1) / s_last;
     }
-    if (sym) c = sym_cost(sc.ntiles, rm, units);
+    if (sym) c = sym_cost(sc.ntiles, rm, units, sc.part_count);
     cost[rm] = c;
     if (best_cost < 0 || c < best_cost) best_cost = c;
   }

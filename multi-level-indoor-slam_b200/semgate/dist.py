@@ -176,6 +176,30 @@ class ShardedRetrieval:
         self.last_all_pairs = "triangle" if res is not None else "rows (candidate buffers overflowed)"
         return res if res is not None else rows()
 
+    def sweep_all_pairs_from_host(self, x_shard_host, ts_all_host, floor_all_host, make_params, shard_lo: int,
+                                  shard_hi: int, n: int, max_floor_diff: int = -1):
+        """End-to-end form of `sweep_all_pairs` for a database that lives in pinned HOST memory, one
+        contiguous row shard per rank (equal shards): every rank uploads and normalises only its own rows
+        (fp32 `[hi-lo, D]`), the normalised bf16 rows meet on every GPU through an NCCL all-gather over
+        NVLink, then the ranks split the triangle of tiles.  Returns the merged TopkResult."""
+        import torch
+        eng = self.engine
+        dev = getattr(eng, "torch_device", None) or torch.device("cuda", eng.device)
+        if (shard_hi - shard_lo) * self.world != n:
+            raise ValueError("sweep_all_pairs_from_host: the ranks' row shards must be equal")
+        mine = eng.normalize_cast(x_shard_host.to(dev, non_blocking=True))
+        if self.world > 1:
+            buf = getattr(self, "_rows_buf", None)
+            if buf is None or buf.shape != (n, mine.shape[1]) or buf.dtype != mine.dtype or buf.device != mine.device:
+                buf = torch.empty((n, mine.shape[1]), dtype=mine.dtype, device=mine.device)
+                self._rows_buf = buf
+            self.dist.all_gather_into_tensor(buf, mine, group=self.group)
+        else:
+            buf = mine
+        ts = ts_all_host.to(dev, non_blocking=True) if ts_all_host is not None else None
+        fl = floor_all_host.to(dev, non_blocking=True) if floor_all_host is not None else None
+        return self.sweep_all_pairs(buf, make_params, ts=ts, floor=fl, max_floor_diff=max_floor_diff)
+
     def sweep_from_host(self, q_host, db_shard_host, ts_all_host, floor_all_host, make_params, shard_lo: int,
                         shard_hi: int, n_q: int, max_floor_diff: int = -1, src: int = 0):
         """End-to-end form of `sweep` for inputs that live in pinned HOST memory.

@@ -126,6 +126,10 @@ def _worker(rank, world, port, out_dir):
             assert sr.last_all_pairs == how
             np.savez(os.path.join(out_dir, f"ap{0 if knob is None else 1}_rank{rank}.npz"), scores=ap.scores.numpy(),
                      idx=ap.idx.numpy(), valid=ap.valid.numpy(), count=ap.count.numpy())
+        sr.engine.overflow_on_rank = None
+        alo, ahi = shard_bounds(n_ap, world, rank)
+        ap2 = sr.sweep_all_pairs_from_host(t(desc[alo:ahi].copy()), tts, tfl, mk, alo, ahi, n_ap, max_floor_diff=0)
+        assert torch.equal(ap2.idx, ap.idx) and torch.equal(ap2.count, ap.count), "host-input all-pairs form differs"
     finally:
         dist.destroy_process_group()
 
