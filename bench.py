@@ -218,10 +218,15 @@ def cpu_sweep(desc, ts, fl, rows: int):
 
 
 def calibrate_rows(desc, ts, fl, target_s: float, lo: int = 256):
-    t = cpu_sweep(desc, ts, fl, lo)
-    # normalisation of the whole database is a fixed cost inside every sweep; scale the rest
-    rows = int(lo * max(target_s, t) / max(t, 1e-3))
-    return int(min(max(rows, lo), desc.shape[0], N_Q)), t
+    """Query rows whose sweep takes about `target_s` seconds here.  Normalising the whole database is a
+    fixed cost inside every sweep, so the time is affine in the rows: two probes give slope and offset."""
+    cpu_sweep(desc, ts, fl, lo)                       # first call pays for page faults / thread start-up
+    t1 = cpu_sweep(desc, ts, fl, lo)
+    t2 = cpu_sweep(desc, ts, fl, 3 * lo)
+    slope = max((t2 - t1) / (2 * lo), 1e-7)
+    fixed = max(t1 - slope * lo, 0.0)
+    rows = int((max(target_s, t2) - fixed) / slope)
+    return int(min(max(rows, lo), desc.shape[0], N_Q)), t1
 
 
 def run_reference(args):
