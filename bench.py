@@ -348,7 +348,7 @@ def run_ours(args):
 
     def step():
         if triangle:
-            res = sr.sweep_all_pairs(full, mk, ts=ts_all, floor=fl_all, max_floor_diff=0)
+            return sr.sweep_all_pairs(full, mk, ts=ts_all, floor=fl_all, max_floor_diff=0, compact=True)
         else:
             res = sr.sweep(q_bf16, db_bf16, mk, lo, q_ts=q_ts, db_ts_shard=db_ts, q_floor=q_fl, db_floor_shard=db_fl,
                            db_floor_all=fl_all, max_floor_diff=0)
@@ -464,8 +464,7 @@ def run_ours(args):
 
         def e2e_step():
             # every rank uploads and normalises its rows; the bf16 rows meet over NVLink (all-gather); triangle sweep
-            res = sr.sweep_all_pairs_from_host(q_host, tsh, flh, mk, lo, hi, N_Q, max_floor_diff=0)
-            oq, om, os_, ov, tot = eng.compact(res)
+            oq, om, os_, ov, tot = sr.sweep_all_pairs_from_host(q_host, tsh, flh, mk, lo, hi, N_Q, max_floor_diff=0, compact=True)
             t = int(tot.item())
             if rank == 0:
                 for h, d in zip(ho, (oq, om, os_, ov)):

@@ -98,6 +98,11 @@ int64_t semgate_launch_count(semgate_handle_t h);
  * 256-column (CTA pairs; 128 x 256 for single-CTA tiles) similarity tiles its schedule computes; mode 2 ran both. */
 int semgate_last_sweep_mode(semgate_handle_t h, int32_t* out_mode, int64_t* out_tiles);
 
+/* The same overflow flag without a host round trip: *out_flag_dev (device uint32) = non-zero iff the last
+ * semgate_gated_topk on this handle was a symmetric sweep (or one part of one) whose candidate buffers
+ * overflowed; stream-ordered copy.  A multi-GPU caller all-reduces it and reads it once, after the merge is queued. */
+int semgate_last_sweep_overflow(semgate_handle_t h, uint32_t* out_flag_dev, semgate_stream_t stream);
+
 /* Testing aid, needs no device: walks the fused kernel's tile schedule for a Q x N sweep on the host exactly as
  * the kernel's warp roles do and checks its invariants (every tile computed once -- in a symmetric sweep every
  * tile on or above the block diagonal and nothing else --, list slots, pacing counters).

@@ -252,6 +252,17 @@ int semgate_profile_read(semgate_handle_t h, double* total_ms, int64_t* n_launch
   return 0;
 }
 
+int semgate_last_sweep_overflow(semgate_handle_t h, uint32_t* out_flag_dev, semgate_stream_t stream) {
+  if (!h || !out_flag_dev) return fail(SEMGATE_EINVAL, "NULL argument");
+  DeviceGuard g(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (h->last_mode == 1 && h->last_sym_flag)
+    CUDA_TRY(cudaMemcpyAsync(out_flag_dev, h->last_sym_flag, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  else
+    CUDA_TRY(cudaMemsetAsync(out_flag_dev, 0, sizeof(uint32_t), st));
+  return 0;
+}
+
 // ---------------------------------------------------------------- schedule self-check (no device needed)
 int semgate_schedule_check(int64_t Q, int64_t N, int32_t d_pad, int32_t cta_group, int32_t sm_count, int32_t symmetric,
                            int32_t part_index, int32_t part_count, int32_t* out_shape, int64_t* out_tiles) {

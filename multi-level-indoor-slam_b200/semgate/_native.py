@@ -29,7 +29,7 @@ SYMBOLS = [
     "semgate_gate_candidates_host", "semgate_spatial_workspace_bytes", "semgate_spatial_count", "semgate_spatial_fill",
     "semgate_spatial_candidates_host", "semgate_rerank_scores", "semgate_rerank_select", "semgate_similarity_matrix",
     "semgate_merge_topk_peers", "semgate_compact_valid", "semgate_stats_workspace_bytes", "semgate_candidate_stats",
-    "semgate_last_sweep_mode", "semgate_schedule_check",
+    "semgate_last_sweep_mode", "semgate_schedule_check", "semgate_last_sweep_overflow",
 ]
 
 
@@ -107,6 +107,7 @@ def load_library():
     lib.semgate_stats_workspace_bytes.restype = sz
     lib.semgate_candidate_stats.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp]
     lib.semgate_last_sweep_mode.argtypes = [vp, P(i32), P(i64)]
+    lib.semgate_last_sweep_overflow.argtypes = [vp, vp, vp]
     lib.semgate_schedule_check.argtypes = [i64, i64, i32, i32, i32, i32, i32, i32, P(i32), P(i64)]
     for name in SYMBOLS:
         getattr(lib, name)   # AttributeError here = the library is older than the header
@@ -201,6 +202,15 @@ class Engine:
         mode, tiles = C.c_int32(0), C.c_int64(0)
         _check(self.lib.semgate_last_sweep_mode(self._h, C.byref(mode), C.byref(tiles)))
         return mode.value, tiles.value
+
+    def last_sweep_overflow(self, out=None):
+        """int32 device tensor [1]: non-zero iff the last (part of a) symmetric sweep overflowed its candidate
+        buffers.  Stream-ordered, no host synchronisation."""
+        torch = self._torch()
+        if out is None:
+            out = torch.empty((1,), dtype=torch.int32, device=self._dev())
+        _check(self.lib.semgate_last_sweep_overflow(self._h, self._ptr(out), self._stream()))
+        return out
 
     @property
     def launch_count(self) -> int:

@@ -77,11 +77,11 @@ class ShardedRetrieval:
             return False
 
     def _exchange_and_merge(self, local_fn, Q: int, k: int, device, q_floor, db_floor_all, max_floor_diff: int,
-                            agree=None):
+                            after_local=None):
         """`local_fn(keys)` runs this rank's sweep, writing its `[Q,k]` key lists into `keys` when given
         (the symmetric-memory buffer) or returning them in `.keys`; the lists of all ranks are then merged
-        on every rank.  `agree()`, if given, is called by every rank after its sweep and before anybody
-        reads a peer's lists; a false answer (collective: the same on all ranks) abandons the merge."""
+        on every rank.  `after_local()`, if given, is called by every rank right after its sweep is queued
+        (stream-ordered work only: nothing here waits for the GPU)."""
         import torch
         if self._use_peer():
             try:
@@ -93,14 +93,14 @@ class ShardedRetrieval:
             else:
                 hdl.barrier(channel=0)      # every rank has finished reading the previous step's keys
                 local_fn(keys)
-                if agree is not None and not agree():
-                    return None
+                if after_local is not None:
+                    after_local()
                 hdl.barrier(channel=1)      # every rank's keys are written
                 return self.engine.merge_topk_peers(hdl.buffer_ptrs_dev, self.world, Q, k, q_floor=q_floor,
                                                     db_floor_all=db_floor_all, max_floor_diff=max_floor_diff)
         local = local_fn(None)
-        if agree is not None and not agree():
-            return None
+        if after_local is not None:
+            after_local()
         buf = self._gather_buf
         if buf is None or buf.shape != (self.world * Q, k) or buf.device != local.keys.device:
             # concatenation along dim 0 is the layout every backend accepts; viewed as [G,Q,k] below
@@ -129,7 +129,7 @@ class ShardedRetrieval:
                                   db_floor=db_floor_shard, want_keys=True, want_lists=False)
         return self._exchange_and_merge(local_fn, Q, k, q_bf16.device, q_floor, db_floor_all, max_floor_diff)
 
-    def sweep_all_pairs(self, x_bf16, make_params, ts=None, floor=None, max_floor_diff: int = -1):
+    def sweep_all_pairs(self, x_bf16, make_params, ts=None, floor=None, max_floor_diff: int = -1, compact: bool = False):
         """All-pairs sweep of a database every rank holds in full (`find_loop_closures` over the whole map:
         the queries ARE the database, place_recognition.py:190 computes X X^T).  Similarity is symmetric, so
         the ranks split the TRIANGLE of tiles instead of the rows: every rank computes its share of the
@@ -137,13 +137,15 @@ class ShardedRetrieval:
         (`semgate_topk_params.part_index / part_count`), then the per-rank lists are merged as in `sweep`.
         Half the tensor work of the row-sharded sweep, same lists.  If any rank's candidate buffers overflow
         (thresholds that admit most of the database) all ranks agree on it and redo the sweep row-sharded.
-        Returns the merged TopkResult (identical on every rank)."""
-        import torch
+        Returns the merged TopkResult (identical on every rank); with `compact=True` the flat candidate
+        arrays of `engine.compact(result)` instead (queued before the host looks at the overflow flag, so the
+        GPU never waits for the host)."""
         eng = self.engine
         n = x_bf16.shape[0]
         params = make_params(0)
+        done = (lambda r: eng.compact(r)) if compact else (lambda r: r)
         if self.world == 1:
-            return eng.gated_topk(x_bf16, x_bf16, params, q_ts=ts, db_ts=ts, q_floor=floor, db_floor=floor)
+            return done(eng.gated_topk(x_bf16, x_bf16, params, q_ts=ts, db_ts=ts, q_floor=floor, db_floor=floor))
         k = params.k if hasattr(params, "k") else params["k"]
         wanted = (params.symmetric if hasattr(params, "symmetric") else params.get("symmetric", 0)) >= 0
 
@@ -153,7 +155,7 @@ class ShardedRetrieval:
                               q_floor=floor, db_floor_shard=None if floor is None else floor[lo:hi], db_floor_all=floor,
                               max_floor_diff=max_floor_diff)
         if not wanted or n <= 256:
-            return rows()
+            return done(rows())
         if hasattr(params, "part_count"):
             params.symmetric, params.part_index, params.part_count = 1, self.rank, self.world
             if params.cta_group == 0:
@@ -168,16 +170,22 @@ class ShardedRetrieval:
             return eng.gated_topk(x_bf16, x_bf16, params, q_ts=ts, db_ts=ts, q_floor=floor, db_floor=floor,
                                   want_keys=True, want_lists=False)
 
-        def agree():
-            over = torch.tensor([1 if eng.last_sweep_mode()[0] == 2 else 0], dtype=torch.int32, device=x_bf16.device)
-            self.dist.all_reduce(over, op=self.dist.ReduceOp.MAX, group=self.group)
-            return int(over.item()) == 0
-        res = self._exchange_and_merge(local_fn, n, k, x_bf16.device, floor, floor, max_floor_diff, agree=agree)
-        self.last_all_pairs = "triangle" if res is not None else "rows (candidate buffers overflowed)"
-        return res if res is not None else rows()
+        # Did any rank's candidate buffers overflow?  The flag is copied and all-reduced on the device while the
+        # exchange and the merge are being queued behind it; the host reads it once, when everything is in flight.
+        over = []
+
+        def after_local():
+            over.append(eng.last_sweep_overflow())
+            self.dist.all_reduce(over[0], op=self.dist.ReduceOp.MAX, group=self.group)
+        res = done(self._exchange_and_merge(local_fn, n, k, x_bf16.device, floor, floor, max_floor_diff, after_local=after_local))
+        if int(over[0].item()) != 0:          # incomplete lists somewhere: every rank redoes the sweep row-sharded
+            self.last_all_pairs = "rows (candidate buffers overflowed)"
+            return done(rows())
+        self.last_all_pairs = "triangle"
+        return res
 
     def sweep_all_pairs_from_host(self, x_shard_host, ts_all_host, floor_all_host, make_params, shard_lo: int,
-                                  shard_hi: int, n: int, max_floor_diff: int = -1):
+                                  shard_hi: int, n: int, max_floor_diff: int = -1, compact: bool = False):
         """End-to-end form of `sweep_all_pairs` for a database that lives in pinned HOST memory, one
         contiguous row shard per rank (equal shards): every rank uploads and normalises only its own rows
         (fp32 `[hi-lo, D]`), the normalised bf16 rows meet on every GPU through an NCCL all-gather over
@@ -198,7 +206,7 @@ class ShardedRetrieval:
             buf = mine
         ts = ts_all_host.to(dev, non_blocking=True) if ts_all_host is not None else None
         fl = floor_all_host.to(dev, non_blocking=True) if floor_all_host is not None else None
-        return self.sweep_all_pairs(buf, make_params, ts=ts, floor=fl, max_floor_diff=max_floor_diff)
+        return self.sweep_all_pairs(buf, make_params, ts=ts, floor=fl, max_floor_diff=max_floor_diff, compact=compact)
 
     def sweep_from_host(self, q_host, db_shard_host, ts_all_host, floor_all_host, make_params, shard_lo: int,
                         shard_hi: int, n_q: int, max_floor_diff: int = -1, src: int = 0):

@@ -86,6 +86,26 @@ def test_tile_schedule_invariants(sym):
             _native.schedule_check(5000, 5000, 4096, 2, 148, False, 1, 2)      # only symmetric sweeps split this way
 
 
+def test_torch_ops_register_without_a_gpu():
+    """torch.ops.semgate.* (the thin PyTorch extension over the C ABI): builds, loads, registers its four
+    operators with CUDA kernels only -- a CPU tensor has nothing to dispatch to."""
+    import importlib.util
+    import torch
+    spec = importlib.util.spec_from_file_location(
+        "semgate_build", os.path.join(ROOT, "multi-level-indoor-slam_b200", "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    b.build_torch_ops()
+    from semgate import ops
+    sg = ops.load()
+    for name in ("normalize_cast", "gated_topk", "merge_topk", "compact"):
+        assert hasattr(sg, name)
+    schema = str(torch.ops.semgate.gated_topk.default._schema)
+    assert "Tensor? q_floor" in schema and "int db_index_offset" in schema
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        sg.normalize_cast(torch.zeros(4, 64))
+
+
 def test_no_gpu_fails_loudly():
     """Without a usable sm_100 device the product path raises; it never falls back."""
     import numpy as np

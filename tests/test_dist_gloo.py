@@ -42,6 +42,9 @@ class OracleEngine:
     def last_sweep_mode(self):
         return self._mode, 0
 
+    def last_sweep_overflow(self, out=None):
+        return torch.tensor([1 if self._mode == 2 else 0], dtype=torch.int32)
+
     def _triangle_part(self, x, params, ts):
         """One part of a symmetric all-pairs sweep: every unordered pair {i, j} belongs to exactly one part
         (here: by the 64-row block of min(i, j), dealt out round-robin -- the kernel's own deal differs, any

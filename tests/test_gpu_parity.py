@@ -865,6 +865,44 @@ def test_symmetric_sweep_parts_merge_to_full_sweep(eng, G):
     _same_lists(a, b, k, 0.5)
 
 
+# --------------------------------------------------------------------------- torch.ops.semgate
+def test_torch_ops_match_the_engine(eng):
+    """The PyTorch operators end in the same kernels as the ctypes engine: identical outputs, including the
+    symmetric sweep taken automatically for aliased arguments, a sharded sweep merged by merge_topk, and compact."""
+    import torch
+    from semgate import _native, ops, synthetic
+    sg = ops.load()
+    n, d, k = 4500, 200, 25
+    desc, ts, fl = synthetic.make_case(n, d, 3, seed=9)
+    x = _t(desc, torch.float32)
+    tts, tfl = _t(ts, torch.float64), _t(fl.astype(np.int32), torch.int32)
+    xb = sg.normalize_cast(x)
+    assert torch.equal(xb, eng.normalize_cast(x)) and xb.shape == (n, 256)
+    p = _native.make_params(k=k, similarity_threshold=0.5, min_time_gap=10.0, max_floor_diff=0)
+    want_ = eng.gated_topk(xb, xb, p, q_ts=tts, db_ts=tts, q_floor=tfl, db_floor=tfl, want_keys=True)
+    sc, ix, va, ct, keys = sg.gated_topk(xb, xb, tfl, tfl, tts, tts, 10.0, 0.5, k, 0, 0, 0)
+    torch.cuda.synchronize()
+    for a, b in ((sc, want_.scores), (ix, want_.idx), (va, want_.valid), (ct, want_.count), (keys, want_.keys)):
+        assert torch.equal(a, b)
+    # two database shards + merge == whole
+    parts = []
+    for lo, hi in ((0, 2000), (2000, n)):
+        parts.append(sg.gated_topk(xb, xb[lo:hi], tfl, tfl[lo:hi].contiguous(), tts, tts[lo:hi].contiguous(), 10.0, 0.5, k, 0, 0, lo)[4])
+    msc, mix, mva, mct, _ = sg.merge_topk(torch.stack(parts), tfl, tfl, 0)
+    assert torch.equal(mix, ix) and torch.equal(msc, sc) and torch.equal(mva, va) and torch.equal(mct, ct)
+    oq, om, os_, ov, total = sg.compact(sc, ix, va, ct)
+    eq, em, es, ev, et = eng.compact(want_)
+    t = int(total.item())
+    assert t == int(et.item()) == int(ct.sum().item())
+    assert torch.equal(oq[:t], eq[:t]) and torch.equal(om[:t], em[:t]) and torch.equal(os_[:t], es[:t]) and torch.equal(ov[:t], ev[:t])
+    # no timestamps / labels, query form (threshold off)
+    q1 = sg.gated_topk(xb[:3].contiguous(), xb, None, None, None, None, 10.0, float("-inf"), 5, -1, 0, 0)
+    r1 = eng.gated_topk(xb[:3].contiguous(), xb, _native.make_params(k=5))
+    assert torch.equal(q1[1], r1.idx) and torch.equal(q1[0], r1.scores)
+    with pytest.raises(RuntimeError):
+        sg.gated_topk(xb.float(), xb, None, None, None, None, 10.0, 0.5, k, 0, 0, 0)      # wrong dtype
+
+
 # --------------------------------------------------------------------------- full-size properties (BASELINE config 2)
 @pytest.mark.parametrize("cg", [1, 2, 4])
 def test_full_size_properties_c2(eng, cg):
