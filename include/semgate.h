@@ -63,8 +63,10 @@ typedef struct semgate_topk_params {
                                    sweeps of disjoint slices); merge this sweep into it in place */
   int32_t symmetric;            /* all-pairs sweeps (queries == database, place_recognition.py:190 computes X X^T):
                                    0 = auto: when q_bf16 == db_bf16, q_ts == db_ts, q_floor == db_floor, Q == N,
-                                   db_index_offset == 0 and the tiles are CTA pairs, every similarity is computed once
-                                   and gated in both directions (half the tensor work, same lists);
+                                   db_index_offset == 0, the tiles are CTA pairs and the sweep is long enough to be
+                                   tensor-bound (Q >= 8192, d_pad >= 1024; handle option "symmetric" = 1 drops the size
+                                   rule), every similarity is computed once and gated in both directions (half the
+                                   tensor work, same lists);
                                    1 = require it (SEMGATE_EINVAL if the arguments do not allow it); -1 = never */
   int32_t part_index;           /* a symmetric sweep split over the GPUs of a box: with part_count = G > 1 (needs  */
   int32_t part_count;           /* symmetric = 1) this call computes part part_index of the tile triangle -- every G-th
@@ -82,8 +84,8 @@ const char* semgate_last_error(void);
 int semgate_create(semgate_handle_t* out, int device);
 int semgate_destroy(semgate_handle_t h);
 int semgate_device_info(semgate_handle_t h, int* sm_count, int* cc_major, int* cc_minor);
-/* options: "cta_group" (0 auto | 1 | 2 | 4); "symmetric" (0 auto | -1 never: handle default for
- * semgate_topk_params.symmetric == 0); "profile" (0|1): bracket every fused-kernel launch with CUDA
+/* options: "cta_group" (0 auto | 1 | 2 | 4); "symmetric" (0 auto by size | 1 whenever the arguments allow |
+ * -1 never: handle default for semgate_topk_params.symmetric == 0); "profile" (0|1): bracket every fused-kernel launch with CUDA
  * events on its own stream */
 int semgate_set_option(semgate_handle_t h, const char* name, int64_t value);
 /* sum of the fused kernel's (K2) device durations since the last read, and how many

@@ -54,7 +54,7 @@ struct semgate_ctx {
   int sm_count = 0;
   int cc_major = 0, cc_minor = 0;
   int cta_group = 0;               // 0 = auto (by problem size), 1, 2
-  int symmetric = 0;               // 0 = auto (symmetric sweep when queries and database alias), -1 = never
+  int symmetric = 0;               // aliased queries/database: 0 = symmetric sweep when it pays (size rule), 1 = whenever possible, -1 = never
   int last_mode = 0;               // last fused sweep: 0 full, 1 symmetric
   const uint32_t* last_sym_flag = nullptr;   // ... and its overflow flag (device)
   cudaStream_t last_stream = nullptr;
@@ -127,8 +127,14 @@ int resolve_cg(semgate_handle_t h, const semgate_topk_params* p, int64_t Q) {
 bool sym_shape_ok(semgate_handle_t h, const semgate_topk_params* p, int64_t Q, int64_t N, int32_t d_pad) {
   return Q == N && Q > 256 && resolve_cg(h, p, Q) == 2 && !use_stream_path(h, p, Q, d_pad) && p->accumulate == 0;
 }
-bool sym_wanted(semgate_handle_t h, const semgate_topk_params* p) {
-  return p->symmetric == 1 || (p->symmetric == 0 && h->symmetric == 0);
+// Automatic choice: halving the tensor work pays once the sweep is tensor-bound and long enough to amortise the
+// two extra launches and the coarser tail of the triangular schedule; short descriptors leave the kernel
+// epilogue-bound, where the column direction costs more than the saved MMAs (measured: 5k x 512-d is 1.4x
+// SLOWER symmetric, 20k x 4096-d 1.5x faster, 1M x 4096-d 2.0x faster).
+bool sym_wanted(semgate_handle_t h, const semgate_topk_params* p, int64_t Q, int32_t d_pad) {
+  if (p->symmetric != 0) return p->symmetric == 1;
+  if (h->symmetric != 0) return h->symmetric == 1;
+  return Q >= 8192 && d_pad >= 1024;
 }
 
 // workspace of a symmetric sweep: [partial lists of either schedule | pacing counters of the full schedule |
@@ -172,6 +178,7 @@ int semgate_create(semgate_handle_t* out, int device) {
   if (env && (env[0] == '1' || env[0] == '2' || env[0] == '4')) h->cta_group = env[0] - '0';
   env = getenv("SEMGATE_SYMMETRIC");
   if (env && env[0] == '0') h->symmetric = -1;
+  if (env && env[0] == '1') h->symmetric = 1;
   DeviceGuard g(device);
   cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate"); }
@@ -209,7 +216,7 @@ int semgate_set_option(semgate_handle_t h, const char* name, int64_t value) {
     return 0;
   }
   if (strcmp(name, "symmetric") == 0) {
-    if (value != 0 && value != -1) return fail(SEMGATE_EINVAL, "symmetric must be 0 (auto) or -1 (never)");
+    if (value != 0 && value != -1 && value != 1) return fail(SEMGATE_EINVAL, "symmetric must be 0 (auto), 1 (whenever possible) or -1 (never)");
     h->symmetric = static_cast<int>(value);
     return 0;
   }
@@ -304,7 +311,7 @@ size_t semgate_topk_workspace_bytes(semgate_handle_t h, int64_t Q, int64_t N, in
   Schedule sc = make_schedule(Q, N, d_pad, cg, h->sm_count);
   size_t need = topk_workspace_bytes(sc, cg, p->k);
   if (use_stream_path(h, p, Q, d_pad)) need = std::max(need, stream_query_workspace_bytes(Q, p->k, h->sm_count));
-  if (sym_wanted(h, p) && sym_shape_ok(h, p, Q, N, d_pad))
+  if (sym_wanted(h, p, Q, d_pad) && sym_shape_ok(h, p, Q, N, d_pad))
     need = std::max(need, sym_layout(sc, make_schedule(Q, N, d_pad, 2, h->sm_count, true, p->part_index, p->part_count), N, p->k).total);
   return align256(need);
 }
@@ -354,7 +361,7 @@ int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const 
   // Symmetric sweep: the queries are the database itself (same rows, stamps and labels), so S = S^T and only
   // the tiles on or above the block diagonal are computed.  Automatic when the arguments alias.
   const bool aliased = q_bf16 == db_bf16 && q_ts == db_ts && q_floor == db_floor && p->db_index_offset == 0;
-  bool sym = sym_wanted(h, p) && sym_shape_ok(h, p, Q, N, d_pad) && aliased;
+  bool sym = sym_wanted(h, p, Q, d_pad) && sym_shape_ok(h, p, Q, N, d_pad) && aliased;
   Schedule sc_sym{};
   SymLayout lay{};
   if (sym) {

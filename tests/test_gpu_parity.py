@@ -780,11 +780,11 @@ def test_symmetric_sweep_overflow_falls_back_to_full_sweep(eng):
     fl = fl.astype(np.int32)
     kw = dict(k=k, thr=-np.inf, gap=10.0, q_ts=ts, db_ts=ts, q_fl=fl, db_fl=fl, mfd=0, cg=2)
     full = run_gpu(eng, desc, desc, sym=-1, **kw)
-    half = run_gpu(eng, desc, desc, sym=0, **kw)
+    half = run_gpu(eng, desc, desc, sym=1, **kw)
     assert half["mode"] == 2, "the buffers must have overflowed"
     _same_lists(full, half, k, -np.inf)
     # a threshold that lets a few dozen candidates per keyframe through stays inside the buffers
-    some = run_gpu(eng, desc, desc, sym=0, **dict(kw, thr=0.3))
+    some = run_gpu(eng, desc, desc, sym=1, **dict(kw, thr=0.3))
     assert some["mode"] == 1
     _same_lists(run_gpu(eng, desc, desc, sym=-1, **dict(kw, thr=0.3)), some, k, 0.3)
 
@@ -821,16 +821,25 @@ def test_symmetric_sweep_argument_rules(eng):
     with pytest.raises(_native.SemgateError):
         eng.gated_topk(x, x, _native.make_params(k=5, cta_group=2, symmetric=1, part_index=2, part_count=2), q_ts=ts, db_ts=ts)
     auto = dict(k=5, cta_group=2, similarity_threshold=0.3)
-    eng.gated_topk(x, y, _native.make_params(**auto), q_ts=ts, db_ts=ts)          # auto: full sweep
-    assert eng.last_sweep_mode()[0] == 0
-    eng.gated_topk(x, x, _native.make_params(**auto), q_ts=ts, db_ts=ts)          # auto: symmetric
-    assert eng.last_sweep_mode() == (1, 6)                                        # 3 blocks: 6 tiles of the 9
-    eng.set_option("symmetric", -1)
+    eng.gated_topk(x, x, _native.make_params(**auto), q_ts=ts, db_ts=ts)          # auto: too small to pay -> full sweep
+    assert eng.last_sweep_mode() == (0, 9)
+    eng.set_option("symmetric", 1)                                                # whenever the arguments allow
     try:
+        eng.gated_topk(x, y, _native.make_params(**auto), q_ts=ts, db_ts=ts)      # different matrices: full sweep
+        assert eng.last_sweep_mode()[0] == 0
+        eng.gated_topk(x, x, _native.make_params(**auto), q_ts=ts, db_ts=ts)
+        assert eng.last_sweep_mode() == (1, 6)                                    # 3 blocks: 6 tiles of the 9
+        eng.set_option("symmetric", -1)
         eng.gated_topk(x, x, _native.make_params(**auto), q_ts=ts, db_ts=ts)
         assert eng.last_sweep_mode() == (0, 9)
     finally:
         eng.set_option("symmetric", 0)
+    # auto by size: a long, tensor-bound all-pairs sweep takes the symmetric schedule by itself
+    big = eng.normalize_cast(torch.randn(8200, 1024, device="cuda"))
+    eng.gated_topk(big, big, _native.make_params(k=5, similarity_threshold=0.3))
+    assert eng.last_sweep_mode()[0] == 1
+    eng.gated_topk(big[:8000], big[:8000], _native.make_params(k=5, similarity_threshold=0.3))
+    assert eng.last_sweep_mode()[0] == 0
 
 
 @pytest.mark.parametrize("G", [2, 3, 8])
