@@ -108,7 +108,10 @@ int semgate_last_sweep_overflow(semgate_handle_t h, uint32_t* out_flag_dev, semg
 /* Testing aid, needs no device: walks the fused kernel's tile schedule for a Q x N sweep on the host exactly as
  * the kernel's warp roles do and checks its invariants (every tile computed once -- in a symmetric sweep every
  * tile on or above the block diagonal and nothing else --, list slots, pacing counters).
- * out_shape[8] = blocks, tiles, rm, s_main, r_last, s_last, pacing window, query blocks L2-resident;
+ * symmetric: 0 full sweep, 1 symmetric sweep by the super-row formula, 2 symmetric sweep by the run table
+ * (what sweeps of up to ~57k keyframes use).
+ * out_shape[8] = blocks, tiles, rm, s_main (run table: most lists of any block), r_last, s_last, pacing window,
+ * query blocks L2-resident;
  * out_tiles[2] = tiles computed, longest unit's tile count (the makespan in tile-times). */
 int semgate_schedule_check(int64_t Q, int64_t N, int32_t d_pad, int32_t cta_group, int32_t sm_count, int32_t symmetric,
                            int32_t part_index, int32_t part_count, int32_t* out_shape, int64_t* out_tiles);

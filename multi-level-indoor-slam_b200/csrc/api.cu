@@ -49,6 +49,14 @@ inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255);
 
 }  // namespace
 
+// a run table (small symmetric sweeps) and its device copy, cached per shape
+struct SymTableDev {
+  int64_t N; int d_pad, part_index, part_count;
+  SymTable host;
+  void* dev = nullptr;
+  Schedule sc_dev;
+};
+
 struct semgate_ctx {
   int device = 0;
   int sm_count = 0;
@@ -64,6 +72,7 @@ struct semgate_ctx {
   cudaStream_t copy_stream = nullptr;   // H2D + normalisation of the next chunk, overlapped with the sweep
   std::vector<cudaEvent_t> chunk_events;
   bool profile = false;            // record CUDA events around every K2 launch
+  std::vector<SymTableDev*> sym_tables;
   std::vector<cudaEvent_t> prof_events;   // pairs (begin, end), on the launching stream
   size_t prof_used = 0;
   void* buf[kNumBufs] = {};
@@ -137,6 +146,56 @@ bool sym_wanted(semgate_handle_t h, const semgate_topk_params* p, int64_t Q, int
   return Q >= 8192 && d_pad >= 1024;
 }
 
+// tiles a symmetric schedule computes (this part's share of the triangle)
+int64_t sym_tiles_owned(const Schedule& sc) {
+  int64_t t = 0;
+  int sr = 0;
+  for (int lo = 0; lo < sc.ntiles; lo += sc.rm, ++sr) {
+    if (!sched_owned(sc, sr)) continue;
+    const int64_t r = std::min(sc.rm, sc.ntiles - lo), len = sc.ntiles - lo;
+    t += r * len - r * (r - 1) / 2;
+  }
+  return t;
+}
+
+// The symmetric schedule of an N x N sweep: a run table (built once per shape, cached with its device copy) for
+// small triangles, the super-row formula otherwise.
+int sym_schedule(semgate_handle_t h, int64_t N, int32_t d_pad, const semgate_topk_params* p, Schedule* out) {
+  if (!sym_table_wanted(N)) {
+    *out = make_schedule(N, N, d_pad, 2, h->sm_count, true, p->part_index, p->part_count);
+    return 0;
+  }
+  const int pc = std::max(p->part_count, 1);
+  for (SymTableDev* t : h->sym_tables)
+    if (t->N == N && t->d_pad == d_pad && t->part_index == p->part_index && t->part_count == pc) { *out = t->sc_dev; return 0; }
+  SymTableDev* t = new (std::nothrow) SymTableDev();
+  if (!t) return fail(SEMGATE_ENOMEM, "out of host memory");
+  t->N = N; t->d_pad = d_pad; t->part_index = p->part_index; t->part_count = pc;
+  build_sym_table(N, d_pad, h->sm_count, p->part_index, pc, &t->host);
+  const size_t b_runs = align256(t->host.runs.size() * sizeof(RunEntry)), b_ub = align256(t->host.unit_begin.size() * sizeof(int)),
+               b_bf = align256(t->host.block_first.size() * sizeof(int));
+  DeviceGuard g(h->device);
+  cudaError_t e = cudaMalloc(&t->dev, b_runs + b_ub + b_bf);
+  if (e != cudaSuccess) { delete t; return cuda_fail(e, "cudaMalloc (run table)"); }
+  char* d = static_cast<char*>(t->dev);
+  e = cudaMemcpy(d, t->host.runs.data(), t->host.runs.size() * sizeof(RunEntry), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d + b_runs, t->host.unit_begin.data(), t->host.unit_begin.size() * sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d + b_runs + b_ub, t->host.block_first.data(), t->host.block_first.size() * sizeof(int), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(t->dev); delete t; return cuda_fail(e, "cudaMemcpy (run table)"); }
+  t->sc_dev = t->host.sc;
+  t->sc_dev.tab_runs = reinterpret_cast<const RunEntry*>(d);
+  t->sc_dev.tab_unit_begin = reinterpret_cast<const int*>(d + b_runs);
+  t->sc_dev.tab_block_first = reinterpret_cast<const int*>(d + b_runs + b_ub);
+  if (h->sym_tables.size() >= 16) {                 // keep the cache small: drop the oldest
+    cudaFree(h->sym_tables.front()->dev);
+    delete h->sym_tables.front();
+    h->sym_tables.erase(h->sym_tables.begin());
+  }
+  h->sym_tables.push_back(t);
+  *out = t->sc_dev;
+  return 0;
+}
+
 // workspace of a symmetric sweep: [partial lists of either schedule | pacing counters of the full schedule |
 // symmetric state: its pacing counters, bounds, counts, flag, candidate buffers]
 struct SymLayout { size_t partial, sync_full, state, total; };
@@ -195,6 +254,7 @@ int semgate_destroy(semgate_handle_t h) {
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   for (cudaEvent_t e : h->chunk_events) cudaEventDestroy(e);
   for (int i = 0; i < kNumBufs; ++i) if (h->buf[i]) cudaFree(h->buf[i]);
+  for (SymTableDev* t : h->sym_tables) { cudaFree(t->dev); delete t; }
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   delete h;
   return 0;
@@ -278,7 +338,14 @@ int semgate_schedule_check(int64_t Q, int64_t N, int32_t d_pad, int32_t cta_grou
   if (symmetric && (cta_group != 2 || Q != N)) return fail(SEMGATE_EINVAL, "schedule_check: a symmetric sweep needs Q == N and CTA pairs");
   if (part_count < 0 || part_index < 0 || part_index >= std::max(part_count, 1) || (part_count > 1 && !symmetric))
     return fail(SEMGATE_EINVAL, "schedule_check: bad part %d of %d", part_index, part_count);
-  const Schedule sc = make_schedule(Q, N, d_pad, cta_group, sm_count, symmetric != 0, part_index, part_count);
+  SymTable table;
+  Schedule sc;
+  if (symmetric == 2) {          // the run table small symmetric sweeps use (host copy)
+    build_sym_table(N, d_pad, sm_count, part_index, part_count, &table);
+    sc = table.sc;
+  } else {
+    sc = make_schedule(Q, N, d_pad, cta_group, sm_count, symmetric != 0, part_index, part_count);
+  }
   int64_t computed = 0, makespan = 0;
   const int err = schedule_selfcheck(sc, topk_units(cta_group, sm_count), &computed, &makespan);
   if (out_shape) {
@@ -311,8 +378,10 @@ size_t semgate_topk_workspace_bytes(semgate_handle_t h, int64_t Q, int64_t N, in
   Schedule sc = make_schedule(Q, N, d_pad, cg, h->sm_count);
   size_t need = topk_workspace_bytes(sc, cg, p->k);
   if (use_stream_path(h, p, Q, d_pad)) need = std::max(need, stream_query_workspace_bytes(Q, p->k, h->sm_count));
-  if (sym_wanted(h, p, Q, d_pad) && sym_shape_ok(h, p, Q, N, d_pad))
-    need = std::max(need, sym_layout(sc, make_schedule(Q, N, d_pad, 2, h->sm_count, true, p->part_index, p->part_count), N, p->k).total);
+  if (sym_wanted(h, p, Q, d_pad) && sym_shape_ok(h, p, Q, N, d_pad)) {
+    Schedule sc_sym{};
+    if (sym_schedule(h, N, d_pad, p, &sc_sym) == 0) need = std::max(need, sym_layout(sc, sc_sym, N, p->k).total);
+  }
   return align256(need);
 }
 
@@ -365,7 +434,7 @@ int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const 
   Schedule sc_sym{};
   SymLayout lay{};
   if (sym) {
-    sc_sym = make_schedule(Q, N, d_pad, 2, h->sm_count, true, p->part_index, p->part_count);
+    if ((rc = sym_schedule(h, N, d_pad, p, &sc_sym))) return rc;
     lay = sym_layout(sc, sc_sym, N, k);
     if (workspace_bytes < lay.total) sym = false;     // a caller that sized its workspace for the full sweep only
   }
@@ -440,7 +509,7 @@ int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const 
   h->last_sym_flag = sym_flag;
   h->last_stream = st;
   h->last_tiles = gemv ? 0 : static_cast<int64_t>(sc.mblocks) * sc.ntiles;
-  if (sym) schedule_selfcheck(sc_sym, topk_units(2, h->sm_count), &h->last_tiles, nullptr);   // host-side count of this part's tiles
+  if (sym) h->last_tiles = sym_tiles_owned(sc_sym);
   return 0;
 }
 

@@ -102,6 +102,8 @@ struct RowList {
 // query blocks.  With very long descriptors (query blocks no longer L2-resident,
 // `a_resident` = 0) both operands are streamed and the same lock-step makes every
 // k-slice of every operand come from DRAM once per super-row step.
+struct RunEntry { int mb, list, nt0, nt1; };   // one run of the run table: block, list number, tiles [nt0, nt1)
+
 struct Schedule {
   int mblocks;      // ceil(Q / BM)            (for pairs: counted in pair-rows of 2*BM)
   int ntiles;       // ceil(N / BN)
@@ -121,6 +123,16 @@ struct Schedule {
                     //    block diagonal are computed, see "Symmetric sweep" below
   int part_index;   // symmetric sweep split over `part_count` GPUs: this launch computes the super-rows that
   int part_count;   //    sched_owned() gives part_index (0 / 0 or 1: everything)
+  // Run table (small symmetric sweeps).  A triangle of a few thousand tiles is coarse for the super-row formula:
+  // every super-row lasts as long as its longest block.  Instead the host cuts every block's tiles into short runs
+  // (super-row by super-row, column chunk by column chunk, so that runs close in the order share database tiles),
+  // deals them in that order to whichever unit is free first, and uploads the result: unit u executes
+  // tab_runs[tab_unit_begin[u] .. tab_unit_begin[u+1]); the lists of block b are numbered
+  // tab_block_first[b] .. tab_block_first[b+1) (none for blocks another part owns).  No pacing in this mode.
+  const RunEntry* tab_runs;
+  const int* tab_unit_begin;
+  const int* tab_block_first;
+  int tab_lists;    // lists in all
 };
 
 // Super-rows get shorter towards the end of a symmetric sweep; dealing them out boustrophedon
@@ -147,6 +159,7 @@ __host__ __device__ __forceinline__ int64_t sched_sync_counters(const Schedule& 
 }
 
 __host__ __device__ __forceinline__ int sched_slots(const Schedule& sc, int mb) {
+  if (sc.tab_runs != nullptr) return sc.tab_block_first[mb + 1] - sc.tab_block_first[mb];
   if (sc.sym) return sched_owned(sc, mb / sc.rm) ? sched_sym_splits(sc, mb / sc.rm) : 0;   // other parts' rows: no lists here
   return mb < sc.n_full * sc.rm ? sc.s_main : sc.s_last;
 }
@@ -158,7 +171,19 @@ __host__ __device__ __forceinline__ int64_t sched_list_offset(const Schedule& sc
   return row < rows_full ? row * sc.s_main * k : (rows_full * sc.s_main + (row - rows_full) * sc.s_last) * k;
 }
 __host__ __device__ __forceinline__ int64_t sched_list_keys(const Schedule& sc, int rows_per_mblock, int k) {
+  if (sc.tab_runs != nullptr) return static_cast<int64_t>(sc.tab_lists) * rows_per_mblock * k;
   return sched_list_offset(sc, static_cast<int64_t>(sc.mblocks) * rows_per_mblock, rows_per_mblock, k);
+}
+// Where row `row` keeps the list of run (block mb, list number `slot`), and how far apart the lists of one row
+// are.  Formula schedules: a row's lists are consecutive.  Run table: list-major, [list][row in block][k].
+__host__ __device__ __forceinline__ int64_t sched_run_list_offset(const Schedule& sc, int mb, int slot, int64_t row,
+                                                                  int rows_per_mblock, int k) {
+  if (sc.tab_runs != nullptr)
+    return (static_cast<int64_t>(slot) * rows_per_mblock + (row - static_cast<int64_t>(mb) * rows_per_mblock)) * k;
+  return sched_list_offset(sc, row, rows_per_mblock, k) + static_cast<int64_t>(slot) * k;
+}
+__host__ __device__ __forceinline__ int64_t sched_list_stride(const Schedule& sc, int rows_per_mblock, int k) {
+  return sc.tab_runs != nullptr ? static_cast<int64_t>(rows_per_mblock) * k : k;
 }
 
 // balanced contiguous split of [0, n) into s parts
@@ -183,6 +208,16 @@ struct Run {
 
 template <typename F>
 __host__ __device__ __forceinline__ void for_each_run(const Schedule& sc, int unit, F&& f) {
+  if (sc.tab_runs != nullptr) {
+    for (int i = sc.tab_unit_begin[unit]; i < sc.tab_unit_begin[unit + 1]; ++i) {
+      const RunEntry e = sc.tab_runs[i];
+      Run run;
+      run.mb = e.mb; run.slot = e.list; run.nt0 = e.nt0; run.nt_first = e.nt0; run.nt1 = e.nt1;
+      run.sync_base = 0; run.short_len = 0; run.units_all = 0; run.units_long = 0;
+      f(run);
+    }
+    return;
+  }
   const int n_sr = sc.n_full + (sc.r_last > 0 ? 1 : 0);
   for (int sr = 0; sr < n_sr; ++sr) {
     if (!sched_owned(sc, sr)) continue;

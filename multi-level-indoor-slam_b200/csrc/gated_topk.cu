@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
+#include <queue>
 #include <vector>
 
 namespace semgate {
@@ -169,15 +170,17 @@ int schedule_selfcheck(const Schedule& sc, int units, int64_t* tiles_computed, i
     int64_t mine = 0;
     for_each_run(sc, u, [&](const Run& run) {
       if (err) return;
-      if (run.mb >= nb || run.slot >= sched_slots(sc, run.mb) || run.slot >= sc.s_max) { err = 2; return; }
-      if (slot_used[static_cast<size_t>(run.mb) * sc.s_max + run.slot]++) { err = 3; return; }
+      if (run.mb < 0 || run.mb >= nb) { err = 2; return; }
+      const int slot = sc.tab_runs ? run.slot - sc.tab_block_first[run.mb] : run.slot;   // list number inside the block
+      if (slot < 0 || slot >= sched_slots(sc, run.mb) || slot >= sc.s_max) { err = 2; return; }
+      if (slot_used[static_cast<size_t>(run.mb) * sc.s_max + slot]++) { err = 3; return; }
       if (run.nt_first < run.nt0 || run.nt_first > run.nt1) { err = 1; return; }
       for (int t = run.nt_first; t < run.nt1; ++t) {
         if (t >= nt || seen[static_cast<size_t>(run.mb) * nt + t]++) { err = 1; return; }
         ++computed; ++mine;
       }
       // every chunk ordinal of the run (computed or skipped) arrives once on the super-row's counters
-      for (int64_t c = 0; c < static_cast<int64_t>(run.nt1 - run.nt0) * sc.cpt; ++c) {
+      for (int64_t c = 0; sc.sync_window > 0 && c < static_cast<int64_t>(run.nt1 - run.nt0) * sc.cpt; ++c) {
         const int64_t at = run.sync_base + c;
         if (at < 0 || at >= n_counters) { err = 4; return; }
         ++arrivals[at];
@@ -203,6 +206,107 @@ int schedule_selfcheck(const Schedule& sc, int units, int64_t* tiles_computed, i
   if (tiles_computed) *tiles_computed = computed;
   if (makespan_tiles) *makespan_tiles = makespan;
   return err;
+}
+
+// ------------------------------------------------------------------ run table (small symmetric sweeps)
+bool sym_table_wanted(int64_t N) {
+  const long force = env_long("SEMGATE_SYM_TABLE", -1);
+  if (force == 0) return false;
+  const int64_t nb = (N + BN - 1) / BN;
+  return nb >= 2 && (force == 1 || nb <= 224);     // beyond ~57k keyframes the super-row formula is within a few % and paces
+}
+
+namespace {
+struct Dealt { std::vector<RunEntry> runs; std::vector<int> owner; std::vector<int> lists_of_block; int64_t makespan = 0; };
+
+// Cut the owned part of the triangle into runs of at most `L` tiles (absolute column chunks, so that neighbouring
+// blocks cut at the same tiles), in the order super-row -> chunk -> block, and deal them in that order to the
+// unit that is free first.
+Dealt deal_runs(int nb, int rm, int L, int units, int part_index, int part_count) {
+  Dealt d;
+  d.lists_of_block.assign(nb, 0);
+  Schedule own{};
+  own.rm = rm; own.part_index = part_index; own.part_count = part_count;
+  using Slot = std::pair<int64_t, int>;   // (busy until, unit)
+  std::priority_queue<Slot, std::vector<Slot>, std::greater<Slot>> free_at;
+  for (int u = 0; u < units; ++u) free_at.push({0, u});
+  int sr = 0;
+  for (int lo = 0; lo < nb; lo += rm, ++sr) {
+    if (!sched_owned(own, sr)) continue;
+    const int r = std::min(rm, nb - lo);
+    for (int c = lo / L; c * L < nb; ++c)
+      for (int j = 0; j < r; ++j) {
+        const int b = lo + j;
+        const int t0 = std::max(c * L, b), t1 = std::min((c + 1) * L, nb);
+        if (t1 <= t0) continue;
+        Slot s = free_at.top();
+        free_at.pop();
+        d.runs.push_back(RunEntry{b, d.lists_of_block[b]++, t0, t1});   // list number inside the block for now
+        d.owner.push_back(s.second);
+        s.first += t1 - t0;
+        d.makespan = std::max(d.makespan, s.first);
+        free_at.push(s);
+      }
+  }
+  return d;
+}
+}  // namespace
+
+void build_sym_table(int64_t N, int d_pad, int sm_count, int part_index, int part_count, SymTable* out) {
+  const int units = topk_units(2, sm_count);
+  const int nb = static_cast<int>((N + BN - 1) / BN);
+  part_count = std::max(part_count, 1);
+  // A few super-row heights and run lengths, judged by the busiest part (every part must cut the triangle the
+  // same way).  Longer runs mean fewer lists per keyframe for K3 to merge, so a shorter run length has to buy 5 %;
+  // taller super-rows mean fewer distinct database tiles in flight, as long as their query blocks stay in L2.
+  const int64_t a_bytes = static_cast<int64_t>(BM) * 2 * d_pad * 2;
+  const int64_t cap = env_long("SEMGATE_RM_CAP_MB", 40) << 20;
+  int best_rm = 1, best_L = 1;
+  int64_t best = -1;
+  for (int L : {8, 6, 4, 2, 1}) {
+    if (L < 4 && nb > 16) break;       // runs of one or two tiles only where there is hardly anything to deal out
+    int rm_L = 1;
+    int64_t best_Lm = -1;
+    for (int rm : {24, 18, 16, 12, 10, 8, 6}) {
+      if (rm != 6 && (rm > nb || rm * a_bytes > cap)) continue;
+      int64_t m = 0;
+      for (int g = 0; g < part_count; ++g) m = std::max(m, deal_runs(nb, std::min(rm, nb), L, units, g, part_count).makespan);
+      if (best_Lm < 0 || m < best_Lm) { best_Lm = m; rm_L = std::min(rm, nb); }
+    }
+    if (best < 0 || best_Lm * 100 < best * 95) { best = best_Lm; best_rm = rm_L; best_L = L; }
+  }
+  Dealt d = deal_runs(nb, best_rm, best_L, units, part_index, part_count);
+  out->block_first.assign(nb + 1, 0);
+  for (int b = 0; b < nb; ++b) out->block_first[b + 1] = out->block_first[b] + d.lists_of_block[b];
+  out->unit_begin.assign(units + 1, 0);
+  for (int o : d.owner) ++out->unit_begin[o + 1];
+  for (int u = 0; u < units; ++u) out->unit_begin[u + 1] += out->unit_begin[u];
+  out->runs.resize(d.runs.size());
+  std::vector<int> at(out->unit_begin.begin(), out->unit_begin.end() - 1);
+  for (size_t i = 0; i < d.runs.size(); ++i) {      // stable: a unit keeps the order it was dealt
+    RunEntry e = d.runs[i];
+    e.list += out->block_first[e.mb];
+    out->runs[at[d.owner[i]]++] = e;
+  }
+  out->makespan = d.makespan;
+  Schedule& sc = out->sc;
+  sc = Schedule{};
+  sc.sym = 1;
+  sc.mblocks = sc.ntiles = nb;
+  sc.rm = best_rm;
+  sc.n_full = nb / best_rm; sc.r_last = nb % best_rm;
+  sc.part_index = part_index; sc.part_count = part_count;
+  sc.s_max = std::max(1, *std::max_element(d.lists_of_block.begin(), d.lists_of_block.end()));
+  sc.s_main = sc.s_last = sc.s_max;
+  sc.a_resident = best_rm * a_bytes <= cap ? 1 : 0;
+  sc.sync_window = 0;
+  const int kblocks = d_pad / BK;
+  sc.pace_kb = std::min(kblocks, 16);
+  sc.cpt = (kblocks + sc.pace_kb - 1) / sc.pace_kb;
+  sc.tab_lists = out->block_first[nb];
+  sc.tab_runs = out->runs.data();                  // host pointers; the caller swaps in the device copies
+  sc.tab_unit_begin = out->unit_begin.data();
+  sc.tab_block_first = out->block_first.data();
 }
 
 // ------------------------------------------------------------------ tensor maps
@@ -319,7 +423,8 @@ int launch_gated_topk(const TopkLaunch& a, const Schedule& sc, uint64_t* partial
   const int units = topk_units(cg, a.sm_count);
   // only units that receive work in some super-row need to exist
   int used = 0;
-  if (sc.n_full > 0) used = std::max(used, sc.rm * std::min(sc.s_main, sc.ntiles));
+  if (sc.tab_runs != nullptr) used = units;
+  else if (sc.n_full > 0) used = std::max(used, sc.rm * std::min(sc.s_main, sc.ntiles));
   if (sc.r_last > 0) used = std::max(used, sc.r_last * std::min(sc.s_last, sym ? sc.r_last : sc.ntiles));
   used = std::min(std::max(used, 1), units);
 

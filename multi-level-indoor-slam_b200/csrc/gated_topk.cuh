@@ -314,7 +314,7 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     for_each_run(sc, unit, [&](const Run& run) {
       const int grow = (run.mb * CSIZE + static_cast<int>(cta_rank)) * BM + row_in_tile;   // global query row
       const bool row_live = grow < p.Q;
-      uint64_t* slot = p.partial + sched_list_offset(sc, row_live ? grow : 0, BM * CSIZE, k) + static_cast<int64_t>(run.slot) * k;
+      uint64_t* slot = p.partial + (row_live ? sched_run_list_offset(sc, run.mb, run.slot, grow, BM * CSIZE, k) : 0);
       double tq = 0.0;
       int32_t qf = kFloorNone;
       if (row_live) {

@@ -196,14 +196,17 @@ merge_topk_kernel(const MergeLaunch a) {
   if (row >= a.Q) return;
   const int k = a.k;
   int n_lists = a.n_lists;
+  int64_t list_stride = a.list_stride;
   const uint64_t* base = a.keys_in + row * a.row_stride;
   // symmetric sweep: the row also owns a buffer of column-direction candidates, unless a buffer overflowed
   // and the full sweep redid the job (then its schedule `sc` describes the lists)
   const bool sym = a.sym_flag != nullptr && (a.sym_force || *a.sym_flag == 0u);
   if (n_lists < 0) {   // the fused kernel's partial lists: list count and offset follow the tile schedule
     const Schedule& sc = sym ? a.sc_sym : a.sc;
-    n_lists = sched_slots(sc, static_cast<int>(row / a.rows_per_mblock));
-    base = a.keys_in + sched_list_offset(sc, row, a.rows_per_mblock, a.k);
+    const int mb = static_cast<int>(row / a.rows_per_mblock);
+    n_lists = sched_slots(sc, mb);
+    base = a.keys_in + sched_run_list_offset(sc, mb, sc.tab_runs != nullptr ? sc.tab_block_first[mb] : 0, row, a.rows_per_mblock, a.k);
+    list_stride = sched_list_stride(sc, a.rows_per_mblock, a.k);
   }
   const int total = n_lists * k;
 
@@ -219,9 +222,9 @@ merge_topk_kernel(const MergeLaunch a) {
     // rows with few lists (most rows: the tail super-row is split finer than the others) take the
     // cheaper 4-keys-per-lane network; warp-uniform choice
     if (P == 8 && total + (have_run ? 64 : 0) <= 128)
-      merge_range<4>(base, 0, total, k, a.list_stride, k, lane, run, have_run, a.list_ptrs, row * k);
+      merge_range<4>(base, 0, total, k, list_stride, k, lane, run, have_run, a.list_ptrs, row * k);
     else
-      merge_range<P>(base, 0, total, k, a.list_stride, k, lane, run, have_run, a.list_ptrs, row * k);
+      merge_range<P>(base, 0, total, k, list_stride, k, lane, run, have_run, a.list_ptrs, row * k);
     if (sym) {
       const int extra = static_cast<int>(min(a.sym_cnt[row], static_cast<uint32_t>(a.sym_cap)));
       if (extra > 0) merge_range<P>(a.sym_ovf + row * a.sym_cap, 0, extra, a.sym_cap, 0, k, lane, run, true);
@@ -229,7 +232,7 @@ merge_topk_kernel(const MergeLaunch a) {
   } else {
     const int per = (total + kRowBlockWarps - 1) / kRowBlockWarps;
     const int e0 = min(total, warp * per), e1 = min(total, e0 + per);
-    merge_range<P>(base, e0, e1, k, a.list_stride, k, lane, run, have_run, a.list_ptrs, row * k);
+    merge_range<P>(base, e0, e1, k, list_stride, k, lane, run, have_run, a.list_ptrs, row * k);
     if (lane < k) stage[warp * k + lane] = run[0];              // k keys per warp, packed
     if (lane + 32 < k) stage[warp * k + 32 + lane] = run[1];
     __syncthreads();
@@ -278,7 +281,7 @@ int launch_merge_topk(const MergeLaunch& a, cudaStream_t st) {
   const unsigned grid = static_cast<unsigned>((a.Q + kMergeWarps - 1) / kMergeWarps);
   // 4 keys per lane cover one batch of 128 new keys (64 when a seeded list rides along)
   int lists = a.n_lists >= 0 ? a.n_lists : std::max(a.sc.s_main, a.sc.s_last);
-  if (a.n_lists < 0 && a.sym_flag != nullptr) lists = std::max(lists, std::max(a.sc_sym.s_main, a.sc_sym.s_last));
+  if (a.n_lists < 0 && a.sym_flag != nullptr) lists = std::max(lists, std::max(a.sc_sym.s_max, std::max(a.sc_sym.s_main, a.sc_sym.s_last)));
   const int64_t keys = static_cast<int64_t>(lists) * a.k;
   if (a.Q <= 2048 && keys >= 1024 && a.sym_flag == nullptr)
     merge_topk_kernel<8, true><<<static_cast<unsigned>(a.Q), kRowBlockWarps * 32, 0, st>>>(a);

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <vector>
 
 #include "common.cuh"
 
@@ -36,6 +37,15 @@ size_t topk_sync_bytes(const Schedule& sc);
 size_t sym_zeroed_bytes(int64_t N, size_t sync_bytes);
 size_t sym_state_bytes(int64_t N, int k, size_t sync_bytes);
 int schedule_selfcheck(const Schedule& sc, int units, int64_t* tiles_computed, int64_t* makespan_tiles);
+// Run table of a small symmetric sweep (see Schedule::tab_runs): built on the host; `sc` points into the vectors.
+struct SymTable {
+  Schedule sc;
+  std::vector<RunEntry> runs;
+  std::vector<int> unit_begin, block_first;
+  int64_t makespan;
+};
+bool sym_table_wanted(int64_t N);
+void build_sym_table(int64_t N, int d_pad, int sm_count, int part_index, int part_count, SymTable* out);
 size_t topk_partial_bytes(const Schedule& sc, int cta_group, int k);      // candidate-key lists (256-byte multiple)
 size_t topk_workspace_bytes(const Schedule& sc, int cta_group, int k);    // lists + pacing counters
 

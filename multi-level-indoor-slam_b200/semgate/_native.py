@@ -141,7 +141,7 @@ def schedule_check(Q: int, N: int, d_pad: int, cta_group: int = 2, sm_count: int
     Returns dict(blocks, tiles, rm, s_main, r_last, s_last, window, resident, computed, makespan)."""
     shape, tiles = (C.c_int32 * 8)(), (C.c_int64 * 2)()
     _check(load_library().semgate_schedule_check(int(Q), int(N), int(d_pad), int(cta_group), int(sm_count),
-                                                 1 if symmetric else 0, int(part_index), int(part_count), shape, tiles))
+                                                 int(symmetric), int(part_index), int(part_count), shape, tiles))
     names = ("blocks", "tiles", "rm", "s_main", "r_last", "s_last", "window", "resident")
     out = dict(zip(names, list(shape)))
     out["computed"], out["makespan"] = int(tiles[0]), int(tiles[1])

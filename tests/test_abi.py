@@ -65,6 +65,9 @@ def test_tile_schedule_invariants(sym):
                 nb = (n + 255) // 256
                 assert r["blocks"] == nb and r["tiles"] == nb
                 assert r["computed"] == (nb * (nb + 1) // 2 if sym else nb * nb)
+                if sym and nb <= 224:      # the run table such sweeps actually use
+                    t = _native.schedule_check(n, n, d_pad, 2, sms, 2)
+                    assert t["computed"] == nb * (nb + 1) // 2 and t["makespan"] <= r["makespan"]
     if not sym:   # rectangular problems, single-CTA tiles
         for Q, N, cg in [(1, 1, 1), (100, 5000, 1), (10000, 100000, 2), (8192, 250000, 2), (1500, 300, 1), (129, 257, 2)]:
             r = _native.schedule_check(Q, N, 4096, cg)
@@ -76,8 +79,9 @@ def test_tile_schedule_invariants(sym):
         with pytest.raises(_native.SemgateError):
             _native.schedule_check(1000, 2000, 4096, 2, 148, True)
         # split over G GPUs: the parts tile the triangle exactly once and are balanced
-        for n, G in [(20000, 2), (56568, 8), (300000, 4), (1000000, 8), (5000, 3)]:
-            parts = [_native.schedule_check(n, n, 4096, 2, 148, True, g, G) for g in range(G)]
+        for n, G, how in [(20000, 2, 1), (56568, 8, 1), (300000, 4, 1), (1000000, 8, 1), (5000, 3, 1),
+                          (28160, 2, 2), (39936, 4, 2), (56320, 8, 2), (700, 8, 2)]:
+            parts = [_native.schedule_check(n, n, 4096, 2, 148, how, g, G) for g in range(G)]
             nb = (n + 255) // 256
             assert sum(p["computed"] for p in parts) == nb * (nb + 1) // 2
             if n >= 300000:

@@ -745,11 +745,14 @@ SYM_CASES = [
 ]
 
 
+@pytest.mark.parametrize("table", ["1", "0"], ids=["runtable", "superrows"])
 @pytest.mark.parametrize("case", SYM_CASES, ids=[f"{c[0]}x{c[1]}k{c[2]}m{c[6]}" for c in SYM_CASES])
-def test_symmetric_sweep_equals_full_sweep(eng, case):
+def test_symmetric_sweep_equals_full_sweep(eng, case, table, monkeypatch):
     """Queries == database: every similarity computed once and gated in both directions gives the lists of the
-    full sweep, and the oracle's."""
+    full sweep, and the oracle's.  Both schedules of the triangle: the host-built run table (what sweeps of this
+    size use) and the super-row formula (what long sweeps use)."""
     from semgate import synthetic
+    monkeypatch.setenv("SEMGATE_SYM_TABLE", table)
     n, d, k, thr, gap, nf, mode, mfd = case
     desc, ts, fl = synthetic.make_case(n, d, nf, seed=n + d)
     fl = fl.astype(np.int32)
@@ -799,6 +802,7 @@ def test_symmetric_sweep_paced(eng, chunks, monkeypatch):
     kw = dict(k=k, thr=0.5, gap=10.0, q_ts=ts, db_ts=ts, q_fl=fl, db_fl=fl, mfd=0, cg=2)
     full = run_gpu(eng, desc, desc, sym=-1, **kw)
     monkeypatch.setenv("SEMGATE_WINDOW_CHUNKS", chunks)
+    monkeypatch.setenv("SEMGATE_SYM_TABLE", "0")          # pacing belongs to the super-row formula
     half = run_gpu(eng, desc, desc, sym=1, **kw)
     assert half["mode"] == 1
     _same_lists(full, half, k, 0.5)
@@ -842,12 +846,14 @@ def test_symmetric_sweep_argument_rules(eng):
     assert eng.last_sweep_mode()[0] == 0
 
 
+@pytest.mark.parametrize("table", ["1", "0"], ids=["runtable", "superrows"])
 @pytest.mark.parametrize("G", [2, 3, 8])
-def test_symmetric_sweep_parts_merge_to_full_sweep(eng, G):
+def test_symmetric_sweep_parts_merge_to_full_sweep(eng, G, table, monkeypatch):
     """The multi-GPU form on one GPU: the G parts of the tile triangle, swept one after the other and merged by
     K3, give the lists of the full sweep."""
     import torch
     from semgate import _native, synthetic
+    monkeypatch.setenv("SEMGATE_SYM_TABLE", table)
     n, d, k = 12000, 128, 25
     desc, ts, fl = synthetic.make_case(n, d, 4, seed=77)
     xb = eng.normalize_cast(_t(desc, torch.float32))
