@@ -275,6 +275,9 @@ void build_sym_table(int64_t N, int d_pad, int sm_count, int part_index, int par
     }
     if (best < 0 || best_Lm * 100 < best * 95) { best = best_Lm; best_rm = rm_L; best_L = L; }
   }
+  // A/B knobs (development): force the run length / super-row height
+  if (env_long("SEMGATE_SYM_RUN", 0) > 0) best_L = static_cast<int>(env_long("SEMGATE_SYM_RUN", 0));
+  if (env_long("SEMGATE_SYM_RM", 0) > 0) best_rm = std::min<int>(nb, static_cast<int>(env_long("SEMGATE_SYM_RM", 0)));
   Dealt d = deal_runs(nb, best_rm, best_L, units, part_index, part_count);
   out->block_first.assign(nb + 1, 0);
   for (int b = 0; b < nb; ++b) out->block_first[b + 1] = out->block_first[b] + d.lists_of_block[b];
@@ -411,7 +414,9 @@ int launch_gated_topk(const TopkLaunch& a, const Schedule& sc, uint64_t* partial
   // query blocks are re-read from L2 for every database tile: keep them; database tiles stream through
   const int hint = static_cast<int>(env_long("SEMGATE_L2_HINT", 2));
   p.policy_q = ((hint == 1 || hint == 2) && sc.a_resident) ? ptx::kL2EvictLast : ptx::kL2EvictNormal;
-  p.policy_db = (hint >= 2 && sc.a_resident) ? ptx::kL2EvictFirst : ptx::kL2EvictNormal;
+  // (run table: the units that share a database tile are not in lock-step, evict-first would throw a tile out
+  //  before its last reader arrives -- measured 1.337 -> 1.290 ms at config 2 without it)
+  p.policy_db = (hint >= 2 && sc.a_resident && sc.tab_runs == nullptr) ? ptx::kL2EvictFirst : ptx::kL2EvictNormal;
 
   // deepest ring that fits the 227 KB per-CTA limit
   int stages = kMaxStages;
