@@ -323,36 +323,75 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       }
       L.reset(row_live ? p.threshold : pos_inf);
       float published = __int_as_float(0xff800000);   // SYM: last bound this thread published for its row
+      // SYM: one column-direction append in flight per thread.  The slot number comes back from a global atomic
+      // (about a microsecond); it is only looked at when the thread's next candidate arrives or the run ends, so
+      // the round trip overlaps the chunks in between instead of stalling the warp at every hit.
+      int pend_col = -1;
+      uint32_t pend_at = 0;
+      uint64_t pend_key = 0;
+      auto complete_append = [&]() {
+        if (pend_col >= 0) {
+          if (pend_at < static_cast<uint32_t>(p.sym_cap)) p.sym_ovf[static_cast<int64_t>(pend_col) * p.sym_cap + pend_at] = pend_key;
+          else *reinterpret_cast<volatile uint32_t*>(p.sym_flag) = 1u;
+          pend_col = -1;
+        }
+      };
+
+      // Per-tile copies of the database timestamps / labels (and, SYM, the columns' admission bounds with
+      // their minimum per 32-column chunk) in shared memory, one buffer per accumulator: every thread fetches
+      // two columns into registers (stage_load) and publishes them behind one named barrier (stage_store).
+      // One barrier per tile is enough: whoever overwrites buffer `a` has passed the barrier of the tile before,
+      // which every epilogue warp only reaches after it finished the tile before that (the buffer's last reader).
+      const bool need_stage = use_time || mask_mode || SYM;
+      double st_ts[2] = {0.0, 0.0};
+      int32_t st_fl[2] = {kFloorNone, kFloorNone};
+      float st_bd[2] = {pos_inf, pos_inf};
+      auto stage_load = [&](int tile, bool cols) {
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int col = tile * BN + et + 128 * jj;
+          if (use_time) st_ts[jj] = col < p.N ? __ldg(p.db_ts + col) : 0.0;
+          if (mask_mode) st_fl[jj] = col < p.N ? __ldg(p.db_floor + col) : kFloorNone;
+          if constexpr (SYM) {
+            float b = pos_inf;                        // beyond N (TMA zero fill) and on the diagonal: nothing passes
+            if (cols && col < p.N) {
+              const uint32_t g = ptx::ld_relaxed_gpu(p.sym_bound + col);
+              b = g != 0u ? ordered_to_score(g) : p.threshold;
+            }
+            st_bd[jj] = b;
+          }
+        }
+      };
+      auto stage_store = [&](uint32_t a) {
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int j = et + 128 * jj;
+          if (use_time) ts_s[a * BN + j] = st_ts[jj];
+          if (mask_mode) fl_s[a * BN + j] = st_fl[jj];
+          if constexpr (SYM) {
+            bd_s[a * BN + j] = st_bd[jj];
+            // the columns of this warp in this pass are exactly chunk j / 32
+            const uint32_t mn = __reduce_min_sync(0xffffffffu, score_to_ordered(st_bd[jj]));
+            if (lane == 0) bmin_s[a * 8 + (j >> 5)] = ordered_to_score(mn);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      };
+      bool staged = false;
 
       for (int nt = run.nt_first; nt < run.nt1; ++nt, ++it) {
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         const int col_base = nt * BN;
         const bool do_cols = SYM && nt != run.mb;   // the diagonal tile holds both orientations of its pairs
-        if (use_time || mask_mode || SYM) {
-          // stage this tile's timestamps / labels while its MMAs run.  One barrier per tile is enough:
-          // whoever overwrites buffer `acc` here has passed the previous tile's barrier, which every
-          // epilogue warp only reaches after it finished the tile before that (the buffer's last reader).
-#pragma unroll
-          for (int j = et; j < BN; j += 128) {
-            const int col = col_base + j;
-            if (use_time) ts_s[acc * BN + j] = col < p.N ? __ldg(p.db_ts + col) : 0.0;
-            if (mask_mode) fl_s[acc * BN + j] = col < p.N ? __ldg(p.db_floor + col) : kFloorNone;
-            if constexpr (SYM) {
-              float b = pos_inf;                      // beyond N (TMA zero fill) and on the diagonal: nothing passes
-              if (do_cols && col < p.N) {
-                const uint32_t g = ptx::ld_relaxed_gpu(p.sym_bound + col);
-                b = g != 0u ? ordered_to_score(g) : p.threshold;
-              }
-              bd_s[acc * BN + j] = b;
-              // columns j of this warp in this pass are exactly chunk j / 32
-              const uint32_t mn = __reduce_min_sync(0xffffffffu, score_to_ordered(b));
-              if (lane == 0) bmin_s[acc * 8 + (j >> 5)] = ordered_to_score(mn);
-            }
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (need_stage && !staged) {    // first tile of a run: nothing was fetched ahead
+          stage_load(nt, do_cols);
+          stage_store(acc);
         }
         ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase);
         ptx::tc_fence_after();
+        // the next tile's stamps / labels / bounds: loads in flight while this tile's chunks are processed
+        const bool ahead = need_stage && nt + 1 < run.nt1;
+        if (ahead) stage_load(nt + 1, SYM && nt + 1 != run.mb);
         const uint32_t t_acc = t_lane + acc * BN;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
@@ -430,12 +469,10 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 if (use_time) ok = !time_excluded(tq, ts_s[j], p.gap);     // |a - b| is symmetric in fp64
                 if (ok && mask_mode) ok = floor_ok(fl_s[j], qf, p.max_floor_diff);
                 if (ok) {
-                  const int col = col_base + c * 32 + i;                   // < N: columns beyond carry +inf bounds
-                  const uint32_t at = atomicAdd(p.sym_cnt + col, 1u);
-                  if (at < static_cast<uint32_t>(p.sym_cap))
-                    p.sym_ovf[static_cast<int64_t>(col) * p.sym_cap + at] = pack_key(s, static_cast<uint32_t>(grow) + p.db_index_offset);
-                  else
-                    *reinterpret_cast<volatile uint32_t*>(p.sym_flag) = 1u;
+                  complete_append();
+                  pend_col = col_base + c * 32 + i;                        // < N: columns beyond carry +inf bounds
+                  pend_key = pack_key(s, static_cast<uint32_t>(grow) + p.db_index_offset);
+                  pend_at = atomicAdd(p.sym_cnt + pend_col, 1u);
                 }
               }
               __syncwarp();
@@ -456,8 +493,11 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           if constexpr (CG == 1) ptx::mbar_arrive(bar_tempty + 8 * acc);
           else ptx::mbar_arrive_cluster(bar_tempty + 8 * acc, pair_leader);
         }
+        if (ahead) stage_store(acc ^ 1u);     // the next tile uses the other accumulator and the other buffer
+        staged = ahead;
       }
 
+      if constexpr (SYM) complete_append();
       // flush this run's list (unsorted, packed at the front; empty slots are key 0)
       if (row_live && p.dense == nullptr) {
         for (int i = 0; i < k; ++i) slot[i] = i < L.cnt ? L.keys[i] : 0ull;
