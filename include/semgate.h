@@ -96,7 +96,8 @@ int64_t semgate_launch_count(semgate_handle_t h);
 
 /* How the last semgate_gated_topk on this handle ran: *out_mode = 0 full sweep, 1 symmetric sweep,
  * 2 symmetric sweep whose candidate buffers overflowed, so that the full sweep behind it produced the
- * result (reads a device flag: synchronises the stream of that call).  *out_tiles (may be NULL) = 256-row x
+ * result (reads a device flag that lives in that call's workspace: synchronises the stream of that call; ask
+ * before the workspace is reused by another sweep or freed).  *out_tiles (may be NULL) = 256-row x
  * 256-column (CTA pairs; 128 x 256 for single-CTA tiles) similarity tiles its schedule computes; mode 2 ran both. */
 int semgate_last_sweep_mode(semgate_handle_t h, int32_t* out_mode, int64_t* out_tiles);
 
@@ -142,6 +143,9 @@ int semgate_similarity_matrix(semgate_handle_t h, const void* q_bf16, int64_t Q,
  *   q_ts/db_ts   fp64 or both NULL (no temporal mask, query(timestamp=None))
  *   q_floor/db_floor  int32 or NULL (no gating)
  *   workspace    >= semgate_topk_workspace_bytes(...)
+ * A handle is not thread-safe; calls on one handle are issued in order.  For small all-pairs sweeps the
+ * symmetric schedule is a host-built table, uploaded once per shape and cached in the handle (the first call for a
+ * shape, semgate_topk_workspace_bytes included, allocates a few hundred KB of device memory and copies synchronously).
  * outputs, each [Q,k], any may be NULL:
  *   out_keys    packed candidates (for semgate_merge_topk across GPUs)
  *   out_scores  fp32 descending, -inf padded;  out_idx int32 global index, -1 padded
