@@ -206,6 +206,9 @@ struct Run {
   int units_long;
 };
 
+// (also walked on the host by schedule_selfcheck with a host-only lambda: that instantiation is never compiled
+//  for the device, so the "host function called from __host__ __device__" diagnostics do not apply)
+#pragma nv_diag_suppress 20011, 20013, 20015
 template <typename F>
 __host__ __device__ __forceinline__ void for_each_run(const Schedule& sc, int unit, F&& f) {
   if (sc.tab_runs != nullptr) {
@@ -241,5 +244,6 @@ __host__ __device__ __forceinline__ void for_each_run(const Schedule& sc, int un
     if (run.nt0 < run.nt1) f(run);
   }
 }
+#pragma nv_diag_default 20011, 20013, 20015
 
 }  // namespace semgate
