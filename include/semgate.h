@@ -29,7 +29,8 @@ extern "C" {
 #endif
 
 #define SEMGATE_VERSION 101
-#define SEMGATE_MAX_K 64
+#define SEMGATE_MAX_K 64          /* candidates per query one sweep keeps (shared-memory list) */
+#define SEMGATE_MAX_K_TOTAL 1024   /* largest k: k > 64 runs as ceil(k / 64) sweeps, see semgate_gated_topk */
 #define SEMGATE_FLOOR_NONE INT32_MIN
 
 #define SEMGATE_EINVAL (-1)       /* bad argument */
@@ -52,7 +53,7 @@ typedef void* semgate_stream_t;   /* cudaStream_t */
 typedef struct semgate_topk_params {
   float similarity_threshold;   /* keep s >= threshold, compared in fp32; -INFINITY disables (query()) */
   double min_time_gap;          /* exclude |t_db - t_q| < gap (strict, fp64) */
-  int32_t k;                    /* 1..SEMGATE_MAX_K */
+  int32_t k;                    /* 1..SEMGATE_MAX_K_TOTAL; above SEMGATE_MAX_K: several sweeps (no accumulate / parts) */
   int32_t max_floor_diff;       /* -1 gating off; 0 strict; 1 non-strict */
   int32_t gate_mode;            /* SEMGATE_GATE_FLAG | SEMGATE_GATE_MASK */
   uint32_t db_index_offset;     /* global index of database row 0 (row-sharded multi-GPU) */
@@ -86,18 +87,23 @@ int semgate_destroy(semgate_handle_t h);
 int semgate_device_info(semgate_handle_t h, int* sm_count, int* cc_major, int* cc_minor);
 /* options: "cta_group" (0 auto | 1 | 2 | 4); "symmetric" (0 auto by size | 1 whenever the arguments allow |
  * -1 never: handle default for semgate_topk_params.symmetric == 0); "profile" (0|1): bracket every fused-kernel launch with CUDA
- * events on its own stream */
+ * events on its own stream; "clock_probe" (0|1): see semgate_clock_probe_read */
 int semgate_set_option(semgate_handle_t h, const char* name, int64_t value);
 /* sum of the fused kernel's (K2) device durations since the last read, and how many
  * launches that covers; synchronises on the recorded events and resets them. */
 int semgate_profile_read(semgate_handle_t h, double* total_ms, int64_t* n_launches);
+/* option "clock_probe" (0|1): every CTA of the fused kernel records {globaltimer, clock64} at entry and exit; this
+ * reads the last sweep's first K2 launch back: the median and minimum over its CTAs of cycles / nanosecond (the SM
+ * clock the kernel really ran at: NVML samples every few ms cannot resolve a 1 ms kernel), the time from the first
+ * CTA's entry to the last one's exit, and the number of CTAs that reported.  Synchronises the sweep's stream. */
+int semgate_clock_probe_read(semgate_handle_t h, double* sm_mhz_median, double* sm_mhz_min, double* span_us, int32_t* n_ctas);
 /* kernels launched through this handle since creation (bench.py's gpu_launches) */
 int64_t semgate_launch_count(semgate_handle_t h);
 
 /* How the last semgate_gated_topk on this handle ran: *out_mode = 0 full sweep, 1 symmetric sweep,
  * 2 symmetric sweep whose candidate buffers overflowed, so that the full sweep behind it produced the
- * result (reads a device flag that lives in that call's workspace: synchronises the stream of that call; ask
- * before the workspace is reused by another sweep or freed).  *out_tiles (may be NULL) = 256-row x
+ * result (reads a device flag the sweep's merge kernel copied into handle-owned memory: synchronises the stream
+ * of that call; the call's workspace may already be reused or freed).  *out_tiles (may be NULL) = 256-row x
  * 256-column (CTA pairs; 128 x 256 for single-CTA tiles) similarity tiles its schedule computes; mode 2 ran both. */
 int semgate_last_sweep_mode(semgate_handle_t h, int32_t* out_mode, int64_t* out_tiles);
 
@@ -144,8 +150,11 @@ int semgate_similarity_matrix(semgate_handle_t h, const void* q_bf16, int64_t Q,
  *   q_floor/db_floor  int32 or NULL (no gating)
  *   workspace    >= semgate_topk_workspace_bytes(...)
  * A handle is not thread-safe; calls on one handle are issued in order.  For small all-pairs sweeps the
- * symmetric schedule is a host-built table, uploaded once per shape and cached in the handle (the first call for a
- * shape, semgate_topk_workspace_bytes included, allocates a few hundred KB of device memory and copies synchronously).
+ * symmetric schedule is a host-built table, cached in the handle per tile count (ceil(N/256)) and uploaded with
+ * cudaMemcpyAsync on the calling stream at its first sweep (that call allocates a few hundred KB of device memory;
+ * semgate_topk_workspace_bytes only builds the host copy).
+ * accumulate = 1 cannot produce out_valid when gating is on (SEMGATE_EINVAL): the seeded lists hold indices of other
+ * database slices, outside db_floor; flag the final lists with semgate_merge_topk and the whole label array.
  * outputs, each [Q,k], any may be NULL:
  *   out_keys    packed candidates (for semgate_merge_topk across GPUs)
  *   out_scores  fp32 descending, -inf padded;  out_idx int32 global index, -1 padded
@@ -174,6 +183,20 @@ int semgate_merge_topk_peers(semgate_handle_t h, const uint64_t* const* peer_key
                              uint64_t* out_keys, float* out_scores, int32_t* out_idx, uint8_t* out_valid,
                              int32_t* out_count, semgate_stream_t stream);
 
+/* The same merge for a SLICE of the query rows, with the peers' overflow flags folded in.  Every rank of a
+ * multi-GPU sweep merges only its own rows [row_begin, row_begin + row_count) of the G per-GPU lists (each
+ * [Q_total, k]; list g of row r = peer_keys[g] + r*k): the NVLink reads drop to 1/G of the replicated merge's.
+ * Outputs are [row_count, k] / [row_count]; q_floor is indexed by the global row.  With out_any_flag != NULL
+ * the kernel also reads one uint32 at peer_keys[g] + flag_offset (offset in 8-byte keys, >= Q_total*k: a word
+ * behind every rank's key buffer, written there by semgate_last_sweep_overflow) for every g and stores their OR
+ * in *out_any_flag (device): whether any rank's part of a split symmetric sweep overflowed, learnt without a
+ * collective of its own.  replaces nothing in the reference (single process); semgate/dist.py is the caller. */
+int semgate_merge_topk_peers_rows(semgate_handle_t h, const uint64_t* const* peer_keys, int32_t G, int64_t Q_total,
+                                  int32_t k, int64_t row_begin, int64_t row_count, int64_t flag_offset,
+                                  const int32_t* q_floor, const int32_t* db_floor_all, int32_t max_floor_diff,
+                                  uint64_t* out_keys, float* out_scores, int32_t* out_idx, uint8_t* out_valid,
+                                  int32_t* out_count, uint32_t* out_any_flag, semgate_stream_t stream);
+
 /* ---- K4: candidate compaction ----------------------------------------------
  * replaces the PlaceMatch append loop (place_recognition.py:890-909): flat arrays
  * ordered (query ascending, score descending).  Outputs need capacity Q*k.
@@ -188,6 +211,14 @@ int semgate_compact(semgate_handle_t h, const float* scores, const int32_t* idx,
 int semgate_compact_valid(semgate_handle_t h, const float* scores, const int32_t* idx, const uint8_t* valid, const int32_t* count,
                           int64_t Q, int32_t k, int32_t* out_query_idx, int32_t* out_match_idx, float* out_similarity,
                           uint8_t* out_is_valid, int64_t* out_total, void* workspace, semgate_stream_t stream);
+
+/* Compaction of a SLICE of the query rows (a rank's share of a multi-GPU sweep, semgate_merge_topk_peers_rows):
+ * the lists are [Q, k] for the rows query_index_offset .. +Q, the emitted query indices are global.
+ * valid_only != 0: as semgate_compact_valid. */
+int semgate_compact_rows(semgate_handle_t h, const float* scores, const int32_t* idx, const uint8_t* valid, const int32_t* count,
+                         int64_t Q, int32_t k, int64_t query_index_offset, int32_t valid_only, int32_t* out_query_idx,
+                         int32_t* out_match_idx, float* out_similarity, uint8_t* out_is_valid, int64_t* out_total,
+                         void* workspace, semgate_stream_t stream);
 
 /* ---- match statistics -------------------------------------------------------
  * replaces SemanticPlaceRecognition.get_statistics (place_recognition.py:913-933) for a
@@ -238,6 +269,23 @@ int semgate_rerank_scores(semgate_handle_t h, const void* local_feats, int64_t n
 int semgate_rerank_select(semgate_handle_t h, const int32_t* cand_idx, const float* combined, const int32_t* count,
                           int64_t Q, int32_t kc, int32_t top_k, int32_t* out_idx, float* out_score, int32_t* out_count,
                           semgate_stream_t stream);
+
+/* ---- find_loop_closures over a device-resident database: one call, caller-owned outputs ---------------
+ * replaces SemanticPlaceRecognition.find_loop_closures (place_recognition.py:851-911) for a database that already
+ * lives on the GPU as normalised bf16 rows (K1 output): K2 + K3 + K4 in one call, flat candidates (query
+ * ascending, similarity descending) into the caller's arrays (capacity n*k each), their number in *out_total_dev
+ * (device int64).  Nothing inside waits for the host.  use_graph != 0: the first call with a given argument set
+ * runs eagerly, the second captures the same launch sequence into a CUDA graph, later calls replay it with one
+ * cudaGraphLaunch (small sweeps are bound by launch overhead: BASELINE config 1 is a 60 us kernel).  The graph
+ * is keyed on every argument, handle option and the params struct; up to 8 are cached per handle.  `stream` must not
+ * be the legacy default stream for that (a capture cannot start there: the call then stays eager). */
+size_t semgate_find_loop_closures_device_workspace_bytes(semgate_handle_t h, int64_t n, int32_t d_pad,
+                                                         const semgate_topk_params* p);
+int semgate_find_loop_closures_device(semgate_handle_t h, const void* x_bf16, int64_t n, int32_t d_pad, const double* ts,
+                                      const int32_t* floor_labels, const semgate_topk_params* p, void* workspace,
+                                      size_t workspace_bytes, int32_t* out_query_idx, int32_t* out_match_idx,
+                                      float* out_similarity, uint8_t* out_is_valid, int64_t* out_total_dev,
+                                      int32_t use_graph, semgate_stream_t stream);
 
 /* ---- host-buffer entry points (the reference-facing calls) ----------------------
  * find_loop_closures over a whole database held in host memory

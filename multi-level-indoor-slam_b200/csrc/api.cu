@@ -43,6 +43,7 @@ int cuda_fail(cudaError_t e, const char* what) {
   } while (0)
 
 constexpr int kNumBufs = 17;
+constexpr int kClkCtas = 1024;     // CTAs the clock probe has room for
 enum BufId { B_X = 0, B_BF16, B_TS, B_FL, B_WS, B_SC, B_IX, B_VA, B_CT, B_OQ, B_OM, B_OS, B_OV, B_TOT, B_CWS, B_QBF16, B_KEYS };
 
 inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
@@ -51,10 +52,25 @@ inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255);
 
 // a run table (small symmetric sweeps) and its device copy, cached per shape
 struct SymTableDev {
-  int64_t N; int d_pad, part_index, part_count;
+  int64_t nb; int d_pad, part_index, part_count;   // keyed by the tile count: ceil(N / 256)
   SymTable host;
   void* dev = nullptr;
+  cudaStream_t upload_stream = nullptr;
+  cudaEvent_t uploaded = nullptr;
   Schedule sc_dev;
+};
+
+// One captured find_loop_closures_device sequence; replayed while every argument is the same.
+struct SweepGraphKey {
+  const void* x; int64_t n; int32_t d_pad; const double* ts; const int32_t* floor; semgate_topk_params p;
+  void* ws; size_t ws_bytes; int32_t* oq; int32_t* om; float* os; uint8_t* ov; int64_t* tot; int cta_group, symmetric;
+};
+struct SweepGraph {
+  SweepGraphKey key;
+  int seen = 0;                    // calls with this key so far (the first runs eagerly, the second is captured)
+  cudaGraphExec_t exec = nullptr;
+  int launches = 0;                // kernels + memsets of one replay
+  int mode = 0; int64_t tiles = 0;
 };
 
 struct semgate_ctx {
@@ -64,7 +80,6 @@ struct semgate_ctx {
   int cta_group = 0;               // 0 = auto (by problem size), 1, 2
   int symmetric = 0;               // aliased queries/database: 0 = symmetric sweep when it pays (size rule), 1 = whenever possible, -1 = never
   int last_mode = 0;               // last fused sweep: 0 full, 1 symmetric
-  const uint32_t* last_sym_flag = nullptr;   // ... and its overflow flag (device)
   cudaStream_t last_stream = nullptr;
   int64_t last_tiles = 0;          // tiles the last fused sweep computed (its schedule's count)
   int64_t launches = 0;
@@ -72,7 +87,13 @@ struct semgate_ctx {
   cudaStream_t copy_stream = nullptr;   // H2D + normalisation of the next chunk, overlapped with the sweep
   std::vector<cudaEvent_t> chunk_events;
   bool profile = false;            // record CUDA events around every K2 launch
-  std::vector<SymTableDev*> sym_tables;
+  std::vector<struct SweepGraph*> graphs;   // semgate_find_loop_closures_device: captured launch sequences
+  bool graphs_broken = false;      // a capture failed on this system: stay eager
+  unsigned long long* clk_dev = nullptr;   // option "clock_probe": per-CTA {globaltimer, clock64} pairs of the last K2 launch
+  int clk_ctas = 0;
+  std::vector<SymTableDev*> sym_tables, sym_retired;
+  uint32_t* flag_dev = nullptr;    // overflow flag of the last symmetric sweep (copied by its merge kernel: the
+                                   // caller's workspace may be reused or freed before anybody asks)
   std::vector<cudaEvent_t> prof_events;   // pairs (begin, end), on the launching stream
   size_t prof_used = 0;
   void* buf[kNumBufs] = {};
@@ -104,7 +125,9 @@ struct DeviceGuard {
 
 int check_params(const semgate_topk_params* p) {
   if (!p) return fail(SEMGATE_EINVAL, "params is NULL");
-  if (p->k < 1 || p->k > SEMGATE_MAX_K) return fail(SEMGATE_EINVAL, "k=%d outside 1..%d", p->k, SEMGATE_MAX_K);
+  if (p->k < 1 || p->k > SEMGATE_MAX_K_TOTAL) return fail(SEMGATE_EINVAL, "k=%d outside 1..%d", p->k, SEMGATE_MAX_K_TOTAL);
+  if (p->k > SEMGATE_MAX_K && (p->accumulate || p->part_count > 1 || p->symmetric == 1))
+    return fail(SEMGATE_EINVAL, "k=%d > %d runs as several sweeps: not with accumulate, part_count > 1 or symmetric = 1", p->k, SEMGATE_MAX_K);
   if (p->max_floor_diff < -1) return fail(SEMGATE_EINVAL, "max_floor_diff=%d", p->max_floor_diff);
   if (p->gate_mode != SEMGATE_GATE_FLAG && p->gate_mode != SEMGATE_GATE_MASK) return fail(SEMGATE_EINVAL, "gate_mode=%d", p->gate_mode);
   if (p->cta_group != 0 && p->cta_group != 1 && p->cta_group != 2 && p->cta_group != 4) return fail(SEMGATE_EINVAL, "cta_group=%d", p->cta_group);
@@ -148,6 +171,7 @@ bool sym_wanted(semgate_handle_t h, const semgate_topk_params* p, int64_t Q, int
 
 // tiles a symmetric schedule computes (this part's share of the triangle)
 int64_t sym_tiles_owned(const Schedule& sc) {
+  if (sc.tab_runs != nullptr) return sc.tab_tiles;
   int64_t t = 0;
   int sr = 0;
   for (int lo = 0; lo < sc.ntiles; lo += sc.rm, ++sr) {
@@ -159,39 +183,55 @@ int64_t sym_tiles_owned(const Schedule& sc) {
 }
 
 // The symmetric schedule of an N x N sweep: a run table (built once per shape, cached with its device copy) for
-// small triangles, the super-row formula otherwise.
-int sym_schedule(semgate_handle_t h, int64_t N, int32_t d_pad, const semgate_topk_params* p, Schedule* out) {
+// small triangles, the super-row formula otherwise.  A table depends on N only through the tile count, so a database
+// that grows keyframe by keyframe builds one per 256 keyframes.  `st_upload` == nullptr: the host copy is enough (size
+// queries); else the device copy is made on first use with cudaMemcpyAsync on that stream (the host vectors live as
+// long as the cache entry) and nothing here synchronises the device.  Evicted tables are freed at semgate_destroy.
+int sym_schedule(semgate_handle_t h, int64_t N, int32_t d_pad, const semgate_topk_params* p, Schedule* out, bool want_device,
+                 cudaStream_t st_upload) {
   if (!sym_table_wanted(N)) {
     *out = make_schedule(N, N, d_pad, 2, h->sm_count, true, p->part_index, p->part_count);
     return 0;
   }
   const int pc = std::max(p->part_count, 1);
-  for (SymTableDev* t : h->sym_tables)
-    if (t->N == N && t->d_pad == d_pad && t->part_index == p->part_index && t->part_count == pc) { *out = t->sc_dev; return 0; }
-  SymTableDev* t = new (std::nothrow) SymTableDev();
-  if (!t) return fail(SEMGATE_ENOMEM, "out of host memory");
-  t->N = N; t->d_pad = d_pad; t->part_index = p->part_index; t->part_count = pc;
-  build_sym_table(N, d_pad, h->sm_count, p->part_index, pc, &t->host);
-  const size_t b_runs = align256(t->host.runs.size() * sizeof(RunEntry)), b_ub = align256(t->host.unit_begin.size() * sizeof(int)),
-               b_bf = align256(t->host.block_first.size() * sizeof(int));
-  DeviceGuard g(h->device);
-  cudaError_t e = cudaMalloc(&t->dev, b_runs + b_ub + b_bf);
-  if (e != cudaSuccess) { delete t; return cuda_fail(e, "cudaMalloc (run table)"); }
-  char* d = static_cast<char*>(t->dev);
-  e = cudaMemcpy(d, t->host.runs.data(), t->host.runs.size() * sizeof(RunEntry), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(d + b_runs, t->host.unit_begin.data(), t->host.unit_begin.size() * sizeof(int), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(d + b_runs + b_ub, t->host.block_first.data(), t->host.block_first.size() * sizeof(int), cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) { cudaFree(t->dev); delete t; return cuda_fail(e, "cudaMemcpy (run table)"); }
-  t->sc_dev = t->host.sc;
-  t->sc_dev.tab_runs = reinterpret_cast<const RunEntry*>(d);
-  t->sc_dev.tab_unit_begin = reinterpret_cast<const int*>(d + b_runs);
-  t->sc_dev.tab_block_first = reinterpret_cast<const int*>(d + b_runs + b_ub);
-  if (h->sym_tables.size() >= 16) {                 // keep the cache small: drop the oldest
-    cudaFree(h->sym_tables.front()->dev);
-    delete h->sym_tables.front();
-    h->sym_tables.erase(h->sym_tables.begin());
+  const int64_t nb = (N + 255) / 256;
+  SymTableDev* t = nullptr;
+  for (SymTableDev* c : h->sym_tables)
+    if (c->nb == nb && c->d_pad == d_pad && c->part_index == p->part_index && c->part_count == pc) { t = c; break; }
+  if (!t) {
+    t = new (std::nothrow) SymTableDev();
+    if (!t) return fail(SEMGATE_ENOMEM, "out of host memory");
+    t->nb = nb; t->d_pad = d_pad; t->part_index = p->part_index; t->part_count = pc;
+    build_sym_table(N, d_pad, h->sm_count, p->part_index, pc, &t->host);
+    if (h->sym_tables.size() >= 256) {              // keep the cache bounded: retire the oldest (freed at destroy: a
+      h->sym_retired.push_back(h->sym_tables.front());   // launch in flight may still read its device copy)
+      h->sym_tables.erase(h->sym_tables.begin());
+    }
+    h->sym_tables.push_back(t);
   }
-  h->sym_tables.push_back(t);
+  if (!want_device) { *out = t->host.sc; return 0; }
+  if (!t->dev) {
+    const size_t b_runs = align256(t->host.runs.size() * sizeof(RunEntry)), b_ub = align256(t->host.unit_begin.size() * sizeof(int)),
+                 b_bf = align256(t->host.block_first.size() * sizeof(int));
+    DeviceGuard g(h->device);
+    cudaError_t e = cudaMalloc(&t->dev, b_runs + b_ub + b_bf);
+    if (e != cudaSuccess) { t->dev = nullptr; return cuda_fail(e, "cudaMalloc (run table)"); }
+    char* d = static_cast<char*>(t->dev);
+    e = cudaMemcpyAsync(d, t->host.runs.data(), t->host.runs.size() * sizeof(RunEntry), cudaMemcpyHostToDevice, st_upload);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + b_runs, t->host.unit_begin.data(), t->host.unit_begin.size() * sizeof(int), cudaMemcpyHostToDevice, st_upload);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + b_runs + b_ub, t->host.block_first.data(), t->host.block_first.size() * sizeof(int), cudaMemcpyHostToDevice, st_upload);
+    if (e != cudaSuccess) { cudaFree(t->dev); t->dev = nullptr; return cuda_fail(e, "cudaMemcpyAsync (run table)"); }
+    t->upload_stream = st_upload;
+    if (cudaEventCreateWithFlags(&t->uploaded, cudaEventDisableTiming) == cudaSuccess) cudaEventRecord(t->uploaded, st_upload);
+    t->sc_dev = t->host.sc;
+    t->sc_dev.tab_runs = reinterpret_cast<const RunEntry*>(d);
+    t->sc_dev.tab_unit_begin = reinterpret_cast<const int*>(d + b_runs);
+    t->sc_dev.tab_block_first = reinterpret_cast<const int*>(d + b_runs + b_ub);
+  } else if (t->upload_stream != st_upload && t->uploaded) {
+    // first used on another stream: order this stream behind the upload (a no-op once it has completed)
+    DeviceGuard g(h->device);
+    cudaStreamWaitEvent(st_upload, t->uploaded, 0);
+  }
   *out = t->sc_dev;
   return 0;
 }
@@ -243,6 +283,9 @@ int semgate_create(semgate_handle_t* out, int device) {
   if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate"); }
   e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { cudaStreamDestroy(h->stream); delete h; return cuda_fail(e, "cudaStreamCreate"); }
+  e = cudaMalloc(reinterpret_cast<void**>(&h->flag_dev), 256);
+  if (e == cudaSuccess) e = cudaMemset(h->flag_dev, 0, 256);
+  if (e != cudaSuccess) { cudaStreamDestroy(h->stream); cudaStreamDestroy(h->copy_stream); delete h; return cuda_fail(e, "cudaMalloc (flag)"); }
   *out = h;
   return 0;
 }
@@ -254,7 +297,11 @@ int semgate_destroy(semgate_handle_t h) {
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   for (cudaEvent_t e : h->chunk_events) cudaEventDestroy(e);
   for (int i = 0; i < kNumBufs; ++i) if (h->buf[i]) cudaFree(h->buf[i]);
-  for (SymTableDev* t : h->sym_tables) { cudaFree(t->dev); delete t; }
+  for (auto* v : {&h->sym_tables, &h->sym_retired})
+    for (SymTableDev* t : *v) { if (t->uploaded) cudaEventDestroy(t->uploaded); if (t->dev) cudaFree(t->dev); delete t; }
+  if (h->flag_dev) cudaFree(h->flag_dev);
+  if (h->clk_dev) cudaFree(h->clk_dev);
+  for (SweepGraph* gph : h->graphs) { if (gph->exec) cudaGraphExecDestroy(gph->exec); delete gph; }
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   delete h;
   return 0;
@@ -284,6 +331,18 @@ int semgate_set_option(semgate_handle_t h, const char* name, int64_t value) {
     h->profile = value != 0;
     return 0;
   }
+  if (strcmp(name, "clock_probe") == 0) {
+    DeviceGuard g(h->device);
+    if (value != 0 && !h->clk_dev) {
+      cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->clk_dev), kClkCtas * 4 * sizeof(unsigned long long));
+      if (e != cudaSuccess) { h->clk_dev = nullptr; return cuda_fail(e, "cudaMalloc (clock probe)"); }
+    } else if (value == 0 && h->clk_dev) {
+      cudaFree(h->clk_dev);
+      h->clk_dev = nullptr;
+    }
+    h->clk_ctas = 0;
+    return 0;
+  }
   return fail(SEMGATE_EINVAL, "unknown option '%s'", name);
 }
 
@@ -293,10 +352,10 @@ int semgate_last_sweep_mode(semgate_handle_t h, int32_t* out_mode, int64_t* out_
   if (!h || !out_mode) return fail(SEMGATE_EINVAL, "NULL argument");
   *out_mode = h->last_mode;
   if (out_tiles) *out_tiles = h->last_tiles;
-  if (h->last_mode == 1 && h->last_sym_flag) {
+  if (h->last_mode == 1) {
     DeviceGuard g(h->device);
     uint32_t flag = 0;
-    CUDA_TRY(cudaMemcpyAsync(&flag, h->last_sym_flag, sizeof(flag), cudaMemcpyDeviceToHost, h->last_stream));
+    CUDA_TRY(cudaMemcpyAsync(&flag, h->flag_dev, sizeof(flag), cudaMemcpyDeviceToHost, h->last_stream));
     CUDA_TRY(cudaStreamSynchronize(h->last_stream));
     if (flag != 0) *out_mode = 2;
   }
@@ -319,12 +378,40 @@ int semgate_profile_read(semgate_handle_t h, double* total_ms, int64_t* n_launch
   return 0;
 }
 
+int semgate_clock_probe_read(semgate_handle_t h, double* sm_mhz_median, double* sm_mhz_min, double* span_us, int32_t* n_ctas) {
+  if (!h || !sm_mhz_median) return fail(SEMGATE_EINVAL, "NULL argument");
+  *sm_mhz_median = 0.0;
+  if (sm_mhz_min) *sm_mhz_min = 0.0;
+  if (span_us) *span_us = 0.0;
+  if (n_ctas) *n_ctas = 0;
+  if (!h->clk_dev || h->clk_ctas <= 0) return 0;
+  DeviceGuard g(h->device);
+  std::vector<unsigned long long> v(static_cast<size_t>(kClkCtas) * 4);
+  CUDA_TRY(cudaStreamSynchronize(h->last_stream));
+  CUDA_TRY(cudaMemcpy(v.data(), h->clk_dev, v.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  std::vector<double> mhz;
+  unsigned long long t_lo = ~0ull, t_hi = 0;
+  for (int i = 0; i < kClkCtas; ++i) {
+    const unsigned long long t0 = v[4 * i], c0 = v[4 * i + 1], t1 = v[4 * i + 2], c1 = v[4 * i + 3];
+    if (t0 == 0 || t1 <= t0 || c1 <= c0) continue;       // CTA did not run (smaller grid) or returned at once
+    mhz.push_back(static_cast<double>(c1 - c0) / static_cast<double>(t1 - t0) * 1e3);
+    t_lo = std::min(t_lo, t0); t_hi = std::max(t_hi, t1);
+  }
+  if (mhz.empty()) return 0;
+  std::sort(mhz.begin(), mhz.end());
+  *sm_mhz_median = mhz[mhz.size() / 2];
+  if (sm_mhz_min) *sm_mhz_min = mhz.front();
+  if (span_us) *span_us = static_cast<double>(t_hi - t_lo) * 1e-3;
+  if (n_ctas) *n_ctas = static_cast<int32_t>(mhz.size());
+  return 0;
+}
+
 int semgate_last_sweep_overflow(semgate_handle_t h, uint32_t* out_flag_dev, semgate_stream_t stream) {
   if (!h || !out_flag_dev) return fail(SEMGATE_EINVAL, "NULL argument");
   DeviceGuard g(h->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (h->last_mode == 1 && h->last_sym_flag)
-    CUDA_TRY(cudaMemcpyAsync(out_flag_dev, h->last_sym_flag, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  if (h->last_mode == 1)
+    CUDA_TRY(cudaMemcpyAsync(out_flag_dev, h->flag_dev, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
   else
     CUDA_TRY(cudaMemsetAsync(out_flag_dev, 0, sizeof(uint32_t), st));
   return 0;
@@ -347,7 +434,7 @@ int semgate_schedule_check(int64_t Q, int64_t N, int32_t d_pad, int32_t cta_grou
     sc = make_schedule(Q, N, d_pad, cta_group, sm_count, symmetric != 0, part_index, part_count);
   }
   int64_t computed = 0, makespan = 0;
-  const int err = schedule_selfcheck(sc, topk_units(cta_group, sm_count), &computed, &makespan);
+  const int err = schedule_selfcheck(sc, topk_units(cta_group, sm_count), &computed, &makespan, symmetric == 2 ? &table.owner_of_block : nullptr);
   if (out_shape) {
     out_shape[0] = sc.mblocks; out_shape[1] = sc.ntiles; out_shape[2] = sc.rm; out_shape[3] = sc.s_main;
     out_shape[4] = sc.r_last; out_shape[5] = sc.s_last; out_shape[6] = sc.sync_window; out_shape[7] = sc.a_resident;
@@ -373,32 +460,44 @@ int semgate_normalize_cast(semgate_handle_t h, const float* x, int64_t n, int32_
 
 // ---------------------------------------------------------------- K2 + K3
 size_t semgate_topk_workspace_bytes(semgate_handle_t h, int64_t Q, int64_t N, int32_t d_pad, const semgate_topk_params* p) {
-  if (!h || !p || Q <= 0 || N <= 0 || p->k < 1 || p->k > SEMGATE_MAX_K) return 256;
+  if (!h || !p || Q <= 0 || N <= 0 || p->k < 1 || p->k > SEMGATE_MAX_K_TOTAL) return 256;
   const int cg = resolve_cg(h, p, Q);
   Schedule sc = make_schedule(Q, N, d_pad, cg, h->sm_count);
+  if (p->k > SEMGATE_MAX_K)   // several passes of <= 64: lists of one pass + the key lists of all passes (the ceilings)
+    return align256(align256(topk_workspace_bytes(sc, cg, SEMGATE_MAX_K)) + static_cast<size_t>(Q) * p->k * sizeof(uint64_t));
   size_t need = topk_workspace_bytes(sc, cg, p->k);
   if (use_stream_path(h, p, Q, d_pad)) need = std::max(need, stream_query_workspace_bytes(Q, p->k, h->sm_count));
   if (sym_wanted(h, p, Q, d_pad) && sym_shape_ok(h, p, Q, N, d_pad)) {
     Schedule sc_sym{};
-    if (sym_schedule(h, N, d_pad, p, &sc_sym) == 0) need = std::max(need, sym_layout(sc, sc_sym, N, p->k).total);
+    if (sym_schedule(h, N, d_pad, p, &sc_sym, false, nullptr) == 0) need = std::max(need, sym_layout(sc, sc_sym, N, p->k).total);
   }
   return align256(need);
 }
 
-int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const void* db_bf16, int64_t N, int32_t d_pad,
-                       const double* q_ts, const double* db_ts, const int32_t* q_floor, const int32_t* db_floor,
-                       const semgate_topk_params* p, void* workspace, size_t workspace_bytes, uint64_t* out_keys,
-                       float* out_scores, int32_t* out_idx, uint8_t* out_valid, int32_t* out_count,
-                       semgate_stream_t stream) {
-  if (!h) return fail(SEMGATE_EINVAL, "handle is NULL");
-  int rc = check_params(p);
-  if (rc) return rc;
+}  // extern "C"
+
+namespace {
+// one pass of a k > 64 sweep: the pass's lists are columns out_col .. out_col + k of rows k_total wide; only keys
+// below the last key of the pass before are admitted
+struct PassInfo { const uint64_t* ceil_keys; int64_t k_total; int out_col; };
+
+int gated_topk_impl(semgate_handle_t h, const void* q_bf16, int64_t Q, const void* db_bf16, int64_t N, int32_t d_pad,
+                    const double* q_ts, const double* db_ts, const int32_t* q_floor, const int32_t* db_floor,
+                    const semgate_topk_params* p, void* workspace, size_t workspace_bytes, uint64_t* out_keys,
+                    float* out_scores, int32_t* out_idx, uint8_t* out_valid, int32_t* out_count,
+                    semgate_stream_t stream, const PassInfo* pass) {
+  int rc = 0;
   if (Q < 0 || N < 0 || Q > INT32_MAX || N > INT32_MAX) return fail(SEMGATE_EINVAL, "gated_topk: bad sizes Q=%lld N=%lld", (long long)Q, (long long)N);
   if (d_pad <= 0 || d_pad % 64 != 0) return fail(SEMGATE_EINVAL, "gated_topk: d_pad=%d must be a positive multiple of 64", d_pad);
   if ((q_ts == nullptr) != (db_ts == nullptr)) return fail(SEMGATE_EINVAL, "gated_topk: q_ts and db_ts must both be given or both be NULL");
   if (static_cast<uint64_t>(p->db_index_offset) + static_cast<uint64_t>(N) > 0xFFFFFFFFull) return fail(SEMGATE_EINVAL, "gated_topk: global index overflows 32 bits");
   if (Q == 0) return 0;
   if (p->accumulate && !out_keys) return fail(SEMGATE_EINVAL, "gated_topk: accumulate needs out_keys");
+  // the seeded lists hold global indices of OTHER database slices; db_floor only covers this one, so their floor
+  // flags cannot be computed here: they come from a final semgate_merge_topk with the whole label array
+  if (p->accumulate && out_valid && q_floor && db_floor && p->max_floor_diff >= 0)
+    return fail(SEMGATE_EINVAL, "gated_topk: accumulate cannot produce out_valid (db_floor covers this slice only); "
+                "flag the final lists with semgate_merge_topk and the whole label array");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DeviceGuard g(h->device);
   const int cg = resolve_cg(h, p, Q);
@@ -408,7 +507,8 @@ int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const 
   m.Q = Q; m.k = k;
   m.keys_out = out_keys; m.scores = out_scores; m.idx = out_idx; m.valid = out_valid; m.count = out_count;
   m.seed_keys = p->accumulate ? out_keys : nullptr;
-  m.q_floor = q_floor; m.db_floor = db_floor; m.floor_index_offset = p->db_index_offset;
+  if (pass) { m.out_stride = pass->k_total; m.out_col = pass->out_col; m.count_add = pass->out_col > 0 ? 1 : 0; }
+  m.q_floor = q_floor; m.db_floor = db_floor; m.floor_index_offset = p->db_index_offset; m.floor_n = N;
   m.max_floor_diff = (q_floor && db_floor) ? p->max_floor_diff : -1;
 
   if (N == 0) {   // empty database: every list is empty (place_recognition.py:134)
@@ -421,7 +521,7 @@ int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const 
   if ((reinterpret_cast<uintptr_t>(q_bf16) & 15) || (reinterpret_cast<uintptr_t>(db_bf16) & 15))
     return fail(SEMGATE_EINVAL, "gated_topk: descriptor matrices must be 16-byte aligned");
 
-  const bool gemv = use_stream_path(h, p, Q, d_pad);
+  const bool gemv = !pass && use_stream_path(h, p, Q, d_pad);
   Schedule sc = make_schedule(Q, N, d_pad, cg, h->sm_count);
   const size_t need = gemv ? stream_query_workspace_bytes(Q, k, h->sm_count) : topk_workspace_bytes(sc, cg, k);
   if (!workspace || workspace_bytes < need)
@@ -430,11 +530,11 @@ int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const 
   // Symmetric sweep: the queries are the database itself (same rows, stamps and labels), so S = S^T and only
   // the tiles on or above the block diagonal are computed.  Automatic when the arguments alias.
   const bool aliased = q_bf16 == db_bf16 && q_ts == db_ts && q_floor == db_floor && p->db_index_offset == 0;
-  bool sym = sym_wanted(h, p, Q, d_pad) && sym_shape_ok(h, p, Q, N, d_pad) && aliased;
+  bool sym = !pass && sym_wanted(h, p, Q, d_pad) && sym_shape_ok(h, p, Q, N, d_pad) && aliased;
   Schedule sc_sym{};
   SymLayout lay{};
   if (sym) {
-    if ((rc = sym_schedule(h, N, d_pad, p, &sc_sym))) return rc;
+    if ((rc = sym_schedule(h, N, d_pad, p, &sc_sym, true, st))) return rc;
     lay = sym_layout(sc, sc_sym, N, k);
     if (workspace_bytes < lay.total) sym = false;     // a caller that sized its workspace for the full sweep only
   }
@@ -450,9 +550,17 @@ int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const 
   a.max_floor_diff = m.max_floor_diff; a.gate_mode = p->gate_mode;
   a.db_index_offset = p->db_index_offset;
   a.cta_group = cg; a.sm_count = h->sm_count;
+  if (pass) { a.ceil_keys = pass->ceil_keys; a.ceil_stride = pass->k_total; }
+  if (h->clk_dev && !gemv) {          // the probe covers the sweep's first K2 launch (the symmetric one, if any)
+    a.clk = h->clk_dev;
+    CUDA_TRY(cudaMemsetAsync(h->clk_dev, 0, kClkCtas * 4 * sizeof(unsigned long long), st));
+    h->clk_ctas = std::min(kClkCtas, h->sm_count);
+  }
   int launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  if (h->profile) {
+  cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+  if (h->profile && cudaStreamIsCapturing(st, &capturing) != cudaSuccess) { cudaGetLastError(); capturing = cudaStreamCaptureStatusNone; }
+  if (h->profile && capturing == cudaStreamCaptureStatusNone) {
     if (h->prof_used + 2 > h->prof_events.size()) {
       cudaEvent_t e0, e1;
       CUDA_TRY(cudaEventCreate(&e0));
@@ -479,6 +587,7 @@ int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const 
       // the full sweep, armed by the overflow flag: a no-op unless some keyframe's candidate buffer ran over
       a.state = ws + lay.partial;
       a.run_if = sym_flag;
+      a.clk = nullptr;
       RC_TRY(launch_gated_topk(a, sc, static_cast<uint64_t*>(workspace), st, &launches), "gated_topk launch");
     }   // one part of a multi-GPU sweep: the caller reads the flag (semgate_last_sweep_mode) and decides with its peers
   } else {
@@ -496,7 +605,7 @@ int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const 
     m.row_stride = 0;
     m.n_lists = -1; m.sc = sc; m.rows_per_mblock = 128 * cg;   // cg = CTAs (128-row query blocks) per schedule unit
     if (sym) {
-      m.sc_sym = sc_sym; m.sym_flag = sym_flag; m.sym_cnt = sym_flag - N;
+      m.sc_sym = sc_sym; m.sym_flag = sym_flag; m.sym_cnt = sym_flag - N; m.sym_flag_copy = h->flag_dev;
       m.sym_force = p->part_count > 1 ? 1 : 0;
       m.sym_cap = sym_capacity(k, N);
       m.sym_ovf = reinterpret_cast<const uint64_t*>(static_cast<char*>(workspace) + lay.partial + lay.sync_full +
@@ -506,10 +615,49 @@ int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const 
   RC_TRY(launch_merge_topk(m, st), "merge_topk launch");
   h->launches += 1;
   h->last_mode = sym ? 1 : 0;
-  h->last_sym_flag = sym_flag;
   h->last_stream = st;
   h->last_tiles = gemv ? 0 : static_cast<int64_t>(sc.mblocks) * sc.ntiles;
   if (sym) h->last_tiles = sym_tiles_owned(sc_sym);
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int semgate_gated_topk(semgate_handle_t h, const void* q_bf16, int64_t Q, const void* db_bf16, int64_t N, int32_t d_pad,
+                       const double* q_ts, const double* db_ts, const int32_t* q_floor, const int32_t* db_floor,
+                       const semgate_topk_params* p, void* workspace, size_t workspace_bytes, uint64_t* out_keys,
+                       float* out_scores, int32_t* out_idx, uint8_t* out_valid, int32_t* out_count,
+                       semgate_stream_t stream) {
+  if (!h) return fail(SEMGATE_EINVAL, "handle is NULL");
+  int rc = check_params(p);
+  if (rc) return rc;
+  if (p->k <= SEMGATE_MAX_K)
+    return gated_topk_impl(h, q_bf16, Q, db_bf16, N, d_pad, q_ts, db_ts, q_floor, db_floor, p, workspace, workspace_bytes, out_keys,
+                           out_scores, out_idx, out_valid, out_count, stream, nullptr);
+  // k > 64 (the reference's k is any integer, place_recognition.py:853,888): ceil(k / 64) sweeps.  A row's list in
+  // shared memory holds 64 candidates; pass p keeps the best 64 among the candidates BELOW the last key pass p-1
+  // kept (keys are unique and totally ordered, so the passes tile the sorted candidate list exactly), and the merge
+  // kernel writes them into columns 64p.. of the k-wide outputs.  A row whose pass came back short has no more
+  // candidates: its ceiling becomes 0 and later passes admit nothing for it.
+  if (Q < 0 || N < 0 || Q > INT32_MAX || N > INT32_MAX) return fail(SEMGATE_EINVAL, "gated_topk: bad sizes Q=%lld N=%lld", (long long)Q, (long long)N);
+  if (Q == 0) return 0;
+  const int k_total = p->k;
+  const size_t need = semgate_topk_workspace_bytes(h, Q, std::max<int64_t>(N, 1), d_pad, p);
+  if (N > 0 && (!workspace || workspace_bytes < need)) return fail(SEMGATE_ENOMEM, "gated_topk: workspace %zu < required %zu bytes", workspace_bytes, need);
+  // the ceilings live in the key lists of all passes: the caller's out_keys, else the tail of the workspace
+  const int cg = resolve_cg(h, p, Q);
+  const size_t pass_ws = align256(topk_workspace_bytes(make_schedule(Q, std::max<int64_t>(N, 1), d_pad, cg, h->sm_count), cg, SEMGATE_MAX_K));
+  uint64_t* keys_all = out_keys ? out_keys : (N > 0 ? reinterpret_cast<uint64_t*>(static_cast<char*>(workspace) + pass_ws) : nullptr);
+  semgate_topk_params pp = *p;
+  pp.symmetric = -1;
+  for (int col = 0; col < k_total; col += SEMGATE_MAX_K) {
+    pp.k = std::min(SEMGATE_MAX_K, k_total - col);
+    PassInfo pass{(col > 0 && keys_all) ? keys_all + (col - 1) : nullptr, k_total, col};
+    rc = gated_topk_impl(h, q_bf16, Q, db_bf16, N, d_pad, q_ts, db_ts, q_floor, db_floor, &pp, workspace, pass_ws, keys_all, out_scores,
+                         out_idx, out_valid, out_count, stream, &pass);
+    if (rc) return rc;
+  }
   return 0;
 }
 
@@ -553,6 +701,38 @@ int semgate_merge_topk_peers(semgate_handle_t h, const uint64_t* const* peer_key
   return 0;
 }
 
+// The same for a slice of the rows, with the peers' overflow flags folded in: every rank merges only its own rows
+// of the G per-GPU lists (1/G of the NVLink reads of the replicated merge) and learns in the same kernel whether any
+// rank's symmetric part overflowed (no collective of its own for that).
+int semgate_merge_topk_peers_rows(semgate_handle_t h, const uint64_t* const* peer_keys, int32_t G, int64_t Q_total, int32_t k,
+                                  int64_t row_begin, int64_t row_count, int64_t flag_offset, const int32_t* q_floor,
+                                  const int32_t* db_floor_all, int32_t max_floor_diff, uint64_t* out_keys, float* out_scores,
+                                  int32_t* out_idx, uint8_t* out_valid, int32_t* out_count, uint32_t* out_any_flag,
+                                  semgate_stream_t stream) {
+  if (!h) return fail(SEMGATE_EINVAL, "handle is NULL");
+  if (G < 1 || G > 1024 || Q_total < 0 || k < 1 || k > SEMGATE_MAX_K || row_begin < 0 || row_count < 0 || row_begin + row_count > Q_total)
+    return fail(SEMGATE_EINVAL, "merge_topk_peers_rows: bad sizes G=%d Q=%lld k=%d rows [%lld, +%lld)", G, (long long)Q_total, k,
+                (long long)row_begin, (long long)row_count);
+  if (!peer_keys) return fail(SEMGATE_EINVAL, "merge_topk_peers_rows: peer_keys is NULL");
+  if (out_any_flag && flag_offset < Q_total * k) return fail(SEMGATE_EINVAL, "merge_topk_peers_rows: the flag word must lie behind the keys");
+  DeviceGuard g(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (row_count == 0) {
+    // nothing to merge here; the flags are still wanted: one block over zero rows
+    if (!out_any_flag) return 0;
+  }
+  MergeLaunch m{};
+  m.keys_in = nullptr; m.list_ptrs = peer_keys; m.Q = row_count; m.k = k;
+  m.row_stride = 0; m.list_stride = 0; m.n_lists = G;
+  m.row_offset = row_begin; m.flag_offset = flag_offset; m.any_flag_out = out_any_flag;
+  m.keys_out = out_keys; m.scores = out_scores; m.idx = out_idx; m.valid = out_valid; m.count = out_count;
+  m.q_floor = q_floor; m.db_floor = db_floor_all; m.floor_index_offset = 0;
+  m.max_floor_diff = (q_floor && db_floor_all) ? max_floor_diff : -1;
+  RC_TRY(launch_merge_topk(m, st), "merge_topk launch");
+  h->launches += 1;
+  return 0;
+}
+
 // ---------------------------------------------------------------- dense similarity (interface parity)
 int semgate_similarity_matrix(semgate_handle_t h, const void* q_bf16, int64_t Q, const void* db_bf16, int64_t N, int32_t d_pad,
                               float* out, int64_t ld_out, semgate_stream_t stream) {
@@ -582,7 +762,7 @@ int semgate_similarity_matrix(semgate_handle_t h, const void* q_bf16, int64_t Q,
 size_t semgate_compact_workspace_bytes(int64_t Q) { return align256(compact_workspace_bytes(Q < 0 ? 0 : Q)); }
 
 static int compact_impl(semgate_handle_t h, const float* scores, const int32_t* idx, const uint8_t* valid, const int32_t* count,
-                        int64_t Q, int32_t k, bool valid_only, int32_t* out_query_idx, int32_t* out_match_idx,
+                        int64_t Q, int32_t k, bool valid_only, int64_t q_offset, int32_t* out_query_idx, int32_t* out_match_idx,
                         float* out_similarity, uint8_t* out_is_valid, int64_t* out_total, void* workspace,
                         semgate_stream_t stream) {
   if (!h) return fail(SEMGATE_EINVAL, "handle is NULL");
@@ -590,7 +770,8 @@ static int compact_impl(semgate_handle_t h, const float* scores, const int32_t* 
   if (Q > 0 && (!scores || !idx || !valid || !count || !out_query_idx || !out_match_idx || !out_similarity || !out_is_valid || !workspace))
     return fail(SEMGATE_EINVAL, "compact: NULL pointer");
   DeviceGuard g(h->device);
-  RC_TRY(launch_compact(scores, idx, valid, count, Q, k, valid_only, out_query_idx, out_match_idx, out_similarity, out_is_valid,
+  if (q_offset < 0 || q_offset + Q > INT32_MAX) return fail(SEMGATE_EINVAL, "compact: query index offset out of range");
+  RC_TRY(launch_compact(scores, idx, valid, count, Q, k, valid_only, q_offset, out_query_idx, out_match_idx, out_similarity, out_is_valid,
                         out_total, workspace, static_cast<cudaStream_t>(stream)), "compact launch");
   h->launches += Q > 0 ? 3 : 0;
   return 0;
@@ -599,15 +780,23 @@ static int compact_impl(semgate_handle_t h, const float* scores, const int32_t* 
 int semgate_compact(semgate_handle_t h, const float* scores, const int32_t* idx, const uint8_t* valid, const int32_t* count,
                     int64_t Q, int32_t k, int32_t* out_query_idx, int32_t* out_match_idx, float* out_similarity,
                     uint8_t* out_is_valid, int64_t* out_total, void* workspace, semgate_stream_t stream) {
-  return compact_impl(h, scores, idx, valid, count, Q, k, false, out_query_idx, out_match_idx, out_similarity, out_is_valid,
+  return compact_impl(h, scores, idx, valid, count, Q, k, false, 0, out_query_idx, out_match_idx, out_similarity, out_is_valid,
                       out_total, workspace, stream);
 }
 
 int semgate_compact_valid(semgate_handle_t h, const float* scores, const int32_t* idx, const uint8_t* valid, const int32_t* count,
                           int64_t Q, int32_t k, int32_t* out_query_idx, int32_t* out_match_idx, float* out_similarity,
                           uint8_t* out_is_valid, int64_t* out_total, void* workspace, semgate_stream_t stream) {
-  return compact_impl(h, scores, idx, valid, count, Q, k, true, out_query_idx, out_match_idx, out_similarity, out_is_valid,
+  return compact_impl(h, scores, idx, valid, count, Q, k, true, 0, out_query_idx, out_match_idx, out_similarity, out_is_valid,
                       out_total, workspace, stream);
+}
+
+int semgate_compact_rows(semgate_handle_t h, const float* scores, const int32_t* idx, const uint8_t* valid, const int32_t* count,
+                         int64_t Q, int32_t k, int64_t query_index_offset, int32_t valid_only, int32_t* out_query_idx,
+                         int32_t* out_match_idx, float* out_similarity, uint8_t* out_is_valid, int64_t* out_total, void* workspace,
+                         semgate_stream_t stream) {
+  return compact_impl(h, scores, idx, valid, count, Q, k, valid_only != 0, query_index_offset, out_query_idx, out_match_idx,
+                      out_similarity, out_is_valid, out_total, workspace, stream);
 }
 
 // ---------------------------------------------------------------- match statistics
@@ -707,6 +896,112 @@ int semgate_rerank_select(semgate_handle_t h, const int32_t* cand_idx, const flo
   return 0;
 }
 
+// ---------------------------------------------------------------- one call, device-resident: K2 + K3 + K4
+namespace {
+struct DeviceSweepLayout { size_t topk, sc, ix, va, ct, cws, total; };
+DeviceSweepLayout device_sweep_layout(semgate_handle_t h, int64_t n, int32_t d_pad, const semgate_topk_params* p) {
+  DeviceSweepLayout l{};
+  const size_t nk = static_cast<size_t>(n) * p->k;
+  l.topk = align256(semgate_topk_workspace_bytes(h, n, n, d_pad, p));
+  l.sc = l.topk; l.ix = l.sc + align256(4 * nk); l.va = l.ix + align256(4 * nk); l.ct = l.va + align256(nk);
+  l.cws = l.ct + align256(4 * static_cast<size_t>(n));
+  l.total = l.cws + semgate_compact_workspace_bytes(n);
+  return l;
+}
+}  // namespace
+
+size_t semgate_find_loop_closures_device_workspace_bytes(semgate_handle_t h, int64_t n, int32_t d_pad, const semgate_topk_params* p) {
+  if (!h || !p || n <= 0 || p->k < 1 || p->k > SEMGATE_MAX_K_TOTAL) return 256;
+  return device_sweep_layout(h, n, d_pad, p).total;
+}
+
+int semgate_find_loop_closures_device(semgate_handle_t h, const void* x_bf16, int64_t n, int32_t d_pad, const double* ts,
+                                      const int32_t* floor_labels, const semgate_topk_params* p, void* workspace,
+                                      size_t workspace_bytes, int32_t* out_query_idx, int32_t* out_match_idx,
+                                      float* out_similarity, uint8_t* out_is_valid, int64_t* out_total_dev, int32_t use_graph,
+                                      semgate_stream_t stream) {
+  if (!h) return fail(SEMGATE_EINVAL, "handle is NULL");
+  int rc = check_params(p);
+  if (rc) return rc;
+  if (!out_total_dev) return fail(SEMGATE_EINVAL, "find_loop_closures_device: out_total_dev is NULL");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DeviceGuard g(h->device);
+  if (n < 2) {                                           // place_recognition.py:864
+    CUDA_TRY(cudaMemsetAsync(out_total_dev, 0, sizeof(int64_t), st));
+    return 0;
+  }
+  if (!x_bf16 || !out_query_idx || !out_match_idx || !out_similarity || !out_is_valid) return fail(SEMGATE_EINVAL, "find_loop_closures_device: NULL pointer");
+  const DeviceSweepLayout l = device_sweep_layout(h, n, d_pad, p);
+  if (!workspace || workspace_bytes < l.total) return fail(SEMGATE_ENOMEM, "find_loop_closures_device: workspace %zu < required %zu bytes", workspace_bytes, l.total);
+  char* ws = static_cast<char*>(workspace);
+  auto run = [&]() -> int {
+    semgate_topk_params pa = *p;
+    pa.db_index_offset = 0; pa.accumulate = 0; pa.part_index = 0; pa.part_count = 0;
+    int r = semgate_gated_topk(h, x_bf16, n, x_bf16, n, d_pad, ts, ts, floor_labels, floor_labels, &pa, ws, l.topk, nullptr,
+                               reinterpret_cast<float*>(ws + l.sc), reinterpret_cast<int32_t*>(ws + l.ix),
+                               reinterpret_cast<uint8_t*>(ws + l.va), reinterpret_cast<int32_t*>(ws + l.ct), st);
+    if (r) return r;
+    return semgate_compact(h, reinterpret_cast<float*>(ws + l.sc), reinterpret_cast<int32_t*>(ws + l.ix), reinterpret_cast<uint8_t*>(ws + l.va),
+                           reinterpret_cast<int32_t*>(ws + l.ct), n, p->k, out_query_idx, out_match_idx, out_similarity, out_is_valid,
+                           out_total_dev, ws + l.cws, st);
+  };
+  // (a capture cannot start on the legacy default stream: such callers stay eager)
+  if (!use_graph || h->graphs_broken || st == nullptr || st == cudaStreamLegacy) return run();
+
+  SweepGraphKey key;
+  memset(&key, 0, sizeof(key));
+  key.x = x_bf16; key.n = n; key.d_pad = d_pad; key.ts = ts; key.floor = floor_labels; key.ws = workspace;
+  // field by field: the caller's struct may carry anything in its padding
+  key.p.similarity_threshold = p->similarity_threshold; key.p.min_time_gap = p->min_time_gap; key.p.k = p->k;
+  key.p.max_floor_diff = p->max_floor_diff; key.p.gate_mode = p->gate_mode; key.p.db_index_offset = p->db_index_offset;
+  key.p.cta_group = p->cta_group; key.p.accumulate = p->accumulate; key.p.symmetric = p->symmetric;
+  key.p.part_index = p->part_index; key.p.part_count = p->part_count;
+  key.ws_bytes = workspace_bytes; key.oq = out_query_idx; key.om = out_match_idx; key.os = out_similarity; key.ov = out_is_valid;
+  key.tot = out_total_dev; key.cta_group = h->cta_group; key.symmetric = h->symmetric;
+  SweepGraph* gph = nullptr;
+  for (SweepGraph* c : h->graphs)
+    if (memcmp(&c->key, &key, sizeof(key)) == 0) { gph = c; break; }
+  if (!gph) {
+    gph = new (std::nothrow) SweepGraph();
+    if (!gph) return fail(SEMGATE_ENOMEM, "out of host memory");
+    gph->key = key;
+    if (h->graphs.size() >= 8) {                       // small cache: drop the oldest
+      if (h->graphs.front()->exec) cudaGraphExecDestroy(h->graphs.front()->exec);
+      delete h->graphs.front();
+      h->graphs.erase(h->graphs.begin());
+    }
+    h->graphs.push_back(gph);
+  }
+  if (gph->exec) {                                       // replay: one launch for the whole sweep
+    CUDA_TRY(cudaGraphLaunch(gph->exec, st));
+    h->launches += gph->launches;
+    h->last_mode = gph->mode; h->last_tiles = gph->tiles; h->last_stream = st;
+    return 0;
+  }
+  if (gph->seen++ == 0) return run();                    // first call: eager (sets kernel attributes, uploads schedules)
+  // second call with the same arguments: capture the sequence (nothing in it waits for the host)
+  const int64_t launches0 = h->launches;
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) { cudaGetLastError(); h->graphs_broken = true; return run(); }
+  rc = run();
+  e = cudaStreamEndCapture(st, &graph);
+  if (rc != 0 || e != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    h->graphs_broken = true;
+    h->launches = launches0;
+    return run();
+  }
+  e = cudaGraphInstantiate(&gph->exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) { cudaGetLastError(); gph->exec = nullptr; h->graphs_broken = true; h->launches = launches0; return run(); }
+  gph->launches = static_cast<int>(h->launches - launches0);
+  gph->mode = h->last_mode; gph->tiles = h->last_tiles;
+  CUDA_TRY(cudaGraphLaunch(gph->exec, st));
+  return 0;
+}
+
 // ---------------------------------------------------------------- host-buffer entry points
 int semgate_find_loop_closures_host(semgate_handle_t h, const float* descriptors, int64_t n, int32_t d,
                                     const double* timestamps, const int32_t* floor_labels, const semgate_topk_params* p,
@@ -745,7 +1040,7 @@ int semgate_find_loop_closures_host(semgate_handle_t h, const float* descriptors
   const int64_t approx_chunks = (n * bytes_per_row) / (24ll << 20);
   std::vector<int64_t> bounds;   // chunk c = rows [bounds[c], bounds[c+1])
   bounds.push_back(0);
-  if (n < 4096 || approx_chunks < 2) {
+  if (n < 4096 || approx_chunks < 2 || k > SEMGATE_MAX_K) {   // (k > 64 runs as several whole sweeps: no accumulation)
     bounds.push_back(n);
   } else {
     static const int kWeights[10] = {4, 4, 4, 4, 3, 3, 2, 2, 1, 1};
@@ -792,6 +1087,12 @@ int semgate_find_loop_closures_host(semgate_handle_t h, const float* descriptors
     CUDA_TRY(cudaStreamWaitEvent(st, h->chunk_events[ci], 0));
     semgate_topk_params pa = *p;
     pa.db_index_offset = 0; pa.accumulate = 0;
+    if (k > SEMGATE_MAX_K) {      // one chunk: the sweep's passes write the decoded lists themselves
+      rc = semgate_gated_topk(h, bf, n, bf, n, d_pad, d_ts, d_ts, d_fl, d_fl, &pa, ws, h->cap[B_WS], d_keys, static_cast<float*>(sc),
+                              static_cast<int32_t*>(ix), static_cast<uint8_t*>(va), static_cast<int32_t*>(ct), st);
+      if (rc) return rc;
+      break;
+    }
     rc = semgate_gated_topk(h, bf + 2ull * r0 * d_pad, rows, bf, r1, d_pad, d_ts ? d_ts + r0 : nullptr, d_ts,
                             d_fl ? d_fl + r0 : nullptr, d_fl, &pa, ws, h->cap[B_WS], d_keys + r0 * k, nullptr, nullptr,
                             nullptr, nullptr, st);
@@ -806,10 +1107,12 @@ int semgate_find_loop_closures_host(semgate_handle_t h, const float* descriptors
     }
   }
   // decode the final key lists, apply the floor flag
-  rc = semgate_merge_topk(h, d_keys, 1, n, k, d_fl, d_fl, (d_fl != nullptr) ? p->max_floor_diff : -1, nullptr,
-                          static_cast<float*>(sc), static_cast<int32_t*>(ix), static_cast<uint8_t*>(va),
-                          static_cast<int32_t*>(ct), st);
-  if (rc) return rc;
+  if (k <= SEMGATE_MAX_K) {
+    rc = semgate_merge_topk(h, d_keys, 1, n, k, d_fl, d_fl, (d_fl != nullptr) ? p->max_floor_diff : -1, nullptr,
+                            static_cast<float*>(sc), static_cast<int32_t*>(ix), static_cast<uint8_t*>(va),
+                            static_cast<int32_t*>(ct), st);
+    if (rc) return rc;
+  }
   rc = semgate_compact(h, static_cast<float*>(sc), static_cast<int32_t*>(ix), static_cast<uint8_t*>(va), static_cast<int32_t*>(ct),
                        n, k, static_cast<int32_t*>(oq), static_cast<int32_t*>(om), static_cast<float*>(os),
                        static_cast<uint8_t*>(ov), static_cast<int64_t*>(tot), cws, st);

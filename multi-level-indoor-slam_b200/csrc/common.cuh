@@ -133,6 +133,7 @@ struct Schedule {
   const int* tab_unit_begin;
   const int* tab_block_first;
   int tab_lists;    // lists in all
+  long long tab_tiles;   // tiles the table computes (this part's share of the triangle)
 };
 
 // Super-rows get shorter towards the end of a symmetric sweep; dealing them out boustrophedon

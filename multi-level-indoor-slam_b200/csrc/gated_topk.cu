@@ -4,6 +4,7 @@
 
 #include <cudaTypedefs.h>
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <mutex>
 #include <queue>
@@ -158,7 +159,7 @@ size_t topk_workspace_bytes(const Schedule& sc, int cta_group, int k) {
 //   2 a run's list slot outside sched_slots(block)      3 two runs of a block share a list slot
 //   4 a pacing counter outside the allocated array      5 arrivals on a counter differ from what waiters expect
 //   6 a block without a flushed list for one of its slots
-int schedule_selfcheck(const Schedule& sc, int units, int64_t* tiles_computed, int64_t* makespan_tiles) {
+int schedule_selfcheck(const Schedule& sc, int units, int64_t* tiles_computed, int64_t* makespan_tiles, const std::vector<int>* owner_of_block) {
   const int nb = sc.mblocks, nt = sc.ntiles;
   std::vector<uint8_t> seen(static_cast<size_t>(nb) * nt, 0);
   std::vector<uint32_t> slot_used(static_cast<size_t>(nb) * std::max(sc.s_max, 1), 0);
@@ -197,7 +198,8 @@ int schedule_selfcheck(const Schedule& sc, int units, int64_t* tiles_computed, i
   if (!err)
     for (int b = 0; b < nb && !err; ++b) {
       for (int t = 0; t < nt; ++t) {
-        const bool want = sc.sym ? (t >= b && sched_owned(sc, b / sc.rm)) : true;
+        const bool mine = owner_of_block ? (*owner_of_block)[b] == sc.part_index : sched_owned(sc, b / sc.rm);
+        const bool want = sc.sym ? (t >= b && mine) : true;
         if ((seen[static_cast<size_t>(b) * nt + t] != 0) != want) { err = 1; break; }
       }
       for (int sl = 0; sl < sched_slots(sc, b) && !err; ++sl)
@@ -217,38 +219,80 @@ bool sym_table_wanted(int64_t N) {
 }
 
 namespace {
-struct Dealt { std::vector<RunEntry> runs; std::vector<int> owner; std::vector<int> lists_of_block; int64_t makespan = 0; };
+struct Dealt { std::vector<RunEntry> runs; std::vector<int> owner; std::vector<int> lists_of_block; int64_t makespan = 0; int64_t tiles = 0; };
+struct Group { int lo, hi; };   // blocks [lo, hi): a "super-row" of the table, its runs share database tiles
 
-// Cut the owned part of the triangle into runs of at most `L` tiles (absolute column chunks, so that neighbouring
-// blocks cut at the same tiles), in the order super-row -> chunk -> block, and deal them in that order to the
-// unit that is free first.
-Dealt deal_runs(int nb, int rm, int L, int units, int part_index, int part_count) {
+// Run length by remaining work ("guided self-scheduling"): long runs (few lists per keyframe for K3, few run starts)
+// while there is plenty left, shorter and shorter ones towards the end so that the units finish together.  With a
+// constant length of 8 the list scheduler below ends 3-5 tile-times above the ideal makespan; this way within one.
+inline int guided_len(int64_t remaining, int units, int max_len) {
+  const int64_t l = (2 * remaining + 3 * units - 1) / (3 * units);      // ceil(remaining / (1.5 * units))
+  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(max_len, l)));
+}
+
+// Cut the groups this part owns into runs (absolute column chunks per group, so that the blocks of a group cut at
+// the same tiles), in the order group -> chunk -> block, and deal them in that order to the unit that is free first.
+Dealt deal_runs(int nb, const std::vector<Group>& groups, const std::vector<int>& group_owner, int part, int units, int max_len) {
   Dealt d;
   d.lists_of_block.assign(nb, 0);
-  Schedule own{};
-  own.rm = rm; own.part_index = part_index; own.part_count = part_count;
   using Slot = std::pair<int64_t, int>;   // (busy until, unit)
   std::priority_queue<Slot, std::vector<Slot>, std::greater<Slot>> free_at;
   for (int u = 0; u < units; ++u) free_at.push({0, u});
-  int sr = 0;
-  for (int lo = 0; lo < nb; lo += rm, ++sr) {
-    if (!sched_owned(own, sr)) continue;
-    const int r = std::min(rm, nb - lo);
-    for (int c = lo / L; c * L < nb; ++c)
-      for (int j = 0; j < r; ++j) {
-        const int b = lo + j;
-        const int t0 = std::max(c * L, b), t1 = std::min((c + 1) * L, nb);
-        if (t1 <= t0) continue;
+  int64_t remaining = 0;
+  for (size_t g = 0; g < groups.size(); ++g)
+    if (group_owner[g] == part)
+      for (int b = groups[g].lo; b < groups[g].hi; ++b) remaining += nb - b;
+  d.tiles = remaining;
+  for (size_t g = 0; g < groups.size(); ++g) {
+    if (group_owner[g] != part) continue;
+    for (int t0g = groups[g].lo; t0g < nb;) {
+      const int t1g = std::min(nb, t0g + guided_len(remaining, units, max_len));
+      for (int b = groups[g].lo; b < groups[g].hi; ++b) {
+        const int t0 = std::max(t0g, b);
+        if (t1g <= t0) continue;
         Slot s = free_at.top();
         free_at.pop();
-        d.runs.push_back(RunEntry{b, d.lists_of_block[b]++, t0, t1});   // list number inside the block for now
+        d.runs.push_back(RunEntry{b, d.lists_of_block[b]++, t0, t1g});   // list number inside the block for now
         d.owner.push_back(s.second);
-        s.first += t1 - t0;
+        s.first += t1g - t0;
+        remaining -= t1g - t0;
         d.makespan = std::max(d.makespan, s.first);
         free_at.push(s);
       }
+      t0g = t1g;
+    }
   }
   return d;
+}
+
+// Groups of blocks for a sweep split over `parts` GPUs: contiguous, about parts * m of them with equal tile counts
+// (tall at the bottom of the triangle, where a block has few tiles; at most rm_cap blocks), given to the parts largest
+// first to whichever has the least so far.  Every part cuts the triangle the same way, so the ownership is a function.
+void balanced_groups(int nb, int parts, int m, int rm_cap, std::vector<Group>* groups, std::vector<int>* owner) {
+  groups->clear();
+  const double total = 0.5 * nb * (nb + 1.0), target = total / (static_cast<double>(parts) * m);
+  double acc = 0.0;
+  int lo = 0;
+  for (int b = 0; b < nb; ++b) {
+    acc += nb - b;
+    if (acc >= target * (groups->size() + 1) - 1e-9 || b + 1 - lo >= rm_cap) { groups->push_back(Group{lo, b + 1}); lo = b + 1; }
+  }
+  if (lo < nb) groups->push_back(Group{lo, nb});
+  std::vector<int64_t> w(groups->size());
+  std::vector<int> order(groups->size());
+  for (size_t g = 0; g < groups->size(); ++g) {
+    order[g] = static_cast<int>(g);
+    const int64_t a = (*groups)[g].lo, e = (*groups)[g].hi;
+    w[g] = (e - a) * nb - (e * (e - 1) - a * (a - 1)) / 2;
+  }
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return w[x] > w[y]; });
+  std::vector<int64_t> load(parts, 0);
+  owner->assign(groups->size(), 0);
+  for (int g : order) {
+    const int pmin = static_cast<int>(std::min_element(load.begin(), load.end()) - load.begin());
+    (*owner)[g] = pmin;
+    load[pmin] += w[g];
+  }
 }
 }  // namespace
 
@@ -256,29 +300,47 @@ void build_sym_table(int64_t N, int d_pad, int sm_count, int part_index, int par
   const int units = topk_units(2, sm_count);
   const int nb = static_cast<int>((N + BN - 1) / BN);
   part_count = std::max(part_count, 1);
-  // A few super-row heights and run lengths, judged by the busiest part (every part must cut the triangle the
-  // same way).  Longer runs mean fewer lists per keyframe for K3 to merge, so a shorter run length has to buy 5 %;
-  // taller super-rows mean fewer distinct database tiles in flight, as long as their query blocks stay in L2.
+  // Taller groups mean fewer distinct database tiles in flight (less DRAM traffic), as long as their query blocks stay
+  // in L2; shorter runs mean a tighter finish but more lists per keyframe for K3 to merge.  Candidates are judged by
+  // the busiest part's makespan (every part must cut the triangle the same way).
   const int64_t a_bytes = static_cast<int64_t>(BM) * 2 * d_pad * 2;
   const int64_t cap = env_long("SEMGATE_RM_CAP_MB", 40) << 20;
-  int best_rm = 1, best_L = 1;
+  const int rm_cap = static_cast<int>(std::max<int64_t>(6, std::min<int64_t>(24, cap / a_bytes)));
+  int max_len = 8;
+  if (env_long("SEMGATE_SYM_RUN", 0) > 0) max_len = static_cast<int>(env_long("SEMGATE_SYM_RUN", 0));   // A/B knob
+  std::vector<Group> groups, best_groups;
+  std::vector<int> owner, best_owner;
   int64_t best = -1;
-  for (int L : {8, 6, 4, 2, 1}) {
-    if (L < 4 && nb > 16) break;       // runs of one or two tiles only where there is hardly anything to deal out
-    int rm_L = 1;
-    int64_t best_Lm = -1;
-    for (int rm : {24, 18, 16, 12, 10, 8, 6}) {
-      if (rm != 6 && (rm > nb || rm * a_bytes > cap)) continue;
-      int64_t m = 0;
-      for (int g = 0; g < part_count; ++g) m = std::max(m, deal_runs(nb, std::min(rm, nb), L, units, g, part_count).makespan);
-      if (best_Lm < 0 || m < best_Lm) { best_Lm = m; rm_L = std::min(rm, nb); }
+  auto consider = [&]() {
+    int64_t m = 0;
+    for (int g = 0; g < part_count; ++g) m = std::max(m, deal_runs(nb, groups, owner, g, units, max_len).makespan);
+    if (best < 0 || m < best) { best = m; best_groups = groups; best_owner = owner; }
+  };
+  if (part_count == 1) {
+    const long forced_rm = env_long("SEMGATE_SYM_RM", 0);                                                   // A/B knob
+    for (int rm : {24, 18, 16, 12, 10, 8, 6}) {                 // tallest first: ties go to the taller groups
+      if (forced_rm > 0) rm = static_cast<int>(forced_rm);
+      else if (rm != 6 && (rm > nb || rm > rm_cap)) continue;
+      rm = std::max(1, std::min(rm, nb));
+      groups.clear();
+      for (int lo = 0; lo < nb; lo += rm) groups.push_back(Group{lo, std::min(nb, lo + rm)});
+      owner.assign(groups.size(), 0);
+      consider();
+      if (forced_rm > 0) break;
     }
-    if (best < 0 || best_Lm * 100 < best * 95) { best = best_Lm; best_rm = rm_L; best_L = L; }
+  } else {
+    for (int m : {3, 4, 6}) {                                   // fewest groups first: ties go to the taller groups
+      balanced_groups(nb, part_count, m, rm_cap, &groups, &owner);
+      consider();
+    }
   }
-  // A/B knobs (development): force the run length / super-row height
-  if (env_long("SEMGATE_SYM_RUN", 0) > 0) best_L = static_cast<int>(env_long("SEMGATE_SYM_RUN", 0));
-  if (env_long("SEMGATE_SYM_RM", 0) > 0) best_rm = std::min<int>(nb, static_cast<int>(env_long("SEMGATE_SYM_RM", 0)));
-  Dealt d = deal_runs(nb, best_rm, best_L, units, part_index, part_count);
+  Dealt d = deal_runs(nb, best_groups, best_owner, part_index, units, max_len);
+  out->owner_of_block.assign(nb, 0);
+  int rm_max = 1;
+  for (size_t g = 0; g < best_groups.size(); ++g) {
+    rm_max = std::max(rm_max, best_groups[g].hi - best_groups[g].lo);
+    for (int b = best_groups[g].lo; b < best_groups[g].hi; ++b) out->owner_of_block[b] = best_owner[g];
+  }
   out->block_first.assign(nb + 1, 0);
   for (int b = 0; b < nb; ++b) out->block_first[b + 1] = out->block_first[b] + d.lists_of_block[b];
   out->unit_begin.assign(units + 1, 0);
@@ -292,21 +354,23 @@ void build_sym_table(int64_t N, int d_pad, int sm_count, int part_index, int par
     out->runs[at[d.owner[i]]++] = e;
   }
   out->makespan = d.makespan;
+  out->tiles = d.tiles;
   Schedule& sc = out->sc;
   sc = Schedule{};
   sc.sym = 1;
   sc.mblocks = sc.ntiles = nb;
-  sc.rm = best_rm;
-  sc.n_full = nb / best_rm; sc.r_last = nb % best_rm;
+  sc.rm = rm_max;
+  sc.n_full = nb / rm_max; sc.r_last = nb % rm_max;
   sc.part_index = part_index; sc.part_count = part_count;
   sc.s_max = std::max(1, *std::max_element(d.lists_of_block.begin(), d.lists_of_block.end()));
   sc.s_main = sc.s_last = sc.s_max;
-  sc.a_resident = best_rm * a_bytes <= cap ? 1 : 0;
+  sc.a_resident = rm_max * a_bytes <= cap ? 1 : 0;
   sc.sync_window = 0;
   const int kblocks = d_pad / BK;
   sc.pace_kb = std::min(kblocks, 16);
   sc.cpt = (kblocks + sc.pace_kb - 1) / sc.pace_kb;
   sc.tab_lists = out->block_first[nb];
+  sc.tab_tiles = d.tiles;
   sc.tab_runs = out->runs.data();                  // host pointers; the caller swaps in the device copies
   sc.tab_unit_begin = out->unit_begin.data();
   sc.tab_block_first = out->block_first.data();
@@ -343,7 +407,7 @@ static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int d_pad, 
 static size_t smem_bytes_for(int cg, int stages, int kstride, bool sym) {
   const size_t stage = A_STAGE_BYTES + static_cast<size_t>(BN / std::min(cg, 2)) * BK * 2;
   return 1024 /*realign slack*/ + stages * stage + static_cast<size_t>(BM) * kstride * 8 +
-         2 * BN * (sizeof(double) + sizeof(int32_t)) /*per-tile timestamps + labels*/ +
+         2 * BN * (sizeof(float) + sizeof(int32_t)) /*per-tile timestamp offsets + labels*/ +
          (sym ? 2 * BN * sizeof(float) + 64 : 0) /*column bounds + chunk minima*/ + 256 /*barriers + tmem slot*/;
 }
 
@@ -378,6 +442,11 @@ int launch_gated_topk(const TopkLaunch& a, const Schedule& sc, uint64_t* partial
   p.threshold = a.threshold;
   p.use_time = (a.q_ts != nullptr && a.db_ts != nullptr) ? 1 : 0;
   p.gap = a.gap;
+  {   // fp32 neighbours of the window length for the pre-test: gap_lo <= gap <= gap_hi
+    const float g = static_cast<float>(a.gap);
+    p.gap_lo = static_cast<double>(g) > a.gap ? nextafterf(g, -INFINITY) : g;
+    p.gap_hi = static_cast<double>(g) < a.gap ? nextafterf(g, INFINITY) : g;
+  }
   p.max_floor_diff = a.max_floor_diff;
   p.gate_mode = a.gate_mode;
   p.db_index_offset = a.db_index_offset;
@@ -388,6 +457,8 @@ int launch_gated_topk(const TopkLaunch& a, const Schedule& sc, uint64_t* partial
   if (a.dense != nullptr) p.sc.sync_window = 0;   // no workspace in dense mode
   p.sync = nullptr;
   p.run_if = a.run_if;
+  p.ceil_keys = a.ceil_keys; p.ceil_stride = a.ceil_stride;
+  p.clk = a.clk;
   const bool sym = sc.sym != 0;
   if (sym) {
     if (cg != 2 || a.Q != a.N || a.q_bf16 != a.db_bf16 || a.dense != nullptr || a.state == nullptr) return static_cast<int>(cudaErrorInvalidValue);

@@ -47,6 +47,7 @@ struct TopkParams {
   float threshold;       // keep s >= threshold (compared in fp32, like numpy's weak-scalar rule)
   int use_time;          // 0: no temporal mask (query(timestamp=None), place_recognition.py:144)
   double gap;            // min_time_gap
+  float gap_lo, gap_hi;  // fp32 neighbours of gap: gap_lo <= gap <= gap_hi (window pre-test, see window_excluded)
   int max_floor_diff;    // -1 off, 0 strict, 1 non-strict
   int gate_mode;         // 0 flag (reference order), 1 mask (exclude cross-floor before top-k)
   uint32_t db_index_offset;   // global index of local database row 0 (multi-GPU shards)
@@ -67,6 +68,11 @@ struct TopkParams {
   uint64_t* sym_ovf;     // [N][sym_cap] appended candidate keys
   int sym_cap;
   const uint32_t* run_if;   // non-null: the whole launch is a no-op unless *run_if != 0 (the full sweep behind a symmetric one)
+  // k > 64 runs as several sweeps: pass p only admits keys BELOW the last key pass p-1 kept for the row
+  unsigned long long* clk;     // non-null: every CTA records {globaltimer, clock64} at entry and exit (4 words per CTA): the SM
+                               // clock the kernel really ran at (a 2 ms NVML sample cannot resolve a 1 ms kernel)
+  const uint64_t* ceil_keys;   // non-null: row r admits key < ceil_keys[r * ceil_stride] only (0: nothing is left for it)
+  int64_t ceil_stride;
   Schedule sc;
 };
 
@@ -96,6 +102,25 @@ __device__ __forceinline__ uint32_t pick32(const uint32_t (&v)[32], int i) {
 //     admissible candidates, hence never above its final k-th score.  K3 merges buffer and lists.
 //     A buffer that overflows (thresholds that admit most of the database) raises sym_flag, and the
 //     full sweep launched right behind (run_if) redoes the job; nothing is lost, only time.
+// Temporal exclusion without fp64 in the common case.  The reference predicate is fp64 `|t_db - t_q| < gap`
+// (place_recognition.py:884); fp64 is slow on this part (43 % of the epilogue's stall samples at config 2 sat on its
+// five instructions).  Both stamps are kept as fp32 offsets from a per-launch base, a = fl32(fl64(t_db - base)),
+// b likewise: |(a - b) - (t_db - t_q)| <= 2^-24 (|a| + |b|) (1 + 2^-23), and the fp32 subtraction adds 2^-24 |a - b|.
+// With the margin m = 2^-22 (|a| + |b| + d) (four times that bound, so its own fp32 rounding does not matter):
+//   d > gap_hi + m  =>  |t_db - t_q| > gap by far more than an fp64 ulp  =>  not excluded,
+//   d < gap_lo - m  =>  excluded,
+// and only in between (pairs within ~1e-6 relative of the window edge, NaN / inf stamps) the exact fp64 test runs on the
+// stamps themselves.  Decisions are bit-identical to the fp64 test (tests/test_window_pretest_model.py emulates this
+// arithmetic in numpy float32 against the fp64 predicate on adversarial stamps).
+__device__ __forceinline__ bool window_excluded(float a, float b, float gap_lo, float gap_hi, const double* t_db_ptr,
+                                                double t_q, double gap) {
+  const float d = fabsf(a - b);
+  const float m = (fabsf(a) + fabsf(b) + d) * 0x1p-22f + 1e-30f;
+  if (d > gap_hi + m) return false;
+  if (d < gap_lo - m) return true;
+  return time_excluded(__ldg(t_db_ptr), t_q, gap);
+}
+
 template <int CG, int MC, bool SYM = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
@@ -103,6 +128,10 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   static_assert(MC == 1 || (MC == 2 && CG == 2), "multicast needs CTA pairs");
   static_assert(!SYM || (CG == 2 && MC == 1), "symmetric sweep: a query block must be one database tile");
   if (p.run_if != nullptr && ptx::ld_relaxed_gpu(p.run_if) == 0u) return;   // grid-uniform, before any barrier
+  if (p.clk != nullptr && threadIdx.x == 0) {
+    p.clk[4 * blockIdx.x + 0] = ptx::globaltimer_ns();
+    p.clk[4 * blockIdx.x + 1] = static_cast<unsigned long long>(clock64());
+  }
   constexpr int CSIZE = CG * MC;                 // CTAs per cluster = per schedule unit
   constexpr uint32_t B_ROWS = BN / CG;           // database rows held by one CTA
   constexpr uint32_t B_LOAD_ROWS = B_ROWS / MC;  // ... of which it fetches this many itself
@@ -120,7 +149,7 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   uint64_t* lists = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * STAGE_BYTES);
   // per-tile copies of the database timestamps / floor labels (one buffer per accumulator): a hit reads
   // them from shared memory instead of paying a dependent global load per hit column
-  double* ts_s = reinterpret_cast<double*>(lists + static_cast<size_t>(BM) * p.kstride);
+  float* ts_s = reinterpret_cast<float*>(lists + static_cast<size_t>(BM) * p.kstride);   // fp32 offsets from ts_base
   int32_t* fl_s = reinterpret_cast<int32_t*>(ts_s + 2 * BN);
   // symmetric sweep: the tile's column bounds and their minimum per 32-column chunk (one set per accumulator)
   float* bd_s = reinterpret_cast<float*>(fl_s + 2 * BN);
@@ -310,17 +339,20 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const bool mask_mode = p.gate_mode == 1 && p.max_floor_diff >= 0 && p.q_floor != nullptr && p.db_floor != nullptr;
     const bool use_time = p.use_time != 0;
     const float pos_inf = __int_as_float(0x7f800000);
+    const double ts_base = use_time ? __ldg(p.db_ts) : 0.0;   // any finite stamp of the launch: offsets stay small
 
     for_each_run(sc, unit, [&](const Run& run) {
       const int grow = (run.mb * CSIZE + static_cast<int>(cta_rank)) * BM + row_in_tile;   // global query row
       const bool row_live = grow < p.Q;
       uint64_t* slot = p.partial + (row_live ? sched_run_list_offset(sc, run.mb, run.slot, grow, BM * CSIZE, k) : 0);
       double tq = 0.0;
+      float tq32 = 0.f;
       int32_t qf = kFloorNone;
       if (row_live) {
-        if (use_time) tq = p.q_ts[grow];
+        if (use_time) { tq = p.q_ts[grow]; tq32 = static_cast<float>(tq - ts_base); }
         if (mask_mode) qf = p.q_floor[grow];
       }
+      const uint64_t ceil_key = (p.ceil_keys != nullptr && row_live) ? __ldg(p.ceil_keys + static_cast<int64_t>(grow) * p.ceil_stride) : ~0ull;
       L.reset(row_live ? p.threshold : pos_inf);
       float published = __int_as_float(0xff800000);   // SYM: last bound this thread published for its row
       // SYM: one column-direction append in flight per thread.  The slot number comes back from a global atomic
@@ -366,7 +398,7 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
           const int j = et + 128 * jj;
-          if (use_time) ts_s[a * BN + j] = st_ts[jj];
+          if (use_time) ts_s[a * BN + j] = static_cast<float>(st_ts[jj] - ts_base);
           if (mask_mode) fl_s[a * BN + j] = st_fl[jj];
           if constexpr (SYM) {
             bd_s[a * BN + j] = st_bd[jj];
@@ -436,9 +468,12 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 const int col = col_base + c * 32 + i;      // local database row
                 if (col < p.N) {                            // TMA zero-fill beyond N must not score
                   bool ok = true;
-                  if (use_time) ok = !time_excluded(ts_s[acc * BN + c * 32 + i], tq, p.gap);
+                  if (use_time) ok = !window_excluded(ts_s[acc * BN + c * 32 + i], tq32, p.gap_lo, p.gap_hi, p.db_ts + col, tq, p.gap);
                   if (ok && mask_mode) ok = floor_ok(qf, fl_s[acc * BN + c * 32 + i], p.max_floor_diff);
-                  if (ok) L.insert(pack_key(s, static_cast<uint32_t>(col) + p.db_index_offset), k);
+                  if (ok) {
+                    const uint64_t key = pack_key(s, static_cast<uint32_t>(col) + p.db_index_offset);
+                    if (key < ceil_key) L.insert(key, k);
+                  }
                 }
               }
             }
@@ -466,7 +501,7 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 const float s = __uint_as_float(pick32(v, i));
                 const int j = acc * BN + c * 32 + i;
                 bool ok = true;
-                if (use_time) ok = !time_excluded(tq, ts_s[j], p.gap);     // |a - b| is symmetric in fp64
+                if (use_time) ok = !window_excluded(ts_s[j], tq32, p.gap_lo, p.gap_hi, p.db_ts + col_base + c * 32 + i, tq, p.gap);   // |a - b| is symmetric
                 if (ok && mask_mode) ok = floor_ok(fl_s[j], qf, p.max_floor_diff);
                 if (ok) {
                   complete_append();
@@ -510,6 +545,10 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   if constexpr (CSIZE > 1) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   if (warp == 1) ptx::tmem_dealloc<CG>(tmem_base, kTmemCols);
+  if (p.clk != nullptr && threadIdx.x == 0) {
+    p.clk[4 * blockIdx.x + 2] = ptx::globaltimer_ns();
+    p.clk[4 * blockIdx.x + 3] = static_cast<unsigned long long>(clock64());
+  }
 }
 
 }  // namespace semgate

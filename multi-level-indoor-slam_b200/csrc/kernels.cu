@@ -193,11 +193,21 @@ merge_topk_kernel(const MergeLaunch a) {
   __shared__ uint64_t stage2[ROWBLOCK ? 4 * kMaxK : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t row = ROWBLOCK ? static_cast<int64_t>(blockIdx.x) : static_cast<int64_t>(blockIdx.x) * kMergeWarps + warp;
+  // per-GPU lists read in place: OR of the peers' overflow flags (one word behind every peer's keys), so that the
+  // exchange needs no collective of its own for it
+  if (a.any_flag_out != nullptr && a.list_ptrs != nullptr && blockIdx.x == 0 && warp == 0) {
+    uint32_t f = 0;
+    for (int g = lane; g < a.n_lists; g += 32) f |= *reinterpret_cast<const volatile uint32_t*>(a.list_ptrs[g] + a.flag_offset);
+    f = __reduce_or_sync(0xffffffffu, f);
+    if (lane == 0) *a.any_flag_out = f;
+  }
+  if (a.sym_flag_copy != nullptr && a.sym_flag != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *a.sym_flag_copy = *a.sym_flag;
   if (row >= a.Q) return;
   const int k = a.k;
   int n_lists = a.n_lists;
   int64_t list_stride = a.list_stride;
-  const uint64_t* base = a.keys_in + row * a.row_stride;
+  const int64_t in_row = row + a.row_offset;      // row of the input lists / query labels (a slice of the rows is merged)
+  const uint64_t* base = a.keys_in + in_row * a.row_stride;
   // symmetric sweep: the row also owns a buffer of column-direction candidates, unless a buffer overflowed
   // and the full sweep redid the job (then its schedule `sc` describes the lists)
   const bool sym = a.sym_flag != nullptr && (a.sym_force || *a.sym_flag == 0u);
@@ -222,9 +232,9 @@ merge_topk_kernel(const MergeLaunch a) {
     // rows with few lists (most rows: the tail super-row is split finer than the others) take the
     // cheaper 4-keys-per-lane network; warp-uniform choice
     if (P == 8 && total + (have_run ? 64 : 0) <= 128)
-      merge_range<4>(base, 0, total, k, list_stride, k, lane, run, have_run, a.list_ptrs, row * k);
+      merge_range<4>(base, 0, total, k, list_stride, k, lane, run, have_run, a.list_ptrs, in_row * k);
     else
-      merge_range<P>(base, 0, total, k, list_stride, k, lane, run, have_run, a.list_ptrs, row * k);
+      merge_range<P>(base, 0, total, k, list_stride, k, lane, run, have_run, a.list_ptrs, in_row * k);
     if (sym) {
       const int extra = static_cast<int>(min(a.sym_cnt[row], static_cast<uint32_t>(a.sym_cap)));
       if (extra > 0) merge_range<P>(a.sym_ovf + row * a.sym_cap, 0, extra, a.sym_cap, 0, k, lane, run, true);
@@ -232,7 +242,7 @@ merge_topk_kernel(const MergeLaunch a) {
   } else {
     const int per = (total + kRowBlockWarps - 1) / kRowBlockWarps;
     const int e0 = min(total, warp * per), e1 = min(total, e0 + per);
-    merge_range<P>(base, e0, e1, k, list_stride, k, lane, run, have_run, a.list_ptrs, row * k);
+    merge_range<P>(base, e0, e1, k, list_stride, k, lane, run, have_run, a.list_ptrs, in_row * k);
     if (lane < k) stage[warp * k + lane] = run[0];              // k keys per warp, packed
     if (lane + 32 < k) stage[warp * k + 32 + lane] = run[1];
     __syncthreads();
@@ -256,15 +266,18 @@ merge_topk_kernel(const MergeLaunch a) {
       const uint64_t key = run[h];
       const bool got = key != 0ull;
       cnt += got ? 1 : 0;
-      const int64_t o = row * k + t;
+      const int64_t o = a.out_stride > 0 ? row * a.out_stride + a.out_col + t : row * k + t;
       if (a.keys_out) a.keys_out[o] = key;
       const uint32_t gi = key_index(key);
       if (a.scores) a.scores[o] = got ? key_score(key) : __int_as_float(0xff800000);
       if (a.idx) a.idx[o] = got ? static_cast<int32_t>(gi) : -1;
       if (a.valid) {
         bool ok = got;
-        if (got && a.max_floor_diff >= 0 && a.q_floor != nullptr && a.db_floor != nullptr)
-          ok = floor_ok(a.q_floor[row], a.db_floor[static_cast<int64_t>(gi) - a.floor_index_offset], a.max_floor_diff);
+        if (got && a.max_floor_diff >= 0 && a.q_floor != nullptr && a.db_floor != nullptr) {
+          // a key from outside the label array (lists seeded from other database slices) cannot be flagged here
+          const int64_t fi = static_cast<int64_t>(gi) - a.floor_index_offset;
+          ok = fi >= 0 && (a.floor_n <= 0 || fi < a.floor_n) && floor_ok(a.q_floor[in_row], a.db_floor[fi], a.max_floor_diff);
+        }
         a.valid[o] = ok ? 1 : 0;
       }
     }
@@ -272,18 +285,18 @@ merge_topk_kernel(const MergeLaunch a) {
   if (a.count) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0) a.count[row] = cnt;
+    if (lane == 0) a.count[row] = a.count_add ? a.count[row] + cnt : cnt;
   }
 }
 
 int launch_merge_topk(const MergeLaunch& a, cudaStream_t st) {
-  if (a.Q <= 0) return 0;
-  const unsigned grid = static_cast<unsigned>((a.Q + kMergeWarps - 1) / kMergeWarps);
+  if (a.Q <= 0 && a.any_flag_out == nullptr) return 0;
+  const unsigned grid = static_cast<unsigned>(std::max<int64_t>(1, (a.Q + kMergeWarps - 1) / kMergeWarps));
   // 4 keys per lane cover one batch of 128 new keys (64 when a seeded list rides along)
   int lists = a.n_lists >= 0 ? a.n_lists : std::max(a.sc.s_main, a.sc.s_last);
   if (a.n_lists < 0 && a.sym_flag != nullptr) lists = std::max(lists, std::max(a.sc_sym.s_max, std::max(a.sc_sym.s_main, a.sc_sym.s_last)));
   const int64_t keys = static_cast<int64_t>(lists) * a.k;
-  if (a.Q <= 2048 && keys >= 1024 && a.sym_flag == nullptr)
+  if (a.Q > 0 && a.Q <= 2048 && keys >= 1024 && a.sym_flag == nullptr)
     merge_topk_kernel<8, true><<<static_cast<unsigned>(a.Q), kRowBlockWarps * 32, 0, st>>>(a);
   else if (keys <= (a.seed_keys ? 64 : 128))
     merge_topk_kernel<4, false><<<grid, kMergeWarps * 32, 0, st>>>(a);
@@ -360,8 +373,8 @@ compact_scan_kernel(int64_t* __restrict__ block_sums, int64_t nblocks, int64_t* 
 __global__ void __launch_bounds__(kScanBlock)
 compact_scatter_kernel(const float* __restrict__ scores, const int32_t* __restrict__ idx, const uint8_t* __restrict__ valid,
                        const int32_t* __restrict__ count, int64_t Q, int k, bool valid_only,
-                       const int64_t* __restrict__ block_offsets, int32_t* __restrict__ out_q, int32_t* __restrict__ out_m,
-                       float* __restrict__ out_s, uint8_t* __restrict__ out_v) {
+                       const int64_t* __restrict__ block_offsets, int64_t q_offset, int32_t* __restrict__ out_q,
+                       int32_t* __restrict__ out_m, float* __restrict__ out_s, uint8_t* __restrict__ out_v) {
   __shared__ int sm[32];
   __shared__ int offs[kScanBlock];
   __shared__ int cnts[kScanBlock];
@@ -380,7 +393,7 @@ compact_scatter_kernel(const float* __restrict__ scores, const int32_t* __restri
     const int64_t src = (row0 + r) * k;
     if (!valid_only) {                        // everything is emitted: straight coalesced copy
       for (int i = lane; i < c; i += 32) {
-        out_q[o + i] = static_cast<int32_t>(row0 + r);
+        out_q[o + i] = static_cast<int32_t>(q_offset + row0 + r);
         out_m[o + i] = idx[src + i];
         out_s[o + i] = scores[src + i];
         out_v[o + i] = valid[src + i];
@@ -395,7 +408,7 @@ compact_scatter_kernel(const float* __restrict__ scores, const int32_t* __restri
       const uint32_t ballot = __ballot_sync(0xffffffffu, emit);
       if (emit) {
         const int64_t d = o + __popc(ballot & ((1u << lane) - 1u));   // order inside the row is kept
-        out_q[d] = static_cast<int32_t>(row0 + r);
+        out_q[d] = static_cast<int32_t>(q_offset + row0 + r);
         out_m[d] = idx[src + i];
         out_s[d] = scores[src + i];
         out_v[d] = vv;
@@ -410,14 +423,14 @@ size_t compact_workspace_bytes(int64_t Q) {
 }
 
 int launch_compact(const float* scores, const int32_t* idx, const uint8_t* valid, const int32_t* count, int64_t Q, int k,
-                   bool valid_only, int32_t* out_q, int32_t* out_m, float* out_s, uint8_t* out_v, int64_t* out_total,
-                   void* workspace, cudaStream_t st) {
+                   bool valid_only, int64_t q_offset, int32_t* out_q, int32_t* out_m, float* out_s, uint8_t* out_v,
+                   int64_t* out_total, void* workspace, cudaStream_t st) {
   if (Q <= 0) return static_cast<int>(cudaMemsetAsync(out_total, 0, sizeof(int64_t), st));
   const int64_t nb = (Q + kScanBlock - 1) / kScanBlock;
   int64_t* bs = static_cast<int64_t*>(workspace);
   compact_count_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, st>>>(count, valid, Q, k, valid_only, bs);
   compact_scan_kernel<<<1, kScanThreads, 0, st>>>(bs, nb, out_total);
-  compact_scatter_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, st>>>(scores, idx, valid, count, Q, k, valid_only, bs,
+  compact_scatter_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, st>>>(scores, idx, valid, count, Q, k, valid_only, bs, q_offset,
                                                                           out_q, out_m, out_s, out_v);
   return static_cast<int>(cudaGetLastError());
 }

@@ -25,6 +25,8 @@ struct TopkLaunch {
                                                   // bounds, counts, flag, candidate buffers); else optional home of the
                                                   // pacing counters (null: behind the partial lists)
   const uint32_t* run_if;                         // non-null: device flag, the launch is a no-op unless it is non-zero
+  unsigned long long* clk;                        // non-null: per-CTA {globaltimer, clock64} at entry / exit (4 words per CTA)
+  const uint64_t* ceil_keys; int64_t ceil_stride; // non-null: row r only admits keys below ceil_keys[r * ceil_stride] (passes of k > 64)
 };
 
 // Tile schedule for a Q x N problem on `units` CTAs (1), CTA pairs (2) or two-pair clusters (4).
@@ -36,13 +38,16 @@ int sym_capacity(int k, int64_t N);
 size_t topk_sync_bytes(const Schedule& sc);
 size_t sym_zeroed_bytes(int64_t N, size_t sync_bytes);
 size_t sym_state_bytes(int64_t N, int k, size_t sync_bytes);
-int schedule_selfcheck(const Schedule& sc, int units, int64_t* tiles_computed, int64_t* makespan_tiles);
+int schedule_selfcheck(const Schedule& sc, int units, int64_t* tiles_computed, int64_t* makespan_tiles,
+                       const std::vector<int>* owner_of_block = nullptr);   // run tables: which part owns each block
 // Run table of a small symmetric sweep (see Schedule::tab_runs): built on the host; `sc` points into the vectors.
 struct SymTable {
   Schedule sc;
   std::vector<RunEntry> runs;
   std::vector<int> unit_begin, block_first;
-  int64_t makespan;
+  std::vector<int> owner_of_block;   // part that computes each block's rows (the same function on every part)
+  int64_t makespan;                  // tile-times of the busiest unit
+  int64_t tiles;                     // tiles this part computes
 };
 bool sym_table_wanted(int64_t N);
 void build_sym_table(int64_t N, int d_pad, int sm_count, int part_index, int part_count, SymTable* out);
@@ -77,21 +82,28 @@ struct MergeLaunch {
   // symmetric sweep: while *sym_flag == 0 the lists follow `sc_sym` and row r also owns the first
   // min(sym_cnt[r], sym_cap) keys of sym_ovf + r * sym_cap; otherwise (overflow: the full sweep ran) `sc` holds
   const uint32_t* sym_flag; const uint32_t* sym_cnt; const uint64_t* sym_ovf; int sym_cap;
+  uint32_t* sym_flag_copy;           // optional: *sym_flag is copied here (memory that outlives the sweep's workspace)
   int sym_force;                     // 1: no full sweep stands behind (one part of a multi-GPU sweep): `sc_sym` always holds
   Schedule sc_sym;
   // outputs (any may be null)
   uint64_t* keys_out;                // [Q,k] sorted descending, 0 padded
   float* scores; int32_t* idx; uint8_t* valid; int32_t* count;
+  int64_t out_stride; int out_col;   // out_stride > 0: the [Q,k] outputs are columns out_col.. of rows out_stride wide
+  int count_add;                     //   (one pass of a k > 64 sweep); count_add: count[row] += instead of =
   const int32_t* q_floor; const int32_t* db_floor; int64_t floor_index_offset;  // valid = gate(q_floor[row], db_floor[idx - off])
+  int64_t floor_n;                   // > 0: labels in db_floor (an index outside is flagged invalid instead of read)
   int max_floor_diff;
+  int64_t row_offset;                // merge rows [row_offset, row_offset + Q) of the input lists / q_floor; outputs are [Q, k]
+  int64_t flag_offset;               // with list_ptrs and any_flag_out: word (u32) at list_ptrs[g] + flag_offset (in keys) is
+  uint32_t* any_flag_out;            //   GPU g's overflow flag; their OR is written to *any_flag_out
 };
 int launch_merge_topk(const MergeLaunch& a, cudaStream_t st);
 
 // K4: padded [Q,k] lists -> flat candidate arrays (query asc, score desc)
 size_t compact_workspace_bytes(int64_t Q);
 int launch_compact(const float* scores, const int32_t* idx, const uint8_t* valid, const int32_t* count, int64_t Q, int k,
-                   bool valid_only, int32_t* out_q, int32_t* out_m, float* out_s, uint8_t* out_v, int64_t* out_total,
-                   void* workspace, cudaStream_t st);
+                   bool valid_only, int64_t q_offset /*added to the emitted query indices*/, int32_t* out_q, int32_t* out_m,
+                   float* out_s, uint8_t* out_v, int64_t* out_total, void* workspace, cudaStream_t st);
 
 // get_statistics (place_recognition.py:913-933) on the device: out[4] = total, valid, sum(sim), sum(valid sim), fp64
 size_t stats_workspace_bytes();

@@ -82,7 +82,7 @@ std::tuple<Tensor, Tensor, Tensor, Tensor, Tensor> gated_topk(
   const int64_t Q = q_bf16.size(0), N = db_bf16.size(0);
   const int dp = static_cast<int>(q_bf16.size(1));
   TORCH_CHECK(N == 0 || db_bf16.size(1) == dp, "gated_topk: query and database descriptor lengths differ");
-  TORCH_CHECK(k >= 1 && k <= SEMGATE_MAX_K, "gated_topk: k outside 1..", SEMGATE_MAX_K);
+  TORCH_CHECK(k >= 1 && k <= SEMGATE_MAX_K_TOTAL, "gated_topk: k outside 1..", SEMGATE_MAX_K_TOTAL);
   c10::cuda::CUDAGuard guard(q_bf16.device());
   semgate_topk_params p{};
   p.similarity_threshold = static_cast<float>(threshold);   // compared in fp32, like numpy's weak-scalar rule

@@ -15,7 +15,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsemgate.so")
 
-MAX_K = 64
+MAX_K = 64            # candidates per query one sweep keeps
+MAX_K_TOTAL = 1024    # largest k: above MAX_K the library runs ceil(k / 64) sweeps
 FLOOR_NONE = -2**31
 GATE_FLAG, GATE_MASK = 0, 1
 EINVAL, EARCH, ENOMEM, EDRIVER, EINDEX = -1, -2, -3, -4, -5
@@ -29,7 +30,8 @@ SYMBOLS = [
     "semgate_gate_candidates_host", "semgate_spatial_workspace_bytes", "semgate_spatial_count", "semgate_spatial_fill",
     "semgate_spatial_candidates_host", "semgate_rerank_scores", "semgate_rerank_select", "semgate_similarity_matrix",
     "semgate_merge_topk_peers", "semgate_compact_valid", "semgate_stats_workspace_bytes", "semgate_candidate_stats",
-    "semgate_last_sweep_mode", "semgate_schedule_check", "semgate_last_sweep_overflow",
+    "semgate_last_sweep_mode", "semgate_schedule_check", "semgate_last_sweep_overflow", "semgate_merge_topk_peers_rows", "semgate_compact_rows", "semgate_clock_probe_read",
+    "semgate_find_loop_closures_device", "semgate_find_loop_closures_device_workspace_bytes",
 ]
 
 
@@ -78,6 +80,10 @@ def load_library():
     lib.semgate_set_option.argtypes = [vp, C.c_char_p, i64]
     lib.semgate_profile_read.argtypes = [vp, P(C.c_double), P(i64)]
     lib.semgate_launch_count.argtypes = [vp]
+    lib.semgate_find_loop_closures_device_workspace_bytes.argtypes = [vp, i64, i32, P(TopkParams)]
+    lib.semgate_find_loop_closures_device_workspace_bytes.restype = sz
+    lib.semgate_find_loop_closures_device.argtypes = [vp, vp, i64, i32, vp, vp, P(TopkParams), vp, sz, vp, vp, vp, vp, vp, i32, vp]
+    lib.semgate_clock_probe_read.argtypes = [vp, P(C.c_double), P(C.c_double), P(C.c_double), P(i32)]
     lib.semgate_launch_count.restype = i64
     lib.semgate_pad_dim.argtypes = [C.c_int]
     lib.semgate_normalize_cast.argtypes = [vp, vp, i64, i32, i64, vp, i32, vp]
@@ -102,6 +108,8 @@ def load_library():
     lib.semgate_rerank_select.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, vp, vp, vp]
     lib.semgate_similarity_matrix.argtypes = [vp, vp, i64, vp, i64, i32, vp, i64, vp]
     lib.semgate_merge_topk_peers.argtypes = [vp, vp, i32, i64, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp]
+    lib.semgate_merge_topk_peers_rows.argtypes = [vp, vp, i32, i64, i32, i64, i64, i64, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.semgate_compact_rows.argtypes = [vp, vp, vp, vp, vp, i64, i32, i64, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.semgate_compact_valid.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.semgate_stats_workspace_bytes.argtypes = []
     lib.semgate_stats_workspace_bytes.restype = sz
@@ -127,8 +135,8 @@ def pad_dim(d: int) -> int:
 def make_params(k: int, similarity_threshold: float = -np.inf, min_time_gap: float = 10.0, max_floor_diff: int = -1,
                 gate_mode: int = GATE_FLAG, db_index_offset: int = 0, cta_group: int = 0,
                 accumulate: bool = False, symmetric: int = 0, part_index: int = 0, part_count: int = 0) -> TopkParams:
-    if not (1 <= int(k) <= MAX_K):
-        raise ValueError(f"k={k} outside 1..{MAX_K}")
+    if not (1 <= int(k) <= MAX_K_TOTAL):
+        raise ValueError(f"k={k} outside 1..{MAX_K_TOTAL}")
     # the reference compares `sim < threshold` in the similarity dtype (fp32): same rounding here
     thr = float(np.float32(similarity_threshold))
     return TopkParams(thr, float(min_time_gap), int(k), int(max_floor_diff), int(gate_mode), int(db_index_offset),
@@ -196,6 +204,13 @@ class Engine:
         ms, n = C.c_double(0.0), C.c_int64(0)
         _check(self.lib.semgate_profile_read(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def clock_probe_read(self):
+        """(median SM MHz, min SM MHz, span in us, CTAs) of the last sweep's K2 launch, from in-kernel clock64 /
+        globaltimer pairs; needs set_option('clock_probe', 1).  Synchronises."""
+        med, mn, span, n = C.c_double(0.0), C.c_double(0.0), C.c_double(0.0), C.c_int32(0)
+        _check(self.lib.semgate_clock_probe_read(self._h, C.byref(med), C.byref(mn), C.byref(span), C.byref(n)))
+        return med.value, mn.value, span.value, n.value
 
     def last_sweep_mode(self):
         """(mode, tiles) of the last gated_topk: 0 full sweep, 1 symmetric, 2 symmetric overflowed -> full redone."""
@@ -369,11 +384,76 @@ class Engine:
                                                      self._stream()))
         return TopkResult(scores, idx, valid, count, keys)
 
+    def merge_topk_peers_rows(self, peer_ptrs_dev: int, G: int, Q: int, k: int, row_begin: int, row_count: int,
+                              q_floor=None, db_floor_all=None, max_floor_diff: int = -1, want_keys: bool = False,
+                              flag_offset: int = 0, any_flag=None) -> TopkResult:
+        """Rows [row_begin, row_begin + row_count) of the G per-GPU `[Q,k]` key buffers merged in place over NVLink
+        (this rank's share of the exchange); `any_flag` (int32 [1] device tensor): receives the OR of the uint32
+        words at `flag_offset` keys behind every peer's buffer base (the ranks' overflow flags)."""
+        torch = self._torch()
+        dev = self._dev()
+        n = int(row_count)
+        scores = torch.empty((n, k), dtype=torch.float32, device=dev)
+        idx = torch.empty((n, k), dtype=torch.int32, device=dev)
+        valid = torch.empty((n, k), dtype=torch.uint8, device=dev)
+        count = torch.empty((n,), dtype=torch.int32, device=dev)
+        keys = torch.empty((n, k), dtype=torch.int64, device=dev) if want_keys else None
+        self._expect(any_flag, torch.int32, "any_flag", 1)
+        _check(self.lib.semgate_merge_topk_peers_rows(self._h, C.c_void_p(int(peer_ptrs_dev)), G, Q, k, int(row_begin), n,
+                                                      int(flag_offset), self._ptr(q_floor), self._ptr(db_floor_all),
+                                                      max_floor_diff, self._ptr(keys), self._ptr(scores), self._ptr(idx),
+                                                      self._ptr(valid), self._ptr(count), self._ptr(any_flag), self._stream()))
+        return TopkResult(scores, idx, valid, count, keys)
+
+    def find_loop_closures_device(self, x_bf16, params: TopkParams, ts=None, floor=None, use_graph: bool = True):
+        """find_loop_closures over a device-resident normalised database in ONE library call (K2 + K3 + K4),
+        replayed as a CUDA graph from the third call with the same arguments on.  Returns
+        (query_idx, match_idx, similarity, is_valid, total) CUDA tensors OWNED BY THE ENGINE: the next call with
+        the same shape overwrites them (that is what keeps the pointers, hence the graph, stable)."""
+        torch = self._torch()
+        self._expect(x_bf16, torch.bfloat16, "x_bf16", 2)
+        self._expect(ts, torch.float64, "ts", 1)
+        self._expect(floor, torch.int32, "floor", 1)
+        n, dp = x_bf16.shape
+        k = params.k
+        dev = x_bf16.device
+        bufs = getattr(self, "_sweep_bufs", None)
+        if bufs is None:
+            bufs = self._sweep_bufs = {}
+        key = (n, dp, k, params.symmetric, params.cta_group)
+        if key not in bufs:
+            if len(bufs) >= 4:
+                bufs.pop(next(iter(bufs)))
+            cap = max(n * k, 1)
+            wsb = int(self.lib.semgate_find_loop_closures_device_workspace_bytes(self._h, n, dp, C.byref(params)))
+            bufs[key] = (torch.empty((max(wsb, 256),), dtype=torch.uint8, device=dev),
+                         torch.empty((cap,), dtype=torch.int32, device=dev), torch.empty((cap,), dtype=torch.int32, device=dev),
+                         torch.empty((cap,), dtype=torch.float32, device=dev), torch.empty((cap,), dtype=torch.uint8, device=dev),
+                         torch.zeros((1,), dtype=torch.int64, device=dev))
+        ws, oq, om, os_, ov, total = bufs[key]
+        cur = torch.cuda.current_stream(self.device)
+        side = None
+        if use_graph and cur.cuda_stream == 0:
+            # a capture cannot start on the legacy default stream: run on a stream of our own, ordered behind and
+            # before the caller's
+            side = getattr(self, "_graph_stream", None)
+            if side is None:
+                side = self._graph_stream = torch.cuda.Stream(device=self.device)
+            side.wait_stream(cur)
+        st = C.c_void_p(side.cuda_stream) if side is not None else self._stream()
+        _check(self.lib.semgate_find_loop_closures_device(
+            self._h, self._ptr(x_bf16), n, dp, self._ptr(ts), self._ptr(floor), C.byref(params), self._ptr(ws), ws.numel(),
+            self._ptr(oq), self._ptr(om), self._ptr(os_), self._ptr(ov), self._ptr(total), 1 if use_graph else 0, st))
+        if side is not None:
+            cur.wait_stream(side)
+        return oq, om, os_, ov, total
+
     # ------------------------------------------------------------------ K4
-    def compact(self, res: TopkResult, valid_only: bool = False):
+    def compact(self, res: TopkResult, valid_only: bool = False, query_offset: int = 0):
         """Padded lists -> (query_idx, match_idx, similarity, is_valid, total) CUDA tensors;
         the arrays have capacity Q*k, the first `total` entries are meaningful.
-        `valid_only`: emit only the floor-consistent candidates (the verifier hand-off list)."""
+        `valid_only`: emit only the floor-consistent candidates (the verifier hand-off list).
+        `query_offset`: the lists are rows query_offset.. of a larger sweep (a rank's share); emitted indices are global."""
         torch = self._torch()
         Q, k = res.scores.shape
         dev = res.scores.device
@@ -385,6 +465,12 @@ class Engine:
         total = torch.zeros((1,), dtype=torch.int64, device=dev)
         wsb = int(self.lib.semgate_compact_workspace_bytes(Q))
         ws = torch.empty((max(wsb, 256),), dtype=torch.uint8, device=dev)
+        if query_offset:
+            _check(self.lib.semgate_compact_rows(self._h, self._ptr(res.scores), self._ptr(res.idx), self._ptr(res.valid),
+                                                 self._ptr(res.count), Q, k, int(query_offset), 1 if valid_only else 0,
+                                                 self._ptr(oq), self._ptr(om), self._ptr(os_), self._ptr(ov), self._ptr(total),
+                                                 self._ptr(ws), self._stream()))
+            return oq, om, os_, ov, total
         fn = self.lib.semgate_compact_valid if valid_only else self.lib.semgate_compact
         _check(fn(self._h, self._ptr(res.scores), self._ptr(res.idx), self._ptr(res.valid),
                   self._ptr(res.count), Q, k, self._ptr(oq), self._ptr(om), self._ptr(os_),

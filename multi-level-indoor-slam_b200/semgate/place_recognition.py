@@ -79,6 +79,18 @@ class MatchArrays:
         return list(zip(self.query_idx.tolist(), self.match_idx.tolist(), self.similarity.astype(np.float64).tolist()))
 
 
+def _effective_k(k, n: int) -> int:
+    """The reference slices `argsort()[::-1][:k]` (place_recognition.py:150,888): any k >= 0 works and more than
+    n candidates never come back.  Here k <= 64 is one sweep, larger k several (up to MAX_K_TOTAL)."""
+    k = int(k)
+    if k < 0:
+        raise ValueError(f"k={k} must not be negative")
+    k = min(k, int(n))
+    if k > _native.MAX_K_TOTAL:
+        raise ValueError(f"k={k} exceeds the library's limit {_native.MAX_K_TOTAL}")
+    return k
+
+
 def _device_index(device) -> int:
     if isinstance(device, int):
         return device
@@ -217,10 +229,11 @@ class BasePlaceRecognition:
         if q.shape[1] != db.d:
             raise ValueError(f"query length {q.shape[1]} != database descriptor length {db.d}")
         qb = eng.normalize_cast(q)
-        params = _native.make_params(k=min(int(k), _native.MAX_K), similarity_threshold=-np.inf,
-                                     min_time_gap=min_time_gap, max_floor_diff=-1)
-        if k > _native.MAX_K:
-            raise ValueError(f"k={k} exceeds the kernel's list capacity {_native.MAX_K}")
+        k = _effective_k(k, db.n)
+        if k == 0:
+            nq = q.shape[0]
+            return np.zeros((nq, 0), np.float32), np.zeros((nq, 0), np.int32), np.zeros((nq,), np.int32)
+        params = _native.make_params(k=k, similarity_threshold=-np.inf, min_time_gap=min_time_gap, max_floor_diff=-1)
         q_ts = db_ts = None
         if timestamps is not None:
             q_ts = torch.from_numpy(np.ascontiguousarray(timestamps, dtype=np.float64)).to(dev)
@@ -467,11 +480,12 @@ class SemanticPlaceRecognition:
             return (empty, self.get_statistics([])) if with_statistics else empty
         if gate_mode not in GATE_MODES:
             raise ValueError(f"gate_mode must be one of {sorted(GATE_MODES)}")
-        if not (1 <= int(k) <= _native.MAX_K):
-            raise ValueError(f"k={k} outside the kernel's list capacity 1..{_native.MAX_K}")
         db = self.vpr._packed()
         eng = db.engine
         n = db.n
+        k = _effective_k(k, n)
+        if k == 0:
+            return (empty, self.get_statistics([])) if with_statistics else empty
         params = _native.make_params(k=int(k), similarity_threshold=self.similarity_threshold,
                                      min_time_gap=self.min_time_gap,
                                      max_floor_diff=0 if enable_floor_gating else -1, gate_mode=GATE_MODES[gate_mode])

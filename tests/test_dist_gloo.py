@@ -123,16 +123,35 @@ def _worker(rank, world, port, out_dir):
         # overflowed part, which must send every rank down the row-sharded path
         n_ap = 700
         x, tts, tfl = t(desc[:n_ap]), t(ts[:n_ap]), t(fl[:n_ap])
+        mk_sym = lambda off: dict(offset=off, k=k, thr=0.3, gap=5.0, mfd=0, symmetric=1)   # small case: force the triangle split
         for knob, how in ((None, "triangle"), (1, "rows (candidate buffers overflowed)")):
             sr.engine.overflow_on_rank = knob
-            ap = sr.sweep_all_pairs(x, mk, ts=tts, floor=tfl, max_floor_diff=0)
+            ap = sr.sweep_all_pairs(x, mk_sym, ts=tts, floor=tfl, max_floor_diff=0)
             assert sr.last_all_pairs == how
+            # deferred form: the same lists, the flag looked at when the result is asked for
+            pend = sr.sweep_all_pairs(x, mk_sym, ts=tts, floor=tfl, max_floor_diff=0, defer=True)
+            ap_d = pend.result()
+            assert pend.overflowed == (knob is not None) and torch.equal(ap_d.idx, ap.idx) and torch.equal(ap_d.count, ap.count)
+            # this rank's share of the rows only
+            part = sr.sweep_all_pairs(x, mk_sym, ts=tts, floor=tfl, max_floor_diff=0, gather=False)
+            plo, phi = shard_bounds(n_ap, world, rank)
+            assert (part.lo, part.hi) == (plo, phi) and torch.equal(part.result.idx, ap.idx[plo:phi])
+            assert torch.equal(part.result.valid, ap.valid[plo:phi]) and torch.equal(part.result.count, ap.count[plo:phi])
             np.savez(os.path.join(out_dir, f"ap{0 if knob is None else 1}_rank{rank}.npz"), scores=ap.scores.numpy(),
                      idx=ap.idx.numpy(), valid=ap.valid.numpy(), count=ap.count.numpy())
         sr.engine.overflow_on_rank = None
         alo, ahi = shard_bounds(n_ap, world, rank)
-        ap2 = sr.sweep_all_pairs_from_host(t(desc[alo:ahi].copy()), tts, tfl, mk, alo, ahi, n_ap, max_floor_diff=0)
+        ap2 = sr.sweep_all_pairs_from_host(t(desc[alo:ahi].copy()), tts, tfl, mk_sym, alo, ahi, n_ap, max_floor_diff=0)
+        assert sr.last_all_pairs == "triangle"
         assert torch.equal(ap2.idx, ap.idx) and torch.equal(ap2.count, ap.count), "host-input all-pairs form differs"
+        # the automatic rule leaves short sweeps / short descriptors to the row-sharded full sweep: same lists
+        ap3 = sr.sweep_all_pairs(x, mk, ts=tts, floor=tfl, max_floor_diff=0)
+        assert sr.last_all_pairs == "rows" and torch.equal(ap3.idx, ap.idx) and torch.equal(ap3.count, ap.count)
+        # a rank's share of a rectangular sweep
+        part = sr.sweep(t(desc[:n_q]), t(desc[lo:hi]), mk, lo, q_ts=t(ts[:n_q]), db_ts_shard=t(ts[lo:hi]), q_floor=t(fl[:n_q]),
+                        db_floor_shard=t(fl[lo:hi]), db_floor_all=t(fl), max_floor_diff=0, gather=False)
+        qlo, qhi = shard_bounds(n_q, world, rank)
+        assert (part.lo, part.hi) == (qlo, qhi) and torch.equal(part.result.idx, res.idx[qlo:qhi])
     finally:
         dist.destroy_process_group()
 
