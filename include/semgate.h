@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SEMGATE_VERSION 101
+#define SEMGATE_VERSION 200
 #define SEMGATE_MAX_K 64          /* candidates per query one sweep keeps (shared-memory list) */
 #define SEMGATE_MAX_K_TOTAL 1024   /* largest k: k > 64 runs as ceil(k / 64) sweeps, see semgate_gated_topk */
 #define SEMGATE_FLOOR_NONE INT32_MIN

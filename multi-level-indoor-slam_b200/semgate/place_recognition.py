@@ -107,9 +107,16 @@ def _device_index(device) -> int:
 
 
 class _PackedDB:
-    """Device-resident database: bf16 normalised rows, fp64 timestamps, int32 floors,
-    grown geometrically and re-synchronised lazily from the Python descriptor list
-    (callers may append PlaceDescriptor objects directly, place_recognition.py:1015-1020)."""
+    """Device-resident database: bf16 normalised rows, fp64 timestamps, int32 floors, grown geometrically and
+    re-synchronised from the Python descriptor list on every call (callers may append, replace or remove
+    PlaceDescriptor objects directly, place_recognition.py:1015-1020; the reference re-reads everything per call,
+    :140, :177, :870-899).
+
+    What is checked per call, for EVERY element (O(n) of host work, no device work unless something changed):
+    the identity of each PlaceDescriptor and of its `descriptor` array (strong references to both are held, so
+    an address cannot be recycled behind our back) -> rows from the first difference on are re-normalised and
+    re-uploaded; every `timestamp` and `floor_label` value -> re-uploaded when any differs (12 B per keyframe).
+    What cannot be seen: the CONTENTS of a descriptor array edited in place.  Call `invalidate()` after that."""
 
     def __init__(self, engine: "_native.Engine"):
         self.engine = engine
@@ -117,14 +124,26 @@ class _PackedDB:
         self.d = None
         self.cap = 0
         self.bf16 = self.ts = self.floor = None
-        self._ids: List[int] = []
+        self._refs: List[PlaceDescriptor] = []      # the records the device rows were built from
+        self._drefs: List[np.ndarray] = []          # ... and their descriptor arrays
+        self._ts_host = np.zeros(0, np.float64)
+        self._fl_host = np.zeros(0, np.int32)
         self.has_floor = False
+
+    def invalidate(self):
+        """Forget the device copy: the next call re-reads and re-uploads every descriptor."""
+        self.n = 0
+        self._refs, self._drefs = [], []
+        self._ts_host, self._fl_host = np.zeros(0, np.float64), np.zeros(0, np.int32)
 
     def _grow(self, need: int, d: int):
         import torch
         if self.d is not None and self.d != d:
-            raise ValueError(f"descriptor length changed from {self.d} to {d}")
+            if self.n:
+                raise ValueError(f"descriptor length changed from {self.d} to {d}")
+            self.cap = 0                       # nothing packed: a new length may start over
         if need <= self.cap:
+            self.d = d
             return
         cap = max(need, int(self.cap * 1.5), 1024)
         dev = torch.device("cuda", self.engine.device)
@@ -134,36 +153,52 @@ class _PackedDB:
         fl = torch.empty((cap,), dtype=torch.int32, device=dev)
         if self.n:
             bf16[:self.n].copy_(self.bf16[:self.n])
-            ts[:self.n].copy_(self.ts[:self.n])
-            fl[:self.n].copy_(self.floor[:self.n])
         self.bf16, self.ts, self.floor, self.cap, self.d = bf16, ts, fl, cap, d
+        self._ts_host, self._fl_host = np.zeros(0, np.float64), np.zeros(0, np.int32)   # new buffers: upload again
+
+    @staticmethod
+    def _first_difference(old: list, new: list) -> int:
+        """Length of the common prefix of two object lists, by identity."""
+        m = min(len(old), len(new))
+        if m == 0:
+            return 0
+        a = np.fromiter(map(id, old[:m]), dtype=np.int64, count=m)
+        b = np.fromiter(map(id, new[:m]), dtype=np.int64, count=m)
+        diff = np.nonzero(a != b)[0]
+        return int(diff[0]) if diff.size else m
 
     def sync(self, descriptors: List[PlaceDescriptor]):
         import torch
         n = len(descriptors)
-        keep = min(self.n, n)
-        # cheap identity probes: first, last and a middle element of the packed prefix
-        probes = {0, keep - 1, keep // 2} if keep else set()
-        if n < self.n or any(self._ids[i] != id(descriptors[i]) for i in probes):
-            self.n, self._ids = 0, []
-            keep = 0
-        if n == keep:
+        drefs = [p.descriptor for p in descriptors]
+        keep = min(self.n, self._first_difference(self._refs, descriptors), self._first_difference(self._drefs, drefs))
+        if n > keep:
+            new = drefs[keep:]
+            x = np.ascontiguousarray(np.vstack([np.asarray(a).reshape(1, -1) for a in new]), dtype=np.float32)
+            d = x.shape[1]
+            self.n = keep                      # rows beyond `keep` are stale: _grow must not carry them over
+            self._grow(n, d)
+            xt = torch.from_numpy(x).to(self.bf16.device, non_blocking=False)
+            self.engine.normalize_cast(xt, out=self.bf16[keep:n])
+        self.n = n
+        self._refs, self._drefs = list(descriptors), drefs
+        if n == 0:
             return
-        new = descriptors[keep:]
-        x = np.ascontiguousarray(np.vstack([np.asarray(p.descriptor).reshape(1, -1) for p in new]), dtype=np.float32)
-        d = x.shape[1]
-        self._grow(n, d)
-        dev = self.bf16.device
-        xt = torch.from_numpy(x).to(dev, non_blocking=False)
-        self.engine.normalize_cast(xt, out=self.bf16[keep:n])
-        self.ts[keep:n] = torch.from_numpy(np.array([float(p.timestamp) for p in new], dtype=np.float64)).to(dev)
-        fl = np.array([_native.FLOOR_NONE if p.floor_label is None else int(p.floor_label) for p in new], dtype=np.int64)
-        real = fl[fl != _native.FLOOR_NONE]
+        # timestamps and labels: read every one, upload when anything differs
+        ts = np.fromiter((float(p.timestamp) for p in descriptors), dtype=np.float64, count=n)
+        fl64 = np.fromiter((_native.FLOOR_NONE if p.floor_label is None else int(p.floor_label) for p in descriptors),
+                           dtype=np.int64, count=n)
+        real = fl64[fl64 != _native.FLOOR_NONE]
         if real.size and (real.max() > 2**31 - 1 or real.min() < -2**31 + 1):
             raise ValueError("floor labels must fit in int32")
-        self.floor[keep:n] = torch.from_numpy(fl.astype(np.int32)).to(dev)
-        self._ids.extend(id(p) for p in new)
-        self.n = n
+        fl = fl64.astype(np.int32)
+        dev = self.bf16.device
+        if not np.array_equal(ts, self._ts_host, equal_nan=True):
+            self.ts[:n] = torch.from_numpy(ts).to(dev)
+            self._ts_host = ts
+        if not np.array_equal(fl, self._fl_host):
+            self.floor[:n] = torch.from_numpy(fl).to(dev)
+            self._fl_host = fl
 
 
 class BasePlaceRecognition:
@@ -185,6 +220,13 @@ class BasePlaceRecognition:
             self._db = _PackedDB(self._engine())
         self._db.sync(self.descriptors)
         return self._db
+
+    def invalidate(self):
+        """Drop the device copy of the database.  Needed only after editing the CONTENTS of a descriptor array
+        in place: appended, replaced or removed PlaceDescriptor objects, replaced `descriptor` arrays and changed
+        `timestamp` / `floor_label` values are picked up by every call on their own."""
+        if self._db is not None:
+            self._db.invalidate()
 
     # -- reference interface ---------------------------------------------------
     def extract_descriptor(self, image: np.ndarray) -> np.ndarray:
@@ -300,13 +342,14 @@ class _LocalStore:
     def __init__(self, engine: "_native.Engine"):
         self.engine = engine
         self.slot: Dict[int, int] = {}     # keyframe index -> row of `feats`
-        self._ids: Dict[int, int] = {}     # keyframe index -> id() of the cached array
+        self._ids: Dict[int, np.ndarray] = {}   # keyframe index -> the cached array itself (a held reference: an
+                                                # address cannot be recycled for a replacement array)
         self.feats = None
         self.P = self.D = None
 
     def sync(self, cache: Dict[int, np.ndarray]):
         import torch
-        new = [k for k, v in cache.items() if self._ids.get(k) != id(v)]
+        new = [k for k, v in cache.items() if self._ids.get(k) is not v]
         if not new:
             return
         first = np.asarray(cache[new[0]])
@@ -330,7 +373,7 @@ class _LocalStore:
             if k not in self.slot:
                 self.slot[k] = len(self.slot)
             self.engine.normalize_cast(torch.from_numpy(np.ascontiguousarray(a)).to(dev), out=self.feats[self.slot[k]])
-            self._ids[k] = id(cache[k])
+            self._ids[k] = cache[k]
 
 
 class CricaVPR(BasePlaceRecognition):

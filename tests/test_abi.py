@@ -30,7 +30,7 @@ def test_library_builds_and_exports_header_symbols():
     from semgate import _native
     assert sorted(_native.SYMBOLS) == declared, "ctypes binding and header disagree"
     lib.semgate_version.restype = ctypes.c_int
-    assert lib.semgate_version() == 101
+    assert lib.semgate_version() == 200
     assert lib.semgate_pad_dim(4096) == 4096 and lib.semgate_pad_dim(100) == 128 and lib.semgate_pad_dim(8448) == 8448
 
 

@@ -1014,6 +1014,16 @@ def test_full_size_properties_large_configs(eng, cfg):
     if cfg == "c3":
         r2 = eng.gated_topk(qb, xb, p, q_ts=qts, db_ts=tts, q_floor=qfl, db_floor=tfl, want_keys=True)
         assert torch.equal(r.keys, r2.keys), "sweep must be deterministic"
+    else:
+        # the aliased arguments above take the symmetric sweep; the full-matrix kernel at 1M x 1M must give the
+        # same lists bit for bit (the full-matrix form was untested at this size)
+        assert eng.last_sweep_mode()[0] == 1
+        pf = _native.make_params(k=k, similarity_threshold=thr, min_time_gap=gap, max_floor_diff=0, symmetric=-1)
+        r2 = eng.gated_topk(qb, xb, pf, q_ts=qts, db_ts=tts, q_floor=qfl, db_floor=tfl, want_keys=True)
+        torch.cuda.synchronize()
+        assert eng.last_sweep_mode()[0] == 0
+        assert torch.equal(r.keys, r2.keys), "symmetric and full-matrix sweeps differ at 1M x 1M"
+        del r2
     # structure, on the device (1M x 25 lists)
     pos = torch.arange(k, device="cuda")[None, :]
     filled = pos < r.count[:, None]
@@ -1146,3 +1156,332 @@ def test_rerank_batch_dinov2_shape(eng):
             assert abs(os_[r, t] - full[int(oi[r, t])]) <= BF16_MODEL_TOL
             assert int(oi[r, t]) == ref[t][0] or abs(full[int(oi[r, t])] - ref[t][1]) <= 2 * BF16_MODEL_TOL
         assert np.all(oi[r, oc[r]:] == -1)
+
+
+# --------------------------------------------------------------------------- round 2: k > 64, row-slice merge, one-call sweep, resync
+@pytest.mark.parametrize("k,cg,Q,N,D", [(100, 1, 300, 900, 128), (100, 2, 300, 900, 128), (65, 1, 70, 700, 64),
+                                        (130, 2, 513, 1400, 192), (200, 0, 3, 2500, 256), (1000, 1, 40, 1100, 64)])
+def test_k_above_64_runs_as_several_sweeps(eng, k, cg, Q, N, D):
+    """The reference's k is any integer (place_recognition.py:853,888); above 64 the library runs ceil(k/64) sweeps,
+    each admitting only keys below the last key of the sweep before.  Against the oracle at the same k: lists,
+    scores, flags; rows with fewer than k admissible candidates end early and stay consistent."""
+    from semgate import synthetic
+    desc, ts, fl = synthetic.make_case(max(Q, N), D, 3, seed=k + Q)
+    fl32 = fl.astype(np.int32)
+    thr = -0.05 if k < 1000 else -np.inf
+    got = run_gpu(eng, desc[:Q], desc[:N], k, thr, 3.0, ts[:Q], ts[:N], fl32[:Q], fl32[:N], mfd=0, cg=cg)
+    check_padded(got, k)
+    assert got["count"].max() > 64, "the case must exercise more than one pass"
+    ref16 = O.gated_topk(desc[:Q], desc[:N], ts[:Q], ts[:N], fl32[:Q], fl32[:N], k=k, threshold=thr, min_time_gap=3.0,
+                         max_floor_diff=0, bf16=True)
+    rep = parity.compare_candidates(O.compact(ref16), O.compact(got), k, thr, tol=BF16_MODEL_TOL)
+    assert rep["max_score_err"] < BF16_MODEL_TOL
+    ref32 = O.gated_topk(desc[:Q], desc[:N], ts[:Q], ts[:N], fl32[:Q], fl32[:N], k=k, threshold=thr, min_time_gap=3.0,
+                         max_floor_diff=0)
+    parity.compare_candidates(O.compact(ref32), O.compact(got), k, thr, tol=parity.SCORE_TOL)
+    parity.check_decisions_exact(O.compact(got), ts[:N], fl32[:N], 3.0, 0, q_ts=ts[:Q], q_floors=fl32[:Q])
+    assert np.array_equal(got["keys"], O.pack_keys(got["scores"], got["idx"]))
+    # the first 64 columns are the single-sweep answer, bit for bit
+    one = run_gpu(eng, desc[:Q], desc[:N], 64, thr, 3.0, ts[:Q], ts[:N], fl32[:Q], fl32[:N], mfd=0, cg=cg)
+    assert np.array_equal(one["idx"], got["idx"][:, :64]) and np.array_equal(one["scores"], got["scores"][:, :64])
+    if k == 100:
+        # a threshold that leaves some rows short of 64, some between 64 and k, some full: later passes must add
+        # nothing to a row that already ran out of candidates
+        thr2 = 0.12
+        got2 = run_gpu(eng, desc[:Q], desc[:N], k, thr2, 3.0, ts[:Q], ts[:N], fl32[:Q], fl32[:N], mfd=0, cg=cg)
+        check_padded(got2, k)
+        c = got2["count"]
+        assert c.min() < 64 < c.max()
+        ref2 = O.gated_topk(desc[:Q], desc[:N], ts[:Q], ts[:N], fl32[:Q], fl32[:N], k=k, threshold=thr2, min_time_gap=3.0,
+                            max_floor_diff=0, bf16=True)
+        parity.compare_candidates(O.compact(ref2), O.compact(got2), k, thr2, tol=BF16_MODEL_TOL)
+
+
+def test_k_above_64_through_the_mirrored_classes_and_host_abi(eng):
+    from semgate import SemanticPlaceRecognition, PlaceDescriptor, _native, synthetic
+    n, d, k = 1200, 128, 100
+    desc, ts, fl = synthetic.make_case(n, d, 3, seed=5)
+    fl32 = fl.astype(np.int32)
+    spr = SemanticPlaceRecognition('mixvpr', 'cuda', similarity_threshold=0.05, min_time_gap=4.0, descriptor_dim=d)
+    for i in range(n):
+        spr.vpr.descriptors.append(PlaceDescriptor(float(ts[i]), desc[i], floor_label=int(fl[i])))
+    arr = spr.find_loop_closures_arrays(enable_floor_gating=True, k=k)
+    got = dict(query_idx=arr.query_idx.astype(np.int64), match_idx=arr.match_idx.astype(np.int64), similarity=arr.similarity,
+               is_valid=arr.is_valid)
+    ref = O.find_loop_closures(desc, ts, fl32, similarity_threshold=0.05, min_time_gap=4.0, k=k)
+    parity.compare_candidates(ref, got, k, 0.05)
+    parity.check_order(got)
+    assert np.bincount(got["query_idx"]).max() > 64
+    # host-buffer C ABI, same k
+    p = _native.make_params(k=k, similarity_threshold=0.05, min_time_gap=4.0, max_floor_diff=0)
+    q, m, s, v = eng.find_loop_closures_host(desc, ts, fl32, p)
+    assert np.array_equal(q, arr.query_idx) and np.array_equal(m, arr.match_idx) and np.array_equal(s, arr.similarity)
+    assert np.array_equal(v, arr.is_valid)
+    # query(): k above the database size comes back with every admissible keyframe, like the reference's slice
+    res = spr.vpr.query(desc[7], timestamp=float(ts[7]), k=5000, min_time_gap=4.0)
+    want = int((np.abs(ts - ts[7]) >= 4.0).sum())
+    assert len(res) == min(want, _native.MAX_K_TOTAL) or len(res) == want
+    sims = np.array([r.similarity for r in res])
+    assert np.all(np.diff(sims) <= 0)
+    assert spr.find_loop_closures(k=0) == []
+    with pytest.raises(ValueError):
+        spr.find_loop_closures(k=-1)
+
+
+def test_accumulate_cannot_flag_other_slices(eng):
+    """the seeded lists of an accumulating sweep hold indices of other database slices; their floor flags
+    cannot come from this slice's labels -> SEMGATE_EINVAL instead of an out-of-bounds read."""
+    import torch
+    from semgate import _native, synthetic
+    desc, ts, fl = synthetic.make_case(1500, 64, 3, seed=2)
+    xb = eng.normalize_cast(_t(desc))
+    tts, tfl = _t(ts), _t(fl.astype(np.int32))
+    kw = dict(k=10, similarity_threshold=0.2, min_time_gap=5.0, max_floor_diff=0)
+    first = eng.gated_topk(xb, xb[:800], _native.make_params(**kw), q_ts=tts, db_ts=tts[:800].contiguous(), q_floor=tfl,
+                           db_floor=tfl[:800].contiguous(), want_keys=True)
+    with pytest.raises(_native.SemgateError) as e:
+        eng.gated_topk(xb, xb[800:], _native.make_params(db_index_offset=800, accumulate=True, **kw), q_ts=tts,
+                       db_ts=tts[800:].contiguous(), q_floor=tfl, db_floor=tfl[800:].contiguous(), want_lists=True, keys=first.keys)
+    assert e.value.code == _native.EINVAL
+    # without gating there is nothing to flag: allowed, and equal to the whole sweep
+    kw2 = dict(kw, max_floor_diff=-1)
+    a = eng.gated_topk(xb, xb[:800], _native.make_params(**kw2), q_ts=tts, db_ts=tts[:800].contiguous(), want_keys=True)
+    b = eng.gated_topk(xb, xb[800:], _native.make_params(db_index_offset=800, accumulate=True, **kw2), q_ts=tts,
+                       db_ts=tts[800:].contiguous(), want_lists=True, keys=a.keys)
+    whole = eng.gated_topk(xb, xb, _native.make_params(**kw2), q_ts=tts, db_ts=tts)
+    torch.cuda.synchronize()
+    assert torch.equal(b.idx, whole.idx) and torch.equal(b.scores, whole.scores)
+
+
+def test_merge_topk_peers_rows_and_flags(eng):
+    """The row-slice form of the peer merge (every rank merges only its own rows and ORs the ranks' overflow
+    flags): equals the same rows of the gathered merge; here all "peers" live on this GPU."""
+    import torch
+    rng = np.random.default_rng(9)
+    for G, Q, k, flags in ((2, 1001, 25, (0, 0)), (8, 333, 25, (0, 0, 0, 1, 0, 0, 0, 0)), (4, 257, 64, (0, 2, 0, 0)), (3, 50, 7, (0, 0, 5))):
+        sc = rng.uniform(-1, 1, size=(G, Q, k)).astype(np.float32)
+        ix = (rng.permutation(G * Q * k).reshape(G, Q, k) % (2 ** 20)).astype(np.int64)
+        ix[rng.uniform(size=ix.shape) > 0.8] = -1
+        keys = torch.from_numpy(O.pack_keys(sc, ix)).cuda()
+        parts = []
+        for g in range(G):
+            buf = torch.zeros((Q * k + 8,), dtype=torch.int64, device="cuda")
+            buf[:Q * k] = keys[g].reshape(-1)
+            buf[Q * k:Q * k + 1].view(torch.int32)[0] = flags[g]
+            parts.append(buf)
+        table = torch.tensor([p.data_ptr() for p in parts], dtype=torch.int64, device="cuda")
+        fl = torch.from_numpy(rng.integers(1, 5, size=2 ** 20).astype(np.int32)).cuda()
+        qf = torch.from_numpy(rng.integers(1, 5, size=Q).astype(np.int32)).cuda()
+        whole = eng.merge_topk(keys, k, q_floor=qf, db_floor_all=fl, max_floor_diff=0, want_keys=True)
+        for r in range(G):
+            lo, hi = (Q * r) // G, (Q * (r + 1)) // G
+            any_flag = torch.full((1,), -7, dtype=torch.int32, device="cuda")
+            mine = eng.merge_topk_peers_rows(table.data_ptr(), G, Q, k, lo, hi - lo, q_floor=qf, db_floor_all=fl,
+                                             max_floor_diff=0, want_keys=True, flag_offset=Q * k, any_flag=any_flag)
+            torch.cuda.synchronize()
+            assert torch.equal(mine.keys, whole.keys[lo:hi]) and torch.equal(mine.idx, whole.idx[lo:hi])
+            assert torch.equal(mine.scores, whole.scores[lo:hi]) and torch.equal(mine.valid, whole.valid[lo:hi])
+            assert torch.equal(mine.count, whole.count[lo:hi])
+            assert (int(any_flag.item()) != 0) == any(flags)
+            # compaction of a row slice emits global query indices
+            oq, om, os_, ov, tot = eng.compact(mine, query_offset=lo)
+            wq, wm, ws_, wv, wt = eng.compact(whole)
+            t = int(tot.item())
+            sel = (wq[:int(wt.item())] >= lo) & (wq[:int(wt.item())] < hi)
+            assert t == int(sel.sum()) and torch.equal(oq[:t], wq[:int(wt.item())][sel]) and torch.equal(om[:t], wm[:int(wt.item())][sel])
+        # zero rows: only the flags
+        any_flag = torch.zeros((1,), dtype=torch.int32, device="cuda")
+        eng.merge_topk_peers_rows(table.data_ptr(), G, Q, k, 0, 0, flag_offset=Q * k, any_flag=any_flag)
+        assert (int(any_flag.item()) != 0) == any(flags)
+
+
+@pytest.mark.parametrize("n,d,sym", [(5000, 512, 0), (1500, 128, 1), (9000, 1024, 0)])
+def test_one_call_device_sweep_and_graph_replay(eng, n, d, sym):
+    """semgate_find_loop_closures_device (K2 + K3 + K4 in one call, caller-owned outputs): eager, captured and replayed
+    runs give the candidates of the three-call path, bit for bit; the replays are single graph launches."""
+    import torch
+    from semgate import _native, synthetic
+    desc, ts, fl = synthetic.make_case(n, d, 3, seed=n)
+    xb = eng.normalize_cast(_t(desc))
+    tts, tfl = _t(ts), _t(fl.astype(np.int32))
+    p = _native.make_params(k=25, similarity_threshold=0.5, min_time_gap=10.0, max_floor_diff=0, symmetric=sym,
+                            cta_group=2 if sym else 0)
+    r = eng.gated_topk(xb, xb, p, q_ts=tts, db_ts=tts, q_floor=tfl, db_floor=tfl)
+    wq, wm, ws_, wv, wt = eng.compact(r)
+    t = int(wt.item())
+    assert t > n // 4
+    for use_graph in (False, True):
+        for call in range(4):
+            oq, om, os_, ov, tot = eng.find_loop_closures_device(xb, p, ts=tts, floor=tfl, use_graph=use_graph)
+            torch.cuda.synchronize()
+            assert int(tot.item()) == t, (use_graph, call)
+            assert torch.equal(oq[:t], wq[:t]) and torch.equal(om[:t], wm[:t]) and torch.equal(os_[:t], ws_[:t]) and torch.equal(ov[:t], wv[:t])
+            om.fill_(-5); tot.zero_()
+    # a changed database (same shapes and pointers, new contents) is picked up by the replay
+    xb[:256].copy_(xb[256:512])
+    r2 = eng.gated_topk(xb, xb, p, q_ts=tts, db_ts=tts, q_floor=tfl, db_floor=tfl)
+    w2 = eng.compact(r2)
+    oq, om, os_, ov, tot = eng.find_loop_closures_device(xb, p, ts=tts, floor=tfl, use_graph=True)
+    torch.cuda.synchronize()
+    t2 = int(w2[4].item())
+    assert int(tot.item()) == t2 and torch.equal(om[:t2], w2[1][:t2]) and torch.equal(os_[:t2], w2[2][:t2])
+
+
+def test_packed_database_resyncs_every_element(eng):
+    """replacing ANY PlaceDescriptor, replacing its descriptor array, or editing a timestamp / floor label
+    in place must show in the next call (the reference re-reads everything per call); editing a descriptor's
+    contents in place needs invalidate()."""
+    from semgate import SemanticPlaceRecognition, PlaceDescriptor, synthetic
+    n, d, k = 900, 128, 10
+    desc, ts, fl = synthetic.make_case(n, d, 3, seed=12)
+    fl32 = fl.astype(np.int32)
+
+    def build():
+        spr = SemanticPlaceRecognition('mixvpr', 'cuda', similarity_threshold=0.4, min_time_gap=5.0, descriptor_dim=d)
+        for i in range(n):
+            spr.vpr.descriptors.append(PlaceDescriptor(float(ts[i]), desc[i].copy(), floor_label=int(fl[i])))
+        return spr
+
+    def same(a, b):
+        return (np.array_equal(a.query_idx, b.query_idx) and np.array_equal(a.match_idx, b.match_idx)
+                and np.array_equal(a.similarity, b.similarity) and np.array_equal(a.is_valid, b.is_valid))
+
+    spr = build()
+    base = spr.find_loop_closures_arrays(k=k)
+    # (1) replace a record that is neither first, middle nor last
+    desc2, ts2, fl2 = desc.copy(), ts.copy(), fl32.copy()
+    desc2[137] = desc[400]
+    spr.vpr.descriptors[137] = PlaceDescriptor(float(ts[137]), desc2[137].copy(), floor_label=int(fl[137]))
+    got = spr.find_loop_closures_arrays(k=k)
+    fresh = SemanticPlaceRecognition('mixvpr', 'cuda', similarity_threshold=0.4, min_time_gap=5.0, descriptor_dim=d)
+    for i in range(n):
+        fresh.vpr.descriptors.append(PlaceDescriptor(float(ts2[i]), desc2[i], floor_label=int(fl2[i])))
+    want = fresh.find_loop_closures_arrays(k=k)
+    assert same(got, want) and not same(got, base)
+    # (2) labels and stamps edited in place; a descriptor array swapped on an existing record
+    spr.vpr.descriptors[55].floor_label = 99
+    spr.vpr.descriptors[56].timestamp = float(ts[700])
+    spr.vpr.descriptors[300].descriptor = desc[301].copy()
+    fresh.vpr.descriptors[55].floor_label = 99
+    fresh.vpr.descriptors[56].timestamp = float(ts[700])
+    fresh.vpr.descriptors[300] = PlaceDescriptor(float(ts2[300]), desc[301].copy(), floor_label=int(fl2[300]))
+    assert same(spr.find_loop_closures_arrays(k=k), fresh.find_loop_closures_arrays(k=k))
+    # (3) removal from the middle, then contents edited in place + invalidate()
+    del spr.vpr.descriptors[10:20]
+    del fresh.vpr.descriptors[10:20]
+    a, b = spr.find_loop_closures_arrays(k=k), fresh.find_loop_closures_arrays(k=k)
+    assert same(a, b) and len(a) > 0
+    spr.vpr.descriptors[5].descriptor[:] = spr.vpr.descriptors[600].descriptor
+    spr.vpr.invalidate()
+    fresh.vpr.descriptors[5] = PlaceDescriptor(fresh.vpr.descriptors[5].timestamp, spr.vpr.descriptors[600].descriptor.copy(),
+                                               floor_label=fresh.vpr.descriptors[5].floor_label)
+    assert same(spr.find_loop_closures_arrays(k=k), fresh.find_loop_closures_arrays(k=k))
+    # (4) emptied and refilled
+    spr.vpr.descriptors = []
+    assert spr.find_loop_closures(k=k) == []
+    spr.vpr.descriptors = list(build().vpr.descriptors)
+    assert same(spr.find_loop_closures_arrays(k=k), base)
+
+
+def test_run_table_is_shared_by_sizes_with_the_same_tile_count(eng):
+    """The symmetric run table depends on N only through ceil(N/256): a database growing keyframe by keyframe reuses
+    it (the cache was keyed on N and rebuilt + synchronised per call)."""
+    from semgate import synthetic
+    desc, ts, fl = synthetic.make_case(1300, 128, 3, seed=4)
+    fl32 = fl.astype(np.int32)
+    for n in (1025, 1026, 1100, 1279, 1280, 1281):
+        args = (desc[:n], desc[:n], 15, 0.35, 5.0, ts[:n], ts[:n], fl32[:n], fl32[:n])
+        a = run_gpu(eng, *args, mfd=0, cg=2, sym=1)
+        b = run_gpu(eng, *args, mfd=0, cg=2, sym=-1)
+        assert a["mode"] == 1 and b["mode"] == 0
+        assert np.array_equal(a["keys"], b["keys"]), n
+
+
+def test_clock_probe_reports_the_kernel_clock(eng):
+    import torch
+    from semgate import _native, synthetic
+    x = synthetic.make_descriptors_device(8192, 1024, "cuda", seed=1)
+    xb = eng.normalize_cast(x)
+    eng.set_option("clock_probe", 1)
+    try:
+        r = eng.gated_topk(xb, xb, _native.make_params(k=25, similarity_threshold=0.5))
+        torch.cuda.synchronize()
+        med, mn, span, ctas = eng.clock_probe_read()
+    finally:
+        eng.set_option("clock_probe", 0)
+    assert ctas >= 100 and 300.0 < mn <= med < 2300.0 and span > 10.0
+    assert int(r.count.sum()) > 0
+
+
+def test_full_size_properties_c4(eng, monkeypatch):
+    """BASELINE config 4 at full size: AnyLoc-shape 49152-d VLAD descriptors, 250k-keyframe database x 8192 queries
+    (24.6 GB of bf16 rows, 768 k-blocks per tile, both operands streaming).  Structure of every list, bit-exact
+    decisions on every returned pair, 48 sampled query rows against an fp32 torch reference, and the same lists from
+    the other schedule regime (query blocks treated as L2-resident: rm/s chosen differently)."""
+    import torch
+    from semgate import _native, synthetic
+    Q, N, D, F = 8192, 250_000, 49_152, 4
+    k, thr, gap = 25, 0.5, 10.0
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60 * 2 ** 30:
+        pytest.skip("needs 60 GB of free device memory")
+    dp = _native.pad_dim(D)
+    xb = torch.empty((N, dp), dtype=torch.bfloat16, device="cuda")
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    places = max(8, N // 20)
+    anchors = torch.randn((places, D), generator=g, device="cuda")
+    step = 2048
+    for s0 in range(0, N, step):
+        e0 = min(N, s0 + step)
+        pid = torch.randint(0, places, (e0 - s0,), generator=g, device="cuda")
+        eng.normalize_cast(anchors[pid] + 0.6 * torch.randn((e0 - s0, D), generator=g, device="cuda"), out=xb[s0:e0])
+    del anchors
+    ts = synthetic.make_timestamps(N)
+    fl = synthetic.make_floors(N, F).astype(np.int32)
+    tts, tfl = _t(ts), _t(fl)
+    p = _native.make_params(k=k, similarity_threshold=thr, min_time_gap=gap, max_floor_diff=0)
+    qb, qts, qfl = xb[:Q], tts[:Q].contiguous(), tfl[:Q].contiguous()
+    shape = _native.schedule_check(Q, N, dp, 2, eng.sm_count)
+    assert shape["resident"] == 0, "49152-d query blocks do not fit the L2 budget: both operands stream"
+    r = eng.gated_topk(qb, xb, p, q_ts=qts, db_ts=tts, q_floor=qfl, db_floor=tfl, want_keys=True)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("SEMGATE_RM_CAP_MB", "4096")          # the other regime: "resident" query blocks, rm / s differ
+    shape2 = _native.schedule_check(Q, N, dp, 2, eng.sm_count)
+    assert (shape2["rm"], shape2["s_main"]) != (shape["rm"], shape["s_main"])
+    r2 = eng.gated_topk(qb, xb, p, q_ts=qts, db_ts=tts, q_floor=qfl, db_floor=tfl, want_keys=True)
+    torch.cuda.synchronize()
+    monkeypatch.delenv("SEMGATE_RM_CAP_MB")
+    assert torch.equal(r.keys, r2.keys), "the lists must not depend on the schedule"
+    pos = torch.arange(k, device="cuda")[None, :]
+    filled = pos < r.count[:, None]
+    assert bool(((r.idx >= 0) == filled).all()) and bool((r.scores[filled] >= thr).all())
+    assert bool((r.scores[:, 1:][filled[:, 1:]] <= r.scores[:, :-1][filled[:, 1:]]).all()), "scores not descending"
+    assert bool((r.idx[filled] < N).all()) and bool((r.valid[~filled] == 0).all())
+    qi = torch.arange(Q, device="cuda")[:, None].expand(Q, k)[filled]
+    mi = r.idx[filled].long()
+    assert not bool(((tts[mi] - tts[qi]).abs() < gap).any()), "a returned pair lies inside the exclusion window"
+    assert bool(((tfl[qi] == tfl[mi]) == (r.valid[filled] != 0)).all()), "floor-gate bits differ"
+    assert int(r.count.sum().item()) > Q
+    rows = np.sort(np.random.default_rng(5).choice(Q, 48, replace=False))
+    # fp32 reference on the sampled rows, database converted 4096 rows at a time (fp32 rows are 196 KB each)
+    rr = torch.from_numpy(rows).cuda()
+    qf32 = qb[rr].float()
+    sims = torch.empty((len(rows), N), dtype=torch.float32, device="cuda")
+    for s0 in range(0, N, 4096):
+        sims[:, s0:s0 + 4096] = qf32 @ xb[s0:s0 + 4096].float().T
+    sims[(tts[None, :] - tts[rr][:, None]).abs() < gap] = -float("inf")
+    top_s, top_i = torch.topk(sims, k, dim=1)
+    top_s, top_i = top_s.cpu().numpy(), top_i.cpu().numpy()
+    ref = {"query_idx": [], "match_idx": [], "similarity": [], "is_valid": []}
+    for a, row in enumerate(rows):
+        for s, j in zip(top_s[a], top_i[a]):
+            if np.isfinite(s) and s >= np.float32(thr):
+                ref["query_idx"].append(int(row)); ref["match_idx"].append(int(j)); ref["similarity"].append(float(s))
+                ref["is_valid"].append(bool(O.floor_ok(fl[row], fl[j], 0)))
+    ref = {key: np.asarray(v) for key, v in ref.items()}
+    sub = dict(scores=r.scores[rr].cpu().numpy(), idx=r.idx[rr].cpu().numpy().astype(np.int64),
+               valid=r.valid[rr].cpu().numpy().astype(bool), count=r.count[rr].cpu().numpy())
+    got = O.compact(sub)
+    got["query_idx"] = rows[got["query_idx"]]
+    rep = parity.compare_candidates(ref, got, k, thr, tol=BF16_MODEL_TOL)
+    assert rep["max_score_err"] <= BF16_MODEL_TOL
