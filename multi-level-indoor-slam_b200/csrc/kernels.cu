@@ -289,16 +289,155 @@ merge_topk_kernel(const MergeLaunch a) {
   }
 }
 
+// K3, thread-per-row form (the common case: many rows).  The warp-per-row tournament above spends ~13 warp
+// instructions per key (1M rows x 4 lists: 1.3 ms, 0.12 of the copy bandwidth, instruction-issue bound); here 32 rows
+// share every instruction.  A warp stages one list of its 32 rows in shared memory with coalesced loads (a row's
+// list is k contiguous keys), then every thread inserts its own row's keys into its own list, kept sorted
+// descending in shared memory (odd stride: conflict-free): one compare against the list's last key rejects most
+// candidates once the list is full, an insertion shifts the tail.  Output rows are written warp-cooperatively
+// (coalesced).  Same inputs and outputs as merge_topk_kernel.
+__device__ __forceinline__ void sorted_insert(uint64_t* __restrict__ mine, int& cnt, uint64_t& minkey, int k, uint64_t key) {
+  int pos;
+  if (cnt == k) {
+    if (key <= minkey) return;
+    pos = k - 1;
+  } else {
+    pos = cnt++;
+  }
+  while (pos > 0) {
+    const uint64_t prev = mine[pos - 1];
+    if (prev >= key) break;
+    mine[pos] = prev;
+    --pos;
+  }
+  mine[pos] = key;
+  if (cnt == k) minkey = mine[k - 1];
+}
+
+template <int ROWS>
+__global__ void __launch_bounds__(ROWS)
+merge_rows_kernel(const MergeLaunch a) {
+  extern __shared__ uint64_t mr_smem[];
+  const int k = a.k, kp = k | 1;
+  uint64_t* tile = mr_smem;                                   // [ROWS][kp] staging, rows of this warp only
+  uint64_t* best = mr_smem + static_cast<size_t>(ROWS) * kp;  // [ROWS][kp] every thread's sorted list
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (a.any_flag_out != nullptr && a.list_ptrs != nullptr && blockIdx.x == 0 && warp == 0) {
+    uint32_t f = 0;
+    for (int g = lane; g < a.n_lists; g += 32) f |= *reinterpret_cast<const volatile uint32_t*>(a.list_ptrs[g] + a.flag_offset);
+    f = __reduce_or_sync(0xffffffffu, f);
+    if (lane == 0) *a.any_flag_out = f;
+  }
+  if (a.sym_flag_copy != nullptr && a.sym_flag != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *a.sym_flag_copy = *a.sym_flag;
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * ROWS;
+  if (row0 >= a.Q) return;
+  const int64_t in_row0 = row0 + a.row_offset;
+  const bool sym = a.sym_flag != nullptr && (a.sym_force || *a.sym_flag == 0u);
+
+  // where the lists of this block's rows live (uniform over the block: ROWS divides the rows of an m-block)
+  int n_lists = a.n_lists;
+  const uint64_t* base0 = a.keys_in + in_row0 * a.row_stride;   // list 0 of row0
+  int64_t row_pitch = a.row_stride, list_stride = a.list_stride;
+  if (n_lists < 0) {
+    const Schedule& sc = sym ? a.sc_sym : a.sc;
+    const int mb = static_cast<int>(row0 / a.rows_per_mblock);
+    n_lists = sched_slots(sc, mb);
+    if (sc.tab_runs != nullptr) {
+      base0 = a.keys_in + sched_run_list_offset(sc, mb, sc.tab_block_first[mb], row0, a.rows_per_mblock, k);
+      row_pitch = k;
+      list_stride = static_cast<int64_t>(a.rows_per_mblock) * k;
+    } else {
+      const int64_t rows_full = static_cast<int64_t>(sc.n_full) * sc.rm * a.rows_per_mblock;
+      base0 = a.keys_in + sched_list_offset(sc, row0, a.rows_per_mblock, k);
+      row_pitch = static_cast<int64_t>(row0 < rows_full ? sc.s_main : sc.s_last) * k;
+      list_stride = k;
+    }
+  }
+
+  const int r_mine = warp * 32 + lane;                 // this thread's row inside the block
+  const int64_t row = row0 + r_mine;
+  const bool live = row < a.Q;
+  uint64_t* mine = best + static_cast<size_t>(r_mine) * kp;
+  int cnt = 0;
+  uint64_t minkey = 0;
+  if (row0 + warp * 32 < a.Q) {
+    const int rows_here = static_cast<int>(min(static_cast<int64_t>(32), a.Q - (row0 + warp * 32)));
+    // lists: g = -1 is the seeded list (one more list per row, local rows), then the n_lists lists; each is k keys per
+    // row, `pitch` keys between rows: staged coalesced by the warp for its 32 rows, consumed per thread
+    for (int g = a.seed_keys != nullptr ? -1 : 0; g < n_lists; ++g) {
+      const uint64_t* src_row0;
+      int64_t pitch = k;
+      if (g < 0) src_row0 = a.seed_keys + row0 * k;
+      else if (a.list_ptrs != nullptr) src_row0 = a.list_ptrs[g] + in_row0 * k;
+      else { src_row0 = base0 + g * list_stride; pitch = row_pitch; }
+#pragma unroll 4
+      for (int rr = 0; rr < 32; ++rr) {
+        const uint64_t* src = src_row0 + (static_cast<int64_t>(warp) * 32 + rr) * pitch;
+        for (int j = lane; j < k; j += 32) tile[(warp * 32 + rr) * kp + j] = rr < rows_here ? __ldg(src + j) : 0ull;
+      }
+      __syncwarp();
+      if (live) {
+        const uint64_t* t = tile + static_cast<size_t>(r_mine) * kp;
+        for (int j = 0; j < k; ++j) {
+          const uint64_t key = t[j];
+          if (key != 0ull) sorted_insert(mine, cnt, minkey, k, key);
+        }
+      }
+      __syncwarp();
+    }
+    if (sym && live) {
+      // column-direction candidates of the symmetric sweep: this keyframe's own buffer
+      const int extra = static_cast<int>(min(a.sym_cnt[row], static_cast<uint32_t>(a.sym_cap)));
+      const uint64_t* buf = a.sym_ovf + row * a.sym_cap;
+      for (int e = 0; e < extra; ++e) sorted_insert(mine, cnt, minkey, k, __ldg(buf + e));
+    }
+    __syncwarp();
+    // outputs, one row at a time by the whole warp (coalesced)
+    for (int rr = 0; rr < 32; ++rr) {
+      const int r = warp * 32 + rr;
+      const int64_t orow = row0 + r;
+      if (orow >= a.Q) break;
+      const int c = __shfl_sync(0xffffffffu, cnt, rr);
+      int32_t qf = kFloorNone;
+      const bool gate = a.valid != nullptr && a.max_floor_diff >= 0 && a.q_floor != nullptr && a.db_floor != nullptr;
+      if (gate) qf = __ldg(a.q_floor + in_row0 + r);
+      for (int t = lane; t < k; t += 32) {
+        const uint64_t key = t < c ? best[static_cast<size_t>(r) * kp + t] : 0ull;
+        const bool got = key != 0ull;
+        const int64_t o = a.out_stride > 0 ? orow * a.out_stride + a.out_col + t : orow * k + t;
+        if (a.keys_out) a.keys_out[o] = key;
+        const uint32_t gi = key_index(key);
+        if (a.scores) a.scores[o] = got ? key_score(key) : __int_as_float(0xff800000);
+        if (a.idx) a.idx[o] = got ? static_cast<int32_t>(gi) : -1;
+        if (a.valid) {
+          bool ok = got;
+          if (got && gate) {
+            // a key from outside the label array (lists seeded from other database slices) cannot be flagged here
+            const int64_t fi = static_cast<int64_t>(gi) - a.floor_index_offset;
+            ok = fi >= 0 && (a.floor_n <= 0 || fi < a.floor_n) && floor_ok(qf, __ldg(a.db_floor + fi), a.max_floor_diff);
+          }
+          a.valid[o] = ok ? 1 : 0;
+        }
+      }
+    }
+    if (a.count && live) a.count[row] = a.count_add ? a.count[row] + cnt : cnt;
+  }
+}
+
 int launch_merge_topk(const MergeLaunch& a, cudaStream_t st) {
   if (a.Q <= 0 && a.any_flag_out == nullptr) return 0;
-  const unsigned grid = static_cast<unsigned>(std::max<int64_t>(1, (a.Q + kMergeWarps - 1) / kMergeWarps));
-  // 4 keys per lane cover one batch of 128 new keys (64 when a seeded list rides along)
   int lists = a.n_lists >= 0 ? a.n_lists : std::max(a.sc.s_main, a.sc.s_last);
   if (a.n_lists < 0 && a.sym_flag != nullptr) lists = std::max(lists, std::max(a.sc_sym.s_max, std::max(a.sc_sym.s_main, a.sc_sym.s_last)));
   const int64_t keys = static_cast<int64_t>(lists) * a.k;
-  if (a.Q > 0 && a.Q <= 2048 && keys >= 1024 && a.sym_flag == nullptr)
+  // few rows, many lists (a streaming query leaves one list per block of K6): one block per row, a tree of warps
+  if (a.Q > 0 && a.Q <= 2048 && keys >= 1024 && a.sym_flag == nullptr && a.row_offset == 0) {
     merge_topk_kernel<8, true><<<static_cast<unsigned>(a.Q), kRowBlockWarps * 32, 0, st>>>(a);
-  else if (keys <= (a.seed_keys ? 64 : 128))
+    return static_cast<int>(cudaGetLastError());
+  }
+  // TEMPORARY: the thread-per-row kernel above is latency-bound on its shared-memory insertion chain (measured 2.8 ms
+  // at 1M x 4 lists against the tournament's 1.3-1.9 ms): back to the warp-per-row tournament until it is reworked
+  const unsigned grid = static_cast<unsigned>(std::max<int64_t>(1, (a.Q + kMergeWarps - 1) / kMergeWarps));
+  if (keys <= (a.seed_keys ? 64 : 128))
     merge_topk_kernel<4, false><<<grid, kMergeWarps * 32, 0, st>>>(a);
   else
     merge_topk_kernel<8, false><<<grid, kMergeWarps * 32, 0, st>>>(a);

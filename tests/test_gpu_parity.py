@@ -707,7 +707,7 @@ def test_errors(eng):
     with pytest.raises(ValueError):
         _native.make_params(k=0)
     with pytest.raises(ValueError):
-        _native.make_params(k=65)
+        _native.make_params(k=_native.MAX_K_TOTAL + 1)
     x = torch.zeros(4, 64, device="cuda", dtype=torch.bfloat16)
     p = _native.make_params(k=3)
     with pytest.raises(_native.SemgateError):
@@ -1182,7 +1182,8 @@ def test_k_above_64_runs_as_several_sweeps(eng, k, cg, Q, N, D):
     parity.check_decisions_exact(O.compact(got), ts[:N], fl32[:N], 3.0, 0, q_ts=ts[:Q], q_floors=fl32[:Q])
     assert np.array_equal(got["keys"], O.pack_keys(got["scores"], got["idx"]))
     # the first 64 columns are the single-sweep answer, bit for bit
-    one = run_gpu(eng, desc[:Q], desc[:N], 64, thr, 3.0, ts[:Q], ts[:N], fl32[:Q], fl32[:N], mfd=0, cg=cg)
+    # (a handful of query rows would take the streaming kernel, whose fp32 sums round differently: pin the tile form)
+    one = run_gpu(eng, desc[:Q], desc[:N], 64, thr, 3.0, ts[:Q], ts[:N], fl32[:Q], fl32[:N], mfd=0, cg=cg or 1)
     assert np.array_equal(one["idx"], got["idx"][:, :64]) and np.array_equal(one["scores"], got["scores"][:, :64])
     if k == 100:
         # a threshold that leaves some rows short of 64, some between 64 and k, some full: later passes must add
@@ -1218,11 +1219,16 @@ def test_k_above_64_through_the_mirrored_classes_and_host_abi(eng):
     assert np.array_equal(q, arr.query_idx) and np.array_equal(m, arr.match_idx) and np.array_equal(s, arr.similarity)
     assert np.array_equal(v, arr.is_valid)
     # query(): k above the database size comes back with every admissible keyframe, like the reference's slice
-    res = spr.vpr.query(desc[7], timestamp=float(ts[7]), k=5000, min_time_gap=4.0)
+    res = spr.vpr.query(desc[7], timestamp=float(ts[7]), k=1000, min_time_gap=4.0)
     want = int((np.abs(ts - ts[7]) >= 4.0).sum())
-    assert len(res) == min(want, _native.MAX_K_TOTAL) or len(res) == want
+    assert len(res) == min(want, 1000)
     sims = np.array([r.similarity for r in res])
     assert np.all(np.diff(sims) <= 0)
+    small = SemanticPlaceRecognition('mixvpr', 'cuda', similarity_threshold=-1.0, min_time_gap=0.0, descriptor_dim=d)
+    for i in range(90):
+        small.vpr.descriptors.append(PlaceDescriptor(float(ts[i]), desc[i], floor_label=int(fl[i])))
+    every = small.vpr.query(desc[200], timestamp=None, k=5000)          # k beyond the database: all 90 come back
+    assert len(every) == 90 and len({m.match_idx for m in every}) == 90
     assert spr.find_loop_closures(k=0) == []
     with pytest.raises(ValueError):
         spr.find_loop_closures(k=-1)
@@ -1390,7 +1396,8 @@ def test_run_table_is_shared_by_sizes_with_the_same_tile_count(eng):
     desc, ts, fl = synthetic.make_case(1300, 128, 3, seed=4)
     fl32 = fl.astype(np.int32)
     for n in (1025, 1026, 1100, 1279, 1280, 1281):
-        args = (desc[:n], desc[:n], 15, 0.35, 5.0, ts[:n], ts[:n], fl32[:n], fl32[:n])
+        x, t, f = desc[:n], ts[:n], fl32[:n]         # the same objects on both sides: aliased on the device
+        args = (x, x, 15, 0.35, 5.0, t, t, f, f)
         a = run_gpu(eng, *args, mfd=0, cg=2, sym=1)
         b = run_gpu(eng, *args, mfd=0, cg=2, sym=-1)
         assert a["mode"] == 1 and b["mode"] == 0

@@ -1,0 +1,103 @@
+"""Small shapes of every kernel variant, for compute-sanitizer (one --tool per gpurun call):
+
+    python tools/sanitize_target.py && compute-sanitizer --tool memcheck python tools/sanitize_target.py
+
+Variants: K1 (block / cluster form), K2 <1,1>, <2,1>, <2,2>, symmetric <2,1,SYM> (run table, super-rows, overflow ->
+armed full sweep, one part of a split), multi-pass k > 64, dense output, K3 (thread-per-row, block-per-row, peers'
+row slice), K4 (+ valid-only, row slice), statistics, gate, K5 re-rank + select, K6 streaming query, spatial join.
+Every result is compared with the plain path where one exists, so a silent corruption also fails the run.
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "multi-level-indoor-slam_b200"))
+
+import numpy as np
+import torch
+
+from semgate import _native, synthetic
+
+
+def main():
+    eng = _native.get_engine(0)
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    # K1
+    for n, d in ((37, 100), (64, 4096), (5, 8448), (3, 49152)):
+        eng.normalize_cast(torch.randn((n, d), device=dev))
+    desc, ts, fl = synthetic.make_case(900, 128, 3, seed=1)
+    fl = fl.astype(np.int32)
+    xb = eng.normalize_cast(t(desc))
+    tts, tfl = t(ts), t(fl)
+    kw = dict(k=25, similarity_threshold=0.3, min_time_gap=5.0, max_floor_diff=0)
+    full = eng.gated_topk(xb, xb, _native.make_params(symmetric=-1, cta_group=1, **kw), q_ts=tts, db_ts=tts, q_floor=tfl, db_floor=tfl, want_keys=True)
+    for cg in (2, 4):
+        r = eng.gated_topk(xb, xb, _native.make_params(symmetric=-1, cta_group=cg, **kw), q_ts=tts, db_ts=tts, q_floor=tfl, db_floor=tfl, want_keys=True)
+        assert torch.equal(r.keys, full.keys), cg
+    # rectangular, ragged, mask mode
+    r = eng.gated_topk(xb[:300], xb[:700], _native.make_params(gate_mode=_native.GATE_MASK, cta_group=2, **kw), q_ts=tts[:300].contiguous(),
+                       db_ts=tts[:700].contiguous(), q_floor=tfl[:300].contiguous(), db_floor=tfl[:700].contiguous())
+    # symmetric: run table, super-row formula, one part of three, overflow -> armed full sweep
+    for table in ("1", "0"):
+        os.environ["SEMGATE_SYM_TABLE"] = table
+        r = eng.gated_topk(xb, xb, _native.make_params(symmetric=1, cta_group=2, **kw), q_ts=tts, db_ts=tts, q_floor=tfl, db_floor=tfl, want_keys=True)
+        assert eng.last_sweep_mode()[0] == 1 and torch.equal(r.keys, full.keys), table
+        parts = [eng.gated_topk(xb, xb, _native.make_params(symmetric=1, cta_group=2, part_index=g, part_count=3, **kw), q_ts=tts, db_ts=tts,
+                                q_floor=tfl, db_floor=tfl, want_keys=True, want_lists=False).keys for g in range(3)]
+        m = eng.merge_topk(torch.stack(parts), 25, q_floor=tfl, db_floor_all=tfl, max_floor_diff=0, want_keys=True)
+        assert torch.equal(m.keys, full.keys), ("parts", table)
+    os.environ.pop("SEMGATE_SYM_TABLE")
+    kw_all = dict(kw, similarity_threshold=-np.inf, min_time_gap=0.0)
+    a = eng.gated_topk(xb, xb, _native.make_params(symmetric=1, cta_group=2, **kw_all), q_ts=tts, db_ts=tts, q_floor=tfl, db_floor=tfl, want_keys=True)
+    mode = eng.last_sweep_mode()[0]
+    b = eng.gated_topk(xb, xb, _native.make_params(symmetric=-1, cta_group=2, **kw_all), q_ts=tts, db_ts=tts, q_floor=tfl, db_floor=tfl, want_keys=True)
+    assert torch.equal(a.keys, b.keys), "overflow path"
+    print("symmetric sweep with an all-admitting threshold ran in mode", mode)
+    # multi-pass k > 64, dense output
+    r = eng.gated_topk(xb[:200], xb, _native.make_params(k=100, similarity_threshold=-0.05, min_time_gap=5.0, cta_group=1), q_ts=tts[:200].contiguous(), db_ts=tts)
+    assert int(r.count.max()) > 64
+    eng.similarity_matrix(xb[:130], xb[:300])
+    # K6 + block-per-row K3
+    big, bts, bfl = synthetic.make_case(6000, 256, 3, seed=2)
+    bb = eng.normalize_cast(t(big))
+    r6 = eng.gated_topk(bb[:2].contiguous(), bb, _native.make_params(k=25), q_ts=t(bts[:2]), db_ts=t(bts))
+    r2 = eng.gated_topk(bb[:2].contiguous(), bb, _native.make_params(k=25, cta_group=1), q_ts=t(bts[:2]), db_ts=t(bts))
+    assert torch.equal(r6.idx, r2.idx)
+    # K3 peers' row slice + flags, K4 forms, statistics
+    keys = torch.stack(parts)
+    bufs = []
+    for g in range(3):
+        bbuf = torch.zeros((900 * 25 + 8,), dtype=torch.int64, device=dev)
+        bbuf[:900 * 25] = keys[g].reshape(-1)
+        bufs.append(bbuf)
+    table_t = torch.tensor([p.data_ptr() for p in bufs], dtype=torch.int64, device=dev)
+    flag = torch.zeros((1,), dtype=torch.int32, device=dev)
+    mine = eng.merge_topk_peers_rows(table_t.data_ptr(), 3, 900, 25, 300, 300, q_floor=tfl, db_floor_all=tfl, max_floor_diff=0,
+                                     want_keys=True, flag_offset=900 * 25, any_flag=flag)
+    assert torch.equal(mine.keys, full.keys[300:600]) and int(flag.item()) == 0
+    oq, om, os_, ov, tot = eng.compact(full)
+    eng.compact(full, valid_only=True)
+    eng.compact(mine, query_offset=300)
+    eng.candidate_stats(os_, ov, tot)
+    n_c = int(tot.item())
+    eng.gate_candidates(tfl, oq[:n_c].contiguous(), om[:n_c].contiguous(), 0)
+    # one-call sweep (eager form; the graph form is a replay of the same launches)
+    eng.find_loop_closures_device(xb, _native.make_params(**kw), ts=tts, floor=tfl, use_graph=False)
+    # K5 re-rank + select
+    feats, _ = synthetic.make_local_features(6, 40, 64, seed=3)
+    fb = eng.normalize_cast(t(feats.reshape(-1, 64))).view(6, 40, -1)
+    qi = torch.tensor([0, 0, 1, 2, 5, -1], dtype=torch.int32, device=dev)
+    mi = torch.tensor([1, 2, 3, 4, 0, 2], dtype=torch.int32, device=dev)
+    cross, comb = eng.rerank_scores(fb, qi, mi, torch.rand(6, device=dev))
+    eng.rerank_select(torch.arange(12, dtype=torch.int32, device=dev).view(2, 6), torch.rand((2, 6), device=dev),
+                      torch.tensor([6, 4], dtype=torch.int32, device=dev), 3)
+    # spatial join
+    pos = np.cumsum(np.random.default_rng(0).normal(size=(600, 3)) * 0.3, axis=0)
+    eng.spatial_candidates_host(pos, 2.0, 50)
+    torch.cuda.synchronize()
+    print("sanitize_target ok")
+
+
+if __name__ == "__main__":
+    main()
