@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "semgate", "libsemgate.so")
 SOURCES = ["api.cu", "gated_topk.cu", "kernels.cu", "spatial.cu", "rerank.cu", "stream_query.cu"]
-HEADERS = ["common.cuh", "ptx.cuh", "gated_topk.cuh", "merge.cuh", "launch.h", os.path.join("..", "..", "include", "semgate.h")]
+HEADERS = ["common.cuh", "ptx.cuh", "gated_topk.cuh", "merge.cuh", "sortnet.cuh", "launch.h", os.path.join("..", "..", "include", "semgate.h")]
 
 
 def _nvcc() -> str:

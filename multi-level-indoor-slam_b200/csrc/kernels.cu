@@ -6,6 +6,7 @@
 //   gate_candidates   : SemanticLoopClosureGate over explicit pairs     (loop_closure_gate.py:60-126)
 #include "launch.h"
 #include "merge.cuh"
+#include "sortnet.cuh"
 
 #include <cuda_bf16.h>
 #include <algorithm>
@@ -289,38 +290,62 @@ merge_topk_kernel(const MergeLaunch a) {
   }
 }
 
-// K3, thread-per-row form (the common case: many rows).  The warp-per-row tournament above spends ~13 warp
-// instructions per key (1M rows x 4 lists: 1.3 ms, 0.12 of the copy bandwidth, instruction-issue bound); here 32 rows
-// share every instruction.  A warp stages one list of its 32 rows in shared memory with coalesced loads (a row's
-// list is k contiguous keys), then every thread inserts its own row's keys into its own list, kept sorted
-// descending in shared memory (odd stride: conflict-free): one compare against the list's last key rejects most
-// candidates once the list is full, an insertion shifts the tail.  Output rows are written warp-cooperatively
-// (coalesced).  Same inputs and outputs as merge_topk_kernel.
-__device__ __forceinline__ void sorted_insert(uint64_t* __restrict__ mine, int& cnt, uint64_t& minkey, int k, uint64_t key) {
-  int pos;
-  if (cnt == k) {
-    if (key <= minkey) return;
-    pos = k - 1;
-  } else {
-    pos = cnt++;
-  }
-  while (pos > 0) {
-    const uint64_t prev = mine[pos - 1];
-    if (prev >= key) break;
-    mine[pos] = prev;
-    --pos;
-  }
-  mine[pos] = key;
-  if (cnt == k) minkey = mine[k - 1];
+// K3, thread-per-row form on register sorting networks (k <= 32, the common case: many rows).
+// The warp-per-row tournament above spends ~13 warp instructions per key (1M rows x 4 lists: 1.3 ms at boost clocks,
+// 0.12 of the copy bandwidth, instruction-issue bound).  Here 32 rows share every instruction and nothing depends on a
+// data-dependent index: a warp stages one list of its 32 rows in shared memory with coalesced loads (a row's list is
+// k contiguous keys), every thread pulls its own row's 32 slots into registers, sorts them with Batcher's odd-even
+// merge network (191 compare-exchanges, all static), folds them into its running sorted top-32 with one
+// max-against-the-reverse step (the result is bitonic) and a 5-stage bitonic merge (80 compare-exchanges).  About
+// 1 900 warp instructions per list for 32 rows, no shared-memory latency chain, no divergence.  (A first thread-per-row
+// version kept the running list sorted in shared memory by shifting: 2.8 ms for the same problem, bound by the
+// LDS -> compare -> STS chain.)  The symmetric sweep's per-keyframe candidate buffers (unsorted, up to sym_cap keys)
+// are first filtered against the row's k-th key by the whole warp with coalesced loads; only the survivors, packed
+// 32 at a time, go through the network.  Same inputs and outputs as merge_topk_kernel.
+__device__ __forceinline__ void ce_desc(uint64_t& a, uint64_t& b) {     // afterwards a >= b
+  const bool sw = a < b;
+  const uint64_t hi = sw ? b : a, lo = sw ? a : b;
+  a = hi; b = lo;
 }
 
-template <int ROWS>
-__global__ void __launch_bounds__(ROWS)
-merge_rows_kernel(const MergeLaunch a) {
-  extern __shared__ uint64_t mr_smem[];
-  const int k = a.k, kp = k | 1;
-  uint64_t* tile = mr_smem;                                   // [ROWS][kp] staging, rows of this warp only
-  uint64_t* best = mr_smem + static_cast<size_t>(ROWS) * kp;  // [ROWS][kp] every thread's sorted list
+// Batcher's odd-even merge sort, 32 inputs, descending: the compare-exchange list is generated (tools/gen_sortnet.py)
+// with literal indices -- a loop nest with computed bounds does not unroll and sends the keys to local memory
+__device__ __forceinline__ void sort32_desc(uint64_t (&c)[32]) {
+#define SEMGATE_CE(x, y) ce_desc(c[x], c[y]);
+  SEMGATE_SORT32_DESC(SEMGATE_CE)
+#undef SEMGATE_CE
+}
+
+// a bitonic sequence of 32 -> sorted descending
+__device__ __forceinline__ void bitonic_merge32_desc(uint64_t (&c)[32]) {
+#pragma unroll
+  for (int stride = 16; stride >= 1; stride >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if ((i & stride) == 0) ce_desc(c[i], c[i | stride]);
+    }
+  }
+}
+
+// this thread's staged row (32 slots in shared memory) -> registers -> sorting network -> folded into its running top-32
+__device__ __forceinline__ void fold_row(const uint64_t* __restrict__ mine, uint64_t (&best)[32]) {
+  uint64_t cur[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) cur[i] = mine[i];
+  __syncwarp();                                           // the staging rows may be refilled
+  sort32_desc(cur);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) best[i] = best[i] > cur[31 - i] ? best[i] : cur[31 - i];    // best desc, cur reversed: bitonic
+  bitonic_merge32_desc(best);
+}
+
+constexpr int kNetRows = 128;      // rows (= threads) per block
+constexpr int kNetPitch = 33;      // staging row pitch in keys (odd: conflict-free 64-bit accesses)
+
+__global__ void __launch_bounds__(kNetRows)
+merge_net_kernel(const MergeLaunch a) {
+  __shared__ uint64_t tile[kNetRows * kNetPitch];          // staging, a warp only touches its own 32 rows
+  const int k = a.k;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (a.any_flag_out != nullptr && a.list_ptrs != nullptr && blockIdx.x == 0 && warp == 0) {
     uint32_t f = 0;
@@ -329,12 +354,13 @@ merge_rows_kernel(const MergeLaunch a) {
     if (lane == 0) *a.any_flag_out = f;
   }
   if (a.sym_flag_copy != nullptr && a.sym_flag != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *a.sym_flag_copy = *a.sym_flag;
-  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * ROWS;
-  if (row0 >= a.Q) return;
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kNetRows;
+  const int64_t wrow0 = row0 + warp * 32;                  // first row of this warp
+  if (wrow0 >= a.Q) return;
   const int64_t in_row0 = row0 + a.row_offset;
   const bool sym = a.sym_flag != nullptr && (a.sym_force || *a.sym_flag == 0u);
 
-  // where the lists of this block's rows live (uniform over the block: ROWS divides the rows of an m-block)
+  // where the lists of this block's rows live (uniform over the block: kNetRows divides the rows of an m-block)
   int n_lists = a.n_lists;
   const uint64_t* base0 = a.keys_in + in_row0 * a.row_stride;   // list 0 of row0
   int64_t row_pitch = a.row_stride, list_stride = a.list_stride;
@@ -354,73 +380,95 @@ merge_rows_kernel(const MergeLaunch a) {
     }
   }
 
-  const int r_mine = warp * 32 + lane;                 // this thread's row inside the block
-  const int64_t row = row0 + r_mine;
-  const bool live = row < a.Q;
-  uint64_t* mine = best + static_cast<size_t>(r_mine) * kp;
-  int cnt = 0;
-  uint64_t minkey = 0;
-  if (row0 + warp * 32 < a.Q) {
-    const int rows_here = static_cast<int>(min(static_cast<int64_t>(32), a.Q - (row0 + warp * 32)));
-    // lists: g = -1 is the seeded list (one more list per row, local rows), then the n_lists lists; each is k keys per
-    // row, `pitch` keys between rows: staged coalesced by the warp for its 32 rows, consumed per thread
-    for (int g = a.seed_keys != nullptr ? -1 : 0; g < n_lists; ++g) {
-      const uint64_t* src_row0;
-      int64_t pitch = k;
-      if (g < 0) src_row0 = a.seed_keys + row0 * k;
-      else if (a.list_ptrs != nullptr) src_row0 = a.list_ptrs[g] + in_row0 * k;
-      else { src_row0 = base0 + g * list_stride; pitch = row_pitch; }
-#pragma unroll 4
-      for (int rr = 0; rr < 32; ++rr) {
-        const uint64_t* src = src_row0 + (static_cast<int64_t>(warp) * 32 + rr) * pitch;
-        for (int j = lane; j < k; j += 32) tile[(warp * 32 + rr) * kp + j] = rr < rows_here ? __ldg(src + j) : 0ull;
-      }
-      __syncwarp();
-      if (live) {
-        const uint64_t* t = tile + static_cast<size_t>(r_mine) * kp;
-        for (int j = 0; j < k; ++j) {
-          const uint64_t key = t[j];
-          if (key != 0ull) sorted_insert(mine, cnt, minkey, k, key);
-        }
-      }
-      __syncwarp();
-    }
-    if (sym && live) {
-      // column-direction candidates of the symmetric sweep: this keyframe's own buffer
-      const int extra = static_cast<int>(min(a.sym_cnt[row], static_cast<uint32_t>(a.sym_cap)));
-      const uint64_t* buf = a.sym_ovf + row * a.sym_cap;
-      for (int e = 0; e < extra; ++e) sorted_insert(mine, cnt, minkey, k, __ldg(buf + e));
+  const int rows_here = static_cast<int>(min(static_cast<int64_t>(32), a.Q - wrow0));
+  uint64_t* wtile = tile + static_cast<size_t>(warp) * 32 * kNetPitch;
+  uint64_t* mine = wtile + static_cast<size_t>(lane) * kNetPitch;
+  uint64_t best[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) best[i] = 0ull;
+
+  // lists: g = -1 is the seeded list (one more list per row, local rows), then the n_lists lists; each is k keys per
+  // row, `pitch` keys between rows
+  for (int g = a.seed_keys != nullptr ? -1 : 0; g < n_lists; ++g) {
+    const uint64_t* src_row0;
+    int64_t pitch = k;
+    if (g < 0) src_row0 = a.seed_keys + row0 * k;
+    else if (a.list_ptrs != nullptr) src_row0 = a.list_ptrs[g] + in_row0 * k;
+    else { src_row0 = base0 + g * list_stride; pitch = row_pitch; }
+#pragma unroll 8
+    for (int rr = 0; rr < 32; ++rr) {
+      const uint64_t* src = src_row0 + (static_cast<int64_t>(warp) * 32 + rr) * pitch;
+      wtile[rr * kNetPitch + lane] = (rr < rows_here && lane < k) ? __ldg(src + lane) : 0ull;
     }
     __syncwarp();
-    // outputs, one row at a time by the whole warp (coalesced)
-    for (int rr = 0; rr < 32; ++rr) {
-      const int r = warp * 32 + rr;
-      const int64_t orow = row0 + r;
-      if (orow >= a.Q) break;
-      const int c = __shfl_sync(0xffffffffu, cnt, rr);
-      int32_t qf = kFloorNone;
-      const bool gate = a.valid != nullptr && a.max_floor_diff >= 0 && a.q_floor != nullptr && a.db_floor != nullptr;
-      if (gate) qf = __ldg(a.q_floor + in_row0 + r);
-      for (int t = lane; t < k; t += 32) {
-        const uint64_t key = t < c ? best[static_cast<size_t>(r) * kp + t] : 0ull;
-        const bool got = key != 0ull;
-        const int64_t o = a.out_stride > 0 ? orow * a.out_stride + a.out_col + t : orow * k + t;
-        if (a.keys_out) a.keys_out[o] = key;
-        const uint32_t gi = key_index(key);
-        if (a.scores) a.scores[o] = got ? key_score(key) : __int_as_float(0xff800000);
-        if (a.idx) a.idx[o] = got ? static_cast<int32_t>(gi) : -1;
-        if (a.valid) {
-          bool ok = got;
-          if (got && gate) {
-            // a key from outside the label array (lists seeded from other database slices) cannot be flagged here
-            const int64_t fi = static_cast<int64_t>(gi) - a.floor_index_offset;
-            ok = fi >= 0 && (a.floor_n <= 0 || fi < a.floor_n) && floor_ok(qf, __ldg(a.db_floor + fi), a.max_floor_diff);
+    fold_row(mine, best);
+  }
+
+  if (sym) {
+    // Column-direction candidates of the symmetric sweep: keyframe r owns min(sym_cnt[r], sym_cap) unsorted keys.  Most
+    // are stale (appended against an early, low bound): the warp walks each of its rows' buffers with coalesced loads,
+    // keeps what beats the row's current 32nd key and packs the survivors into the staging row, 32 at most per pass.
+    const int64_t row = wrow0 + lane;
+    const int extra = lane < rows_here ? static_cast<int>(min(a.sym_cnt[row], static_cast<uint32_t>(a.sym_cap))) : 0;
+    int done = 0;                                          // keys of this lane's row consumed so far
+    while (__any_sync(0xffffffffu, done < extra)) {
+      // the bar: this row's 32nd best key so far (0 while it has fewer).  k <= 32, so nothing below it can reach the
+      // top k; a literal index on purpose: best[k - 1] would be a data-dependent index and push the keys out of registers
+      const uint64_t kth = best[31];
+      for (int rr = 0; rr < 32; ++rr) {
+        const int ex = __shfl_sync(0xffffffffu, extra, rr);
+        int e0 = __shfl_sync(0xffffffffu, done, rr);
+        const uint64_t bar = __shfl_sync(0xffffffffu, kth, rr);
+        int count = 0;
+        if (e0 < ex) {
+          const uint64_t* buf = a.sym_ovf + (wrow0 + rr) * a.sym_cap;
+          while (e0 < ex) {
+            const uint64_t key = e0 + lane < ex ? __ldg(buf + e0 + lane) : 0ull;
+            const bool keep = key > bar;
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);
+            const int n = __popc(m);
+            if (count + n > 32) break;                      // does not fit any more: next pass (count > 0 here)
+            if (keep) wtile[rr * kNetPitch + count + __popc(m & ((1u << lane) - 1u))] = key;
+            count += n;
+            e0 += 32;
           }
-          a.valid[o] = ok ? 1 : 0;
         }
+        if (lane >= count) wtile[rr * kNetPitch + lane] = 0ull;
+        if (lane == rr) done = min(e0, ex);
+      }
+      __syncwarp();
+      fold_row(mine, best);
+    }
+  }
+
+  // outputs: registers -> staging rows -> one row at a time by the whole warp (coalesced)
+#pragma unroll
+  for (int i = 0; i < 32; ++i) mine[i] = best[i];
+  __syncwarp();
+  const bool gate = a.valid != nullptr && a.max_floor_diff >= 0 && a.q_floor != nullptr && a.db_floor != nullptr;
+  for (int rr = 0; rr < rows_here; ++rr) {
+    const int64_t orow = wrow0 + rr;
+    const uint64_t key = lane < k ? wtile[rr * kNetPitch + lane] : 0ull;
+    const bool got = key != 0ull;
+    const int c = __popc(__ballot_sync(0xffffffffu, got));
+    if (lane < k) {
+      const int64_t o = a.out_stride > 0 ? orow * a.out_stride + a.out_col + lane : orow * k + lane;
+      if (a.keys_out) a.keys_out[o] = key;
+      const uint32_t gi = key_index(key);
+      if (a.scores) a.scores[o] = got ? key_score(key) : __int_as_float(0xff800000);
+      if (a.idx) a.idx[o] = got ? static_cast<int32_t>(gi) : -1;
+      if (a.valid) {
+        bool ok = got;
+        if (got && gate) {
+          // a key from outside the label array (lists seeded from other database slices) cannot be flagged here
+          const int64_t fi = static_cast<int64_t>(gi) - a.floor_index_offset;
+          ok = fi >= 0 && (a.floor_n <= 0 || fi < a.floor_n) &&
+               floor_ok(__ldg(a.q_floor + in_row0 + warp * 32 + rr), __ldg(a.db_floor + fi), a.max_floor_diff);
+        }
+        a.valid[o] = ok ? 1 : 0;
       }
     }
-    if (a.count && live) a.count[row] = a.count_add ? a.count[row] + cnt : cnt;
+    if (a.count && lane == 0) a.count[orow] = a.count_add ? a.count[orow] + c : c;
   }
 }
 
@@ -434,8 +482,11 @@ int launch_merge_topk(const MergeLaunch& a, cudaStream_t st) {
     merge_topk_kernel<8, true><<<static_cast<unsigned>(a.Q), kRowBlockWarps * 32, 0, st>>>(a);
     return static_cast<int>(cudaGetLastError());
   }
-  // TEMPORARY: the thread-per-row kernel above is latency-bound on its shared-memory insertion chain (measured 2.8 ms
-  // at 1M x 4 lists against the tournament's 1.3-1.9 ms): back to the warp-per-row tournament until it is reworked
+  if (a.k <= 32) {          // thread-per-row on register sorting networks (kNetRows divides the rows of an m-block)
+    const unsigned grid = static_cast<unsigned>(std::max<int64_t>(1, (a.Q + kNetRows - 1) / kNetRows));
+    merge_net_kernel<<<grid, kNetRows, 0, st>>>(a);
+    return static_cast<int>(cudaGetLastError());
+  }
   const unsigned grid = static_cast<unsigned>(std::max<int64_t>(1, (a.Q + kMergeWarps - 1) / kMergeWarps));
   if (keys <= (a.seed_keys ? 64 : 128))
     merge_topk_kernel<4, false><<<grid, kMergeWarps * 32, 0, st>>>(a);

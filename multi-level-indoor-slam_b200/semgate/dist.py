@@ -88,7 +88,8 @@ class ShardedRetrieval:
         self._peer_ok = None       # agreed by all ranks at first use
         self.peer_error = None     # why "auto" fell back, if it did
         self.last_all_pairs = None # how the last sweep_all_pairs ran
-        self._flag_host = []       # pinned int32 words for deferred overflow checks (recycled)
+        self._flag_host = None     # pinned int32 words for deferred overflow checks (one block, slots recycled)
+        self._flag_next = 0
 
     # -- peer-memory exchange ----------------------------------------------------
     def _symm_keys(self, Q: int, k: int, device):
@@ -262,9 +263,17 @@ class ShardedRetrieval:
         sym = self._param(params, "symmetric")
         wanted = sym == 1 or (sym == 0 and n >= 8192 and x_bf16.shape[1] >= 1024)
 
+        def make_rows_params(off):
+            p = make_params(off)               # a row shard is not an all-pairs sweep: never symmetric
+            if hasattr(p, "symmetric"):
+                p.symmetric = -1
+            else:
+                p["symmetric"] = -1
+            return p
+
         def rows():
             lo, hi = shard_bounds(n, self.world, self.rank)
-            r = self.sweep(x_bf16, x_bf16[lo:hi], make_params, lo, q_ts=ts, db_ts_shard=None if ts is None else ts[lo:hi],
+            r = self.sweep(x_bf16, x_bf16[lo:hi], make_rows_params, lo, q_ts=ts, db_ts_shard=None if ts is None else ts[lo:hi],
                            q_floor=floor, db_floor_shard=None if floor is None else floor[lo:hi], db_floor_all=floor,
                            max_floor_diff=max_floor_diff, gather=gather)
             return self._finish(r, compact)
@@ -298,7 +307,14 @@ class ShardedRetrieval:
         import torch
         if any_flag.device.type != "cuda":
             return any_flag, None
-        host = torch.empty((1,), dtype=torch.int32, pin_memory=True)
+        # one pinned block for all flags, slots handed out round-robin (allocating pinned memory per step would cost
+        # a millisecond and synchronise); 4096 sweeps may be pending before a slot comes round again
+        if self._flag_host is None:
+            self._flag_host = torch.zeros((4096,), dtype=torch.int32, pin_memory=True)
+            self._flag_next = 0
+        i = self._flag_next
+        self._flag_next = (i + 1) % self._flag_host.shape[0]
+        host = self._flag_host[i:i + 1]
         host.copy_(any_flag, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
