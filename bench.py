@@ -942,9 +942,9 @@ def run_ours(args):
 
     if world == 1 and not args.no_extra:
         flops_step = roofline["flops_per_launch"]
-        for name, fn in (("sustained", lambda: sustained_leg(torch, eng, lambda: step(), 2.2, flops_step, sus_tf, local)),
-                         ("companions", lambda: companions_leg(torch, eng, peak_hbm)),
-                         ("c1", lambda: c1_leg(torch, eng, peak_tf))):
+        for name, fn in (("companions", lambda: companions_leg(torch, eng, peak_hbm)),
+                         ("c1", lambda: c1_leg(torch, eng, peak_tf)),
+                         ("sustained", lambda: sustained_leg(torch, eng, lambda: step(), 2.2, flops_step, sus_tf, local))):
             try:
                 base[name] = fn()
             except Exception as e:      # noqa: BLE001

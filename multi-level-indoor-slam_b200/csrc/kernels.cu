@@ -327,12 +327,12 @@ __device__ __forceinline__ void bitonic_merge32_desc(uint64_t (&c)[32]) {
   }
 }
 
-// this thread's staged row (32 slots in shared memory) -> registers -> sorting network -> folded into its running top-32
-__device__ __forceinline__ void fold_row(const uint64_t* __restrict__ mine, uint64_t (&best)[32]) {
+// this thread's packed row (its first `cnt` of 32 slots in shared memory) -> registers -> sorting network -> folded
+// into its running top-32
+__device__ __forceinline__ void fold_row(const uint64_t* __restrict__ mine, int cnt, uint64_t (&best)[32]) {
   uint64_t cur[32];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) cur[i] = mine[i];
-  __syncwarp();                                           // the staging rows may be refilled
+  for (int i = 0; i < 32; ++i) cur[i] = i < cnt ? mine[i] : 0ull;
   sort32_desc(cur);
 #pragma unroll
   for (int i = 0; i < 32; ++i) best[i] = best[i] > cur[31 - i] ? best[i] : cur[31 - i];    // best desc, cur reversed: bitonic
@@ -340,11 +340,17 @@ __device__ __forceinline__ void fold_row(const uint64_t* __restrict__ mine, uint
 }
 
 constexpr int kNetRows = 128;      // rows (= threads) per block
-constexpr int kNetPitch = 33;      // staging row pitch in keys (odd: conflict-free 64-bit accesses)
+constexpr int kNetPitch = 33;      // shared-memory row pitch in keys (odd: conflict-free 64-bit accesses)
 
+// Candidate keys reach a row from several sources: its partial lists (k slots each, mostly sparse: a run of a few tiles
+// leaves a handful of candidates), a seeded list, the symmetric sweep's buffer.  Each source is staged raw by the warp
+// (coalesced), every thread appends its row's non-empty keys to its pack row, and the network only runs when some row
+// of the warp could not take another source: the number of network passes follows the keys, not the sources.
 __global__ void __launch_bounds__(kNetRows)
 merge_net_kernel(const MergeLaunch a) {
-  __shared__ uint64_t tile[kNetRows * kNetPitch];          // staging, a warp only touches its own 32 rows
+  extern __shared__ uint64_t net_smem[];
+  uint64_t* raw = net_smem;                                            // [kNetRows][kNetPitch] staging
+  uint64_t* pack = net_smem + static_cast<size_t>(kNetRows) * kNetPitch;   // [kNetRows][kNetPitch] packed keys per row
   const int k = a.k;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (a.any_flag_out != nullptr && a.list_ptrs != nullptr && blockIdx.x == 0 && warp == 0) {
@@ -381,11 +387,13 @@ merge_net_kernel(const MergeLaunch a) {
   }
 
   const int rows_here = static_cast<int>(min(static_cast<int64_t>(32), a.Q - wrow0));
-  uint64_t* wtile = tile + static_cast<size_t>(warp) * 32 * kNetPitch;
-  uint64_t* mine = wtile + static_cast<size_t>(lane) * kNetPitch;
+  uint64_t* wraw = raw + static_cast<size_t>(warp) * 32 * kNetPitch;
+  const uint64_t* raw_mine = wraw + static_cast<size_t>(lane) * kNetPitch;
+  uint64_t* mine = pack + (static_cast<size_t>(warp) * 32 + lane) * kNetPitch;
   uint64_t best[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) best[i] = 0ull;
+  int cnt = 0;                                              // keys in this thread's pack row
 
   // lists: g = -1 is the seeded list (one more list per row, local rows), then the n_lists lists; each is k keys per
   // row, `pitch` keys between rows
@@ -395,60 +403,72 @@ merge_net_kernel(const MergeLaunch a) {
     if (g < 0) src_row0 = a.seed_keys + row0 * k;
     else if (a.list_ptrs != nullptr) src_row0 = a.list_ptrs[g] + in_row0 * k;
     else { src_row0 = base0 + g * list_stride; pitch = row_pitch; }
-#pragma unroll 8
-    for (int rr = 0; rr < 32; ++rr) {
-      const uint64_t* src = src_row0 + (static_cast<int64_t>(warp) * 32 + rr) * pitch;
-      wtile[rr * kNetPitch + lane] = (rr < rows_here && lane < k) ? __ldg(src + lane) : 0ull;
-    }
+    src_row0 += static_cast<int64_t>(warp) * 32 * pitch + lane;
+    uint64_t v[32];
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) v[rr] = (rr < rows_here && lane < k) ? __ldg(src_row0 + rr * pitch) : 0ull;   // 32 loads in flight
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) wraw[rr * kNetPitch + lane] = v[rr];
     __syncwarp();
-    fold_row(mine, best);
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      if (j < k) {
+        const uint64_t key = raw_mine[j];
+        if (key != 0ull) mine[cnt++] = key;
+      }
+    }
+    __syncwarp();                                           // the staging rows may be refilled
+    if (__any_sync(0xffffffffu, cnt > 32 - k)) {            // some row could not take another list
+      fold_row(mine, cnt, best);
+      cnt = 0;
+    }
   }
 
   if (sym) {
-    // Column-direction candidates of the symmetric sweep: keyframe r owns min(sym_cnt[r], sym_cap) unsorted keys.  Most
-    // are stale (appended against an early, low bound): the warp walks each of its rows' buffers with coalesced loads,
-    // keeps what beats the row's current 32nd key and packs the survivors into the staging row, 32 at most per pass.
+    // Column-direction candidates of the symmetric sweep: keyframe r owns min(sym_cnt[r], sym_cap) unsorted keys, 16 at
+    // a time here (two rows per load instruction).  What cannot reach the top 32 any more is dropped before packing.
     const int64_t row = wrow0 + lane;
     const int extra = lane < rows_here ? static_cast<int>(min(a.sym_cnt[row], static_cast<uint32_t>(a.sym_cap))) : 0;
-    int done = 0;                                          // keys of this lane's row consumed so far
-    while (__any_sync(0xffffffffu, done < extra)) {
-      // the bar: this row's 32nd best key so far (0 while it has fewer).  k <= 32, so nothing below it can reach the
-      // top k; a literal index on purpose: best[k - 1] would be a data-dependent index and push the keys out of registers
-      const uint64_t kth = best[31];
-      for (int rr = 0; rr < 32; ++rr) {
+    int chunks = (extra + 15) >> 4;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) chunks = max(chunks, __shfl_xor_sync(0xffffffffu, chunks, o));
+    const int half = lane >> 4, l16 = lane & 15;
+    for (int c = 0; c < chunks; ++c) {
+      if (__any_sync(0xffffffffu, cnt > 16)) {              // room for 16 more in every row?
+        fold_row(mine, cnt, best);
+        cnt = 0;
+      }
+      uint64_t v[16];
+#pragma unroll
+      for (int r2 = 0; r2 < 16; ++r2) {
+        const int rr = 2 * r2 + half;
         const int ex = __shfl_sync(0xffffffffu, extra, rr);
-        int e0 = __shfl_sync(0xffffffffu, done, rr);
-        const uint64_t bar = __shfl_sync(0xffffffffu, kth, rr);
-        int count = 0;
-        if (e0 < ex) {
-          const uint64_t* buf = a.sym_ovf + (wrow0 + rr) * a.sym_cap;
-          while (e0 < ex) {
-            const uint64_t key = e0 + lane < ex ? __ldg(buf + e0 + lane) : 0ull;
-            const bool keep = key > bar;
-            const uint32_t m = __ballot_sync(0xffffffffu, keep);
-            const int n = __popc(m);
-            if (count + n > 32) break;                      // does not fit any more: next pass (count > 0 here)
-            if (keep) wtile[rr * kNetPitch + count + __popc(m & ((1u << lane) - 1u))] = key;
-            count += n;
-            e0 += 32;
-          }
-        }
-        if (lane >= count) wtile[rr * kNetPitch + lane] = 0ull;
-        if (lane == rr) done = min(e0, ex);
+        const int e = c * 16 + l16;
+        v[r2] = e < ex ? __ldg(a.sym_ovf + (wrow0 + rr) * a.sym_cap + e) : 0ull;
+      }
+#pragma unroll
+      for (int r2 = 0; r2 < 16; ++r2) wraw[(2 * r2 + half) * kNetPitch + l16] = v[r2];
+      __syncwarp();
+      const uint64_t bar = best[31];                        // literal index on purpose (see fold_row): keys below the
+#pragma unroll                                              // row's 32nd best so far cannot reach its top k <= 32
+      for (int j = 0; j < 16; ++j) {
+        const uint64_t key = raw_mine[j];
+        if (key > bar) mine[cnt++] = key;
       }
       __syncwarp();
-      fold_row(mine, best);
     }
   }
+  if (__any_sync(0xffffffffu, cnt > 0)) fold_row(mine, cnt, best);
 
   // outputs: registers -> staging rows -> one row at a time by the whole warp (coalesced)
+  __syncwarp();
 #pragma unroll
-  for (int i = 0; i < 32; ++i) mine[i] = best[i];
+  for (int i = 0; i < 32; ++i) wraw[lane * kNetPitch + i] = best[i];
   __syncwarp();
   const bool gate = a.valid != nullptr && a.max_floor_diff >= 0 && a.q_floor != nullptr && a.db_floor != nullptr;
   for (int rr = 0; rr < rows_here; ++rr) {
     const int64_t orow = wrow0 + rr;
-    const uint64_t key = lane < k ? wtile[rr * kNetPitch + lane] : 0ull;
+    const uint64_t key = lane < k ? wraw[rr * kNetPitch + lane] : 0ull;
     const bool got = key != 0ull;
     const int c = __popc(__ballot_sync(0xffffffffu, got));
     if (lane < k) {
@@ -484,7 +504,10 @@ int launch_merge_topk(const MergeLaunch& a, cudaStream_t st) {
   }
   if (a.k <= 32) {          // thread-per-row on register sorting networks (kNetRows divides the rows of an m-block)
     const unsigned grid = static_cast<unsigned>(std::max<int64_t>(1, (a.Q + kNetRows - 1) / kNetRows));
-    merge_net_kernel<<<grid, kNetRows, 0, st>>>(a);
+    const size_t smem = 2 * static_cast<size_t>(kNetRows) * kNetPitch * sizeof(uint64_t);      // 67.6 KB: staging + pack rows
+    cudaError_t e = cudaFuncSetAttribute(merge_net_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    merge_net_kernel<<<grid, kNetRows, smem, st>>>(a);
     return static_cast<int>(cudaGetLastError());
   }
   const unsigned grid = static_cast<unsigned>(std::max<int64_t>(1, (a.Q + kMergeWarps - 1) / kMergeWarps));
