@@ -179,6 +179,7 @@ int launch_normalize_cast(const float* x, int64_t n, int d, int64_t ld, void* ou
 // common case (s*k <= 128 keys) is a single batch with P = 4.  Keys are unique
 // (distinct database rows), 0 = empty.
 constexpr int kMergeWarps = 8;
+constexpr int kGatherCap = 64;     // sparse-row fast path: at most this many non-empty keys per row (two per lane)
 
 // ROWBLOCK = false: one warp per row (8 rows per block).  ROWBLOCK = true (few rows, many lists: a
 // streaming query leaves one list per block of K6): one 32-warp block per row, a three-level tree —
@@ -192,6 +193,7 @@ merge_topk_kernel(const MergeLaunch a) {
   static_assert(P == 4 || P == 8, "keys per lane");
   __shared__ uint64_t stage[ROWBLOCK ? kRowBlockWarps * kMaxK : 1];
   __shared__ uint64_t stage2[ROWBLOCK ? 4 * kMaxK : 1];
+  __shared__ uint64_t gathered[ROWBLOCK ? 1 : kMergeWarps * kGatherCap];   // sparse rows: the row's non-empty keys
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t row = ROWBLOCK ? static_cast<int64_t>(blockIdx.x) : static_cast<int64_t>(blockIdx.x) * kMergeWarps + warp;
   // per-GPU lists read in place: OR of the peers' overflow flags (one word behind every peer's keys), so that the
@@ -229,16 +231,69 @@ merge_topk_kernel(const MergeLaunch a) {
     if (lane + 32 < k) run[1] = seed[lane + 32];
     have_run = true;
   }
+  bool done = false;
   if constexpr (!ROWBLOCK) {
-    // rows with few lists (most rows: the tail super-row is split finer than the others) take the
-    // cheaper 4-keys-per-lane network; warp-uniform choice
-    if (P == 8 && total + (have_run ? 64 : 0) <= 128)
-      merge_range<4>(base, 0, total, k, list_stride, k, lane, run, have_run, a.list_ptrs, in_row * k);
-    else
-      merge_range<P>(base, 0, total, k, list_stride, k, lane, run, have_run, a.list_ptrs, in_row * k);
-    if (sym) {
+    // Sparse rows first.  A run of a few tiles leaves a handful of candidates in its k slots, so a row's dozen lists
+    // (and its symmetric-sweep buffer) usually hold a few dozen keys between hundreds of empty slots: gather the
+    // non-empty ones (coalesced scan, ballot + prefix), and if they fit kGatherCap, rank them by counting -- every lane
+    // compares its two keys with each gathered key (a shared-memory broadcast) -- and scatter by rank.  ~10 instructions
+    // per 32 slots scanned plus ~8 per key, where the tournament below pays ~700 per batch of 256 slots.
+    uint64_t* wg = gathered + warp * kGatherCap;
+    int n = 0;
+    bool fits = true;
+    auto push = [&](uint64_t key) {
+      const bool nz = key != 0ull;
+      const uint32_t m = __ballot_sync(0xffffffffu, nz);
+      const int c = __popc(m);
+      if (n + c > kGatherCap) { fits = false; return; }
+      if (nz) wg[n + __popc(m & ((1u << lane) - 1u))] = key;
+      n += c;
+    };
+    if (have_run) { push(run[0]); if (fits) push(run[1]); }
+    for (int e0 = 0; e0 < total && fits; e0 += 32) {
+      const int e = e0 + lane;
+      uint64_t v = 0ull;
+      if (e < total) {
+        const int g = e / k, j = e - g * k;
+        v = a.list_ptrs ? a.list_ptrs[g][in_row * k + j] : base[static_cast<int64_t>(g) * list_stride + j];
+      }
+      push(v);
+    }
+    if (sym && fits) {
       const int extra = static_cast<int>(min(a.sym_cnt[row], static_cast<uint32_t>(a.sym_cap)));
-      if (extra > 0) merge_range<P>(a.sym_ovf + row * a.sym_cap, 0, extra, a.sym_cap, 0, k, lane, run, true);
+      const uint64_t* buf = a.sym_ovf + row * a.sym_cap;
+      for (int e0 = 0; e0 < extra && fits; e0 += 32) push(e0 + lane < extra ? buf[e0 + lane] : 0ull);
+    }
+    if (fits) {
+      __syncwarp();
+      const uint64_t k0 = lane < n ? wg[lane] : 0ull, k1 = lane + 32 < n ? wg[lane + 32] : 0ull;
+      int r0 = 0, r1 = 0;
+      for (int j = 0; j < n; ++j) {
+        const uint64_t x = wg[j];
+        r0 += x > k0 ? 1 : 0;
+        r1 += x > k1 ? 1 : 0;
+      }
+      __syncwarp();                                         // everybody has read the gathered keys
+      if (lane < n) wg[r0] = k0;                            // keys are unique: the ranks are a permutation of 0 .. n-1
+      if (lane + 32 < n) wg[r1] = k1;
+      __syncwarp();
+      const int keep = min(n, k);
+      run[0] = lane < keep ? wg[lane] : 0ull;
+      run[1] = lane + 32 < keep ? wg[lane + 32] : 0ull;
+      done = true;
+    }
+  }
+  if constexpr (!ROWBLOCK) {
+    if (!done) {
+      // the general case: rows with few lists take the cheaper 4-keys-per-lane network; warp-uniform choice
+      if (P == 8 && total + (have_run ? 64 : 0) <= 128)
+        merge_range<4>(base, 0, total, k, list_stride, k, lane, run, have_run, a.list_ptrs, in_row * k);
+      else
+        merge_range<P>(base, 0, total, k, list_stride, k, lane, run, have_run, a.list_ptrs, in_row * k);
+      if (sym) {
+        const int extra = static_cast<int>(min(a.sym_cnt[row], static_cast<uint32_t>(a.sym_cap)));
+        if (extra > 0) merge_range<P>(a.sym_ovf + row * a.sym_cap, 0, extra, a.sym_cap, 0, k, lane, run, true);
+      }
     }
   } else {
     const int per = (total + kRowBlockWarps - 1) / kRowBlockWarps;
@@ -502,7 +557,10 @@ int launch_merge_topk(const MergeLaunch& a, cudaStream_t st) {
     merge_topk_kernel<8, true><<<static_cast<unsigned>(a.Q), kRowBlockWarps * 32, 0, st>>>(a);
     return static_cast<int>(cudaGetLastError());
   }
-  if (a.k <= 32) {          // thread-per-row on register sorting networks (kNetRows divides the rows of an m-block)
+  // many rows, a few (possibly full) lists each, e.g. the per-GPU lists of a sharded 1M sweep: thread-per-row on register
+  // sorting networks (1M x 4 full lists: 0.98 ms against the tournament's 1.3-1.9 ms); everything else -- in particular
+  // the sparse lists of run-table sweeps -- goes to the warp-per-row kernel and its gather-and-rank fast path
+  if (a.k <= 32 && a.Q >= 65536 && lists <= 8 && a.sym_flag == nullptr) {
     const unsigned grid = static_cast<unsigned>(std::max<int64_t>(1, (a.Q + kNetRows - 1) / kNetRows));
     const size_t smem = 2 * static_cast<size_t>(kNetRows) * kNetPitch * sizeof(uint64_t);      // 67.6 KB: staging + pack rows
     cudaError_t e = cudaFuncSetAttribute(merge_net_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
