@@ -771,11 +771,19 @@ def run_ours(args):
     sampler = ClockSampler(local).start() if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    t_host0 = time.perf_counter()
     e0.record()
-    pend = [step() for _ in range(args.steps)]
+    pend = []
+    for i in range(args.steps):
+        marks[i].record()
+        pend.append(step())
+    marks[args.steps].record()
     e1.record()
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3
     barrier()
     ms = e0.elapsed_time(e1)
+    per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))
     launches = eng.launch_count - launches0
     k2_ms, k2_n = eng.profile_read()
     clocks = sampler.stop() if sampler else None
@@ -855,6 +863,10 @@ def run_ours(args):
         "scaling": "strong" if (STRONG and not ALLPAIRS) else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": workload_config(world), "queries_per_s": N_Q * args.steps / (ms * 1e-3),
         "candidates_per_step": total_candidates, "steps_overflowed": steps_overflowed, "parity": par,
+        "step_ms_distribution": {"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1],
+                                 "host_enqueue_ms_per_step": host_enqueue_ms / args.steps,
+                                 "note": "per-step CUDA-event intervals inside the timed region (diagnostic; `ms_per_step` is the "
+                                         "whole region / steps); a host slower than the GPU shows as host_enqueue > median"},
         "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks,
         "all_pairs_split": sr.last_all_pairs if world > 1 else None,
         "cta_group": args.cta_group or os.environ.get("SEMGATE_CTA_GROUP", "auto (2 for Q >= 4096)"),
