@@ -250,19 +250,33 @@ merge_topk_kernel(const MergeLaunch a) {
       n += c;
     };
     if (have_run) { push(run[0]); if (fits) push(run[1]); }
-    for (int e0 = 0; e0 < total && fits; e0 += 32) {
-      const int e = e0 + lane;
-      uint64_t v = 0ull;
-      if (e < total) {
-        const int g = e / k, j = e - g * k;
-        v = a.list_ptrs ? a.list_ptrs[g][in_row * k + j] : base[static_cast<int64_t>(g) * list_stride + j];
+    // (four loads in flight per pass: the scan is a chain of global-memory latencies otherwise)
+    for (int e0 = 0; e0 < total && fits; e0 += 128) {
+      uint64_t v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * 32 + lane;
+        v[u] = 0ull;
+        if (e < total) {
+          const int g = e / k, j = e - g * k;
+          v[u] = a.list_ptrs ? a.list_ptrs[g][in_row * k + j] : base[static_cast<int64_t>(g) * list_stride + j];
+        }
       }
-      push(v);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (fits && e0 + u * 32 < total) push(v[u]);
     }
     if (sym && fits) {
       const int extra = static_cast<int>(min(a.sym_cnt[row], static_cast<uint32_t>(a.sym_cap)));
       const uint64_t* buf = a.sym_ovf + row * a.sym_cap;
-      for (int e0 = 0; e0 < extra && fits; e0 += 32) push(e0 + lane < extra ? buf[e0 + lane] : 0ull);
+      for (int e0 = 0; e0 < extra && fits; e0 += 128) {
+        uint64_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = e0 + u * 32 + lane < extra ? buf[e0 + u * 32 + lane] : 0ull;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (fits && e0 + u * 32 < extra) push(v[u]);
+      }
     }
     if (fits) {
       __syncwarp();
@@ -657,25 +671,36 @@ compact_scatter_kernel(const float* __restrict__ scores, const int32_t* __restri
   cnts[threadIdx.x] = row < Q ? count[row] : 0;
   __syncthreads();
   const int64_t base = block_offsets[blockIdx.x];
+  if (!valid_only) {
+    // Everything is emitted: one thread per OUTPUT element.  The block's rows start at offs[]; a binary search over
+    // them finds the element's row, its position in the row follows.  Loads of different elements are independent
+    // and the stores are perfectly coalesced (a warp-per-row copy loop was a chain of latencies: 25 us for 20k rows).
+    const int total = offs[kScanBlock - 1] + cnts[kScanBlock - 1];
+    for (int o = threadIdx.x; o < total; o += kScanBlock) {
+      int lo = 0, hi = kScanBlock - 1;               // last row whose offset is <= o (rows with no entries share offsets:
+      while (lo < hi) {                              // the LAST of them is the one that owns o only if it has entries,
+        const int mid = (lo + hi + 1) >> 1;          // and a row with entries always has a larger offset than o's owner)
+        if (offs[mid] <= o) lo = mid; else hi = mid - 1;
+      }
+      const int i = o - offs[lo];
+      const int64_t src = (row0 + lo) * k + i;
+      out_q[base + o] = static_cast<int32_t>(q_offset + row0 + lo);
+      out_m[base + o] = __ldg(idx + src);
+      out_s[base + o] = __ldg(scores + src);
+      out_v[base + o] = __ldg(valid + src);
+    }
+    return;
+  }
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int r = w; r < kScanBlock && row0 + r < Q; r += (kScanBlock >> 5)) {
     const int c = cnts[r];
     int64_t o = base + offs[r];
     const int64_t src = (row0 + r) * k;
-    if (!valid_only) {                        // everything is emitted: straight coalesced copy
-      for (int i = lane; i < c; i += 32) {
-        out_q[o + i] = static_cast<int32_t>(q_offset + row0 + r);
-        out_m[o + i] = idx[src + i];
-        out_s[o + i] = scores[src + i];
-        out_v[o + i] = valid[src + i];
-      }
-      continue;
-    }
     for (int i0 = 0; i0 < c; i0 += 32) {
       const int i = i0 + lane;
       const bool live = i < c;
       const uint8_t vv = live ? valid[src + i] : 0;
-      const bool emit = live && (!valid_only || vv != 0);
+      const bool emit = live && vv != 0;
       const uint32_t ballot = __ballot_sync(0xffffffffu, emit);
       if (emit) {
         const int64_t d = o + __popc(ballot & ((1u << lane) - 1u));   // order inside the row is kept

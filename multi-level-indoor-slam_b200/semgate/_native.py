@@ -462,7 +462,7 @@ class Engine:
         om = torch.empty((cap,), dtype=torch.int32, device=dev)
         os_ = torch.empty((cap,), dtype=torch.float32, device=dev)
         ov = torch.empty((cap,), dtype=torch.uint8, device=dev)
-        total = torch.zeros((1,), dtype=torch.int64, device=dev)
+        total = torch.empty((1,), dtype=torch.int64, device=dev)     # always written by the kernels
         wsb = int(self.lib.semgate_compact_workspace_bytes(Q))
         ws = torch.empty((max(wsb, 256),), dtype=torch.uint8, device=dev)
         if query_offset:
