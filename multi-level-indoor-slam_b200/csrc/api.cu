@@ -773,7 +773,7 @@ static int compact_impl(semgate_handle_t h, const float* scores, const int32_t* 
   if (q_offset < 0 || q_offset + Q > INT32_MAX) return fail(SEMGATE_EINVAL, "compact: query index offset out of range");
   RC_TRY(launch_compact(scores, idx, valid, count, Q, k, valid_only, q_offset, out_query_idx, out_match_idx, out_similarity, out_is_valid,
                         out_total, workspace, static_cast<cudaStream_t>(stream)), "compact launch");
-  h->launches += Q > 0 ? 3 : 0;
+  h->launches += Q > 0 ? 2 : 0;      // state memset + the one-pass kernel
   return 0;
 }
 

@@ -592,7 +592,6 @@ int launch_merge_topk(const MergeLaunch& a, cudaStream_t st) {
 
 // =========================================================================== K4
 constexpr int kScanBlock = 128;     // rows per block of the count / scatter kernels (many small blocks: all SMs busy)
-constexpr int kScanThreads = 1024;  // threads of the single-block scan over the block sums
 
 __device__ __forceinline__ int block_exclusive_scan(int v, int* smem /*>=32*/, int* total) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -627,59 +626,84 @@ __device__ __forceinline__ int row_emit_count(const int32_t* __restrict__ count,
   return n;
 }
 
-__global__ void __launch_bounds__(kScanBlock)
-compact_count_kernel(const int32_t* __restrict__ count, const uint8_t* __restrict__ valid, int64_t Q, int k, bool valid_only,
-                     int64_t* __restrict__ block_sums) {
-  __shared__ int sm[32];
-  __shared__ int tot;
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * kScanBlock + threadIdx.x;
-  const int v = row < Q ? row_emit_count(count, valid, row, k, valid_only) : 0;
-  block_exclusive_scan(v, sm, &tot);
-  if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+// One pass: a block takes a ticket (its tile of kScanBlock rows), scans its rows' counts, publishes the tile's total,
+// looks back over the tiles before it for its offset ("decoupled look-back": a tile publishes first its own total,
+// then, once known, the inclusive prefix; a later tile adds totals backwards until it meets an inclusive prefix) and
+// scatters.  Tickets make the order of tiles the order in which blocks started, so every tile a block waits for is
+// already running or done.  One launch where count -> scan -> scatter were three: small sweeps are launch-bound.
+// state: [tiles] 64-bit words = value << 2 | flag (0 nothing yet, 1 tile total, 2 inclusive prefix), then the ticket
+// counter; zeroed by the caller per launch.
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
 }
-
-__global__ void __launch_bounds__(kScanThreads)
-compact_scan_kernel(int64_t* __restrict__ block_sums, int64_t nblocks, int64_t* __restrict__ out_total) {
-  // serial-in-chunks exclusive scan; nblocks = ceil(Q / kScanBlock)
-  __shared__ int sm[32];
-  __shared__ int tot;
-  int64_t carry = 0;
-  for (int64_t b0 = 0; b0 < nblocks; b0 += kScanThreads) {
-    const int64_t i = b0 + threadIdx.x;
-    const int v = i < nblocks ? static_cast<int>(block_sums[i]) : 0;
-    const int ex = block_exclusive_scan(v, sm, &tot);
-    if (i < nblocks) block_sums[i] = carry + ex;
-    carry += tot;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *out_total = carry;
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 __global__ void __launch_bounds__(kScanBlock)
-compact_scatter_kernel(const float* __restrict__ scores, const int32_t* __restrict__ idx, const uint8_t* __restrict__ valid,
-                       const int32_t* __restrict__ count, int64_t Q, int k, bool valid_only,
-                       const int64_t* __restrict__ block_offsets, int64_t q_offset, int32_t* __restrict__ out_q,
-                       int32_t* __restrict__ out_m, float* __restrict__ out_s, uint8_t* __restrict__ out_v) {
+compact_onepass_kernel(const float* __restrict__ scores, const int32_t* __restrict__ idx, const uint8_t* __restrict__ valid,
+                       const int32_t* __restrict__ count, int64_t Q, int k, bool valid_only, unsigned long long* __restrict__ state,
+                       int64_t q_offset, int32_t* __restrict__ out_q, int32_t* __restrict__ out_m, float* __restrict__ out_s,
+                       uint8_t* __restrict__ out_v, int64_t* __restrict__ out_total) {
   __shared__ int sm[32];
   __shared__ int offs[kScanBlock];
   __shared__ int cnts[kScanBlock];
-  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kScanBlock;
+  __shared__ int tot_s;
+  __shared__ unsigned tile_s;
+  __shared__ long long base_s;
+  const unsigned tiles = gridDim.x;
+  if (threadIdx.x == 0) tile_s = atomicAdd(reinterpret_cast<unsigned*>(state + tiles), 1u);
+  __syncthreads();
+  const unsigned tile = tile_s;
+  const int64_t row0 = static_cast<int64_t>(tile) * kScanBlock;
   const int64_t row = row0 + threadIdx.x;
   const int v = row < Q ? row_emit_count(count, valid, row, k, valid_only) : 0;
-  const int ex = block_exclusive_scan(v, sm, nullptr);
+  const int ex = block_exclusive_scan(v, sm, &tot_s);
   offs[threadIdx.x] = ex;
   cnts[threadIdx.x] = row < Q ? count[row] : 0;
   __syncthreads();
-  const int64_t base = block_offsets[blockIdx.x];
+  if (threadIdx.x == 0) {
+    const unsigned long long tot = static_cast<unsigned long long>(tot_s);
+    unsigned long long prefix = 0;
+    if (tile > 0) {
+      st_release_u64(state + tile, (tot << 2) | 1ull);
+      long long j = static_cast<long long>(tile) - 1;
+      uint64_t t0 = 0;
+      uint32_t spins = 0;
+      while (true) {
+        const unsigned long long sv = ld_acquire_u64(state + j);
+        if ((sv & 3ull) == 0ull) {                       // that tile has not published yet: it is running (tickets)
+          if ((++spins & 0xFFFu) == 0) {                 // bounded like every wait in this library: a bug must trap
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) __trap();
+          }
+          continue;
+        }
+        prefix += sv >> 2;
+        if ((sv & 3ull) == 2ull) break;                  // inclusive prefix: everything before is in it
+        --j;                                             // (tile 0 always publishes an inclusive prefix: j stays >= 0)
+      }
+    }
+    st_release_u64(state + tile, ((prefix + tot) << 2) | 2ull);
+    base_s = static_cast<long long>(prefix);
+    if (tile == tiles - 1) *out_total = static_cast<int64_t>(prefix + tot);
+  }
+  __syncthreads();
+  const int64_t base = base_s;
   if (!valid_only) {
     // Everything is emitted: one thread per OUTPUT element.  The block's rows start at offs[]; a binary search over
-    // them finds the element's row, its position in the row follows.  Loads of different elements are independent
-    // and the stores are perfectly coalesced (a warp-per-row copy loop was a chain of latencies: 25 us for 20k rows).
-    const int total = offs[kScanBlock - 1] + cnts[kScanBlock - 1];
+    // them finds the element's row (the last row whose offset is <= the element: rows without entries share their
+    // successor's offset and never win), its position in the row follows.  Loads of different elements are
+    // independent and the stores are perfectly coalesced.
+    const int total = tot_s;
     for (int o = threadIdx.x; o < total; o += kScanBlock) {
-      int lo = 0, hi = kScanBlock - 1;               // last row whose offset is <= o (rows with no entries share offsets:
-      while (lo < hi) {                              // the LAST of them is the one that owns o only if it has entries,
-        const int mid = (lo + hi + 1) >> 1;          // and a row with entries always has a larger offset than o's owner)
+      int lo = 0, hi = kScanBlock - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
         if (offs[mid] <= o) lo = mid; else hi = mid - 1;
       }
       const int i = o - offs[lo];
@@ -715,7 +739,7 @@ compact_scatter_kernel(const float* __restrict__ scores, const int32_t* __restri
 }
 
 size_t compact_workspace_bytes(int64_t Q) {
-  return static_cast<size_t>((Q + kScanBlock - 1) / kScanBlock + 1) * sizeof(int64_t);
+  return static_cast<size_t>((Q + kScanBlock - 1) / kScanBlock + 2) * sizeof(int64_t);
 }
 
 int launch_compact(const float* scores, const int32_t* idx, const uint8_t* valid, const int32_t* count, int64_t Q, int k,
@@ -723,11 +747,11 @@ int launch_compact(const float* scores, const int32_t* idx, const uint8_t* valid
                    int64_t* out_total, void* workspace, cudaStream_t st) {
   if (Q <= 0) return static_cast<int>(cudaMemsetAsync(out_total, 0, sizeof(int64_t), st));
   const int64_t nb = (Q + kScanBlock - 1) / kScanBlock;
-  int64_t* bs = static_cast<int64_t*>(workspace);
-  compact_count_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, st>>>(count, valid, Q, k, valid_only, bs);
-  compact_scan_kernel<<<1, kScanThreads, 0, st>>>(bs, nb, out_total);
-  compact_scatter_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, st>>>(scores, idx, valid, count, Q, k, valid_only, bs, q_offset,
-                                                                          out_q, out_m, out_s, out_v);
+  unsigned long long* state = static_cast<unsigned long long*>(workspace);
+  cudaError_t e = cudaMemsetAsync(state, 0, static_cast<size_t>(nb + 1) * sizeof(unsigned long long), st);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  compact_onepass_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, st>>>(scores, idx, valid, count, Q, k, valid_only, state, q_offset,
+                                                                          out_q, out_m, out_s, out_v, out_total);
   return static_cast<int>(cudaGetLastError());
 }
 
