@@ -163,34 +163,41 @@ class ClockSampler:
 
     def _pump(self):
         nv = self.nv
-        names = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
-                 ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
-                 ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
-                 ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
         while self.running:
             try:
                 mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
                 util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
                 watts = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
                 mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                self.samples.append((float(mhz), float(watts), float(util)))
-                for nm, bit in names:
-                    if mask & bit:
-                        self.reasons.add(nm)
+                self.samples.append((float(mhz), float(watts), float(util), time.perf_counter(), int(mask)))
             except Exception:
                 pass
             time.sleep(0.002)
 
-    def stop(self):
+    def window(self, t0: float, t1: float):
+        """Summary of the samples taken between two time.perf_counter() stamps (the sampler itself is started before
+        the warm-up, so that NVML's first-call costs and its driver locks stay out of the timed region)."""
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        rows = [r for r in list(self.samples) if t0 <= r[3] <= t1]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        a = np.array([r[:3] for r in rows])
+        nv = self.nv
+        names = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                 ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                 ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+        reasons = sorted({nm for r in rows for nm, bit in names if r[4] & bit})
+        return {"sm_mhz": float(np.median(a[:, 0])), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": int(a.shape[0]), "power_w": float(np.median(a[:, 1]))}
+
+    def stop(self, t0: float = None, t1: float = None):
         if self.nv is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         self.running = False
         self.thread.join(timeout=2)
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
-        a = np.array(self.samples)
-        return {"sm_mhz": float(np.median(a[:, 0])), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": int(a.shape[0]), "power_w": float(np.median(a[:, 1]))}
+        return self.window(-1e30 if t0 is None else t0, 1e30 if t1 is None else t1)
 
 
 # --------------------------------------------------------------------------- inputs (both arms)
@@ -762,14 +769,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    import gc
     warm = max(args.warmup, 3)
+    sampler = ClockSampler(local).start() if rank == 0 else None     # before the warm-up: see ClockSampler.window
     pend = [step() for _ in range(warm)]
     barrier()
     [resolve(o) for o in pend]
     eng.profile_read()
     launches0 = eng.launch_count
-    sampler = ClockSampler(local).start() if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gc.collect()
+    gc.disable()                                  # no collector pauses between the enqueues of the timed region
     barrier()
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     t_host0 = time.perf_counter()
@@ -782,11 +792,13 @@ def run_ours(args):
     e1.record()
     host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3
     barrier()
+    t_host1 = time.perf_counter()
+    gc.enable()
     ms = e0.elapsed_time(e1)
     per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))
     launches = eng.launch_count - launches0
     k2_ms, k2_n = eng.profile_read()
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_host0, t_host1) if sampler else None
     steps_overflowed = sum(1 for o in pend if (resolve(o) is not None and getattr(o, "overflowed", False)))
     out = resolve(pend[-1])
     total = out[4].clone()

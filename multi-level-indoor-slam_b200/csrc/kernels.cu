@@ -664,18 +664,22 @@ compact_onepass_kernel(const float* __restrict__ scores, const int32_t* __restri
   offs[threadIdx.x] = ex;
   cnts[threadIdx.x] = row < Q ? count[row] : 0;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
+    // look-back by the first warp, 32 tiles at a time: lane l inspects tile j - l (a tile before tile 0 counts as an
+    // inclusive prefix of 0); the nearest inclusive prefix ends the walk, everything nearer contributes its total
+    const int lane = threadIdx.x;
     const unsigned long long tot = static_cast<unsigned long long>(tot_s);
     unsigned long long prefix = 0;
     if (tile > 0) {
-      st_release_u64(state + tile, (tot << 2) | 1ull);
+      if (lane == 0) st_release_u64(state + tile, (tot << 2) | 1ull);
       long long j = static_cast<long long>(tile) - 1;
       uint64_t t0 = 0;
       uint32_t spins = 0;
       while (true) {
-        const unsigned long long sv = ld_acquire_u64(state + j);
-        if ((sv & 3ull) == 0ull) {                       // that tile has not published yet: it is running (tickets)
-          if ((++spins & 0xFFFu) == 0) {                 // bounded like every wait in this library: a bug must trap
+        const long long at = j - lane;
+        const unsigned long long sv = at >= 0 ? ld_acquire_u64(state + at) : 2ull;
+        if (__any_sync(0xffffffffu, (sv & 3ull) == 0ull)) {   // some tile of the window has not published yet: it is
+          if ((++spins & 0xFFFu) == 0) {                      // running (tickets).  Bounded like every wait here.
             uint64_t now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             if (t0 == 0) t0 = now;
@@ -683,14 +687,21 @@ compact_onepass_kernel(const float* __restrict__ scores, const int32_t* __restri
           }
           continue;
         }
-        prefix += sv >> 2;
-        if ((sv & 3ull) == 2ull) break;                  // inclusive prefix: everything before is in it
-        --j;                                             // (tile 0 always publishes an inclusive prefix: j stays >= 0)
+        const uint32_t incl = __ballot_sync(0xffffffffu, (sv & 3ull) == 2ull);
+        const int stop = incl ? __ffs(incl) - 1 : 31;         // nearest inclusive prefix in the window, if any
+        unsigned long long part = lane <= stop ? (sv >> 2) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        prefix += part;
+        if (incl) break;
+        j -= 32;
       }
     }
-    st_release_u64(state + tile, ((prefix + tot) << 2) | 2ull);
-    base_s = static_cast<long long>(prefix);
-    if (tile == tiles - 1) *out_total = static_cast<int64_t>(prefix + tot);
+    if (lane == 0) {
+      st_release_u64(state + tile, ((prefix + tot) << 2) | 2ull);
+      base_s = static_cast<long long>(prefix);
+      if (tile == tiles - 1) *out_total = static_cast<int64_t>(prefix + tot);
+    }
   }
   __syncthreads();
   const int64_t base = base_s;
