@@ -143,6 +143,8 @@ class ClockSampler:
 
     def start(self):
         try:
+            if os.environ.get("SEMGATE_BENCH_NO_NVML"):      # A/B aid: does the sampler itself disturb the run?
+                raise RuntimeError("disabled")
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
@@ -180,6 +182,10 @@ class ClockSampler:
         if self.nv is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         rows = [r for r in list(self.samples) if t0 <= r[3] <= t1]
+        note = None
+        if not rows:      # an NVML query can take longer than a 20 ms timed region: take the samples right around it
+            rows = [r for r in list(self.samples) if t0 - 0.05 <= r[3] <= t1 + 0.05]
+            note = "no sample fell inside the timed region; these are the samples within 50 ms of it"
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
         a = np.array([r[:3] for r in rows])
@@ -189,8 +195,11 @@ class ClockSampler:
                  ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
                  ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
         reasons = sorted({nm for r in rows for nm, bit in names if r[4] & bit})
-        return {"sm_mhz": float(np.median(a[:, 0])), "sm_max_mhz": self.max_mhz, "reasons": reasons,
-                "samples": int(a.shape[0]), "power_w": float(np.median(a[:, 1]))}
+        out = {"sm_mhz": float(np.median(a[:, 0])), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+               "samples": int(a.shape[0]), "power_w": float(np.median(a[:, 1]))}
+        if note:
+            out["note"] = note
+        return out
 
     def stop(self, t0: float = None, t1: float = None):
         if self.nv is None:
@@ -483,21 +492,26 @@ def c5_leg(torch, dist, eng, sr, dev, rank, world, peak_tf, peak_src, steps=3, w
             dist.barrier()
         torch.cuda.synchronize()
 
-    pend = [step() for _ in range(warmup)]
+    for _ in range(warmup):
+        step().result()
     barrier()
     eng.profile_read()
     sampler = ClockSampler(dev.index).start() if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    pend += [step() for _ in range(steps)]
+    pend, cur = [], None
+    for _ in range(steps):
+        if cur is not None:
+            pend.append(cur.forget_value())
+        cur = step()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / steps
     k2_ms, k2_n = eng.profile_read()
     clocks = sampler.stop() if sampler else None
-    overflowed = sum(1 for p in pend if (p.result() is not None and p.overflowed))
-    out4 = pend[-1].result()
+    out4 = cur.result()
+    overflowed = sum(1 for p in pend if p.check()) + (1 if cur.overflowed else 0)
     total = out4[4].clone()
     roof, k2_avg = k2_roofline(eng, k2_ms, k2_n, n, n, n, _native.pad_dim(dim), peak_tf, peak_src, ms)
     how = sr.last_all_pairs if world > 1 else "one GPU"
@@ -772,9 +786,9 @@ def run_ours(args):
     import gc
     warm = max(args.warmup, 3)
     sampler = ClockSampler(local).start() if rank == 0 else None     # before the warm-up: see ClockSampler.window
-    pend = [step() for _ in range(warm)]
+    for _ in range(warm):
+        out = resolve(step())
     barrier()
-    [resolve(o) for o in pend]
     eng.profile_read()
     launches0 = eng.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -784,10 +798,14 @@ def run_ours(args):
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     t_host0 = time.perf_counter()
     e0.record()
-    pend = []
+    # (only the newest step's outputs stay alive: holding every step's arrays would send the caching allocator to
+    #  cudaMalloc inside the timed region -- measured as random 10-100 ms host stalls)
+    pend, out = [], None
     for i in range(args.steps):
         marks[i].record()
-        pend.append(step())
+        if hasattr(out, "forget_value"):
+            pend.append(out.forget_value())
+        out = step()
     marks[args.steps].record()
     e1.record()
     host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3
@@ -799,8 +817,10 @@ def run_ours(args):
     launches = eng.launch_count - launches0
     k2_ms, k2_n = eng.profile_read()
     clocks = sampler.stop(t_host0, t_host1) if sampler else None
-    steps_overflowed = sum(1 for o in pend if (resolve(o) is not None and getattr(o, "overflowed", False)))
-    out = resolve(pend[-1])
+    steps_overflowed = sum(1 for o in pend if o.check())
+    last_pending = out
+    out = resolve(out)
+    steps_overflowed += 1 if getattr(last_pending, "overflowed", False) else 0
     total = out[4].clone()
     roofline, k2_avg = k2_roofline(eng, k2_ms, k2_n, N_Q, (hi - lo) if (world > 1 and not allpairs) else n_db_total, n_db_total, dp,
                                    peak_tf, peak_src, ms / args.steps)

@@ -57,6 +57,22 @@ class PendingSweep:
         self._value, self._flag, self._event, self._redo, self._owner = value, flag_host, event, redo, owner
         self.overflowed = None
 
+    def forget_value(self):
+        """Drop the queued result (its device memory goes back to the allocator at once) but keep the flag: a caller
+        that pipelines many sweeps and only wants to know afterwards whether any overflowed (`check()`)."""
+        self._value = None
+        return self
+
+    def check(self) -> bool:
+        """True iff this sweep's candidate buffers overflowed somewhere (waits for its flag only; no redo)."""
+        if self._redo is None and self.overflowed is None:
+            return False
+        if self.overflowed is None:
+            if self._event is not None:
+                self._event.synchronize()
+            self.overflowed = bool(int(self._flag[0]) != 0)
+        return self.overflowed
+
     def result(self):
         if self._redo is not None:
             if self._event is not None:
