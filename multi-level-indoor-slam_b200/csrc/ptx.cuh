@@ -160,6 +160,51 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t cta) {
   return r;
 }
 
+// 3-D tile load issued from a CTA of a cta_group::2 pair (`bar` may name the leader's barrier)
+__device__ __forceinline__ void tma_load_3d_cg2(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// ---------------------------------------------------------------- distributed shared memory (data, not only barriers)
+// `addr` is a shared::cluster address (mapa).  The reds / stores are relaxed; the release-arrive below publishes them.
+__device__ __forceinline__ void red_max_u32_cluster(uint32_t addr, uint32_t v) {
+  asm volatile("red.relaxed.cluster.shared::cluster.max.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_f32_cluster(uint32_t addr, float v) {
+  asm volatile("st.relaxed.cluster.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+// release at cluster scope: everything this thread wrote before (remote reds / stores included) is visible to
+// whoever acquires the phase.  Costs a fence; meant for once-per-work-item hand-offs, not per stage.
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(cta) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_acquire_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (!mbar_try_wait_acquire_cluster(bar, parity)) {
+    if ((++spins & 0xFFFu) == 0) {
+      uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > SEMGATE_WAIT_TIMEOUT_NS) __trap();
+    }
+  }
+}
+
 // ---------------------------------------------------------------- cluster
 __device__ __forceinline__ void cluster_arrive() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");

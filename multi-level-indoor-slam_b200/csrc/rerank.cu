@@ -61,6 +61,42 @@ __device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const void* desc, u
       ::"r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
 }
 
+// Column maxima of a 32 x 32 block held one row per lane: lane l returns max over the warp's rows of column l.
+// Five exchange steps (xor 16 ... 1): at each step a lane keeps the half of its columns whose index bit equals its own
+// lane bit, sends the other half to its partner and folds what it receives -- 31 SHFL + 31 FMNMX + 62 SEL, all
+// independent within a step.  (One REDUX per column, the round-1 form, measured ~57 clocks per column: the
+// reductions go through the uniform datapath one at a time and the epilogue, not operand delivery, bounded K5.)
+__device__ __forceinline__ float colmax32(const float (&v)[32], int lane) {
+  float a[16], b[8], c[4], d[2];
+  bool hi = (lane & 16) != 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float send = hi ? v[j] : v[j + 16], keep = hi ? v[j + 16] : v[j];
+    a[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+  }
+  hi = (lane & 8) != 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float send = hi ? a[j] : a[j + 8], keep = hi ? a[j + 8] : a[j];
+    b[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+  }
+  hi = (lane & 4) != 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float send = hi ? b[j] : b[j + 4], keep = hi ? b[j + 4] : b[j];
+    c[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+  }
+  hi = (lane & 2) != 0;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float send = hi ? c[j] : c[j + 2], keep = hi ? c[j + 2] : c[j];
+    d[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 2));
+  }
+  hi = (lane & 1) != 0;
+  const float send = hi ? d[0] : d[1], keep = hi ? d[1] : d[0];
+  return fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+}
+
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 __device__ __forceinline__ bool pair_ok(const RerankParams& p, long long pr, int& q, int& m) {
@@ -243,17 +279,15 @@ rerank_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
             ptx::tmem_ld_32x32(t_acc + c * 32, v);
             ptx::tmem_wait_ld();
             const int nv = min(32, ncols - c * 32);
-            uint32_t mine = 0u;
+            float x[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const float x = __uint_as_float(v[i]);
-              const bool cv = i < nv;                            // warp-uniform
-              if (cv) rmax = fmaxf(rmax, x);
-              const uint32_t o = (row_valid && cv) ? score_to_ordered(x) : 0u;
-              const uint32_t red = __reduce_max_sync(0xffffffffu, o);
-              if (lane == i) mine = red;
+              const float xi = __uint_as_float(v[i]);
+              if (i < nv) rmax = fmaxf(rmax, xi);                // warp-uniform
+              x[i] = row_valid ? xi : neg_inf;
             }
-            if (lane < nv) atomicMax(&colmax[nt * BN + c * 32 + lane], mine);
+            const float cm = colmax32(x, lane);
+            if (lane < nv) atomicMax(&colmax[nt * BN + c * 32 + lane], score_to_ordered(cm));
           }
           ptx::tc_fence_before();
           __syncwarp();
@@ -293,6 +327,324 @@ rerank_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   if (warp == 1) ptx::tmem_dealloc<1>(tmem_base, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Pair form (round 2): one CTA PAIR per (query, candidate) pair, `tcgen05.mma.cta_group::2` tiles of 256 candidate
+// patches x `bn` query patches -- every staged byte feeds twice the MMA work of the single-CTA form (128 x bn), which
+// was bound by operand delivery into the SMs (7.2 MB staged per 529 x 768 pair at ~11 TB/s, tensor pipe 30 % active).
+//
+// Patch counts are not multiples of 256 (DINOv2 at 322 x 322: P = 529 = 2 * 256 + 17).  Padding the candidate side to
+// three pair tiles would spend a third of the MMAs on zero rows, so when at most 32 candidate patches are left over
+// they become a STRIP: during the first pass over the query tiles the staged query rows (the B operand of the main
+// MMA, K-major and 128-byte swizzled like any A operand) are multiplied a second time as the A operand of a
+// 256 x 32 MMA against the left-over candidate patches, which stay resident in shared memory for the whole pair
+// (32 rows x feature length: 24 KB per CTA at 768-d).  Those small accumulators (one per query tile) sit behind the
+// two main ones in TMEM and are read with the tile they belong to.  P = 529: 512 x 544 + 544 x 32 multiplied for
+// 529 x 529 wanted (94 %), where the single-CTA form multiplies 640 x 576 (76 %).
+//
+// Row maxima of a main tile (a candidate patch's best query patch) stay in the owning thread's register across the
+// query tiles; column maxima (a query patch's best candidate patch) and the strip's maxima go through shared-memory
+// atomicMax on order-preserving integer images.  The odd CTA pushes its arrays into the even CTA's over distributed
+// shared memory at the end of the pair (red.max + a release-arrive on a barrier of the even CTA), which finishes the
+// score.  Arrays, partial sums and the merge barrier are double-buffered by pair parity; the MMA pipeline keeps the
+// two CTAs within two tiles of each other, so no other hand-shake is needed.
+struct PairParams {
+  int P, kblocks, stages, n_feat;
+  int mt2;          // 256-row pair tiles over the candidate's patches
+  int nt;           // n-tiles over the query's patches
+  int bn;           // n-tile width (multiple of 32)
+  int strip_rows;   // candidate patches [mt2 * 256, P) handled by the strip MMAs (0: none)
+  int pp;           // P rounded up to 32
+  uint32_t b_bytes;       // (bn / 2) rows of one k-block: this CTA's half of the B operand
+  uint32_t stage_bytes;   // b_bytes + 16 KiB (B first: the strip MMA reads 128 rows from the B base, which must stay inside the stage)
+  long long M;
+  const int32_t* q_idx;
+  const int32_t* m_idx;
+  const float* global_sim;
+  float* out_cross;
+  float* out_combined;
+};
+constexpr int kPMaxStages = 8;
+constexpr uint32_t kStripKbBytes = 16 * RBK * 2;   // one k-block of this CTA's half of the strip operand: 16 rows
+
+__device__ __forceinline__ bool pair_ok2(const PairParams& p, long long pr, int& q, int& m) {
+  q = p.q_idx[pr];
+  m = p.m_idx[pr];
+  return q >= 0 && m >= 0 && q < p.n_feat && m < p.n_feat;
+}
+
+__global__ void __launch_bounds__(kRThreads, 1)
+rerank_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                   const __grid_constant__ CUtensorMap tmap_s, const PairParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stages = p.stages;
+  uint8_t* smem_st = smem;                                                              // [stages][B | A]
+  uint8_t* smem_s = smem + static_cast<size_t>(stages) * p.stage_bytes;                 // strip operand, [kblocks][16 rows]
+  const int arr_len = p.pp + 32;                                                        // column maxima, then the strip's 32
+  uint32_t* arrs = reinterpret_cast<uint32_t*>(smem_s + (p.strip_rows ? static_cast<size_t>(p.kblocks) * kStripKbBytes : 0));
+  float* scratch = reinterpret_cast<float*>(arrs + 2 * arr_len);                        // [2][16]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + 32);
+  const uint32_t bar_full = ptx::smem_u32(bars);
+  const uint32_t bar_empty = bar_full + 8 * kPMaxStages;
+  const uint32_t bar_tfull = bar_empty + 8 * kPMaxStages;
+  const uint32_t bar_tempty = bar_tfull + 16;
+  const uint32_t bar_sfull = bar_tempty + 16;
+  const uint32_t bar_sfree = bar_sfull + 8;
+  const uint32_t bar_merge = bar_sfree + 8;                                             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPMaxStages + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const long long cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int BN = p.bn, NT = p.nt, MT2 = p.mt2;
+  const bool strip = p.strip_rows > 0;
+
+  ptx::cluster_sync();                               // the peer must be resident before a pair-wide TMEM allocation
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&tmap_a);
+    ptx::prefetch_tensormap(&tmap_b);
+    ptx::prefetch_tensormap(&tmap_s);
+    for (int s = 0; s < stages; ++s) { ptx::mbar_init(bar_full + 8 * s, 2); ptx::mbar_init(bar_empty + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(bar_tfull + 8 * a, 1);
+      ptx::mbar_init(bar_tempty + 8 * a, 8);         // four epilogue warps of each CTA
+      ptx::mbar_init(bar_merge + 8 * a, 128);        // every epilogue thread of the odd CTA
+    }
+    ptx::mbar_init(bar_sfull, 2);
+    ptx::mbar_init(bar_sfree, 1);
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+  }
+  for (int c = threadIdx.x; c < 2 * arr_len; c += kRThreads) arrs[c] = 0u;
+  if (warp == 1) ptx::tmem_alloc<2>(ptx::smem_u32(tmem_slot), 512);
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  // columns of n-tile `t` that are multiplied (multiple of 16) -- each CTA stages half of them
+  auto tile_nw = [&](int t) { return (min(BN, p.P - t * BN) + 15) & ~15; };
+
+  uint32_t stage = 0, phase = 0, it = 0, pc = 0;     // pc: valid pairs so far (every role counts the same)
+
+  if (warp == 0) {
+    // ----------------------------------------------------------- TMA producer (both CTAs, each its halves)
+    for (long long g = cluster_id; g < p.M; g += n_clusters) {
+      int q, m;
+      if (!pair_ok2(p, g, q, m)) continue;
+      if (strip) {
+        ptx::mbar_wait(bar_sfree, (pc & 1u) ^ 1u);   // the previous pair's strip MMAs have read it
+        if (ptx::elect_one()) {
+          const uint32_t fb = ptx::mapa(bar_sfull, 0);
+          if (leader) ptx::mbar_arrive_expect_tx(bar_sfull, 2u * static_cast<uint32_t>(p.kblocks) * kStripKbBytes);
+          for (int kb = 0; kb < p.kblocks; ++kb)
+            ptx::tma_load_3d_cg2(ptx::smem_u32(smem_s) + kb * kStripKbBytes, &tmap_s, fb, kb * RBK, MT2 * 256 + static_cast<int>(rank) * 16, m);
+          if (!leader) ptx::mbar_arrive_cluster(bar_sfull, 0);
+        }
+        __syncwarp();
+      }
+      for (int mt = 0; mt < MT2; ++mt)
+        for (int nt = 0; nt < NT; ++nt) {
+          const int b_row = nt * BN + static_cast<int>(rank) * (tile_nw(nt) >> 1);
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            if (ptx::elect_one()) {
+              const uint32_t fb_local = bar_full + 8 * stage;
+              const uint32_t fb = ptx::mapa(fb_local, 0);
+              const uint32_t dst = ptx::smem_u32(smem_st) + stage * p.stage_bytes;
+              if (leader) ptx::mbar_arrive_expect_tx(fb_local, 2u * p.stage_bytes);
+              ptx::tma_load_3d_cg2(dst, &tmap_b, fb, kb * RBK, b_row, q);
+              ptx::tma_load_3d_cg2(dst + p.b_bytes, &tmap_a, fb, kb * RBK, mt * 256 + static_cast<int>(rank) * RBM, m);
+              if (!leader) ptx::mbar_arrive_cluster(fb_local, 0);
+            }
+            __syncwarp();
+            if (++stage == static_cast<uint32_t>(stages)) { stage = 0; phase ^= 1; }
+          }
+        }
+      ++pc;
+    }
+  } else if (warp == 1) {
+    // ----------------------------------------------------------- MMA issuer (leader CTA)
+    if (leader) {
+      const uint64_t desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_st));
+      const uint64_t sdesc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_s));
+      constexpr uint32_t idesc_strip = ptx::make_idesc_bf16_f32(256, 32);
+      for (long long g = cluster_id; g < p.M; g += n_clusters) {
+        int q, m;
+        if (!pair_ok2(p, g, q, m)) continue;
+        for (int mt = 0; mt < MT2; ++mt)
+          for (int nt = 0; nt < NT; ++nt, ++it) {
+            const uint32_t idesc = ptx::make_idesc_bf16_f32(256, static_cast<uint32_t>(tile_nw(nt)));
+            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+            const bool do_strip = strip && mt == 0;
+            ptx::mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+            if (do_strip && nt == 0) ptx::mbar_wait(bar_sfull, pc & 1u);
+            ptx::tc_fence_after();
+            const uint32_t d_main = tmem_base + acc * BN;
+            const uint32_t d_strip = tmem_base + 2 * BN + 32 * nt;
+            for (int kb = 0; kb < p.kblocks; ++kb) {
+              ptx::mbar_wait(bar_full + 8 * stage, phase);
+              ptx::tc_fence_after();
+              const uint64_t bdesc = desc0 + static_cast<uint64_t>((stage * p.stage_bytes) >> 4);
+              const uint64_t adesc = bdesc + static_cast<uint64_t>(p.b_bytes >> 4);
+              const uint64_t sdesc = sdesc0 + static_cast<uint64_t>((kb * kStripKbBytes) >> 4);
+              if (ptx::elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < RBK / RUK; ++kk)
+                  ptx::umma_bf16<2>(d_main, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb | kk) != 0);
+                if (do_strip) {
+                  // the staged query rows once more, as the M operand against the resident left-over candidate patches
+#pragma unroll
+                  for (int kk = 0; kk < RBK / RUK; ++kk)
+                    ptx::umma_bf16<2>(d_strip, bdesc + 2 * kk, sdesc + 2 * kk, idesc_strip, (kb | kk) != 0);
+                }
+                ptx::umma_commit_cg2_mc(bar_empty + 8 * stage, 0b11);
+                if (kb == p.kblocks - 1) {
+                  if (do_strip && nt == NT - 1) ptx::umma_commit_cg2_mc(bar_sfree, 0b11);
+                  ptx::umma_commit_cg2_mc(bar_tfull + 8 * acc, 0b11);
+                }
+              }
+              __syncwarp();
+              if (++stage == static_cast<uint32_t>(stages)) { stage = 0; phase ^= 1; }
+            }
+          }
+        ++pc;
+      }
+      if (it > 0) {                                  // the peer's epilogue arrives remotely on our barriers: drain
+        const uint32_t last = it - 1;
+        ptx::mbar_wait(bar_tempty + 8 * (last & 1), (last >> 1) & 1);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ----------------------------------------------------------- epilogue: row / column maxima (both CTAs)
+    const int quad = warp & 3;
+    const int row_in_tile = quad * 32 + lane;
+    const int et = (warp - 2) * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const float neg_inf = __int_as_float(0xff800000);
+    const int row_limit = strip ? MT2 * 256 : p.P;   // candidate patches covered by main tiles
+    for (long long g = cluster_id; g < p.M; g += n_clusters) {
+      int q, m;
+      if (!pair_ok2(p, g, q, m)) {
+        if (leader && et == 0) {
+          p.out_cross[g] = __int_as_float(0x7fc00000);          // no cached features: global score only (:749)
+          p.out_combined[g] = p.global_sim[g];
+        }
+        continue;
+      }
+      const uint32_t par = pc & 1u;
+      uint32_t* arr = arrs + par * arr_len;
+      float* scr = scratch + par * 16;
+      float rsum = 0.f;
+      for (int mt = 0; mt < MT2; ++mt) {
+        const bool row_valid = mt * 256 + static_cast<int>(rank) * RBM + row_in_tile < row_limit;
+        float rmax = neg_inf;
+        for (int nt = 0; nt < NT; ++nt, ++it) {
+          const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+          ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase);
+          ptx::tc_fence_after();
+          const uint32_t t_acc = t_lane + acc * BN;
+          const int ncols = min(BN, p.P - nt * BN);
+          for (int c = 0; c * 32 < ncols; ++c) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32(t_acc + c * 32, v);
+            ptx::tmem_wait_ld();
+            const int nv = min(32, ncols - c * 32);
+            float x[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float xi = __uint_as_float(v[i]);
+              if (i < nv) rmax = fmaxf(rmax, xi);                // warp-uniform
+              x[i] = row_valid ? xi : neg_inf;
+            }
+            const float cm = colmax32(x, lane);
+            if (lane < nv) atomicMax(&arr[nt * BN + c * 32 + lane], score_to_ordered(cm));
+          }
+          if (strip && mt == 0) {
+            // rows: the query patches this CTA staged for the tile; columns: the left-over candidate patches
+            const int half = tile_nw(nt) >> 1;
+            const int qrow = nt * BN + static_cast<int>(rank) * half + row_in_tile;
+            const bool qv = row_in_tile < half && qrow < p.P;
+            uint32_t v[32];
+            ptx::tmem_ld_32x32(t_lane + 2 * BN + 32 * nt, v);
+            ptx::tmem_wait_ld();
+            float r2 = neg_inf;
+            float x[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float xi = __uint_as_float(v[i]);
+              if (i < p.strip_rows) r2 = fmaxf(r2, xi);          // warp-uniform
+              x[i] = qv ? xi : neg_inf;
+            }
+            const float cm = colmax32(x, lane);
+            const uint32_t cmo = score_to_ordered(cm);
+            if (lane < p.strip_rows && cmo != score_to_ordered(neg_inf)) atomicMax(&arr[p.pp + lane], cmo);
+            if (qv) atomicMax(&arr[qrow], score_to_ordered(r2));
+          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) ptx::mbar_arrive(bar_tempty + 8 * acc);
+            else ptx::mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
+          }
+        }
+        if (row_valid) rsum += rmax;
+      }
+      // ---- finish the pair
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
+      if (!leader) {
+        epi_bar();                                                // every warp's atomics have landed
+        for (int c = et; c < arr_len; c += 128) {
+          const uint32_t vv = arr[c];
+          if (vv != 0u) {
+            ptx::red_max_u32_cluster(ptx::mapa(ptx::smem_u32(arr + c), 0), vv);
+            arr[c] = 0u;
+          }
+        }
+        if (lane == 0) ptx::st_f32_cluster(ptx::mapa(ptx::smem_u32(scr + 4 + (warp - 2)), 0), rsum);
+        ptx::mbar_arrive_release_cluster(bar_merge + 8 * par, 0);
+      } else {
+        if (lane == 0) scr[warp - 2] = rsum;
+        ptx::mbar_wait_acquire_cluster(bar_merge + 8 * par, (pc >> 1) & 1u);
+        epi_bar();                                                // ... and ours
+        float csum = 0.f, ssum = 0.f;
+        for (int c = et; c < p.P; c += 128) {
+          csum += ordered_to_score(arr[c]);
+          arr[c] = 0u;
+        }
+        if (et < 32) {
+          if (et < p.strip_rows) ssum = ordered_to_score(arr[p.pp + et]);
+          arr[p.pp + et] = 0u;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          csum += __shfl_xor_sync(0xffffffffu, csum, o);
+          ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+        }
+        if (lane == 0) { scr[8 + warp - 2] = csum; if (warp == 2) scr[12] = ssum; }
+        epi_bar();
+        if (et == 0) {
+          const float rs = ((scr[0] + scr[1]) + (scr[2] + scr[3])) + ((scr[4] + scr[5]) + (scr[6] + scr[7])) + scr[12];
+          const float cs = (scr[8] + scr[9]) + (scr[10] + scr[11]);
+          const float inv = 1.0f / static_cast<float>(p.P);
+          const float cross = sqrtf((rs * inv) * (cs * inv));
+          p.out_cross[g] = cross;
+          p.out_combined[g] = 0.5f * p.global_sim[g] + 0.5f * cross;
+        }
+      }
+      ++pc;
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  if (warp == 1) ptx::tmem_dealloc<2>(tmem_base, 512);
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   static std::once_flag once;
@@ -322,13 +674,88 @@ int make_tmap3(CUtensorMap* m, const void* base, int n_feat, int P, int dl_pad, 
 
 }  // namespace
 
+namespace {
+constexpr int kPairFormNotApplicable = -77;
+
+// the pair form's tiling for P patches x dl_pad features; false: use a round-1 form
+bool pair_tiling(int P, int dl_pad, PairParams& p, size_t& smem) {
+  if (P <= RBM) return false;                          // one 128-row tile: a CTA pair would multiply zeros
+  const int kblocks = dl_pad / RBK;
+  const int full = P / 256, rem = P - full * 256;
+  for (int want_strip = 1; want_strip >= 0; --want_strip) {
+    const bool strip = want_strip && full >= 1 && rem > 0 && rem <= 32;
+    if (want_strip && !strip) continue;
+    const int bnmax = strip ? 192 : RBN;
+    // at least two tiles per pair: the double-buffered merge arrays rely on the MMA pipeline keeping the CTAs of a pair
+    // within two TILES of each other, which must be less than two PAIRS
+    const int mt2 = strip ? full : (P + 255) / 256;
+    int nt = (P + bnmax - 1) / bnmax;
+    if (mt2 * nt < 2) nt = 2;
+    const int bn = (((P + nt - 1) / nt) + 31) & ~31;
+    if (bn > bnmax) continue;
+    if (strip && 2 * bn + 32 * nt > 512) continue;     // TMEM: two main accumulators + one strip accumulator per n-tile
+    p.P = P; p.kblocks = kblocks; p.mt2 = mt2; p.nt = nt; p.bn = bn;
+    p.strip_rows = strip ? rem : 0;
+    p.pp = (P + 31) & ~31;
+    p.b_bytes = static_cast<uint32_t>(bn / 2) * RBK * 2;
+    p.stage_bytes = p.b_bytes + RA_BYTES;
+    const size_t fixed = 1024 + (strip ? static_cast<size_t>(kblocks) * kStripKbBytes : 0) + static_cast<size_t>(2 * (p.pp + 32)) * 4 + 128 +
+                         (2 * kPMaxStages + 8) * 8 + 16;
+    if (fixed + 3 * static_cast<size_t>(p.stage_bytes) > 232448) continue;
+    int stages = static_cast<int>((232448 - fixed) / p.stage_bytes);
+    stages = std::min(stages, kPMaxStages);
+    p.stages = std::min(stages, std::max(3, kblocks * 2));
+    smem = fixed + static_cast<size_t>(p.stages) * p.stage_bytes;
+    return true;
+  }
+  return false;
+}
+
+int launch_rerank_pair(const void* feats_bf16, int n_feat, int P, int dl_pad, const int32_t* q_idx, const int32_t* m_idx,
+                       const float* global_sim, int64_t M, float* out_cross, float* out_combined, int sm_count, cudaStream_t st) {
+  PairParams p{};
+  size_t smem = 0;
+  if (!pair_tiling(P, dl_pad, p, smem)) return kPairFormNotApplicable;
+  CUtensorMap ta, tb, ts;
+  int rc = make_tmap3(&ta, feats_bf16, n_feat, P, dl_pad, RBM);
+  if (rc) return rc;
+  rc = make_tmap3(&tb, feats_bf16, n_feat, P, dl_pad, static_cast<uint32_t>(p.bn / 2));
+  if (rc) return rc;
+  rc = make_tmap3(&ts, feats_bf16, n_feat, P, dl_pad, 16);
+  if (rc) return rc;
+  p.n_feat = n_feat;
+  p.M = M;
+  p.q_idx = q_idx; p.m_idx = m_idx; p.global_sim = global_sim;
+  p.out_cross = out_cross; p.out_combined = out_combined;
+  const unsigned clusters = static_cast<unsigned>(std::min<int64_t>(M, std::max(1, sm_count / 2)));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * 2);
+  cfg.blockDim = dim3(kRThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaFuncSetAttribute(rerank_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  return static_cast<int>(cudaLaunchKernelEx(&cfg, rerank_pair_kernel, ta, tb, ts, p));
+}
+}  // namespace
+
 int launch_rerank(const void* feats_bf16, int n_feat, int P, int dl_pad, const int32_t* q_idx, const int32_t* m_idx,
                   const float* global_sim, int64_t M, float* out_cross, float* out_combined, int sm_count,
                   cudaStream_t st) {
   if (M <= 0) return 0;
-  // two-CTA clusters with a multicast query operand unless SEMGATE_RERANK_CLUSTER=1 asks for single CTAs
+  // The pair form (one CTA pair per candidate pair) wherever its tiling applies; SEMGATE_RERANK_CLUSTER=1 / 2 asks for
+  // the round-1 forms (single CTAs / two pairs per 2-CTA cluster in lock-step), which also serve P <= 128.
+  const char* form_env = getenv("SEMGATE_RERANK_CLUSTER");
+  if (form_env == nullptr || atoi(form_env) == 0) {
+    const int rc = launch_rerank_pair(feats_bf16, n_feat, P, dl_pad, q_idx, m_idx, global_sim, M, out_cross, out_combined, sm_count, st);
+    if (rc != kPairFormNotApplicable) return rc;
+  }
   int csize = 2;
-  if (const char* e = getenv("SEMGATE_RERANK_CLUSTER")) csize = atoi(e) == 1 ? 1 : 2;
+  if (form_env) csize = atoi(form_env) == 1 ? 1 : 2;
   if (M < 2) csize = 1;
   // n-tile width: split the P columns evenly over ceil(P / 256) tiles, in multiples of 32
   const int nt_count = (P + RBN - 1) / RBN;

@@ -1129,6 +1129,47 @@ def test_rerank_cluster_lockstep_cases(eng, monkeypatch):
             assert np.isnan(cross[i]) and comb[i] == g[i]
 
 
+@pytest.mark.parametrize("P,D", [(129, 64), (200, 128), (257, 64), (280, 192), (288, 64), (300, 128), (529, 768), (544, 64), (545, 128),
+                                 (800, 128), (1030, 64)])
+def test_rerank_pair_form(eng, monkeypatch, P, D):
+    """K5 pair form (one CTA pair per candidate pair, cta_group::2 tiles; left-over candidate patches as strip MMAs when
+    P = 256 a + r, r <= 32) against the single-CTA form and an fp32 reference of the same op on the same bf16 rows, over
+    patch counts that hit every tiling case: one / several pair tiles, with and without a strip, ragged last n-tile;
+    pairs without cached features; a second launch over the same buffers (the merge arrays come back clean)."""
+    import torch
+    n, M = 20, 203
+    g = torch.Generator(device="cuda").manual_seed(P * 7 + D)
+    x = torch.randn((n * P, D), device="cuda", generator=g) + 0.3
+    fb = eng.normalize_cast(x).view(n, P, -1)
+    qi = torch.randint(0, n, (M,), device="cuda", dtype=torch.int32, generator=g)
+    mi = torch.randint(0, n, (M,), device="cuda", dtype=torch.int32, generator=g)
+    qi[7] = -1
+    mi[11] = n + 3
+    qi[M - 1] = -1
+    qi[20:45] = 3
+    gs = torch.rand((M,), device="cuda", generator=g)
+    monkeypatch.delenv("SEMGATE_RERANK_CLUSTER", raising=False)
+    cross, comb = eng.rerank_scores(fb, qi, mi, gs)
+    cross2, _ = eng.rerank_scores(fb, qi, mi, gs)
+    monkeypatch.setenv("SEMGATE_RERANK_CLUSTER", "1")
+    cross1, comb1 = eng.rerank_scores(fb, qi, mi, gs)
+    torch.cuda.synchronize()
+    monkeypatch.delenv("SEMGATE_RERANK_CLUSTER")
+    ff = fb.float()
+    valid = ((qi >= 0) & (mi >= 0) & (qi < n) & (mi < n)).cpu().numpy()
+    ref = np.full(M, np.nan, np.float32)
+    for i in np.nonzero(valid)[0]:
+        c = ff[int(qi[i])] @ ff[int(mi[i])].T
+        ref[i] = float(torch.sqrt(c.max(dim=1).values.mean() * c.max(dim=0).values.mean()))
+    cross, comb, cross1, cross2 = cross.cpu().numpy(), comb.cpu().numpy(), cross1.cpu().numpy(), cross2.cpu().numpy()
+    assert np.array_equal(np.isnan(cross), ~valid) and np.array_equal(np.isnan(cross1), ~valid)
+    assert np.array_equal(cross, cross2, equal_nan=True)
+    assert np.max(np.abs(cross[valid] - ref[valid])) <= 2e-6          # the maxima are exact; only the order of the fp32 sums differs
+    assert np.max(np.abs(cross[valid] - cross1[valid])) <= 2e-6
+    gsn = gs.cpu().numpy()
+    assert np.array_equal(comb[~valid], gsn[~valid]) and np.allclose(comb[valid], 0.5 * gsn[valid] + 0.5 * cross[valid], atol=1e-6)
+
+
 def test_rerank_batch_dinov2_shape(eng):
     """529 patches x 768-d (DINOv2 at 322x322): a batch of pairs against the oracle, and the batched
     per-query selection against per-query Python sorting."""

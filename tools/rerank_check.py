@@ -1,0 +1,110 @@
+"""K5 forms against each other and a torch fp32 reference of the same op (bf16 rows): pair form (one CTA pair per
+candidate pair, strip MMAs for left-over patches) vs the round-1 forms, over patch counts that hit every tiling case;
+then the DINOv2-shape timing of each form.     python tools/rerank_check.py [pairs_for_timing]"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "multi-level-indoor-slam_b200"))
+from semgate import _native  # noqa: E402
+
+
+def torch_ref(feats, qi, mi):
+    out = []
+    for q, m in zip(qi.tolist(), mi.tolist()):
+        if q < 0 or m < 0 or q >= feats.shape[0] or m >= feats.shape[0]:
+            out.append(float("nan"))
+            continue
+        c = feats[q].float() @ feats[m].float().T
+        out.append(float(torch.sqrt(c.max(dim=1).values.mean() * c.max(dim=0).values.mean())))
+    return np.array(out, np.float32)
+
+
+def run(eng, form, feats, qi, mi, gs):
+    if form is None:
+        os.environ.pop("SEMGATE_RERANK_CLUSTER", None)
+    else:
+        os.environ["SEMGATE_RERANK_CLUSTER"] = form
+    cross, comb = eng.rerank_scores(feats, qi, mi, gs)
+    torch.cuda.synchronize()
+    os.environ.pop("SEMGATE_RERANK_CLUSTER", None)
+    return cross.cpu().numpy(), comb.cpu().numpy()
+
+
+def main():
+    eng = _native.get_engine(0)
+    ok = True
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for P, D in ((129, 64), (200, 128), (256, 128), (257, 64), (280, 192), (288, 64), (300, 128), (512, 64), (529, 768), (530, 128), (544, 64),
+                 (545, 128), (600, 64), (769, 64), (800, 128), (1024, 64), (1030, 64), (100, 128)):
+        n = 24
+        x = torch.randn((n * P, D), device="cuda", generator=g) + 0.3
+        feats = eng.normalize_cast(x).view(n, P, -1)
+        M = 301
+        qi = torch.randint(0, n, (M,), device="cuda", dtype=torch.int32, generator=g)
+        mi = torch.randint(0, n, (M,), device="cuda", dtype=torch.int32, generator=g)
+        qi[7] = -1; mi[11] = n + 3; qi[300] = -1                       # no cached features
+        qi[20:45] = 3                                                  # a query's candidates are consecutive
+        gs = torch.rand((M,), device="cuda", generator=g)
+        new, newc = run(eng, None, feats, qi, mi, gs)
+        old, oldc = run(eng, "1", feats, qi, mi, gs)
+        ref = torch_ref(feats, qi, mi)
+        nan_same = np.array_equal(np.isnan(new), np.isnan(ref)) and np.array_equal(np.isnan(old), np.isnan(ref))
+        v = ~np.isnan(ref)
+        e_new = float(np.max(np.abs(new[v] - ref[v])))
+        e_old = float(np.max(np.abs(old[v] - ref[v])))
+        e_no = float(np.max(np.abs(new[v] - old[v])))
+        comb_ok = np.allclose(newc[v], 0.5 * gs.cpu().numpy()[v] + 0.5 * new[v], atol=1e-6) and np.array_equal(newc[~v], gs.cpu().numpy()[~v])
+        good = nan_same and e_new <= 2e-5 and e_no <= 2e-5 and comb_ok
+        ok &= good
+        print(f"P={P:5d} D={D:4d}: |pair - ref| {e_new:.2e}  |r1 - ref| {e_old:.2e}  |pair - r1| {e_no:.2e}  nan {nan_same} comb {comb_ok}  {'ok' if good else 'FAILED'}",
+              flush=True)
+    # twice the same launch: the merge buffers must come back clean
+    a1, _ = run(eng, None, feats, qi, mi, gs)
+    a2, _ = run(eng, None, feats, qi, mi, gs)
+    same = np.array_equal(a1, a2, equal_nan=True)
+    ok &= same
+    print("repeat launch identical:", same)
+
+    # ---- timing, DINOv2 shape
+    pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
+    nf, P, Dl, kc = 2000, 529, 768, 25
+    feats = torch.empty((nf, P, _native.pad_dim(Dl)), dtype=torch.bfloat16, device="cuda")
+    for s0 in range(0, nf, 250):
+        x = torch.randn((250 * P, Dl), device="cuda")
+        eng.normalize_cast(x, out=feats[s0:s0 + 250].view(250 * P, -1))
+    nq = pairs // kc
+    qi = torch.arange(nq, device="cuda", dtype=torch.int32).repeat_interleave(kc) % nf
+    mi = torch.randint(0, nf, (nq * kc,), device="cuda", dtype=torch.int32)
+    gs = torch.rand((nq * kc,), device="cuda")
+    res = {}
+    for form in (None, "2", "1"):
+        if form is None:
+            os.environ.pop("SEMGATE_RERANK_CLUSTER", None)
+        else:
+            os.environ["SEMGATE_RERANK_CLUSTER"] = form
+        for _ in range(2):
+            eng.rerank_scores(feats, qi, mi, gs)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng.rerank_scores(feats, qi, mi, gs)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        med = sorted(ts)[len(ts) // 2]
+        res["pair" if form is None else "round1_cluster" + form] = {"ms": med, "pairs_per_s": nq * kc / med * 1e3,
+                                                                    "tflops_useful": 2.0 * P * P * 768 * nq * kc / med / 1e9}
+    os.environ.pop("SEMGATE_RERANK_CLUSTER", None)
+    print(json.dumps({"shape": [nq * kc, P, Dl], "forms": res, "all_checks_ok": bool(ok)}))
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
