@@ -85,6 +85,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 
+// non-blocking probe (try_wait may suspend the thread for a system-dependent time before it reports failure:
+// measured ~2.5 us per failed probe, which is a k-block's worth of MMAs)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+
 // Bounded wait: a protocol bug must surface as a launch failure, never as a hung
 // GPU.  The timer is only consulted after many failed probes.
 #ifndef SEMGATE_WAIT_TIMEOUT_NS
@@ -254,6 +266,28 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// The four K = 16 MMAs of one 64-wide k-block, cta_group::2, from the LOW words of the two shared-memory descriptors
+// (make_smem_desc_sw128: the high word is the constant kSmemDescHi; stepping 16 bf16 inside the 128-byte swizzle row adds
+// 2 to the address field, which never carries out of the low word).  32-bit arithmetic on uniform values instead of four
+// 64-bit descriptor adds per operand: the issuing thread's loop is what bounds a kernel whose k-blocks are short.
+constexpr uint32_t kSmemDescHi = 0x40004040u;       // SBO = 1024 >> 4 | version 1 << 14 | SWIZZLE_128B << 29
+__device__ __forceinline__ uint32_t smem_desc_lo_sw128(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ void umma4_bf16_cg2(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate_first) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t.reg .b32 a1, b1;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 q, %4, %4;\n\t"
+      "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t"
+      "add.u32 a1, %1, 2;\n\tadd.u32 b1, %2, 2;\n\tmov.b64 da, {a1, %5};\n\tmov.b64 db, {b1, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, q;\n\t"
+      "add.u32 a1, %1, 4;\n\tadd.u32 b1, %2, 4;\n\tmov.b64 da, {a1, %5};\n\tmov.b64 db, {b1, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, q;\n\t"
+      "add.u32 a1, %1, 6;\n\tadd.u32 b1, %2, 6;\n\tmov.b64 da, {a1, %5};\n\tmov.b64 db, {b1, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, q;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate_first), "r"(kSmemDescHi) : "memory");
 }
 
 // All MMAs issued so far by this thread arrive on `bar` (this CTA) once complete.

@@ -98,6 +98,7 @@ __device__ __forceinline__ float colmax32(const float (&v)[32], int lane) {
 }
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar2() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ bool pair_ok(const RerankParams& p, long long pr, int& q, int& m) {
   q = m = -1;
@@ -328,34 +329,47 @@ rerank_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Pair form (round 2): one CTA PAIR per (query, candidate) pair, `tcgen05.mma.cta_group::2` tiles of 256 candidate
-// patches x `bn` query patches -- every staged byte feeds twice the MMA work of the single-CTA form (128 x bn), which
-// was bound by operand delivery into the SMs (7.2 MB staged per 529 x 768 pair at ~11 TB/s, tensor pipe 30 % active).
+// Pair form (round 2): one CTA PAIR per (query, candidate) pair, `tcgen05.mma.cta_group::2` tiles of 256 query patches
+// (M, 128 per CTA) x `bn` candidate patches (N, half staged by each CTA).  Measured history at 529 x 768, 100k pairs:
+//   round 1, single CTAs, 128 x 192 tiles, one REDUX per column          73.1 ms   588 TFLOP/s useful
+//   ... column maxima by a shuffle butterfly (colmax32)                  54.0 ms   796   (the epilogue had bounded it)
+//   pair tiles 256 x 192, left-over patches as strip MMAs                42.7 ms  1007   (L2 -> SM delivery: 11.7 TB/s,
+//                                                                                 tensor pipe 78 %, profiles/r02_k5_pair.md)
+//   candidate tile kept in a shared-memory ring across the m-tiles       see DESIGN.md
 //
-// Patch counts are not multiples of 256 (DINOv2 at 322 x 322: P = 529 = 2 * 256 + 17).  Padding the candidate side to
-// three pair tiles would spend a third of the MMAs on zero rows, so when at most 32 candidate patches are left over
-// they become a STRIP: during the first pass over the query tiles the staged query rows (the B operand of the main
-// MMA, K-major and 128-byte swizzled like any A operand) are multiplied a second time as the A operand of a
-// 256 x 32 MMA against the left-over candidate patches, which stay resident in shared memory for the whole pair
-// (32 rows x feature length: 24 KB per CTA at 768-d).  Those small accumulators (one per query tile) sit behind the
-// two main ones in TMEM and are read with the tile they belong to.  P = 529: 512 x 544 + 544 x 32 multiplied for
-// 529 x 529 wanted (94 %), where the single-CTA form multiplies 640 x 576 (76 %).
+// Left-over patches.  Patch counts are not multiples of 256 (DINOv2 at 322 x 322: P = 529 = 2 * 256 + 17).  Padding the
+// M side to three pair tiles would spend a third of the MMAs on zero rows, so when at most 32 query patches are left
+// over they become a STRIP: in the pass of the first m-tile the staged candidate rows (the B operand of the main MMA,
+// K-major and 128-byte swizzled like any A operand) are multiplied once more, as the M operand of a 256 x 32 MMA
+// against the left-over query patches.  Those small accumulators (one per n-tile) sit behind the two main ones in TMEM
+// and are read with the tile they belong to.  P = 529: 512 x 544 + 544 x 32 multiplied for 529 x 529 wanted (94 %), where
+// the single-CTA form multiplies 640 x 576 (76 %).
 //
-// Row maxima of a main tile (a candidate patch's best query patch) stay in the owning thread's register across the
-// query tiles; column maxima (a query patch's best candidate patch) and the strip's maxima go through shared-memory
-// atomicMax on order-preserving integer images.  The odd CTA pushes its arrays into the even CTA's over distributed
-// shared memory at the end of the pair (red.max + a release-arrive on a barrier of the even CTA), which finishes the
-// score.  Arrays, partial sums and the merge barrier are double-buffered by pair parity; the MMA pipeline keeps the
-// two CTAs within two tiles of each other, so no other hand-shake is needed.
+// RING.  With k-block stages that hold both operands, every (m-tile, n-tile) stages 128 + bn/2 rows per CTA and k-block.
+// The ring form loops n-tiles outside, m-tiles inside and keeps the CTA's half of the candidate tile -- all its
+// k-blocks -- in shared memory (one slot per k-block, 144 KB at 768-d x 96 rows): a slot is filled once, read by every
+// m-tile's pass (and by the strip MMA), and released by the last one, so the next n-tile's (or next pair's) k-block is
+// fetched a whole pass ahead, which also hides the DRAM latency of the candidate's features (the query's are L2-hot: its
+// 25 candidates are consecutive pairs).  Only the query k-blocks stream through a short stage ring.  Rows staged per CTA
+// and pair at P = 529: 6 x 128 + 3 x 96 = 1056 against 6 x (128 + 96) = 1344.
+//
+// Maxima.  Row maxima (a query patch's best candidate patch) live in a per-thread shared-memory slot per m-tile; column
+// maxima (a candidate patch's best query patch) and the strip's go through shared-memory atomicMax on order-preserving
+// integer images.  The odd CTA pushes its arrays into the even CTA's over distributed shared memory at the end of the
+// pair (red.max + a release-arrive on a barrier of the even CTA), which finishes the score.  Arrays, partial sums and the
+// merge barrier are double-buffered by pair parity; the MMA pipeline keeps the CTAs of a pair within two tiles of each
+// other (and a pair has at least two tiles), so no other hand-shake is needed.
 struct PairParams {
-  int P, kblocks, stages, n_feat;
-  int mt2;          // 256-row pair tiles over the candidate's patches
-  int nt;           // n-tiles over the query's patches
-  int bn;           // n-tile width (multiple of 32)
-  int strip_rows;   // candidate patches [mt2 * 256, P) handled by the strip MMAs (0: none)
-  int pp;           // P rounded up to 32
-  uint32_t b_bytes;       // (bn / 2) rows of one k-block: this CTA's half of the B operand
-  uint32_t stage_bytes;   // b_bytes + 16 KiB (B first: the strip MMA reads 128 rows from the B base, which must stay inside the stage)
+  int P, kblocks, n_feat;
+  int stages;          // stage ring: query k-blocks (RING) or query + candidate k-blocks
+  int mt2;             // 256-row pair tiles over the query's patches
+  int nt;              // n-tiles over the candidate's patches
+  int bn;              // n-tile width (multiple of 32)
+  int strip_rows;      // query patches [mt2 * 256, P) handled by the strip MMAs (0: none)
+  int strip_resident;  // the strip operand stays in shared memory for the whole pair (1) or rides in the first m-tile's stages (0)
+  int pp;              // P rounded up to 32
+  uint32_t b_bytes;       // (bn / 2) rows of one k-block: this CTA's half of the candidate operand
+  uint32_t stage_bytes;   // one stage: [candidate half (not RING)] [query rows, 16 KiB] [strip rows, 2 KiB (streamed strip)]
   long long M;
   const int32_t* q_idx;
   const int32_t* m_idx;
@@ -364,6 +378,8 @@ struct PairParams {
   float* out_combined;
 };
 constexpr int kPMaxStages = 8;
+constexpr int kPThreads = 384;                       // warps: 0 stage producer, 1 MMA issuer, 2..5 and 8..11 epilogue, 6 ring producer, 7 idle
+constexpr int kPMaxKb = 16;                        // ring slots (k-blocks of the candidate tile): features up to 1024-d
 constexpr uint32_t kStripKbBytes = 16 * RBK * 2;   // one k-block of this CTA's half of the strip operand: 16 rows
 
 __device__ __forceinline__ bool pair_ok2(const PairParams& p, long long pr, int& q, int& m) {
@@ -372,33 +388,43 @@ __device__ __forceinline__ bool pair_ok2(const PairParams& p, long long pr, int&
   return q >= 0 && m >= 0 && q < p.n_feat && m < p.n_feat;
 }
 
-__global__ void __launch_bounds__(kRThreads, 1)
+template <bool RING, int ST>
+__global__ void __launch_bounds__(kPThreads, 1)
 rerank_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_s, const PairParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int stages = p.stages;
-  uint8_t* smem_st = smem;                                                              // [stages][B | A]
-  uint8_t* smem_s = smem + static_cast<size_t>(stages) * p.stage_bytes;                 // strip operand, [kblocks][16 rows]
+  const int stages = p.stages, KB = p.kblocks;
+  const bool strip = p.strip_rows > 0;
+  const bool s_res = strip && p.strip_resident != 0, s_str = strip && p.strip_resident == 0;
+  // [candidate ring (RING)] [stages] [resident strip operand] [maxima] [row maxima] [partial sums] [barriers]
+  uint8_t* smem_ring = smem;
+  uint8_t* smem_st = smem + (RING ? static_cast<size_t>(KB) * p.b_bytes : 0);
+  uint8_t* smem_s = smem_st + static_cast<size_t>(stages) * p.stage_bytes;
   const int arr_len = p.pp + 32;                                                        // column maxima, then the strip's 32
-  uint32_t* arrs = reinterpret_cast<uint32_t*>(smem_s + (p.strip_rows ? static_cast<size_t>(p.kblocks) * kStripKbBytes : 0));
-  float* scratch = reinterpret_cast<float*>(arrs + 2 * arr_len);                        // [2][16]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + 32);
+  uint32_t* arrs = reinterpret_cast<uint32_t*>(smem_s + (s_res ? static_cast<size_t>(KB) * kStripKbBytes : 0));
+  float* rm_s = reinterpret_cast<float*>(arrs + 2 * arr_len);                           // [2 parities][2 sets][mt2][128]
+  float* scratch = rm_s + 4 * p.mt2 * RBM;                                              // [2][24]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + 48);
   const uint32_t bar_full = ptx::smem_u32(bars);
   const uint32_t bar_empty = bar_full + 8 * kPMaxStages;
-  const uint32_t bar_tfull = bar_empty + 8 * kPMaxStages;
+  const uint32_t bar_bfull = bar_empty + 8 * kPMaxStages;
+  const uint32_t bar_bempty = bar_bfull + 8 * kPMaxKb;
+  const uint32_t bar_tfull = bar_bempty + 8 * kPMaxKb;
   const uint32_t bar_tempty = bar_tfull + 16;
   const uint32_t bar_sfull = bar_tempty + 16;
   const uint32_t bar_sfree = bar_sfull + 8;
   const uint32_t bar_merge = bar_sfree + 8;                                             // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPMaxStages + 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPMaxStages + 2 * kPMaxKb + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = rank == 0;
   const long long cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
   const int BN = p.bn, NT = p.nt, MT2 = p.mt2;
-  const bool strip = p.strip_rows > 0;
+  // offsets inside a stage
+  const uint32_t st_a = RING ? 0u : p.b_bytes;       // query rows (the candidate half comes first: the strip MMA reads 128 rows
+  const uint32_t st_s = st_a + RA_BYTES;             //   from its base, which must stay inside the stage); strip rows last
 
   ptx::cluster_sync();                               // the peer must be resident before a pair-wide TMEM allocation
   if (threadIdx.x == 0) {
@@ -406,17 +432,18 @@ rerank_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     ptx::prefetch_tensormap(&tmap_b);
     ptx::prefetch_tensormap(&tmap_s);
     for (int s = 0; s < stages; ++s) { ptx::mbar_init(bar_full + 8 * s, 2); ptx::mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < kPMaxKb; ++s) { ptx::mbar_init(bar_bfull + 8 * s, 2); ptx::mbar_init(bar_bempty + 8 * s, 1); }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(bar_tfull + 8 * a, 1);
-      ptx::mbar_init(bar_tempty + 8 * a, 8);         // four epilogue warps of each CTA
-      ptx::mbar_init(bar_merge + 8 * a, 128);        // every epilogue thread of the odd CTA
+      ptx::mbar_init(bar_tempty + 8 * a, 16);        // eight epilogue warps of each CTA
+      ptx::mbar_init(bar_merge + 8 * a, 256);        // every epilogue thread of the odd CTA
     }
     ptx::mbar_init(bar_sfull, 2);
     ptx::mbar_init(bar_sfree, 1);
     ptx::fence_barrier_init();
     ptx::fence_proxy_async();
   }
-  for (int c = threadIdx.x; c < 2 * arr_len; c += kRThreads) arrs[c] = 0u;
+  for (int c = threadIdx.x; c < 2 * arr_len; c += kPThreads) arrs[c] = 0u;
   if (warp == 1) ptx::tmem_alloc<2>(ptx::smem_u32(tmem_slot), 512);
   ptx::tc_fence_before();
   ptx::cluster_sync();
@@ -433,82 +460,130 @@ rerank_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     for (long long g = cluster_id; g < p.M; g += n_clusters) {
       int q, m;
       if (!pair_ok2(p, g, q, m)) continue;
-      if (strip) {
+      if (s_res) {
         ptx::mbar_wait(bar_sfree, (pc & 1u) ^ 1u);   // the previous pair's strip MMAs have read it
         if (ptx::elect_one()) {
           const uint32_t fb = ptx::mapa(bar_sfull, 0);
-          if (leader) ptx::mbar_arrive_expect_tx(bar_sfull, 2u * static_cast<uint32_t>(p.kblocks) * kStripKbBytes);
-          for (int kb = 0; kb < p.kblocks; ++kb)
-            ptx::tma_load_3d_cg2(ptx::smem_u32(smem_s) + kb * kStripKbBytes, &tmap_s, fb, kb * RBK, MT2 * 256 + static_cast<int>(rank) * 16, m);
+          if (leader) ptx::mbar_arrive_expect_tx(bar_sfull, 2u * static_cast<uint32_t>(KB) * kStripKbBytes);
+          for (int kb = 0; kb < KB; ++kb)
+            ptx::tma_load_3d_cg2(ptx::smem_u32(smem_s) + kb * kStripKbBytes, &tmap_s, fb, kb * RBK, MT2 * 256 + static_cast<int>(rank) * 16, q);
           if (!leader) ptx::mbar_arrive_cluster(bar_sfull, 0);
         }
         __syncwarp();
       }
-      for (int mt = 0; mt < MT2; ++mt)
-        for (int nt = 0; nt < NT; ++nt) {
-          const int b_row = nt * BN + static_cast<int>(rank) * (tile_nw(nt) >> 1);
-          for (int kb = 0; kb < p.kblocks; ++kb) {
+      for (int nt = 0; nt < NT; ++nt) {
+        const int b_row = nt * BN + static_cast<int>(rank) * (tile_nw(nt) >> 1);
+        for (int mt = 0; mt < MT2; ++mt) {
+          const bool with_s = s_str && mt == 0;
+          const int a_row = mt * 256 + static_cast<int>(rank) * RBM;
+          const uint32_t tx = 2u * ((RING ? 0u : p.b_bytes) + RA_BYTES + (with_s ? kStripKbBytes : 0u));
+          for (int kb = 0; kb < KB; ++kb) {
             ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
             if (ptx::elect_one()) {
               const uint32_t fb_local = bar_full + 8 * stage;
               const uint32_t fb = ptx::mapa(fb_local, 0);
               const uint32_t dst = ptx::smem_u32(smem_st) + stage * p.stage_bytes;
-              if (leader) ptx::mbar_arrive_expect_tx(fb_local, 2u * p.stage_bytes);
-              ptx::tma_load_3d_cg2(dst, &tmap_b, fb, kb * RBK, b_row, q);
-              ptx::tma_load_3d_cg2(dst + p.b_bytes, &tmap_a, fb, kb * RBK, mt * 256 + static_cast<int>(rank) * RBM, m);
+              if (leader) ptx::mbar_arrive_expect_tx(fb_local, tx);
+              if constexpr (!RING) ptx::tma_load_3d_cg2(dst, &tmap_b, fb, kb * RBK, b_row, m);
+              ptx::tma_load_3d_cg2(dst + st_a, &tmap_a, fb, kb * RBK, a_row, q);
+              if (with_s) ptx::tma_load_3d_cg2(dst + st_s, &tmap_s, fb, kb * RBK, MT2 * 256 + static_cast<int>(rank) * 16, q);
               if (!leader) ptx::mbar_arrive_cluster(fb_local, 0);
             }
             __syncwarp();
             if (++stage == static_cast<uint32_t>(stages)) { stage = 0; phase ^= 1; }
           }
         }
+      }
       ++pc;
+    }
+  } else if (warp == 6) {
+    // ----------------------------------------------------------- RING: the candidate ring's own producer (both CTAs)
+    // One slot per k-block; a slot is refilled as soon as the last m-tile's pass of the tile before has read it, so the
+    // ring runs a whole pass ahead of the MMAs by itself -- no look-ahead bookkeeping, and the stage producer's loop
+    // stays as short as the plain form's (one warp issuing both streams took ~900 clocks per k-block: the MMA issuer
+    // spent half its time waiting for query stages that were not even requested yet).
+    if constexpr (RING) {
+      uint32_t bt = 0;                               // candidate tiles so far = use count of every slot
+      for (long long g = cluster_id; g < p.M; g += n_clusters) {
+        int q, m;
+        if (!pair_ok2(p, g, q, m)) continue;
+        for (int nt = 0; nt < NT; ++nt, ++bt) {
+          const int b_row = nt * BN + static_cast<int>(rank) * (tile_nw(nt) >> 1);
+          for (int kb = 0; kb < KB; ++kb) {
+            ptx::mbar_wait(bar_bempty + 8 * kb, (bt & 1u) ^ 1u);
+            if (ptx::elect_one()) {
+              const uint32_t fb_local = bar_bfull + 8 * kb;
+              if (leader) ptx::mbar_arrive_expect_tx(fb_local, 2u * p.b_bytes);
+              ptx::tma_load_3d_cg2(ptx::smem_u32(smem_ring) + kb * p.b_bytes, &tmap_b, ptx::mapa(fb_local, 0), kb * RBK, b_row, m);
+              if (!leader) ptx::mbar_arrive_cluster(fb_local, 0);
+            }
+            __syncwarp();
+          }
+        }
+      }
     }
   } else if (warp == 1) {
     // ----------------------------------------------------------- MMA issuer (leader CTA)
     if (leader) {
-      const uint64_t desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_st));
-      const uint64_t sdesc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_s));
+      const uint32_t lo_st0 = ptx::smem_desc_lo_sw128(ptx::smem_u32(smem_st));      // low descriptor words (ptx::umma4_bf16_cg2)
+      const uint32_t lo_ring0 = ptx::smem_desc_lo_sw128(ptx::smem_u32(smem_ring));
+      const uint32_t lo_s0 = ptx::smem_desc_lo_sw128(ptx::smem_u32(smem_s));
       constexpr uint32_t idesc_strip = ptx::make_idesc_bf16_f32(256, 32);
+      uint32_t bt = 0;                               // candidate tiles so far: use count of the ring slots
       for (long long g = cluster_id; g < p.M; g += n_clusters) {
         int q, m;
         if (!pair_ok2(p, g, q, m)) continue;
-        for (int mt = 0; mt < MT2; ++mt)
-          for (int nt = 0; nt < NT; ++nt, ++it) {
-            const uint32_t idesc = ptx::make_idesc_bf16_f32(256, static_cast<uint32_t>(tile_nw(nt)));
+        for (int nt = 0; nt < NT; ++nt, ++bt) {
+          const uint32_t idesc = ptx::make_idesc_bf16_f32(256, static_cast<uint32_t>(tile_nw(nt)));
+          for (int mt = 0; mt < MT2; ++mt, ++it) {
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
             const bool do_strip = strip && mt == 0;
             ptx::mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
-            if (do_strip && nt == 0) ptx::mbar_wait(bar_sfull, pc & 1u);
+            if (s_res && nt == 0 && mt == 0) ptx::mbar_wait(bar_sfull, pc & 1u);
             ptx::tc_fence_after();
             const uint32_t d_main = tmem_base + acc * BN;
             const uint32_t d_strip = tmem_base + 2 * BN + 32 * nt;
-            for (int kb = 0; kb < p.kblocks; ++kb) {
-              ptx::mbar_wait(bar_full + 8 * stage, phase);
+            // one k-block: wait for its stage (and, first pass of a RING tile, its ring slot), issue, release
+            auto step = [&](int kb, uint32_t sg, uint32_t ph) {
+              ptx::mbar_wait(bar_full + 8 * sg, ph);
+              if (RING && mt == 0) ptx::mbar_wait(bar_bfull + 8 * kb, bt & 1u);
               ptx::tc_fence_after();
-              const uint64_t bdesc = desc0 + static_cast<uint64_t>((stage * p.stage_bytes) >> 4);
-              const uint64_t adesc = bdesc + static_cast<uint64_t>(p.b_bytes >> 4);
-              const uint64_t sdesc = sdesc0 + static_cast<uint64_t>((kb * kStripKbBytes) >> 4);
+              const uint32_t st_lo = lo_st0 + ((sg * p.stage_bytes) >> 4);
+              const uint32_t a_lo = st_lo + (st_a >> 4);
+              const uint32_t b_lo = RING ? lo_ring0 + ((static_cast<uint32_t>(kb) * p.b_bytes) >> 4) : st_lo;
               if (ptx::elect_one()) {
-#pragma unroll
-                for (int kk = 0; kk < RBK / RUK; ++kk)
-                  ptx::umma_bf16<2>(d_main, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb | kk) != 0);
+                ptx::umma4_bf16_cg2(d_main, a_lo, b_lo, idesc, static_cast<uint32_t>(kb));
                 if (do_strip) {
-                  // the staged query rows once more, as the M operand against the resident left-over candidate patches
-#pragma unroll
-                  for (int kk = 0; kk < RBK / RUK; ++kk)
-                    ptx::umma_bf16<2>(d_strip, bdesc + 2 * kk, sdesc + 2 * kk, idesc_strip, (kb | kk) != 0);
+                  // the staged candidate rows once more, as the M operand against the left-over query patches
+                  const uint32_t s_lo = s_res ? lo_s0 + ((static_cast<uint32_t>(kb) * kStripKbBytes) >> 4) : st_lo + (st_s >> 4);
+                  ptx::umma4_bf16_cg2(d_strip, b_lo, s_lo, idesc_strip, static_cast<uint32_t>(kb));
                 }
-                ptx::umma_commit_cg2_mc(bar_empty + 8 * stage, 0b11);
-                if (kb == p.kblocks - 1) {
-                  if (do_strip && nt == NT - 1) ptx::umma_commit_cg2_mc(bar_sfree, 0b11);
+                ptx::umma_commit_cg2_mc(bar_empty + 8 * sg, 0b11);
+                if (RING && mt == MT2 - 1) ptx::umma_commit_cg2_mc(bar_bempty + 8 * kb, 0b11);
+                if (kb == KB - 1) {
+                  if (s_res && mt == 0 && nt == NT - 1) ptx::umma_commit_cg2_mc(bar_sfree, 0b11);
                   ptx::umma_commit_cg2_mc(bar_tfull + 8 * acc, 0b11);
                 }
               }
               __syncwarp();
-              if (++stage == static_cast<uint32_t>(stages)) { stage = 0; phase ^= 1; }
+            };
+            if constexpr (ST > 0) {
+              // the stage count divides the k-blocks of a tile: stage indices are compile-time inside the unrolled group, so
+              // barrier addresses and descriptors are loop-invariant (the run-time form spent ~110 instructions per k-block
+              // on them, 560 clocks on a scheduler it shares with an epilogue warp, against 384 clocks of MMAs)
+              for (int kb0 = 0; kb0 < KB; kb0 += ST) {
+#pragma unroll
+                for (int sg = 0; sg < ST; ++sg) step(kb0 + sg, static_cast<uint32_t>(sg), phase);
+                phase ^= 1;
+              }
+            } else {
+              for (int kb = 0; kb < KB; ++kb) {
+                step(kb, stage, phase);
+                if (++stage == static_cast<uint32_t>(stages)) { stage = 0; phase ^= 1; }
+              }
             }
           }
+        }
         ++pc;
       }
       if (it > 0) {                                  // the peer's epilogue arrives remotely on our barriers: drain
@@ -517,14 +592,19 @@ rerank_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp != 7) {
     // ----------------------------------------------------------- epilogue: row / column maxima (both CTAs)
+    // Two sets of four warps (2..5 and 8..11; a warp reads the TMEM lanes of quad warp % 4): set s takes the 32-column
+    // chunks c = s, s + 2, ... of every tile.  One set was as slow as the MMAs (a chunk is ~250 instructions and a chain of
+    // five dependent shuffle levels), so every form of this kernel -- whatever it staged -- ended at ~30 us per pair.
+    const int set = warp >= 8 ? 1 : 0;
     const int quad = warp & 3;
     const int row_in_tile = quad * 32 + lane;
-    const int et = (warp - 2) * 32 + lane;
+    const int et = (set ? (warp - 8) : (warp - 2)) * 32 + lane + set * 128;     // 0..255 among the epilogue threads
+    const int ew = et >> 5;                                                      // 0..7
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const float neg_inf = __int_as_float(0xff800000);
-    const int row_limit = strip ? MT2 * 256 : p.P;   // candidate patches covered by main tiles
+    const int row_limit = strip ? MT2 * 256 : p.P;   // query patches covered by main tiles
     for (long long g = cluster_id; g < p.M; g += n_clusters) {
       int q, m;
       if (!pair_ok2(p, g, q, m)) {
@@ -536,18 +616,21 @@ rerank_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
       const uint32_t par = pc & 1u;
       uint32_t* arr = arrs + par * arr_len;
-      float* scr = scratch + par * 16;
-      float rsum = 0.f;
-      for (int mt = 0; mt < MT2; ++mt) {
-        const bool row_valid = mt * 256 + static_cast<int>(rank) * RBM + row_in_tile < row_limit;
-        float rmax = neg_inf;
-        for (int nt = 0; nt < NT; ++nt, ++it) {
+      float* scr = scratch + par * 24;
+      float* rm_pair = rm_s + par * (2 * MT2 * RBM);               // partial row maxima, [set][mt][row in tile]; the other set reads
+      float* rm_mine = rm_pair + set * (MT2 * RBM);                // them at the end of the pair, hence one copy per pair parity
+      for (int mt = 0; mt < MT2; ++mt) rm_mine[mt * RBM + row_in_tile] = neg_inf;     // this thread's slots only
+      for (int nt = 0; nt < NT; ++nt) {
+        const int ncols = min(BN, p.P - nt * BN);
+        const int strip_set = ((ncols + 31) >> 5) & 1;           // the set with fewer main chunks (or set 0) reads the strip
+        for (int mt = 0; mt < MT2; ++mt, ++it) {
           const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+          const bool row_valid = mt * 256 + static_cast<int>(rank) * RBM + row_in_tile < row_limit;
+          float rmax = rm_mine[mt * RBM + row_in_tile];
           ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase);
           ptx::tc_fence_after();
           const uint32_t t_acc = t_lane + acc * BN;
-          const int ncols = min(BN, p.P - nt * BN);
-          for (int c = 0; c * 32 < ncols; ++c) {
+          for (int c = set; c * 32 < ncols; c += 2) {
             uint32_t v[32];
             ptx::tmem_ld_32x32(t_acc + c * 32, v);
             ptx::tmem_wait_ld();
@@ -562,11 +645,12 @@ rerank_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             const float cm = colmax32(x, lane);
             if (lane < nv) atomicMax(&arr[nt * BN + c * 32 + lane], score_to_ordered(cm));
           }
-          if (strip && mt == 0) {
-            // rows: the query patches this CTA staged for the tile; columns: the left-over candidate patches
+          rm_mine[mt * RBM + row_in_tile] = rmax;
+          if (strip && mt == 0 && set == strip_set) {
+            // rows: the candidate patches this CTA staged for the tile; columns: the left-over query patches
             const int half = tile_nw(nt) >> 1;
-            const int qrow = nt * BN + static_cast<int>(rank) * half + row_in_tile;
-            const bool qv = row_in_tile < half && qrow < p.P;
+            const int crow = nt * BN + static_cast<int>(rank) * half + row_in_tile;
+            const bool cvld = row_in_tile < half && crow < p.P;
             uint32_t v[32];
             ptx::tmem_ld_32x32(t_lane + 2 * BN + 32 * nt, v);
             ptx::tmem_wait_ld();
@@ -576,12 +660,11 @@ rerank_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             for (int i = 0; i < 32; ++i) {
               const float xi = __uint_as_float(v[i]);
               if (i < p.strip_rows) r2 = fmaxf(r2, xi);          // warp-uniform
-              x[i] = qv ? xi : neg_inf;
+              x[i] = cvld ? xi : neg_inf;
             }
             const float cm = colmax32(x, lane);
-            const uint32_t cmo = score_to_ordered(cm);
-            if (lane < p.strip_rows && cmo != score_to_ordered(neg_inf)) atomicMax(&arr[p.pp + lane], cmo);
-            if (qv) atomicMax(&arr[qrow], score_to_ordered(r2));
+            if (lane < p.strip_rows) atomicMax(&arr[p.pp + lane], score_to_ordered(cm));
+            if (cvld) atomicMax(&arr[crow], score_to_ordered(r2));
           }
           ptx::tc_fence_before();
           __syncwarp();
@@ -590,28 +673,32 @@ rerank_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             else ptx::mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
           }
         }
-        if (row_valid) rsum += rmax;
       }
       // ---- finish the pair
+      epi_bar2();                                                 // every warp's atomics and partial row maxima have landed
+      float rsum = 0.f;
+      if (set == 0) {
+        for (int mt = 0; mt < MT2; ++mt)
+          if (mt * 256 + static_cast<int>(rank) * RBM + row_in_tile < row_limit)
+            rsum += fmaxf(rm_pair[mt * RBM + row_in_tile], rm_pair[(MT2 + mt) * RBM + row_in_tile]);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
+        for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
+      }
       if (!leader) {
-        epi_bar();                                                // every warp's atomics have landed
-        for (int c = et; c < arr_len; c += 128) {
+        for (int c = et; c < arr_len; c += 256) {
           const uint32_t vv = arr[c];
           if (vv != 0u) {
             ptx::red_max_u32_cluster(ptx::mapa(ptx::smem_u32(arr + c), 0), vv);
             arr[c] = 0u;
           }
         }
-        if (lane == 0) ptx::st_f32_cluster(ptx::mapa(ptx::smem_u32(scr + 4 + (warp - 2)), 0), rsum);
+        if (set == 0 && lane == 0) ptx::st_f32_cluster(ptx::mapa(ptx::smem_u32(scr + 4 + ew), 0), rsum);
         ptx::mbar_arrive_release_cluster(bar_merge + 8 * par, 0);
       } else {
-        if (lane == 0) scr[warp - 2] = rsum;
+        if (set == 0 && lane == 0) scr[ew] = rsum;
         ptx::mbar_wait_acquire_cluster(bar_merge + 8 * par, (pc >> 1) & 1u);
-        epi_bar();                                                // ... and ours
         float csum = 0.f, ssum = 0.f;
-        for (int c = et; c < p.P; c += 128) {
+        for (int c = et; c < p.P; c += 256) {
           csum += ordered_to_score(arr[c]);
           arr[c] = 0u;
         }
@@ -624,11 +711,11 @@ rerank_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           csum += __shfl_xor_sync(0xffffffffu, csum, o);
           ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
         }
-        if (lane == 0) { scr[8 + warp - 2] = csum; if (warp == 2) scr[12] = ssum; }
-        epi_bar();
+        if (lane == 0) { scr[8 + ew] = csum; if (ew == 0) scr[16] = ssum; }
+        epi_bar2();
         if (et == 0) {
-          const float rs = ((scr[0] + scr[1]) + (scr[2] + scr[3])) + ((scr[4] + scr[5]) + (scr[6] + scr[7])) + scr[12];
-          const float cs = (scr[8] + scr[9]) + (scr[10] + scr[11]);
+          const float rs = ((scr[0] + scr[1]) + (scr[2] + scr[3])) + ((scr[4] + scr[5]) + (scr[6] + scr[7])) + scr[16];
+          const float cs = ((scr[8] + scr[9]) + (scr[10] + scr[11])) + ((scr[12] + scr[13]) + (scr[14] + scr[15]));
           const float inv = 1.0f / static_cast<float>(p.P);
           const float cross = sqrtf((rs * inv) * (cs * inv));
           p.out_cross[g] = cross;
@@ -644,6 +731,7 @@ rerank_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   ptx::tc_fence_after();
   if (warp == 1) ptx::tmem_dealloc<2>(tmem_base, 512);
 }
+
 
 PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -677,11 +765,12 @@ int make_tmap3(CUtensorMap* m, const void* base, int n_feat, int P, int dl_pad, 
 namespace {
 constexpr int kPairFormNotApplicable = -77;
 
-// the pair form's tiling for P patches x dl_pad features; false: use a round-1 form
-bool pair_tiling(int P, int dl_pad, PairParams& p, size_t& smem) {
+// the pair form's tiling for P patches x dl_pad features; false: use a round-1 form.  `ring`: in = allowed, out = chosen.
+bool pair_tiling(int P, int dl_pad, PairParams& p, size_t& smem, bool& ring, int strip_mode) {
   if (P <= RBM) return false;                          // one 128-row tile: a CTA pair would multiply zeros
   const int kblocks = dl_pad / RBK;
   const int full = P / 256, rem = P - full * 256;
+  const bool ring_allowed = ring && kblocks <= kPMaxKb;
   for (int want_strip = 1; want_strip >= 0; --want_strip) {
     const bool strip = want_strip && full >= 1 && rem > 0 && rem <= 32;
     if (want_strip && !strip) continue;
@@ -698,15 +787,30 @@ bool pair_tiling(int P, int dl_pad, PairParams& p, size_t& smem) {
     p.strip_rows = strip ? rem : 0;
     p.pp = (P + 31) & ~31;
     p.b_bytes = static_cast<uint32_t>(bn / 2) * RBK * 2;
-    p.stage_bytes = p.b_bytes + RA_BYTES;
-    const size_t fixed = 1024 + (strip ? static_cast<size_t>(kblocks) * kStripKbBytes : 0) + static_cast<size_t>(2 * (p.pp + 32)) * 4 + 128 +
-                         (2 * kPMaxStages + 8) * 8 + 16;
-    if (fixed + 3 * static_cast<size_t>(p.stage_bytes) > 232448) continue;
-    int stages = static_cast<int>((232448 - fixed) / p.stage_bytes);
-    stages = std::min(stages, kPMaxStages);
-    p.stages = std::min(stages, std::max(3, kblocks * 2));
-    smem = fixed + static_cast<size_t>(p.stages) * p.stage_bytes;
-    return true;
+    const size_t fixed = 1024 + static_cast<size_t>(2 * (p.pp + 32)) * 4 + static_cast<size_t>(4 * mt2) * RBM * 4 + 192 +
+                         (2 * kPMaxStages + 2 * kPMaxKb + 8) * 8 + 16;
+    // candidate ring first (fewest bytes staged), then plain stages; the strip operand resident or streamed, whichever
+    // leaves more stages (streamed on a tie: it frees a slot's worth of shared memory for the ring)
+    for (int r = ring_allowed ? 1 : 0; r >= 0; --r) {
+      int best_stages = 0, best_res = 0;
+      for (int res = 1; res >= 0; --res) {
+        if (!strip && res == 0) continue;
+        if (strip && strip_mode >= 0 && res != strip_mode) continue;
+        const size_t stage_bytes = (r ? 0 : p.b_bytes) + RA_BYTES + ((strip && !res) ? kStripKbBytes : 0);
+        const size_t other = fixed + (r ? static_cast<size_t>(kblocks) * p.b_bytes : 0) + ((strip && res) ? static_cast<size_t>(kblocks) * kStripKbBytes : 0);
+        if (other + 3 * stage_bytes > 232448) continue;
+        const int st = static_cast<int>(std::min<size_t>((232448 - other) / stage_bytes, kPMaxStages));
+        if (st >= best_stages) { best_stages = st; best_res = res; }
+      }
+      if (best_stages < 3) continue;
+      p.strip_resident = best_res;
+      p.stage_bytes = static_cast<uint32_t>((r ? 0 : p.b_bytes) + RA_BYTES + ((strip && !best_res) ? kStripKbBytes : 0));
+      p.stages = best_stages;
+      smem = fixed + (r ? static_cast<size_t>(kblocks) * p.b_bytes : 0) + ((strip && best_res) ? static_cast<size_t>(kblocks) * kStripKbBytes : 0) +
+             static_cast<size_t>(p.stages) * p.stage_bytes;
+      ring = r != 0;
+      return true;
+    }
   }
   return false;
 }
@@ -715,7 +819,13 @@ int launch_rerank_pair(const void* feats_bf16, int n_feat, int P, int dl_pad, co
                        const float* global_sim, int64_t M, float* out_cross, float* out_combined, int sm_count, cudaStream_t st) {
   PairParams p{};
   size_t smem = 0;
-  if (!pair_tiling(P, dl_pad, p, smem)) return kPairFormNotApplicable;
+  // A/B knobs (defaults are the measured best): SEMGATE_RERANK_RING=0 forbids the candidate ring,
+  // SEMGATE_RERANK_STRIP=1 / 0 pins the strip operand resident / streamed
+  bool ring = true;
+  int strip_mode = -1;
+  if (const char* e = getenv("SEMGATE_RERANK_RING")) ring = atoi(e) != 0;
+  if (const char* e = getenv("SEMGATE_RERANK_STRIP")) strip_mode = atoi(e) != 0 ? 1 : 0;
+  if (!pair_tiling(P, dl_pad, p, smem, ring, strip_mode)) return kPairFormNotApplicable;
   CUtensorMap ta, tb, ts;
   int rc = make_tmap3(&ta, feats_bf16, n_feat, P, dl_pad, RBM);
   if (rc) return rc;
@@ -730,18 +840,36 @@ int launch_rerank_pair(const void* feats_bf16, int n_feat, int P, int dl_pad, co
   const unsigned clusters = static_cast<unsigned>(std::min<int64_t>(M, std::max(1, sm_count / 2)));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * 2);
-  cfg.blockDim = dim3(kRThreads);
+  cfg.blockDim = dim3(kPThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t e = cudaFuncSetAttribute(rerank_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  if (e != cudaSuccess) return static_cast<int>(e);
-  return static_cast<int>(cudaLaunchKernelEx(&cfg, rerank_pair_kernel, ta, tb, ts, p));
+  auto launch = [&](auto kernel) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    return cudaLaunchKernelEx(&cfg, kernel, ta, tb, ts, p);
+  };
+  // compile-time stage counts that divide the k-blocks of a tile (see the MMA issuer); otherwise the run-time ring
+  int ust = 0;
+  if (const char* e = getenv("SEMGATE_RERANK_UNROLL")) ust = atoi(e) != 0 ? 0 : -1;
+  if (ust == 0) {
+    for (int cand : {6, 4, 3}) if (p.stages >= cand && p.kblocks % cand == 0) { ust = cand; break; }
+    if (ust > 0) {
+      smem -= static_cast<size_t>(p.stages - ust) * p.stage_bytes;
+      p.stages = ust;
+    }
+  }
+  cfg.dynamicSmemBytes = smem;
+  cudaError_t e;
+  if (ring) e = ust == 6 ? launch(rerank_pair_kernel<true, 6>) : ust == 4 ? launch(rerank_pair_kernel<true, 4>) : ust == 3 ? launch(rerank_pair_kernel<true, 3>) : launch(rerank_pair_kernel<true, 0>);
+  else e = ust == 6 ? launch(rerank_pair_kernel<false, 6>) : ust == 4 ? launch(rerank_pair_kernel<false, 4>) : ust == 3 ? launch(rerank_pair_kernel<false, 3>) : launch(rerank_pair_kernel<false, 0>);
+  return static_cast<int>(e);
 }
 }  // namespace
+
 
 int launch_rerank(const void* feats_bf16, int n_feat, int P, int dl_pad, const int32_t* q_idx, const int32_t* m_idx,
                   const float* global_sim, int64_t M, float* out_cross, float* out_combined, int sm_count,

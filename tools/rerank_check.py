@@ -38,8 +38,9 @@ def run(eng, form, feats, qi, mi, gs):
 def main():
     eng = _native.get_engine(0)
     ok = True
+    timing_only = len(sys.argv) > 2 and sys.argv[2] == "timing-only"
     g = torch.Generator(device="cuda").manual_seed(5)
-    for P, D in ((129, 64), (200, 128), (256, 128), (257, 64), (280, 192), (288, 64), (300, 128), (512, 64), (529, 768), (530, 128), (544, 64),
+    for P, D in () if timing_only else ((129, 64), (200, 128), (256, 128), (257, 64), (280, 192), (288, 64), (300, 128), (512, 64), (529, 768), (530, 128), (544, 64),
                  (545, 128), (600, 64), (769, 64), (800, 128), (1024, 64), (1030, 64), (100, 128)):
         n = 24
         x = torch.randn((n * P, D), device="cuda", generator=g) + 0.3
@@ -63,12 +64,13 @@ def main():
         ok &= good
         print(f"P={P:5d} D={D:4d}: |pair - ref| {e_new:.2e}  |r1 - ref| {e_old:.2e}  |pair - r1| {e_no:.2e}  nan {nan_same} comb {comb_ok}  {'ok' if good else 'FAILED'}",
               flush=True)
-    # twice the same launch: the merge buffers must come back clean
-    a1, _ = run(eng, None, feats, qi, mi, gs)
-    a2, _ = run(eng, None, feats, qi, mi, gs)
-    same = np.array_equal(a1, a2, equal_nan=True)
-    ok &= same
-    print("repeat launch identical:", same)
+    if not timing_only:
+        # twice the same launch: the merge buffers must come back clean
+        a1, _ = run(eng, None, feats, qi, mi, gs)
+        a2, _ = run(eng, None, feats, qi, mi, gs)
+        same = np.array_equal(a1, a2, equal_nan=True)
+        ok &= same
+        print("repeat launch identical:", same)
 
     # ---- timing, DINOv2 shape
     pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
