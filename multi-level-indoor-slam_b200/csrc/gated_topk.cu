@@ -18,7 +18,7 @@ static long env_long(const char* name, long dflt) {
   return (e && *e) ? atol(e) : dflt;
 }
 
-static size_t smem_bytes_for(int cg, int stages, int kstride, bool sym = false);
+static size_t smem_bytes_for(int cg, int stages, int kstride, bool sym = false, int sets = 1);
 constexpr size_t kSmemLimit = 232448;   // 227 KB per CTA
 
 // Schedule units (CTAs, CTA pairs, or 4-CTA clusters of two pairs) that are co-resident.  A cluster
@@ -404,11 +404,12 @@ static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int d_pad, 
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
 }
 
-static size_t smem_bytes_for(int cg, int stages, int kstride, bool sym) {
+static size_t smem_bytes_for(int cg, int stages, int kstride, bool sym, int sets) {
   const size_t stage = A_STAGE_BYTES + static_cast<size_t>(BN / std::min(cg, 2)) * BK * 2;
   return 1024 /*realign slack*/ + stages * stage + static_cast<size_t>(BM) * kstride * 8 +
          2 * BN * (sizeof(float) + sizeof(int32_t)) /*per-tile timestamp offsets + labels*/ +
-         (sym ? 2 * BN * sizeof(float) + 64 : 0) /*column bounds + chunk minima*/ + 256 /*barriers + tmem slot*/;
+         (sym ? 2 * BN * sizeof(float) + 64 : 0) /*column bounds + chunk minima*/ +
+         (sets == 2 ? static_cast<size_t>(BM) * 24 : 0) /*shared row-list state*/ + 128 /*chunk stamp ranges*/ + 256 /*barriers + tmem slot*/;
 }
 
 // Symmetric sweep: candidate-buffer depth per keyframe and the layout of its state behind the pacing counters:
@@ -489,12 +490,16 @@ int launch_gated_topk(const TopkLaunch& a, const Schedule& sc, uint64_t* partial
   //  before its last reader arrives -- measured 1.337 -> 1.290 ms at config 2 without it)
   p.policy_db = (hint >= 2 && sc.a_resident && sc.tab_runs == nullptr) ? ptx::kL2EvictFirst : ptx::kL2EvictNormal;
 
+  // Two epilogue sets where the epilogue, not the MMAs, bounds the kernel: descriptors of up to 1024 elements (a tile's
+  // MMAs take at most 16 k-blocks; config 1, 5k x 512-d: K2 50 -> see DESIGN.md).  Plain list-building sweeps only.
+  int sets = (!sym && cg != 4 && a.dense == nullptr && p.kblocks <= 16) ? 2 : 1;
+  if (const char* e = getenv("SEMGATE_EPI_SETS")) { const int v = atoi(e); if (v == 1 || (v == 2 && !sym && cg != 4 && a.dense == nullptr)) sets = v; }
   // deepest ring that fits the 227 KB per-CTA limit
   int stages = kMaxStages;
-  while (stages > 2 && smem_bytes_for(cg, stages, p.kstride, sym) > kSmemLimit) --stages;
+  while (stages > 2 && smem_bytes_for(cg, stages, p.kstride, sym, sets) > kSmemLimit) --stages;
   stages = std::min(stages, std::max(2, p.kblocks));
   p.stages = stages;
-  const size_t smem = smem_bytes_for(cg, stages, p.kstride, sym);
+  const size_t smem = smem_bytes_for(cg, stages, p.kstride, sym, sets);
 
   const int units = topk_units(cg, a.sm_count);
   // only units that receive work in some super-row need to exist
@@ -506,7 +511,7 @@ int launch_gated_topk(const TopkLaunch& a, const Schedule& sc, uint64_t* partial
 
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(used * cg));
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(64 + 128 * sets);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -521,8 +526,8 @@ int launch_gated_topk(const TopkLaunch& a, const Schedule& sc, uint64_t* partial
   };
   if (sym) e = launch(gated_topk_kernel<2, 1, true>);
   else if (cg == 4) e = launch(gated_topk_kernel<2, 2>);
-  else if (cg == 2) e = launch(gated_topk_kernel<2, 1>);
-  else e = launch(gated_topk_kernel<1, 1>);
+  else if (cg == 2) e = sets == 2 ? launch(gated_topk_kernel<2, 1, false, 2>) : launch(gated_topk_kernel<2, 1>);
+  else e = sets == 2 ? launch(gated_topk_kernel<1, 1, false, 2>) : launch(gated_topk_kernel<1, 1>);
   if (e != cudaSuccess) return static_cast<int>(e);
   if (launches) ++*launches;
   return 0;

@@ -121,12 +121,13 @@ __device__ __forceinline__ bool window_excluded(float a, float b, float gap_lo, 
   return time_excluded(__ldg(t_db_ptr), t_q, gap);
 }
 
-template <int CG, int MC, bool SYM = false>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int CG, int MC, bool SYM = false, int SETS = 1>
+__global__ void __launch_bounds__(64 + 128 * SETS, 1)
 gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
                   const TopkParams p) {
   static_assert(MC == 1 || (MC == 2 && CG == 2), "multicast needs CTA pairs");
   static_assert(!SYM || (CG == 2 && MC == 1), "symmetric sweep: a query block must be one database tile");
+  static_assert(SETS == 1 || (SETS == 2 && !SYM && MC == 1), "two epilogue sets: plain sweeps only");
   if (p.run_if != nullptr && ptx::ld_relaxed_gpu(p.run_if) == 0u) return;   // grid-uniform, before any barrier
   if (p.clk != nullptr && threadIdx.x == 0) {
     p.clk[4 * blockIdx.x + 0] = ptx::globaltimer_ns();
@@ -154,7 +155,15 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   // symmetric sweep: the tile's column bounds and their minimum per 32-column chunk (one set per accumulator)
   float* bd_s = reinterpret_cast<float*>(fl_s + 2 * BN);
   float* bmin_s = bd_s + (SYM ? 2 * BN : 0);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bmin_s + (SYM ? 16 : 0));
+  // SETS == 2: a row's list is filled by two threads (one per epilogue set), so its state lives here, behind a lock
+  uint64_t* rs_minkey = reinterpret_cast<uint64_t*>(bmin_s + (SYM ? 16 : 0));
+  int* rs_cnt = reinterpret_cast<int*>(rs_minkey + (SETS == 2 ? BM : 0));
+  int* rs_minpos = rs_cnt + (SETS == 2 ? BM : 0);
+  float* rs_f = reinterpret_cast<float*>(rs_minpos + (SETS == 2 ? BM : 0));
+  int* rs_lock = reinterpret_cast<int*>(rs_f + (SETS == 2 ? BM : 0));
+  // smallest / largest staged stamp of every 32-column chunk (one set per accumulator): [2][8][2]
+  float* trange_s = reinterpret_cast<float*>(rs_lock + (SETS == 2 ? BM : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(trange_s + 32);
   // barrier slots: full[kMaxStages] empty[kMaxStages] tmem_full[2] tmem_empty[2]
   const uint32_t bar_full = ptx::smem_u32(bars);
   const uint32_t bar_empty = bar_full + 8 * kMaxStages;
@@ -182,7 +191,7 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(bar_tfull + 8 * a, 1);      // one tcgen05.commit
-      ptx::mbar_init(bar_tempty + 8 * a, 4 * CG); // one arrive per epilogue warp (of both CTAs)
+      ptx::mbar_init(bar_tempty + 8 * a, 4 * CG * SETS); // one arrive per epilogue warp (of both CTAs)
     }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async();
@@ -329,12 +338,20 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     __syncwarp();
   } else {
     // ===================================================== epilogue: gate + threshold + running top-k
+    // SETS == 2 (short descriptors: the epilogue, not the MMAs, bounds the kernel -- one warp per scheduler runs a chunk's
+    // ~235 dependent instructions at 0.17 IPC): warps 2..5 and 6..9 are two sets, a warp reads the TMEM lanes of quad
+    // warp % 4, set s takes the 32-column chunks c = s, s + 2, ...; the two threads of a row share its list (SharedRowList).
+    const int set = SETS == 2 ? ((warp - 2) >> 2) : 0;
     const int quad = warp & 3;
     const int row_in_tile = quad * 32 + lane;
-    const int et = (warp - 2) * 32 + lane;            // 0..127 among the epilogue threads
+    const int et = ((warp - 2) & 3) * 32 + lane;      // 0..127 among the epilogue threads of a set
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    auto epi_sync = [&]() { if constexpr (SETS == 2) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 1, 128;" ::: "memory"); };
     RowList L;
     L.keys = lists + static_cast<size_t>(row_in_tile) * p.kstride;
+    SharedRowList SL;
+    SL.keys = L.keys; SL.cnt = rs_cnt + row_in_tile; SL.min_pos = rs_minpos + row_in_tile; SL.min_key = rs_minkey + row_in_tile;
+    SL.f = rs_f + row_in_tile; SL.lock = rs_lock + row_in_tile;
     const int k = p.k;
     const bool mask_mode = p.gate_mode == 1 && p.max_floor_diff >= 0 && p.q_floor != nullptr && p.db_floor != nullptr;
     const bool use_time = p.use_time != 0;
@@ -354,6 +371,10 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       }
       const uint64_t ceil_key = (p.ceil_keys != nullptr && row_live) ? __ldg(p.ceil_keys + static_cast<int64_t>(grow) * p.ceil_stride) : ~0ull;
       L.reset(row_live ? p.threshold : pos_inf);
+      if constexpr (SETS == 2) {
+        if (set == 0) SL.reset(row_live ? p.threshold : pos_inf);
+        epi_sync();                                   // (also: the flush of the run before has read the list)
+      }
       float published = __int_as_float(0xff800000);   // SYM: last bound this thread published for its row
       // SYM: one column-direction append in flight per thread.  The slot number comes back from a global atomic
       // (about a microsecond); it is only looked at when the thread's next candidate arrives or the run ends, so
@@ -376,13 +397,15 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       // which every epilogue warp only reaches after it finished the tile before that (the buffer's last reader).
       const bool need_stage = use_time || mask_mode || SYM;
       double st_ts[2] = {0.0, 0.0};
+      bool st_in[2] = {false, false};
       int32_t st_fl[2] = {kFloorNone, kFloorNone};
       float st_bd[2] = {pos_inf, pos_inf};
       auto stage_load = [&](int tile, bool cols) {
+        if (SETS == 2 && set != 0) return;
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
           const int col = tile * BN + et + 128 * jj;
-          if (use_time) st_ts[jj] = col < p.N ? __ldg(p.db_ts + col) : 0.0;
+          if (use_time) { st_in[jj] = col < p.N; st_ts[jj] = st_in[jj] ? __ldg(p.db_ts + col) : 0.0; }
           if (mask_mode) st_fl[jj] = col < p.N ? __ldg(p.db_floor + col) : kFloorNone;
           if constexpr (SYM) {
             float b = pos_inf;                        // beyond N (TMA zero fill) and on the diagonal: nothing passes
@@ -397,8 +420,23 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       auto stage_store = [&](uint32_t a) {
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
+          if (SETS == 2 && set != 0) break;
           const int j = et + 128 * jj;
-          if (use_time) ts_s[a * BN + j] = static_cast<float>(st_ts[jj] - ts_base);
+          if (use_time) {
+            const float off = static_cast<float>(st_ts[jj] - ts_base);
+            ts_s[a * BN + j] = off;
+            // the chunk's stamp range (this warp's columns in this pass are exactly chunk j / 32): columns beyond N do not
+            // count, a NaN / inf stamp makes the range infinite (such a chunk is never skipped)
+            const bool fin = off - off == 0.0f;
+            float lo = !st_in[jj] ? pos_inf : (fin ? off : -pos_inf);
+            float hi = !st_in[jj] ? -pos_inf : (fin ? off : pos_inf);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+              hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            }
+            if (lane == 0) { trange_s[(a * 8 + (j >> 5)) * 2] = lo; trange_s[(a * 8 + (j >> 5)) * 2 + 1] = hi; }
+          }
           if (mask_mode) fl_s[a * BN + j] = st_fl[jj];
           if constexpr (SYM) {
             bd_s[a * BN + j] = st_bd[jj];
@@ -407,7 +445,7 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             if (lane == 0) bmin_s[a * 8 + (j >> 5)] = ordered_to_score(mn);
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        epi_sync();
       };
       bool staged = false;
 
@@ -426,7 +464,7 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         if (ahead) stage_load(nt + 1, SYM && nt + 1 != run.mb);
         const uint32_t t_acc = t_lane + acc * BN;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = set; c < BN / 32; c += SETS) {
           uint32_t v[32];
           ptx::tmem_ld_32x32(t_acc + c * 32, v);
           ptx::tmem_wait_ld();
@@ -450,12 +488,26 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           float mx = __uint_as_float(v[0]);
 #pragma unroll
           for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-          const bool hit = mx >= L.f;
+          const float bound = SETS == 2 ? SL.bound() : L.f;   // (shared list: a stale bound is only lower, never higher)
+          // Temporal neighbours score high and are all thrown out by the window: in an all-pairs sweep every row meets a
+          // few chunks that lie INSIDE its exclusion window, where each of its 32 columns would walk the slow path only to
+          // fail the window test (config 1: half of all slow-path iterations, all on the units that own diagonal tiles).
+          // With the chunk's stamp range [lo, hi]: every column's d = |a - b| <= dmax = max(hi - b, b - lo) (fp32 subtraction
+          // is monotone) and its margin m <= M, so dmax < gap_lo - M is window_excluded()'s own "excluded" verdict for all 32.
+          bool in_window = false;
+          if (use_time) {
+            const float lo = trange_s[(acc * 8 + c) * 2], hi = trange_s[(acc * 8 + c) * 2 + 1];
+            const float dmax = fmaxf(hi - tq32, tq32 - lo);
+            const float M = (fmaxf(fabsf(lo), fabsf(hi)) + fabsf(tq32) + dmax) * 0x1p-22f + 1e-30f;
+            in_window = dmax < p.gap_lo - M;             // false for NaN / inf stamps and empty ranges (dmax = -inf handled below)
+            if (lo > hi) in_window = false;
+          }
+          const bool hit = mx >= bound && !in_window;
           if (__any_sync(0xffffffffu, hit)) {
             uint32_t m = 0;
             if (hit) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) m |= (__uint_as_float(v[i]) >= L.f ? 1u : 0u) << i;
+              for (int i = 0; i < 32; ++i) m |= (__uint_as_float(v[i]) >= bound ? 1u : 0u) << i;
             }
             // every lane walks its own hit columns; the score comes out of the registers already
             // loaded (a 31-select tree; a second trip to TMEM per hit column would serialise the warp:
@@ -464,7 +516,7 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
               const int i = __ffs(m) - 1;
               m &= m - 1;
               const float s = __uint_as_float(pick32(v, i));
-              if (s >= L.f) {                               // the bound may have risen since the mask was built
+              if (s >= (SETS == 2 ? SL.bound() : L.f)) {     // the bound may have risen since the mask was built
                 const int col = col_base + c * 32 + i;      // local database row
                 if (col < p.N) {                            // TMA zero-fill beyond N must not score
                   bool ok = true;
@@ -472,7 +524,7 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                   if (ok && mask_mode) ok = floor_ok(qf, fl_s[acc * BN + c * 32 + i], p.max_floor_diff);
                   if (ok) {
                     const uint64_t key = pack_key(s, static_cast<uint32_t>(col) + p.db_index_offset);
-                    if (key < ceil_key) L.insert(key, k);
+                    if (key < ceil_key) { if constexpr (SETS == 2) SL.insert(key, k); else L.insert(key, k); }
                   }
                 }
               }
@@ -534,7 +586,13 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 
       if constexpr (SYM) complete_append();
       // flush this run's list (unsorted, packed at the front; empty slots are key 0)
-      if (row_live && p.dense == nullptr) {
+      if constexpr (SETS == 2) {
+        epi_sync();                                   // both sets are done with the run's last tile
+        if (set == 0 && row_live && p.dense == nullptr) {
+          const int cnt = *SL.cnt;
+          for (int i = 0; i < k; ++i) slot[i] = i < cnt ? L.keys[i] : 0ull;
+        }
+      } else if (row_live && p.dense == nullptr) {
         for (int i = 0; i < k; ++i) slot[i] = i < L.cnt ? L.keys[i] : 0ull;
       }
     });
