@@ -627,6 +627,23 @@ def companions_leg(torch, eng, peak_hbm):
     oq = oq % fl.shape[0]
     ms = timeit(lambda: eng.gate_candidates(fl, oq[:M], om[:M], 0))
     add("gate_candidates (pairs in the order K4 emits)", [M], ms, 9 * M, candidates_per_s=M / ms * 1e3)
+    del res, oq, om, os_, ov, fl
+    # K5: CricaVPR cross-correlation re-rank (place_recognition.py:669-757), DINOv2 shape (529 patches x 768-d), 25 candidates
+    # per query -- tensor-bound: reported against the measured bf16 peak, useful FLOPs = 2 P^2 D per pair
+    nf, P, Dl, kc, nq = 1000, 529, 768, 25, 2000
+    feats = torch.empty((nf, P, _native.pad_dim(Dl)), dtype=torch.bfloat16, device="cuda")
+    for s0 in range(0, nf, 250):
+        xx = torch.randn((250 * P, Dl), device="cuda")
+        eng.normalize_cast(xx, out=feats[s0:s0 + 250].view(250 * P, -1))
+    qi = torch.arange(nq, device="cuda", dtype=torch.int32).repeat_interleave(kc) % nf
+    mi = torch.randint(0, nf, (nq * kc,), device="cuda", dtype=torch.int32)
+    gs = torch.rand((nq * kc,), device="cuda")
+    ms = timeit(lambda: eng.rerank_scores(feats, qi, mi, gs), iters=5, warm=2)
+    peak_tf = measured_peaks()[0]
+    tf = 2.0 * P * P * Dl * nq * kc / ms / 1e9
+    out.append({"kernel": "K5 rerank_scores (cross-correlation re-rank, pair form)", "shape": [nq * kc, P, Dl], "ms": ms,
+                "pairs_per_s": nq * kc / ms * 1e3, "tflops_useful": tf, "frac_of_tensor_peak": tf / peak_tf,
+                "note": "useful FLOPs 2*P*P*D per pair (the tiling multiplies 512 x 544 + 544 x 32 of the 529 x 529 wanted)"})
     return {"hbm_peak_gbs": peak_hbm, "kernels": out}
 
 
