@@ -616,8 +616,15 @@ def companions_leg(torch, eng, peak_hbm):
     del x, o
     Q, k = 1_000_000, TOPK
     keys = torch.randint(1, 2 ** 62, (4, Q, k), device="cuda", dtype=torch.int64)
-    add("K3 merge_topk (4 lists per row)", [4, Q, k], timeit(lambda: eng.merge_topk(keys, k)), Q * k * (8 * 4 + 9) + 4 * Q)
+    add("K3 merge_topk (4 full lists per row, unsorted: a synthetic worst case)", [4, Q, k], timeit(lambda: eng.merge_topk(keys, k)),
+        Q * k * (8 * 4 + 9) + 4 * Q)
     res = eng.merge_topk(keys, k)
+    keys_sorted = torch.sort(keys, dim=2, descending=True).values.contiguous()
+    add("K3 merge_topk (4 full sorted lists per row: the per-GPU lists of a sharded sweep)", [4, Q, k],
+        timeit(lambda: eng.merge_topk(keys_sorted, k)), Q * k * (8 * 4 + 9) + 4 * Q)
+    same = bool(torch.equal(eng.merge_topk(keys_sorted, k).idx, res.idx))
+    out[-1]["equals_unsorted_merge"] = same
+    del keys_sorted
     del keys
     add("K4 compact", [Q, k], timeit(lambda: eng.compact(res)), Q * k * (9 + 13) + 4 * Q)
     oq, om, os_, ov, tot = eng.compact(res)

@@ -398,11 +398,23 @@ __device__ __forceinline__ void bitonic_merge32_desc(uint64_t (&c)[32]) {
 
 // this thread's packed row (its first `cnt` of 32 slots in shared memory) -> registers -> sorting network -> folded
 // into its running top-32
-__device__ __forceinline__ void fold_row(const uint64_t* __restrict__ mine, int cnt, uint64_t (&best)[32]) {
+// Lists that are already sorted -- the per-GPU lists of a sharded sweep (each is a K3 output), a seeded list -- skip the
+// sorting network (191 of the ~300 compare-exchanges per list): 31 compares per row and a warp vote decide, so any
+// input is still handled.  `have_best` (warp-uniform): the first fold of a row is a copy.
+__device__ __forceinline__ void fold_row(const uint64_t* __restrict__ mine, int cnt, uint64_t (&best)[32], bool& have_best) {
   uint64_t cur[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) cur[i] = i < cnt ? mine[i] : 0ull;
-  sort32_desc(cur);
+  bool sorted = true;
+#pragma unroll
+  for (int i = 0; i < 31; ++i) sorted &= cur[i] >= cur[i + 1];
+  if (!__all_sync(0xffffffffu, sorted)) sort32_desc(cur);
+  if (!have_best) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) best[i] = cur[i];
+    have_best = true;
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 32; ++i) best[i] = best[i] > cur[31 - i] ? best[i] : cur[31 - i];    // best desc, cur reversed: bitonic
   bitonic_merge32_desc(best);
@@ -463,6 +475,7 @@ merge_net_kernel(const MergeLaunch a) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) best[i] = 0ull;
   int cnt = 0;                                              // keys in this thread's pack row
+  bool have_best = false;
 
   // lists: g = -1 is the seeded list (one more list per row, local rows), then the n_lists lists; each is k keys per
   // row, `pitch` keys between rows
@@ -488,7 +501,7 @@ merge_net_kernel(const MergeLaunch a) {
     }
     __syncwarp();                                           // the staging rows may be refilled
     if (__any_sync(0xffffffffu, cnt > 32 - k)) {            // some row could not take another list
-      fold_row(mine, cnt, best);
+      fold_row(mine, cnt, best, have_best);
       cnt = 0;
     }
   }
@@ -504,7 +517,7 @@ merge_net_kernel(const MergeLaunch a) {
     const int half = lane >> 4, l16 = lane & 15;
     for (int c = 0; c < chunks; ++c) {
       if (__any_sync(0xffffffffu, cnt > 16)) {              // room for 16 more in every row?
-        fold_row(mine, cnt, best);
+        fold_row(mine, cnt, best, have_best);
         cnt = 0;
       }
       uint64_t v[16];
@@ -527,7 +540,7 @@ merge_net_kernel(const MergeLaunch a) {
       __syncwarp();
     }
   }
-  if (__any_sync(0xffffffffu, cnt > 0)) fold_row(mine, cnt, best);
+  if (__any_sync(0xffffffffu, cnt > 0)) fold_row(mine, cnt, best, have_best);
 
   // outputs: registers -> staging rows -> one row at a time by the whole warp (coalesced)
   __syncwarp();

@@ -373,6 +373,35 @@ def test_merge_topk_kernel_exact(eng, G, k, fill):
     assert m.count.cpu().numpy()[5] == 0 and np.all(m.idx.cpu().numpy()[5] == -1)
 
 
+@pytest.mark.parametrize("G,k,order", [(4, 25, "sorted"), (8, 25, "sorted"), (4, 25, "mixed"), (3, 32, "unsorted"), (2, 7, "sorted")])
+def test_merge_many_rows_sorted_lists(eng, G, k, order):
+    """K3's thread-per-row network kernel (many rows, a few lists) skips the sorting network for lists that arrive sorted
+    (the per-GPU lists of a sharded sweep are K3 outputs): sorted, unsorted and mixed inputs (some warps take the short
+    cut, some do not; short and empty lists) against a numpy sort of the same keys."""
+    import torch
+    rng = np.random.default_rng(G * 1000 + k)
+    Q = 65536 + 77
+    keys = rng.integers(1, 2 ** 62, size=(G, Q, k), dtype=np.int64).view(np.uint64)
+    fill = rng.integers(0, k + 1, size=(G, Q))
+    fill[:, ::5] = k                                             # plenty of full lists
+    keys[np.arange(k)[None, None, :] >= fill[:, :, None]] = 0   # lists end early (0 = empty), row 3 of list 0 is empty
+    keys[0, 3] = 0
+    if order in ("sorted", "mixed"):
+        keys = np.sort(keys, axis=2)[:, :, ::-1].copy()
+    if order == "mixed":
+        sel = rng.uniform(size=Q) < 0.02                        # a few rows per warp break the order
+        shuf = keys[:, sel].copy()
+        rng.shuffle(shuf, axis=2)
+        keys[:, sel] = shuf
+    m = eng.merge_topk(torch.from_numpy(keys.view(np.int64)).cuda(), k, want_keys=True)
+    torch.cuda.synchronize()
+    flat = keys.transpose(1, 0, 2).reshape(Q, G * k)
+    want = np.sort(flat, axis=1)[:, ::-1][:, :k]
+    got = m.keys.cpu().numpy().view(np.uint64)
+    assert np.array_equal(got, want)
+    assert np.array_equal(m.count.cpu().numpy(), (want != 0).sum(axis=1))
+
+
 def test_valid_only_compaction_and_device_statistics(eng):
     """§8f rank 4: the floor-consistent hand-off list (geometric_verification.py:709 skips cross-floor pairs) and
     get_statistics (place_recognition.py:913-933) reduced on the device, against the host path and the oracle."""
