@@ -89,6 +89,8 @@ struct semgate_ctx {
   bool profile = false;            // record CUDA events around every K2 launch
   std::vector<struct SweepGraph*> graphs;   // semgate_find_loop_closures_device: captured launch sequences
   bool graphs_broken = false;      // a capture failed on this system: stay eager
+  // one-call sweep in flight: K3 zeroes the compaction state, K3 / K4 launch as programmatic dependents (MergeLaunch)
+  unsigned long long* fl_zero = nullptr; int fl_zero_words = 0; bool fl_pdl = false;
   unsigned long long* clk_dev = nullptr;   // option "clock_probe": per-CTA {globaltimer, clock64} pairs of the last K2 launch
   int clk_ctas = 0;
   std::vector<SymTableDev*> sym_tables, sym_retired;
@@ -116,6 +118,11 @@ struct semgate_ctx {
 };
 
 namespace {
+
+bool env_flag_default(const char* name, bool dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) != 0 : dflt;
+}
 
 struct DeviceGuard {
   int prev = -1;
@@ -612,6 +619,7 @@ int gated_topk_impl(semgate_handle_t h, const void* q_bf16, int64_t Q, const voi
                                                     sym_zeroed_bytes(N, topk_sync_bytes(sc_sym)));
     }
   }
+  m.zero_ptr = h->fl_zero; m.zero_words = h->fl_zero_words; m.pdl = h->fl_pdl ? 1 : 0;
   RC_TRY(launch_merge_topk(m, st), "merge_topk launch");
   h->launches += 1;
   h->last_mode = sym ? 1 : 0;
@@ -771,9 +779,10 @@ static int compact_impl(semgate_handle_t h, const float* scores, const int32_t* 
     return fail(SEMGATE_EINVAL, "compact: NULL pointer");
   DeviceGuard g(h->device);
   if (q_offset < 0 || q_offset + Q > INT32_MAX) return fail(SEMGATE_EINVAL, "compact: query index offset out of range");
+  const bool handoff = h->fl_zero != nullptr && h->fl_zero == workspace;     // the one-call sweep: K3 has zeroed the state
   RC_TRY(launch_compact(scores, idx, valid, count, Q, k, valid_only, q_offset, out_query_idx, out_match_idx, out_similarity, out_is_valid,
-                        out_total, workspace, static_cast<cudaStream_t>(stream)), "compact launch");
-  h->launches += Q > 0 ? 2 : 0;      // state memset + the one-pass kernel
+                        out_total, workspace, static_cast<cudaStream_t>(stream), handoff, handoff && h->fl_pdl), "compact launch");
+  h->launches += Q > 0 ? (handoff ? 1 : 2) : 0;      // (state memset +) the one-pass kernel
   return 0;
 }
 
@@ -937,6 +946,17 @@ int semgate_find_loop_closures_device(semgate_handle_t h, const void* x_bf16, in
   auto run = [&]() -> int {
     semgate_topk_params pa = *p;
     pa.db_index_offset = 0; pa.accumulate = 0; pa.part_index = 0; pa.part_count = 0;
+    // K3 zeroes the compaction's look-back state (no memset node between K3 and K4) and both launch as programmatic
+    // dependents of the kernel before them; single-pass sweeps only (k > 64 merges once per pass)
+    struct Handoff {
+      semgate_handle_t h;
+      ~Handoff() { h->fl_zero = nullptr; h->fl_zero_words = 0; h->fl_pdl = false; }
+    } handoff{h};
+    if (p->k <= SEMGATE_MAX_K) {
+      h->fl_zero = reinterpret_cast<unsigned long long*>(ws + l.cws);
+      h->fl_zero_words = compact_state_words(n);
+      h->fl_pdl = env_flag_default("SEMGATE_PDL", true);
+    }
     int r = semgate_gated_topk(h, x_bf16, n, x_bf16, n, d_pad, ts, ts, floor_labels, floor_labels, &pa, ws, l.topk, nullptr,
                                reinterpret_cast<float*>(ws + l.sc), reinterpret_cast<int32_t*>(ws + l.ix),
                                reinterpret_cast<uint8_t*>(ws + l.va), reinterpret_cast<int32_t*>(ws + l.ct), st);

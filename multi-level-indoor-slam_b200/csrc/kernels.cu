@@ -171,6 +171,25 @@ int launch_normalize_cast(const float* x, int64_t n, int d, int64_t ld, void* ou
   return static_cast<int>(cudaGetLastError());
 }
 
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while the kernel before it drains; nothing that kernel wrote may be read before this returns.  A no-op otherwise.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void zero_handoff(const MergeLaunch& a) {
+  if (a.zero_ptr != nullptr && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < a.zero_words; i += blockDim.x) a.zero_ptr[i] = 0ull;
+}
+
+template <typename Kernel, typename... Args>
+static cudaError_t launch_maybe_pdl(bool pdl, Kernel kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // =========================================================================== K3
 // One warp per query row.  Every lane keeps P candidate keys sorted descending in
 // registers (a fixed compare-exchange network); then k rounds of "warp-wide max over
@@ -196,6 +215,8 @@ merge_topk_kernel(const MergeLaunch a) {
   __shared__ uint64_t gathered[ROWBLOCK ? 1 : kMergeWarps * kGatherCap];   // sparse rows: the row's non-empty keys
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t row = ROWBLOCK ? static_cast<int64_t>(blockIdx.x) : static_cast<int64_t>(blockIdx.x) * kMergeWarps + warp;
+  griddep_wait();
+  zero_handoff(a);
   // per-GPU lists read in place: OR of the peers' overflow flags (one word behind every peer's keys), so that the
   // exchange needs no collective of its own for it
   if (a.any_flag_out != nullptr && a.list_ptrs != nullptr && blockIdx.x == 0 && warp == 0) {
@@ -434,6 +455,8 @@ merge_net_kernel(const MergeLaunch a) {
   uint64_t* pack = net_smem + static_cast<size_t>(kNetRows) * kNetPitch;   // [kNetRows][kNetPitch] packed keys per row
   const int k = a.k;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  griddep_wait();
+  zero_handoff(a);
   if (a.any_flag_out != nullptr && a.list_ptrs != nullptr && blockIdx.x == 0 && warp == 0) {
     uint32_t f = 0;
     for (int g = lane; g < a.n_lists; g += 32) f |= *reinterpret_cast<const volatile uint32_t*>(a.list_ptrs[g] + a.flag_offset);
@@ -581,8 +604,7 @@ int launch_merge_topk(const MergeLaunch& a, cudaStream_t st) {
   const int64_t keys = static_cast<int64_t>(lists) * a.k;
   // few rows, many lists (a streaming query leaves one list per block of K6): one block per row, a tree of warps
   if (a.Q > 0 && a.Q <= 2048 && keys >= 1024 && a.sym_flag == nullptr && a.row_offset == 0) {
-    merge_topk_kernel<8, true><<<static_cast<unsigned>(a.Q), kRowBlockWarps * 32, 0, st>>>(a);
-    return static_cast<int>(cudaGetLastError());
+    return static_cast<int>(launch_maybe_pdl(a.pdl != 0, merge_topk_kernel<8, true>, dim3(static_cast<unsigned>(a.Q)), dim3(kRowBlockWarps * 32), 0, st, a));
   }
   // many rows, a few (possibly full) lists each, e.g. the per-GPU lists of a sharded 1M sweep: thread-per-row on register
   // sorting networks (1M x 4 full lists: 0.98 ms against the tournament's 1.3-1.9 ms); everything else -- in particular
@@ -592,15 +614,12 @@ int launch_merge_topk(const MergeLaunch& a, cudaStream_t st) {
     const size_t smem = 2 * static_cast<size_t>(kNetRows) * kNetPitch * sizeof(uint64_t);      // 67.6 KB: staging + pack rows
     cudaError_t e = cudaFuncSetAttribute(merge_net_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
-    merge_net_kernel<<<grid, kNetRows, smem, st>>>(a);
-    return static_cast<int>(cudaGetLastError());
+    return static_cast<int>(launch_maybe_pdl(a.pdl != 0, merge_net_kernel, dim3(grid), dim3(kNetRows), smem, st, a));
   }
   const unsigned grid = static_cast<unsigned>(std::max<int64_t>(1, (a.Q + kMergeWarps - 1) / kMergeWarps));
   if (keys <= (a.seed_keys ? 64 : 128))
-    merge_topk_kernel<4, false><<<grid, kMergeWarps * 32, 0, st>>>(a);
-  else
-    merge_topk_kernel<8, false><<<grid, kMergeWarps * 32, 0, st>>>(a);
-  return static_cast<int>(cudaGetLastError());
+    return static_cast<int>(launch_maybe_pdl(a.pdl != 0, merge_topk_kernel<4, false>, dim3(grid), dim3(kMergeWarps * 32), 0, st, a));
+  return static_cast<int>(launch_maybe_pdl(a.pdl != 0, merge_topk_kernel<8, false>, dim3(grid), dim3(kMergeWarps * 32), 0, st, a));
 }
 
 // =========================================================================== K4
@@ -667,6 +686,7 @@ compact_onepass_kernel(const float* __restrict__ scores, const int32_t* __restri
   __shared__ unsigned tile_s;
   __shared__ long long base_s;
   const unsigned tiles = gridDim.x;
+  griddep_wait();
   if (threadIdx.x == 0) tile_s = atomicAdd(reinterpret_cast<unsigned*>(state + tiles), 1u);
   __syncthreads();
   const unsigned tile = tile_s;
@@ -768,16 +788,18 @@ size_t compact_workspace_bytes(int64_t Q) {
 
 int launch_compact(const float* scores, const int32_t* idx, const uint8_t* valid, const int32_t* count, int64_t Q, int k,
                    bool valid_only, int64_t q_offset, int32_t* out_q, int32_t* out_m, float* out_s, uint8_t* out_v,
-                   int64_t* out_total, void* workspace, cudaStream_t st) {
+                   int64_t* out_total, void* workspace, cudaStream_t st, bool state_zeroed, bool pdl) {
   if (Q <= 0) return static_cast<int>(cudaMemsetAsync(out_total, 0, sizeof(int64_t), st));
   const int64_t nb = (Q + kScanBlock - 1) / kScanBlock;
   unsigned long long* state = static_cast<unsigned long long*>(workspace);
-  cudaError_t e = cudaMemsetAsync(state, 0, static_cast<size_t>(nb + 1) * sizeof(unsigned long long), st);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  compact_onepass_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, st>>>(scores, idx, valid, count, Q, k, valid_only, state, q_offset,
-                                                                          out_q, out_m, out_s, out_v, out_total);
-  return static_cast<int>(cudaGetLastError());
+  if (!state_zeroed) {      // (the one-call sweep lets K3 zero it: compact_state_words)
+    cudaError_t e = cudaMemsetAsync(state, 0, static_cast<size_t>(nb + 1) * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  return static_cast<int>(launch_maybe_pdl(pdl, compact_onepass_kernel, dim3(static_cast<unsigned>(nb)), dim3(kScanBlock), 0, st, scores, idx, valid,
+                                           count, Q, k, valid_only, state, q_offset, out_q, out_m, out_s, out_v, out_total));
 }
+int compact_state_words(int64_t Q) { return static_cast<int>((Q + kScanBlock - 1) / kScanBlock + 1); }
 
 // =========================================================================== match statistics
 // get_statistics (place_recognition.py:913-933) over a device-resident candidate list: number of

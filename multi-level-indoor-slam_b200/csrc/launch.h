@@ -96,14 +96,20 @@ struct MergeLaunch {
   int64_t row_offset;                // merge rows [row_offset, row_offset + Q) of the input lists / q_floor; outputs are [Q, k]
   int64_t flag_offset;               // with list_ptrs and any_flag_out: word (u32) at list_ptrs[g] + flag_offset (in keys) is
   uint32_t* any_flag_out;            //   GPU g's overflow flag; their OR is written to *any_flag_out
+  // one-call sweep (semgate_find_loop_closures_device): this launch also zeroes `zero_words` 64-bit words at `zero_ptr`
+  // (the compaction's look-back state, so that no memset node sits between K3 and K4), and `pdl` launches the kernel as a
+  // programmatic dependent of the kernel before it (its launch overlaps that kernel's tail; griddepcontrol.wait at entry)
+  unsigned long long* zero_ptr; int zero_words; int pdl;
 };
 int launch_merge_topk(const MergeLaunch& a, cudaStream_t st);
 
 // K4: padded [Q,k] lists -> flat candidate arrays (query asc, score desc)
 size_t compact_workspace_bytes(int64_t Q);
+int compact_state_words(int64_t Q);   // 64-bit words of the workspace that must be zero when the kernel starts
 int launch_compact(const float* scores, const int32_t* idx, const uint8_t* valid, const int32_t* count, int64_t Q, int k,
                    bool valid_only, int64_t q_offset /*added to the emitted query indices*/, int32_t* out_q, int32_t* out_m,
-                   float* out_s, uint8_t* out_v, int64_t* out_total, void* workspace, cudaStream_t st);
+                   float* out_s, uint8_t* out_v, int64_t* out_total, void* workspace, cudaStream_t st, bool state_zeroed = false,
+                   bool pdl = false);
 
 // get_statistics (place_recognition.py:913-933) on the device: out[4] = total, valid, sum(sim), sum(valid sim), fp64
 size_t stats_workspace_bytes();
