@@ -442,6 +442,7 @@ int launch_gated_topk(const TopkLaunch& a, const Schedule& sc, uint64_t* partial
   p.kstride = a.k | 1;
   p.threshold = a.threshold;
   p.use_time = (a.q_ts != nullptr && a.db_ts != nullptr) ? 1 : 0;
+  p.window_skip = static_cast<int>(env_long("SEMGATE_WINDOW_SKIP", 1)) != 0 ? 1 : 0;
   p.gap = a.gap;
   {   // fp32 neighbours of the window length for the pre-test: gap_lo <= gap <= gap_hi
     const float g = static_cast<float>(a.gap);

@@ -46,6 +46,7 @@ struct TopkParams {
   int stages;            // smem ring depth
   float threshold;       // keep s >= threshold (compared in fp32, like numpy's weak-scalar rule)
   int use_time;          // 0: no temporal mask (query(timestamp=None), place_recognition.py:144)
+  int window_skip;       // 1: chunks that lie wholly inside a row's exclusion window skip the slow path (A/B knob, default on)
   double gap;            // min_time_gap
   float gap_lo, gap_hi;  // fp32 neighbours of gap: gap_lo <= gap <= gap_hi (window pre-test, see window_excluded)
   int max_floor_diff;    // -1 off, 0 strict, 1 non-strict
@@ -495,7 +496,7 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           // With the chunk's stamp range [lo, hi]: every column's d = |a - b| <= dmax = max(hi - b, b - lo) (fp32 subtraction
           // is monotone) and its margin m <= M, so dmax < gap_lo - M is window_excluded()'s own "excluded" verdict for all 32.
           bool in_window = false;
-          if (use_time) {
+          if (use_time && p.window_skip) {
             const float lo = trange_s[(acc * 8 + c) * 2], hi = trange_s[(acc * 8 + c) * 2 + 1];
             const float dmax = fmaxf(hi - tq32, tq32 - lo);
             const float M = (fmaxf(fabsf(lo), fabsf(hi)) + fabsf(tq32) + dmax) * 0x1p-22f + 1e-30f;

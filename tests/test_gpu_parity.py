@@ -282,6 +282,39 @@ def test_epoch_scale_timestamps_need_fp64(eng):
     assert (d == 2.5).sum() == (dr == 2.5).sum(), "pairs exactly min_time_gap apart are kept (strict <)"
 
 
+@pytest.mark.parametrize("D,cg,sym", [(64, 1, 0), (64, 2, 0), (192, 2, 0), (2048, 2, 0), (1024, 2, 1)])
+def test_window_chunks_of_a_real_sequence(eng, D, cg, sym):
+    """A sequence whose temporal neighbours look alike (a slow random walk of the descriptor, 10 Hz keyframes, 10 s
+    window): every row meets several 32-column chunks that lie wholly inside its exclusion window and full of scores above
+    the threshold -- the case the epilogue's chunk-level window test skips.  With stamps that break the pattern (NaN,
+    +-inf, a block out of order, a run of equal stamps, a window edge on a chunk border) the lists must equal the
+    oracle's and every decision the fp64 predicate, for one and two epilogue sets, CTA pairs and the symmetric sweep."""
+    n, k, gap, thr = 1500, 25, 10.0, 0.6
+    rng = np.random.default_rng(D + cg)
+    steps = rng.standard_normal((n, D)).astype(np.float32)
+    desc = np.cumsum(0.05 * steps, axis=0) + rng.standard_normal((1, D)).astype(np.float32)     # neighbours: cosine ~ 0.99
+    desc[700:] += 3.0 * rng.standard_normal((1, D)).astype(np.float32)                         # a second place
+    desc[1100:1300] = desc[300:500] + 0.02 * rng.standard_normal((200, D)).astype(np.float32)  # a revisit: real loop closures
+    ts = 1000.0 + 0.1 * np.arange(n)
+    ts[64] = np.nan
+    ts[200] = np.inf
+    ts[333] = -np.inf
+    ts[400:464] = ts[400:464][::-1].copy()        # out of order inside a block
+    ts[600:640] = ts[600]                        # equal stamps
+    ts[900] = ts[800] + gap                       # exactly `gap` from row 800: kept (strict <)
+    got = run_gpu(eng, desc, desc, k, thr, gap, ts, ts, cg=cg, sym=sym)
+    assert got["mode"] == sym
+    ref = O.gated_topk(desc, desc, ts, ts, k=k, threshold=thr, min_time_gap=gap, max_floor_diff=-1, bf16=True)
+    c = O.compact(got)
+    assert len(c["query_idx"]) > 2000
+    parity.compare_candidates(O.compact(ref), c, k, thr, tol=BF16_MODEL_TOL)
+    parity.check_decisions_exact(c, ts, None, gap, -1)
+    # the same sweep without the window: the neighbours come back, i.e. the window did decide something
+    free = O.compact(run_gpu(eng, desc, desc, k, thr, 0.0, ts, ts, cg=cg, sym=sym))
+    near = lambda cc: int((np.abs(cc["match_idx"] - cc["query_idx"]) < 50).sum())
+    assert near(free) > 10000 and near(c) < near(free) // 20
+
+
 def test_adversarial_ascending_scores(eng):
     """Every new column beats the current k-th score (threshold -1, similarity strictly rising
     with the index): the running list is replaced on every element.  Operands are fed as raw
