@@ -84,7 +84,7 @@ struct semgate_ctx {
   int64_t last_tiles = 0;          // tiles the last fused sweep computed (its schedule's count)
   int64_t launches = 0;
   cudaStream_t stream = nullptr;   // used by the *_host entry points (compute)
-  cudaStream_t copy_stream = nullptr;   // H2D + normalisation of the next chunk, overlapped with the sweep
+  cudaStream_t copy_stream = nullptr;   // H2D of the next chunks, back to back, overlapped with the sweeps
   std::vector<cudaEvent_t> chunk_events;
   bool profile = false;            // record CUDA events around every K2 launch
   std::vector<struct SweepGraph*> graphs;   // semgate_find_loop_closures_device: captured launch sequences
@@ -1063,13 +1063,25 @@ int semgate_find_loop_closures_host(semgate_handle_t h, const float* descriptors
   if (n < 4096 || approx_chunks < 2 || k > SEMGATE_MAX_K) {   // (k > 64 runs as several whole sweeps: no accumulation)
     bounds.push_back(n);
   } else {
-    static const int kWeights[10] = {4, 4, 4, 4, 3, 3, 2, 2, 1, 1};
-    const int nw = static_cast<int>(std::min<int64_t>(10, std::max<int64_t>(2, approx_chunks)));
+    // Measured at config 2 (tools/e2e_chunks.py): a chunk's sweeps must finish under the next chunk's copy, and every chunk
+    // costs the compute stream ~0.1 ms of launches whatever its size, so chunks below ~1 000 rows (16 MB) LENGTHEN the tail:
+    // 4,4,4,4,3,3,2,2,1,1 (round 1) 6.76 ms, ...,2,2,2 6.54 ms, this one 6.51 ms; SEMGATE_E2E_CHUNKS overrides (A/B)
+    int kWeights[12] = {0, 0, 6, 5, 5, 4, 4, 3, 3, 2, 2, 2};
+    int nw = static_cast<int>(std::min<int64_t>(10, std::max<int64_t>(2, approx_chunks)));
+    if (const char* e = getenv("SEMGATE_E2E_CHUNKS")) {     // comma-separated weights, first chunk first
+      int vals[12], cnt = 0;
+      for (const char* q = e; *q && cnt < 12;) { vals[cnt++] = std::max(1, atoi(q)); while (*q && *q != ',') ++q; if (*q == ',') ++q; }
+      if (cnt >= 1) {
+        for (int i = 0; i < 12; ++i) kWeights[i] = 0;
+        for (int i = 0; i < cnt; ++i) kWeights[12 - cnt + i] = vals[i];
+        nw = cnt;
+      }
+    }
     int wsum = 0;
-    for (int i = 0; i < nw; ++i) wsum += kWeights[10 - nw + i];
+    for (int i = 0; i < nw; ++i) wsum += kWeights[12 - nw + i];
     int acc = 0;
     for (int i = 0; i < nw; ++i) {
-      acc += kWeights[10 - nw + i];
+      acc += kWeights[12 - nw + i];
       int64_t b = (i == nw - 1) ? n : ((n * acc / wsum + 127) / 128) * 128;   // 128-row aligned cuts
       b = std::min(b, n);
       if (b > bounds.back()) bounds.push_back(b);
@@ -1101,10 +1113,11 @@ int semgate_find_loop_closures_host(semgate_handle_t h, const float* descriptors
   uint64_t* d_keys = static_cast<uint64_t*>(keys);
   for (int64_t ci = 0; ci < nchunks; ++ci) {
     const int64_t r0 = bounds[ci], r1 = bounds[ci + 1], rows = r1 - r0;
+    // the copy stream carries nothing but copies, back to back; the chunk is normalised on the compute stream
     CUDA_TRY(cudaMemcpyAsync(static_cast<float*>(dx) + r0 * d, descriptors + r0 * d, sizeof(float) * rows * d, cudaMemcpyHostToDevice, cs));
-    if ((rc = semgate_normalize_cast(h, static_cast<float*>(dx) + r0 * d, rows, d, d, bf + 2ull * r0 * d_pad, d_pad, cs))) return rc;
     CUDA_TRY(cudaEventRecord(h->chunk_events[ci], cs));
     CUDA_TRY(cudaStreamWaitEvent(st, h->chunk_events[ci], 0));
+    if ((rc = semgate_normalize_cast(h, static_cast<float*>(dx) + r0 * d, rows, d, d, bf + 2ull * r0 * d_pad, d_pad, st))) return rc;
     semgate_topk_params pa = *p;
     pa.db_index_offset = 0; pa.accumulate = 0;
     if (k > SEMGATE_MAX_K) {      // one chunk: the sweep's passes write the decoded lists themselves
