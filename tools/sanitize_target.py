@@ -4,7 +4,8 @@
 
 Variants: K1 (block / cluster form), K2 <1,1>, <2,1>, <2,2>, symmetric <2,1,SYM> (run table, super-rows, overflow ->
 armed full sweep, one part of a split), multi-pass k > 64, dense output, K3 (thread-per-row, block-per-row, peers'
-row slice), K4 (+ valid-only, row slice), statistics, gate, K5 re-rank + select, K6 streaming query, spatial join.
+row slice, sorted lists), K4 (+ valid-only, row slice), statistics, gate, K5 re-rank (single-CTA and pair forms) + select,
+K6 streaming query, spatial join, K2 with one / two epilogue sets, the one-call sweep (K3 -> K4 hand-off).
 Every result is compared with the plain path where one exists, so a silent corruption also fails the run.
 """
 import os
@@ -92,6 +93,30 @@ def main():
     cross, comb = eng.rerank_scores(fb, qi, mi, torch.rand(6, device=dev))
     eng.rerank_select(torch.arange(12, dtype=torch.int32, device=dev).view(2, 6), torch.rand((2, 6), device=dev),
                       torch.tensor([6, 4], dtype=torch.int32, device=dev), 3)
+    # K5 pair form: ring + strip (P = 280), plain stages (ring forbidden), no strip (P = 300), against the single-CTA form
+    for P in (280, 300):
+        f2, _ = synthetic.make_local_features(8, P, 128, seed=P)
+        fb2 = eng.normalize_cast(t(f2.reshape(-1, 128))).view(8, P, -1)
+        q2 = torch.tensor([0, 0, 1, 2, 5, -1, 7, 3, 3], dtype=torch.int32, device=dev)
+        m2 = torch.tensor([1, 2, 3, 4, 0, 2, 99, 6, 5], dtype=torch.int32, device=dev)
+        g2 = torch.rand(9, device=dev)
+        outs = []
+        for env in ({}, {"SEMGATE_RERANK_RING": "0"}, {"SEMGATE_RERANK_UNROLL": "0"}, {"SEMGATE_RERANK_CLUSTER": "1"}):
+            os.environ.update(env)
+            outs.append(eng.rerank_scores(fb2, q2, m2, g2)[0].clone())
+            for kk in env:
+                os.environ.pop(kk)
+        for o in outs[1:]:
+            assert torch.allclose(o, outs[0], atol=2e-6, equal_nan=True), P
+    # K2 with two epilogue sets against one (short descriptors take two by default), K3 network kernel on sorted lists
+    os.environ["SEMGATE_EPI_SETS"] = "1"
+    one = eng.gated_topk(xb, xb, _native.make_params(symmetric=-1, cta_group=2, **kw), q_ts=tts, db_ts=tts, q_floor=tfl, db_floor=tfl, want_keys=True)
+    os.environ.pop("SEMGATE_EPI_SETS")
+    assert torch.equal(one.keys, full.keys), "epilogue sets"
+    ks = torch.sort(torch.randint(1, 2 ** 62, (3, 66000, 25), device=dev, dtype=torch.int64), dim=2, descending=True).values.contiguous()
+    ms = eng.merge_topk(ks, 25, want_keys=True)
+    want = torch.sort(ks.permute(1, 0, 2).reshape(66000, 75), dim=1, descending=True).values[:, :25]
+    assert torch.equal(ms.keys, want), "sorted-list merge"
     # spatial join
     pos = np.cumsum(np.random.default_rng(0).normal(size=(600, 3)) * 0.3, axis=0)
     eng.spatial_candidates_host(pos, 2.0, 50)
