@@ -491,9 +491,11 @@ int launch_gated_topk(const TopkLaunch& a, const Schedule& sc, uint64_t* partial
   //  before its last reader arrives -- measured 1.337 -> 1.290 ms at config 2 without it)
   p.policy_db = (hint >= 2 && sc.a_resident && sc.tab_runs == nullptr) ? ptx::kL2EvictFirst : ptx::kL2EvictNormal;
 
-  // Two epilogue sets where the epilogue, not the MMAs, bounds the kernel: descriptors of up to 1024 elements (a tile's
-  // MMAs take at most 16 k-blocks; config 1, 5k x 512-d: K2 50 -> see DESIGN.md).  Plain list-building sweeps only.
-  int sets = (!sym && cg != 4 && a.dense == nullptr && p.kblocks <= 16) ? 2 : 1;
+  // Two epilogue sets (plain list-building sweeps only) are OPT-IN, SEMGATE_EPI_SETS=2: with short descriptors and SPARSE hits
+  // (the benchmark's input) they take 3-11 % off the kernel, but the two threads of a row share its list under a lock, and
+  // on a sequence with long revisits (hundreds of hits per row, both threads inserting all the time) the same sweep is
+  // 1.4-1.7x SLOWER (5k x 512-d: 109 -> 182 us, 20k x 512-d: 580 -> 838 us).  Real inputs look like the latter.
+  int sets = 1;
   if (const char* e = getenv("SEMGATE_EPI_SETS")) { const int v = atoi(e); if (v == 1 || (v == 2 && !sym && cg != 4 && a.dense == nullptr)) sets = v; }
   // deepest ring that fits the 227 KB per-CTA limit
   int stages = kMaxStages;

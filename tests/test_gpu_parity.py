@@ -315,6 +315,32 @@ def test_window_chunks_of_a_real_sequence(eng, D, cg, sym):
     assert near(free) > 10000 and near(c) < near(free) // 20
 
 
+@pytest.mark.parametrize("cg", [1, 2])
+def test_two_epilogue_sets_give_the_same_lists(eng, monkeypatch, cg):
+    """SEMGATE_EPI_SETS=2 (opt-in): two epilogue warps per TMEM quarter, the two threads of a row share its list under a
+    lock.  Same keys as one set, bit for bit: sparse hits, a dense sequence (every row hundreds of hits: both threads
+    insert all the time), mask mode, k = 64, a ragged rectangular sweep, a multi-pass k = 100 sweep."""
+    from semgate import synthetic
+    rng = np.random.default_rng(cg)
+    n, D = 1300, 96
+    desc, ts, fl = synthetic.make_case(n, D, 3, seed=5)
+    fl32 = fl.astype(np.int32)
+    dense = np.repeat(rng.standard_normal((13, D)).astype(np.float32), 100, axis=0) + 0.2 * rng.standard_normal((n, D)).astype(np.float32)
+    cases = [dict(q=desc, db=desc, k=25, thr=0.3, gap=5.0, mfd=0, mode=0), dict(q=dense, db=dense, k=25, thr=0.5, gap=2.0, mfd=-1, mode=0),
+             dict(q=dense, db=dense, k=64, thr=-1.0, gap=0.0, mfd=0, mode=1), dict(q=desc[:333], db=desc[:1111], k=9, thr=0.2, gap=5.0, mfd=1, mode=0),
+             dict(q=dense[:200], db=dense, k=100, thr=0.4, gap=1.0, mfd=-1, mode=0)]
+    for c in cases:
+        nq, nd = len(c["q"]), len(c["db"])
+        outs = {}
+        for sets in ("1", "2"):
+            monkeypatch.setenv("SEMGATE_EPI_SETS", sets)
+            outs[sets] = run_gpu(eng, c["q"], c["db"] if c["db"] is not c["q"] else c["q"], c["k"], c["thr"], c["gap"], ts[:nq], ts[:nd] if nd != nq else ts[:nq],
+                                 fl32[:nq], fl32[:nd] if nd != nq else fl32[:nq], mfd=c["mfd"], mode=c["mode"], cg=cg, sym=-1)
+        monkeypatch.delenv("SEMGATE_EPI_SETS")
+        assert np.array_equal(outs["1"]["keys"], outs["2"]["keys"]) and np.array_equal(outs["1"]["valid"], outs["2"]["valid"])
+        assert outs["1"]["count"].sum() > 500
+
+
 def test_adversarial_ascending_scores(eng):
     """Every new column beats the current k-th score (threshold -1, similarity strictly rising
     with the index): the running list is replaced on every element.  Operands are fed as raw

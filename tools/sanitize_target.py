@@ -108,8 +108,8 @@ def main():
                 os.environ.pop(kk)
         for o in outs[1:]:
             assert torch.allclose(o, outs[0], atol=2e-6, equal_nan=True), P
-    # K2 with two epilogue sets against one (short descriptors take two by default), K3 network kernel on sorted lists
-    os.environ["SEMGATE_EPI_SETS"] = "1"
+    # K2 with two epilogue sets (opt-in) against one, K3 network kernel on sorted lists
+    os.environ["SEMGATE_EPI_SETS"] = "2"
     one = eng.gated_topk(xb, xb, _native.make_params(symmetric=-1, cta_group=2, **kw), q_ts=tts, db_ts=tts, q_floor=tfl, db_floor=tfl, want_keys=True)
     os.environ.pop("SEMGATE_EPI_SETS")
     assert torch.equal(one.keys, full.keys), "epilogue sets"
