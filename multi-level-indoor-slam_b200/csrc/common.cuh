@@ -83,51 +83,6 @@ struct RowList {
   }
 };
 
-// The same list filled by two threads (K2 with two epilogue sets: each thread of a row takes every other 32-column chunk):
-// state in shared memory, updates under a per-row spin lock.  The two threads sit in different warps, so a lane never
-// waits for a lane of its own warp.  bound() is read without the lock: it only rises, a stale value admits a key that
-// insert() then rejects.
-struct SharedRowList {
-  uint64_t* keys;
-  int* cnt;
-  int* min_pos;
-  uint64_t* min_key;
-  float* f;
-  int* lock;
-
-  __device__ __forceinline__ void reset(float thr) { *cnt = 0; *min_pos = 0; *min_key = 0; *f = thr; *lock = 0; }
-  __device__ __forceinline__ float bound() const { return *reinterpret_cast<volatile float*>(f); }
-
-  __device__ __forceinline__ void insert(uint64_t key, int k) {
-    volatile uint64_t* vk = keys;
-    while (atomicCAS(lock, 0, 1) != 0) { }
-    __threadfence_block();
-    const int c = *reinterpret_cast<volatile int*>(cnt);
-    bool scan = false;
-    if (c < k) {
-      vk[c] = key;
-      *reinterpret_cast<volatile int*>(cnt) = c + 1;
-      scan = c + 1 == k;
-    } else if (key > *reinterpret_cast<volatile uint64_t*>(min_key)) {
-      vk[*reinterpret_cast<volatile int*>(min_pos)] = key;
-      scan = true;
-    }
-    if (scan) {
-      uint64_t mk = vk[0];
-      int mp = 0;
-      for (int i = 1; i < k; ++i) {
-        const uint64_t v = vk[i];
-        if (v < mk) { mk = v; mp = i; }
-      }
-      *reinterpret_cast<volatile uint64_t*>(min_key) = mk;
-      *reinterpret_cast<volatile int*>(min_pos) = mp;
-      *reinterpret_cast<volatile float*>(f) = key_score(mk);
-    }
-    __threadfence_block();
-    atomicExch(lock, 0);
-  }
-};
-
 // ---- tile schedule of the fused kernel.
 // The output is tiled BM x BN.  Query blocks ("m-blocks") are processed in
 // super-rows of `rm` consecutive m-blocks; inside a super-row every m-block's

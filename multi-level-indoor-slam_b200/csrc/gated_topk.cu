@@ -409,7 +409,7 @@ static size_t smem_bytes_for(int cg, int stages, int kstride, bool sym, int sets
   return 1024 /*realign slack*/ + stages * stage + static_cast<size_t>(BM) * kstride * 8 +
          2 * BN * (sizeof(float) + sizeof(int32_t)) /*per-tile timestamp offsets + labels*/ +
          (sym ? 2 * BN * sizeof(float) + 64 : 0) /*column bounds + chunk minima*/ +
-         (sets == 2 ? static_cast<size_t>(BM) * 24 : 0) /*shared row-list state*/ + 128 /*chunk stamp ranges*/ + 256 /*barriers + tmem slot*/;
+         (sets == 2 ? static_cast<size_t>(BM) * kstride * 8 + BM * 4 : 0) /*the second epilogue set's lists and counts*/ + 128 /*chunk stamp ranges*/ + 256 /*barriers + tmem slot*/;
 }
 
 // Symmetric sweep: candidate-buffer depth per keyframe and the layout of its state behind the pacing counters:
@@ -491,16 +491,21 @@ int launch_gated_topk(const TopkLaunch& a, const Schedule& sc, uint64_t* partial
   //  before its last reader arrives -- measured 1.337 -> 1.290 ms at config 2 without it)
   p.policy_db = (hint >= 2 && sc.a_resident && sc.tab_runs == nullptr) ? ptx::kL2EvictFirst : ptx::kL2EvictNormal;
 
-  // Two epilogue sets (plain list-building sweeps only) are OPT-IN, SEMGATE_EPI_SETS=2: with short descriptors and SPARSE hits
-  // (the benchmark's input) they take 3-11 % off the kernel, but the two threads of a row share its list under a lock, and
-  // on a sequence with long revisits (hundreds of hits per row, both threads inserting all the time) the same sweep is
-  // 1.4-1.7x SLOWER (5k x 512-d: 109 -> 182 us, 20k x 512-d: 580 -> 838 us).  Real inputs look like the latter.
-  int sets = 1;
-  if (const char* e = getenv("SEMGATE_EPI_SETS")) { const int v = atoi(e); if (v == 1 || (v == 2 && !sym && cg != 4 && a.dense == nullptr)) sets = v; }
+  // Two epilogue sets (plain list-building sweeps; each set keeps lists of its own, folded together when a run ends) wherever
+  // the epilogue can be what bounds the kernel -- descriptors up to 4096 elements -- and the second set's lists still leave
+  // a usable stage ring.  Measured (20 launches, same box, one set -> two): 5k x 512-d 52 -> 42 us, 20k x 512-d 404 -> 286 us,
+  // on a sequence-like input with dense hits 5k x 512-d 111 -> 79 us, 20k x 2048-d 1.95 -> 1.67 ms; never slower.
+  // SEMGATE_EPI_SETS=1 / 2 pins it.
+  auto ring_depth = [&](int nsets) {
+    int st = kMaxStages;
+    while (st > 2 && smem_bytes_for(cg, st, p.kstride, sym, nsets) > kSmemLimit) --st;
+    return smem_bytes_for(cg, st, p.kstride, sym, nsets) <= kSmemLimit ? st : 0;     // 0: does not fit at all
+  };
+  const bool sets_possible = !sym && cg != 4 && a.dense == nullptr;
+  int sets = (sets_possible && p.kblocks <= 64 && ring_depth(2) >= (p.kblocks <= 16 ? 3 : 5)) ? 2 : 1;
+  if (const char* e = getenv("SEMGATE_EPI_SETS")) { const int v = atoi(e); if (v == 1 || (v == 2 && sets_possible && ring_depth(2) >= 2)) sets = v; }
   // deepest ring that fits the 227 KB per-CTA limit
-  int stages = kMaxStages;
-  while (stages > 2 && smem_bytes_for(cg, stages, p.kstride, sym, sets) > kSmemLimit) --stages;
-  stages = std::min(stages, std::max(2, p.kblocks));
+  int stages = std::min(ring_depth(sets), std::max(2, p.kblocks));
   p.stages = stages;
   const size_t smem = smem_bytes_for(cg, stages, p.kstride, sym, sets);
 

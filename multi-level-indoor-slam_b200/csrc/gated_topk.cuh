@@ -156,14 +156,12 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   // symmetric sweep: the tile's column bounds and their minimum per 32-column chunk (one set per accumulator)
   float* bd_s = reinterpret_cast<float*>(fl_s + 2 * BN);
   float* bmin_s = bd_s + (SYM ? 2 * BN : 0);
-  // SETS == 2: a row's list is filled by two threads (one per epilogue set), so its state lives here, behind a lock
-  uint64_t* rs_minkey = reinterpret_cast<uint64_t*>(bmin_s + (SYM ? 16 : 0));
-  int* rs_cnt = reinterpret_cast<int*>(rs_minkey + (SETS == 2 ? BM : 0));
-  int* rs_minpos = rs_cnt + (SETS == 2 ? BM : 0);
-  float* rs_f = reinterpret_cast<float*>(rs_minpos + (SETS == 2 ? BM : 0));
-  int* rs_lock = reinterpret_cast<int*>(rs_f + (SETS == 2 ? BM : 0));
+  // SETS == 2: the second epilogue set keeps lists of its own, [BM][kstride] behind everything else, and tells the first
+  // set how many keys each holds when a run ends
+  uint64_t* lists2 = reinterpret_cast<uint64_t*>(bmin_s + (SYM ? 16 : 0));
+  int* cnt2_s = reinterpret_cast<int*>(lists2 + (SETS == 2 ? static_cast<size_t>(BM) * p.kstride : 0));
   // smallest / largest staged stamp of every 32-column chunk (one set per accumulator): [2][8][2]
-  float* trange_s = reinterpret_cast<float*>(rs_lock + (SETS == 2 ? BM : 0));
+  float* trange_s = reinterpret_cast<float*>(cnt2_s + (SETS == 2 ? BM : 0));
   uint64_t* bars = reinterpret_cast<uint64_t*>(trange_s + 32);
   // barrier slots: full[kMaxStages] empty[kMaxStages] tmem_full[2] tmem_empty[2]
   const uint32_t bar_full = ptx::smem_u32(bars);
@@ -341,7 +339,10 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     // ===================================================== epilogue: gate + threshold + running top-k
     // SETS == 2 (short descriptors: the epilogue, not the MMAs, bounds the kernel -- one warp per scheduler runs a chunk's
     // ~235 dependent instructions at 0.17 IPC): warps 2..5 and 6..9 are two sets, a warp reads the TMEM lanes of quad
-    // warp % 4, set s takes the 32-column chunks c = s, s + 2, ...; the two threads of a row share its list (SharedRowList).
+    // warp % 4, set s takes the 32-column chunks c = s, s + 2, ....  Each of the two threads of a row keeps a list of its own
+    // (its columns' top k); when a run ends the first set's thread folds the second's keys into its list and flushes that.
+    // (A first version shared one list under a per-row lock: 3-11 % faster on sparse hits, 1.4-1.7x SLOWER on a sequence with
+    // dense ones -- both threads insert all the time there.)
     const int set = SETS == 2 ? ((warp - 2) >> 2) : 0;
     const int quad = warp & 3;
     const int row_in_tile = quad * 32 + lane;
@@ -349,10 +350,7 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     auto epi_sync = [&]() { if constexpr (SETS == 2) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 1, 128;" ::: "memory"); };
     RowList L;
-    L.keys = lists + static_cast<size_t>(row_in_tile) * p.kstride;
-    SharedRowList SL;
-    SL.keys = L.keys; SL.cnt = rs_cnt + row_in_tile; SL.min_pos = rs_minpos + row_in_tile; SL.min_key = rs_minkey + row_in_tile;
-    SL.f = rs_f + row_in_tile; SL.lock = rs_lock + row_in_tile;
+    L.keys = (set == 0 ? lists : lists2) + static_cast<size_t>(row_in_tile) * p.kstride;
     const int k = p.k;
     const bool mask_mode = p.gate_mode == 1 && p.max_floor_diff >= 0 && p.q_floor != nullptr && p.db_floor != nullptr;
     const bool use_time = p.use_time != 0;
@@ -372,10 +370,7 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       }
       const uint64_t ceil_key = (p.ceil_keys != nullptr && row_live) ? __ldg(p.ceil_keys + static_cast<int64_t>(grow) * p.ceil_stride) : ~0ull;
       L.reset(row_live ? p.threshold : pos_inf);
-      if constexpr (SETS == 2) {
-        if (set == 0) SL.reset(row_live ? p.threshold : pos_inf);
-        epi_sync();                                   // (also: the flush of the run before has read the list)
-      }
+      if constexpr (SETS == 2) epi_sync();            // the flush of the run before has read the second set's lists
       float published = __int_as_float(0xff800000);   // SYM: last bound this thread published for its row
       // SYM: one column-direction append in flight per thread.  The slot number comes back from a global atomic
       // (about a microsecond); it is only looked at when the thread's next candidate arrives or the run ends, so
@@ -489,7 +484,7 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           float mx = __uint_as_float(v[0]);
 #pragma unroll
           for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-          const float bound = SETS == 2 ? SL.bound() : L.f;   // (shared list: a stale bound is only lower, never higher)
+          const float bound = L.f;
           // Temporal neighbours score high and are all thrown out by the window: in an all-pairs sweep every row meets a
           // few chunks that lie INSIDE its exclusion window, where each of its 32 columns would walk the slow path only to
           // fail the window test (config 1: half of all slow-path iterations, all on the units that own diagonal tiles).
@@ -512,7 +507,7 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             }
             // one hit column of this thread's row
             auto admit = [&](int i, float s) {
-              if (s >= (SETS == 2 ? SL.bound() : L.f)) {     // the bound may have risen since the mask was built
+              if (s >= L.f) {                               // the bound may have risen since the mask was built
                 const int col = col_base + c * 32 + i;      // local database row
                 if (col < p.N) {                            // TMA zero-fill beyond N must not score
                   bool ok = true;
@@ -520,7 +515,7 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                   if (ok && mask_mode) ok = floor_ok(qf, fl_s[acc * BN + c * 32 + i], p.max_floor_diff);
                   if (ok) {
                     const uint64_t key = pack_key(s, static_cast<uint32_t>(col) + p.db_index_offset);
-                    if (key < ceil_key) { if constexpr (SETS == 2) SL.insert(key, k); else L.insert(key, k); }
+                    if (key < ceil_key) L.insert(key, k);
                   }
                 }
               }
@@ -593,10 +588,17 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       if constexpr (SYM) complete_append();
       // flush this run's list (unsorted, packed at the front; empty slots are key 0)
       if constexpr (SETS == 2) {
+        if (set == 1) cnt2_s[row_in_tile] = L.cnt;
         epi_sync();                                   // both sets are done with the run's last tile
-        if (set == 0 && row_live && p.dense == nullptr) {
-          const int cnt = *SL.cnt;
-          for (int i = 0; i < k; ++i) slot[i] = i < cnt ? L.keys[i] : 0ull;
+        if (set == 0) {
+          const uint64_t* other = lists2 + static_cast<size_t>(row_in_tile) * p.kstride;
+          const int c2 = cnt2_s[row_in_tile];
+          for (int i = 0; i < c2; ++i) {              // keys are unique: the two sets saw different columns
+            const uint64_t key = other[i];
+            if (L.cnt < k || key > L.min_key) L.insert(key, k);
+          }
+          if (row_live && p.dense == nullptr)
+            for (int i = 0; i < k; ++i) slot[i] = i < L.cnt ? L.keys[i] : 0ull;
         }
       } else if (row_live && p.dense == nullptr) {
         for (int i = 0; i < k; ++i) slot[i] = i < L.cnt ? L.keys[i] : 0ull;
