@@ -501,8 +501,11 @@ int launch_gated_topk(const TopkLaunch& a, const Schedule& sc, uint64_t* partial
     while (st > 2 && smem_bytes_for(cg, st, p.kstride, sym, nsets) > kSmemLimit) --st;
     return smem_bytes_for(cg, st, p.kstride, sym, nsets) <= kSmemLimit ? st : 0;     // 0: does not fit at all
   };
-  const bool sets_possible = !sym && cg != 4 && a.dense == nullptr;
-  int sets = (sets_possible && p.kblocks <= 64 && ring_depth(2) >= (p.kblocks <= 16 ? 3 : 5)) ? 2 : 1;
+  const bool sets_possible = cg != 4 && a.dense == nullptr;
+  // (symmetric sweeps: run-table schedules only, i.e. up to ~57k keyframes -- 20k x 1024-d 815 -> 581 us, 20k x 4096-d with dense
+  //  hits 2.07 -> 1.70 ms, the benchmark's config 2 unchanged (1.063 vs 1.060 ms); the long super-row sweeps are MMA-bound
+  //  for seconds and keep the sixth stage: 1M x 4096-d 2.854 s with one set, 2.87 s with two)
+  int sets = (sets_possible && (!sym || sc.tab_runs != nullptr) && p.kblocks <= 64 && ring_depth(2) >= (p.kblocks <= 16 ? 3 : 5)) ? 2 : 1;
   if (const char* e = getenv("SEMGATE_EPI_SETS")) { const int v = atoi(e); if (v == 1 || (v == 2 && sets_possible && ring_depth(2) >= 2)) sets = v; }
   // deepest ring that fits the 227 KB per-CTA limit
   int stages = std::min(ring_depth(sets), std::max(2, p.kblocks));
@@ -532,7 +535,7 @@ int launch_gated_topk(const TopkLaunch& a, const Schedule& sc, uint64_t* partial
     if (ee != cudaSuccess) return ee;
     return cudaLaunchKernelEx(&cfg, kernel, tq, tdb, p);
   };
-  if (sym) e = launch(gated_topk_kernel<2, 1, true>);
+  if (sym) e = sets == 2 ? launch(gated_topk_kernel<2, 1, true, 2>) : launch(gated_topk_kernel<2, 1, true>);
   else if (cg == 4) e = launch(gated_topk_kernel<2, 2>);
   else if (cg == 2) e = sets == 2 ? launch(gated_topk_kernel<2, 1, false, 2>) : launch(gated_topk_kernel<2, 1>);
   else e = sets == 2 ? launch(gated_topk_kernel<1, 1, false, 2>) : launch(gated_topk_kernel<1, 1>);

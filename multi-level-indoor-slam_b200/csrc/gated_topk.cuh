@@ -128,7 +128,7 @@ gated_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                   const TopkParams p) {
   static_assert(MC == 1 || (MC == 2 && CG == 2), "multicast needs CTA pairs");
   static_assert(!SYM || (CG == 2 && MC == 1), "symmetric sweep: a query block must be one database tile");
-  static_assert(SETS == 1 || (SETS == 2 && !SYM && MC == 1), "two epilogue sets: plain sweeps only");
+  static_assert(SETS == 1 || (SETS == 2 && MC == 1), "two epilogue sets: not with two-pair clusters");
   if (p.run_if != nullptr && ptx::ld_relaxed_gpu(p.run_if) == 0u) return;   // grid-uniform, before any barrier
   if (p.clk != nullptr && threadIdx.x == 0) {
     p.clk[4 * blockIdx.x + 0] = ptx::globaltimer_ns();
