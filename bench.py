@@ -994,6 +994,28 @@ def run_ours(args):
                   "compaction, D2H of each rank's candidates"}
     base["e2e"] = e2e
 
+    # ---- the same call for a caller whose extractor already produces half precision (NOT the headline: the reference hands
+    #      over fp32 rows, place_recognition.py:297): semgate_find_loop_closures_host_dtype on the same rows rounded to fp16
+    if world == 1:
+        try:
+            q16 = torch.from_numpy(desc_h.astype(np.float16)).pin_memory()
+            q16n = q16.numpy()
+            n16 = len(eng.find_loop_closures_host(q16n, ts_h, fl_h, p, out=outs)[0])
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                n16 = len(eng.find_loop_closures_host(q16n, ts_h, fl_h, p, out=outs)[0])
+            s16 = time.perf_counter() - t0
+            base["e2e_fp16_host_input"] = {
+                "value": pairs_per_step * e2e_steps / s16, "unit": UNIT, "ms_per_step": s16 / e2e_steps * 1e3,
+                "h2d_bytes_per_step": int(q16n.nbytes + ts_h.nbytes + fl_h.nbytes), "d2h_bytes_per_step": int(n16 * 13 + 8),
+                "steps": e2e_steps, "candidates": int(n16),
+                "api": "semgate_find_loop_closures_host_dtype(SEMGATE_DTYPE_F16): the same host rows rounded to fp16, pinned",
+                "note": "not the headline e2e: input precision differs from the reference's fp32 rows (candidates are those of "
+                        "the fp16-rounded rows; bit-identical to the fp32 call on their widened image, tests/test_gpu_parity.py)"}
+            del q16, q16n
+        except Exception as e:      # noqa: BLE001
+            base["e2e_fp16_host_input"] = {"failed": f"{type(e).__name__}: {e}"[:400]}
+
     # ---- BASELINE config 5 in the same run, every N (skipped only on request)
     if not args.no_c5:
         try:

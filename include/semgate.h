@@ -133,6 +133,16 @@ int semgate_pad_dim(int d);
 int semgate_normalize_cast(semgate_handle_t h, const float* x, int64_t n, int32_t d, int64_t ld, void* out_bf16,
                            int32_t d_pad, semgate_stream_t stream);
 
+/* The same for descriptors that are already half precision (the reference runs its extractors on the GPU,
+ * place_recognition.py:291-297; under autocast their output is fp16 / bf16 and `.cpu().numpy()` keeps that).
+ * dtype: SEMGATE_DTYPE_*.  Elements are widened exactly and every sum runs in the same order as the fp32
+ * form, so a half-precision row gives bit for bit what its fp32 image gives. */
+#define SEMGATE_DTYPE_F32 0
+#define SEMGATE_DTYPE_F16 1
+#define SEMGATE_DTYPE_BF16 2
+int semgate_normalize_cast_dtype(semgate_handle_t h, const void* x, int32_t dtype, int64_t n, int32_t d, int64_t ld,
+                                 void* out_bf16, int32_t d_pad, semgate_stream_t stream);
+
 /* ---- dense similarity matrix (interface parity only) ---------------------
  * replaces `desc_matrix_norm @ desc_matrix_norm.T` (place_recognition.py:190) and
  * `np.dot(database_norm, query_norm)` (:171) for callers that really want the scores
@@ -296,6 +306,15 @@ int semgate_find_loop_closures_host(semgate_handle_t h, const float* descriptors
                                     const double* timestamps, const int32_t* floor_labels,
                                     const semgate_topk_params* p, int32_t* out_query_idx, int32_t* out_match_idx,
                                     float* out_similarity, uint8_t* out_is_valid, int64_t capacity, int64_t* out_total);
+
+/* The same call for a host database of fp16 / bf16 descriptors (dtype: SEMGATE_DTYPE_*; _F32 is the call
+ * above): half the bytes cross PCIe, which is what bounds the fp32 form.  Candidates
+ * are bit-identical to the fp32 call on the widened descriptors. */
+int semgate_find_loop_closures_host_dtype(semgate_handle_t h, const void* descriptors, int32_t dtype, int64_t n, int32_t d,
+                                          const double* timestamps, const int32_t* floor_labels,
+                                          const semgate_topk_params* p, int32_t* out_query_idx, int32_t* out_match_idx,
+                                          float* out_similarity, uint8_t* out_is_valid, int64_t capacity,
+                                          int64_t* out_total);
 
 /* batched query() against a database in host memory (place_recognition.py:117-163):
  * padded outputs [nq,k] + count[nq]. */

@@ -453,16 +453,22 @@ int semgate_schedule_check(int64_t Q, int64_t N, int32_t d_pad, int32_t cta_grou
 }
 
 // ---------------------------------------------------------------- K1
-int semgate_normalize_cast(semgate_handle_t h, const float* x, int64_t n, int32_t d, int64_t ld, void* out_bf16, int32_t d_pad,
-                           semgate_stream_t stream) {
+int semgate_normalize_cast_dtype(semgate_handle_t h, const void* x, int32_t dtype, int64_t n, int32_t d, int64_t ld,
+                                 void* out_bf16, int32_t d_pad, semgate_stream_t stream) {
   if (!h) return fail(SEMGATE_EINVAL, "handle is NULL");
+  if (dtype != SEMGATE_DTYPE_F32 && dtype != SEMGATE_DTYPE_F16 && dtype != SEMGATE_DTYPE_BF16) return fail(SEMGATE_EINVAL, "normalize_cast: unknown dtype %d", dtype);
   if (n < 0 || d <= 0 || ld < d || d_pad < d || d_pad % 64 != 0) return fail(SEMGATE_EINVAL, "normalize_cast: bad shape n=%lld d=%d ld=%lld d_pad=%d", (long long)n, d, (long long)ld, d_pad);
   if (n == 0) return 0;
   if (!x || !out_bf16) return fail(SEMGATE_EINVAL, "normalize_cast: NULL pointer");
   DeviceGuard g(h->device);
-  RC_TRY(launch_normalize_cast(x, n, d, ld, out_bf16, d_pad, static_cast<cudaStream_t>(stream)), "normalize_cast launch");
+  RC_TRY(launch_normalize_cast_any(x, dtype, n, d, ld, out_bf16, d_pad, static_cast<cudaStream_t>(stream)), "normalize_cast launch");
   h->launches += 1;
   return 0;
+}
+
+int semgate_normalize_cast(semgate_handle_t h, const float* x, int64_t n, int32_t d, int64_t ld, void* out_bf16, int32_t d_pad,
+                           semgate_stream_t stream) {
+  return semgate_normalize_cast_dtype(h, x, SEMGATE_DTYPE_F32, n, d, ld, out_bf16, d_pad, stream);
 }
 
 // ---------------------------------------------------------------- K2 + K3
@@ -1027,7 +1033,18 @@ int semgate_find_loop_closures_host(semgate_handle_t h, const float* descriptors
                                     const double* timestamps, const int32_t* floor_labels, const semgate_topk_params* p,
                                     int32_t* out_query_idx, int32_t* out_match_idx, float* out_similarity,
                                     uint8_t* out_is_valid, int64_t capacity, int64_t* out_total) {
+  return semgate_find_loop_closures_host_dtype(h, descriptors, SEMGATE_DTYPE_F32, n, d, timestamps, floor_labels, p, out_query_idx,
+                                               out_match_idx, out_similarity, out_is_valid, capacity, out_total);
+}
+
+int semgate_find_loop_closures_host_dtype(semgate_handle_t h, const void* descriptors_any, int32_t dtype, int64_t n, int32_t d,
+                                          const double* timestamps, const int32_t* floor_labels, const semgate_topk_params* p,
+                                          int32_t* out_query_idx, int32_t* out_match_idx, float* out_similarity,
+                                          uint8_t* out_is_valid, int64_t capacity, int64_t* out_total) {
   if (!h) return fail(SEMGATE_EINVAL, "handle is NULL");
+  if (dtype != SEMGATE_DTYPE_F32 && dtype != SEMGATE_DTYPE_F16 && dtype != SEMGATE_DTYPE_BF16) return fail(SEMGATE_EINVAL, "find_loop_closures: unknown dtype %d", dtype);
+  const size_t esz = dtype == SEMGATE_DTYPE_F32 ? 4 : 2;           // bytes per descriptor element in host memory
+  const char* descriptors = static_cast<const char*>(descriptors_any);
   int rc = check_params(p);
   if (rc) return rc;
   if (!out_total) return fail(SEMGATE_EINVAL, "out_total is NULL");
@@ -1039,7 +1056,7 @@ int semgate_find_loop_closures_host(semgate_handle_t h, const float* descriptors
   const int k = p->k;
   const int d_pad = semgate_pad_dim(d);
   void *dx = nullptr, *dbf = nullptr, *dts = nullptr, *dfl = nullptr, *ws = nullptr, *sc = nullptr, *ix = nullptr, *va = nullptr, *ct = nullptr, *oq = nullptr, *om = nullptr, *os = nullptr, *ov = nullptr, *tot = nullptr, *cws = nullptr;
-  if ((rc = h->reserve(B_X, sizeof(float) * n * d, &dx))) return rc;
+  if ((rc = h->reserve(B_X, esz * n * d, &dx))) return rc;
   if ((rc = h->reserve(B_BF16, 2ull * n * d_pad, &dbf))) return rc;
   if (timestamps && (rc = h->reserve(B_TS, 8ull * n, &dts))) return rc;
   if (floor_labels && (rc = h->reserve(B_FL, 4ull * n, &dfl))) return rc;
@@ -1056,7 +1073,7 @@ int semgate_find_loop_closures_host(semgate_handle_t h, const float* descriptors
   // key lists.  Top-k under a total order is an associative merge, so the result equals one sweep.
   // Chunk sizes shrink towards the end: what cannot overlap with PCIe is the work the LAST chunk
   // completes, and that is proportional to its size.
-  const int64_t bytes_per_row = static_cast<int64_t>(d) * 4;
+  const int64_t bytes_per_row = static_cast<int64_t>(d) * 4;   // chunks are cut by rows (launch cost per chunk), whatever the element size
   const int64_t approx_chunks = (n * bytes_per_row) / (24ll << 20);
   std::vector<int64_t> bounds;   // chunk c = rows [bounds[c], bounds[c+1])
   bounds.push_back(0);
@@ -1114,10 +1131,11 @@ int semgate_find_loop_closures_host(semgate_handle_t h, const float* descriptors
   for (int64_t ci = 0; ci < nchunks; ++ci) {
     const int64_t r0 = bounds[ci], r1 = bounds[ci + 1], rows = r1 - r0;
     // the copy stream carries nothing but copies, back to back; the chunk is normalised on the compute stream
-    CUDA_TRY(cudaMemcpyAsync(static_cast<float*>(dx) + r0 * d, descriptors + r0 * d, sizeof(float) * rows * d, cudaMemcpyHostToDevice, cs));
+    char* dxc = static_cast<char*>(dx) + esz * r0 * d;
+    CUDA_TRY(cudaMemcpyAsync(dxc, descriptors + esz * r0 * d, esz * rows * d, cudaMemcpyHostToDevice, cs));
     CUDA_TRY(cudaEventRecord(h->chunk_events[ci], cs));
     CUDA_TRY(cudaStreamWaitEvent(st, h->chunk_events[ci], 0));
-    if ((rc = semgate_normalize_cast(h, static_cast<float*>(dx) + r0 * d, rows, d, d, bf + 2ull * r0 * d_pad, d_pad, st))) return rc;
+    if ((rc = semgate_normalize_cast_dtype(h, dxc, dtype, rows, d, d, bf + 2ull * r0 * d_pad, d_pad, st))) return rc;
     semgate_topk_params pa = *p;
     pa.db_index_offset = 0; pa.accumulate = 0;
     if (k > SEMGATE_MAX_K) {      // one chunk: the sweep's passes write the decoded lists themselves

@@ -9,6 +9,7 @@
 #include "sortnet.cuh"
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <algorithm>
 
 namespace semgate {
@@ -39,14 +40,37 @@ __device__ __forceinline__ void store_bf16x4(__nv_bfloat16* dst, float a, float 
   *reinterpret_cast<uint2*>(dst) = u;
 }
 
-// one block per row (grid-stride over rows); VEC: 16-byte loads are legal
-template <bool VEC>
+// Four consecutive elements of a row as fp32.  Half-precision inputs (IEEE fp16 / bf16, e.g. descriptors an extractor
+// produced under autocast) are widened exactly; the element -> thread mapping and the order of the sums are the same for
+// every input type, so a half-precision row gives bit for bit what its fp32 image gives.
+template <bool STREAM>
+__device__ __forceinline__ float4 load4(const float* row, int i) {
+  return STREAM ? __ldcs(reinterpret_cast<const float4*>(row) + i) : __ldg(reinterpret_cast<const float4*>(row) + i);
+}
+template <bool STREAM>
+__device__ __forceinline__ float4 load4(const __half* row, int i) {
+  const uint2 u = STREAM ? __ldcs(reinterpret_cast<const uint2*>(row) + i) : __ldg(reinterpret_cast<const uint2*>(row) + i);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <bool STREAM>
+__device__ __forceinline__ float4 load4(const __nv_bfloat16* row, int i) {
+  const uint2 u = STREAM ? __ldcs(reinterpret_cast<const uint2*>(row) + i) : __ldg(reinterpret_cast<const uint2*>(row) + i);
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                     __uint_as_float(u.y & 0xffff0000u));
+}
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// one block per row (grid-stride over rows); VEC: vector loads of four elements are legal
+template <bool VEC, typename T>
 __global__ void __launch_bounds__(kNormThreads)
-normalize_cast_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ld, __nv_bfloat16* __restrict__ out, int d_pad) {
+normalize_cast_kernel(const T* __restrict__ x, int64_t n, int d, int64_t ld, __nv_bfloat16* __restrict__ out, int d_pad) {
   __shared__ float red[32];
   const int tid = threadIdx.x;
   for (int64_t row = blockIdx.x; row < n; row += gridDim.x) {
-    const float* xr = x + row * ld;
+    const T* xr = x + row * ld;
     __nv_bfloat16* orow = out + row * static_cast<int64_t>(d_pad);
     float ss = 0.f;
     if constexpr (VEC) {
@@ -55,11 +79,11 @@ normalize_cast_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ld,
 #pragma unroll
       for (int c = 0; c < kNormCache; ++c) {
         const int i = c * kNormThreads + tid;
-        cache[c] = i < nv ? __ldg(reinterpret_cast<const float4*>(xr) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        cache[c] = i < nv ? load4<false>(xr, i) : make_float4(0.f, 0.f, 0.f, 0.f);
         ss += cache[c].x * cache[c].x + cache[c].y * cache[c].y + cache[c].z * cache[c].z + cache[c].w * cache[c].w;
       }
       for (int i = kNormCache * kNormThreads + tid; i < nv; i += kNormThreads) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(xr) + i);
+        const float4 v = load4<false>(xr, i);
         ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
       }
       const float denom = sqrtf(block_sum(ss, red)) + 1e-8f;
@@ -69,14 +93,14 @@ normalize_cast_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ld,
         if (i < nv) store_bf16x4(orow + 4 * i, cache[c].x / denom, cache[c].y / denom, cache[c].z / denom, cache[c].w / denom);
       }
       for (int i = kNormCache * kNormThreads + tid; i < nv; i += kNormThreads) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(xr) + i);   // second touch: L2
+        const float4 v = load4<false>(xr, i);   // second touch: L2
         store_bf16x4(orow + 4 * i, v.x / denom, v.y / denom, v.z / denom, v.w / denom);
       }
       for (int i = nv + tid; i < (d_pad >> 2); i += kNormThreads) store_bf16x4(orow + 4 * i, 0.f, 0.f, 0.f, 0.f);
     } else {
-      for (int i = tid; i < d; i += kNormThreads) { const float v = xr[i]; ss += v * v; }
+      for (int i = tid; i < d; i += kNormThreads) { const float v = to_f32(xr[i]); ss += v * v; }
       const float denom = sqrtf(block_sum(ss, red)) + 1e-8f;
-      for (int i = tid; i < d_pad; i += kNormThreads) orow[i] = __float2bfloat16_rn(i < d ? xr[i] / denom : 0.f);
+      for (int i = tid; i < d_pad; i += kNormThreads) orow[i] = __float2bfloat16_rn(i < d ? to_f32(xr[i]) / denom : 0.f);
     }
   }
 }
@@ -97,8 +121,9 @@ __device__ __forceinline__ float ld_dsmem_f32(const float* local, uint32_t cta) 
   return v;
 }
 
+template <typename T>
 __global__ void __launch_bounds__(kNormThreads)
-normalize_cast_cluster_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ld, __nv_bfloat16* __restrict__ out,
+normalize_cast_cluster_kernel(const T* __restrict__ x, int64_t n, int d, int64_t ld, __nv_bfloat16* __restrict__ out,
                               int d_pad, int csize) {
   __shared__ float red[32];
   __shared__ float partial[2];
@@ -110,14 +135,14 @@ normalize_cast_cluster_kernel(const float* __restrict__ x, int64_t n, int d, int
   const int v0 = static_cast<int>(rank) * (kNormLongChunk >> 2);   // this CTA's first float4 of the row
   int par = 0;
   for (int64_t row = cluster_id; row < n; row += n_clusters, par ^= 1) {
-    const float4* xr = reinterpret_cast<const float4*>(x + row * ld);
+    const T* xr = x + row * ld;
     __nv_bfloat16* orow = out + row * static_cast<int64_t>(d_pad);
     float4 cache[kNormLongCache];
     float ss = 0.f;
 #pragma unroll
     for (int c = 0; c < kNormLongCache; ++c) {
       const int i = v0 + c * kNormThreads + tid;
-      cache[c] = i < nv ? __ldcs(xr + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      cache[c] = i < nv ? load4<true>(xr, i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int c = 0; c < kNormLongCache; ++c)
@@ -142,9 +167,11 @@ normalize_cast_cluster_kernel(const float* __restrict__ x, int64_t n, int d, int
   if (csize > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-int launch_normalize_cast(const float* x, int64_t n, int d, int64_t ld, void* out_bf16, int d_pad, cudaStream_t st) {
+template <typename T>
+static int launch_normalize_cast_t(const T* x, int64_t n, int d, int64_t ld, void* out_bf16, int d_pad, cudaStream_t st) {
   if (n <= 0) return 0;
-  const bool vec = (d % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  // four elements per vector load: 16 bytes of fp32, 8 bytes of fp16 / bf16
+  const bool vec = (d % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & (4 * sizeof(T) - 1)) == 0);
   if (vec && d > 4096 && d_pad <= 8 * kNormLongChunk) {
     int csize = (d_pad + kNormLongChunk - 1) / kNormLongChunk;       // 1, 2, 3..8 -> round up to a power of two
     while (csize & (csize - 1)) ++csize;
@@ -160,15 +187,29 @@ int launch_normalize_cast(const float* x, int64_t n, int d, int64_t ld, void* ou
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = static_cast<unsigned>(csize); attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return static_cast<int>(cudaLaunchKernelEx(&cfg, normalize_cast_cluster_kernel, x, n, d, ld,
+    return static_cast<int>(cudaLaunchKernelEx(&cfg, normalize_cast_cluster_kernel<T>, x, n, d, ld,
                                                static_cast<__nv_bfloat16*>(out_bf16), d_pad, csize));
   }
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(n, 148 * 16));
   if (vec)
-    normalize_cast_kernel<true><<<grid, kNormThreads, 0, st>>>(x, n, d, ld, static_cast<__nv_bfloat16*>(out_bf16), d_pad);
+    normalize_cast_kernel<true, T><<<grid, kNormThreads, 0, st>>>(x, n, d, ld, static_cast<__nv_bfloat16*>(out_bf16), d_pad);
   else
-    normalize_cast_kernel<false><<<grid, kNormThreads, 0, st>>>(x, n, d, ld, static_cast<__nv_bfloat16*>(out_bf16), d_pad);
+    normalize_cast_kernel<false, T><<<grid, kNormThreads, 0, st>>>(x, n, d, ld, static_cast<__nv_bfloat16*>(out_bf16), d_pad);
   return static_cast<int>(cudaGetLastError());
+}
+
+int launch_normalize_cast(const float* x, int64_t n, int d, int64_t ld, void* out_bf16, int d_pad, cudaStream_t st) {
+  return launch_normalize_cast_t<float>(x, n, d, ld, out_bf16, d_pad, st);
+}
+
+// dtype: SEMGATE_DTYPE_F32 / _F16 / _BF16 (semgate.h)
+int launch_normalize_cast_any(const void* x, int dtype, int64_t n, int d, int64_t ld, void* out_bf16, int d_pad, cudaStream_t st) {
+  switch (dtype) {
+    case 0: return launch_normalize_cast_t<float>(static_cast<const float*>(x), n, d, ld, out_bf16, d_pad, st);
+    case 1: return launch_normalize_cast_t<__half>(static_cast<const __half*>(x), n, d, ld, out_bf16, d_pad, st);
+    case 2: return launch_normalize_cast_t<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(x), n, d, ld, out_bf16, d_pad, st);
+    default: return static_cast<int>(cudaErrorInvalidValue);
+  }
 }
 
 // Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start

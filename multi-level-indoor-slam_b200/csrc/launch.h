@@ -68,6 +68,8 @@ int launch_stream_query(const TopkLaunch& a, uint64_t* partial /*[Q][lists][k]*/
 
 // K1
 int launch_normalize_cast(const float* x, int64_t n, int d, int64_t ld, void* out_bf16, int d_pad, cudaStream_t st);
+int launch_normalize_cast_any(const void* x, int dtype /*SEMGATE_DTYPE_**/, int64_t n, int d, int64_t ld, void* out_bf16, int d_pad,
+                              cudaStream_t st);
 
 // K3: merge `n_lists` candidate lists per row into one sorted list.
 struct MergeLaunch {

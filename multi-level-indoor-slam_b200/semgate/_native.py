@@ -18,13 +18,15 @@ LIB_PATH = os.path.join(_HERE, "libsemgate.so")
 MAX_K = 64            # candidates per query one sweep keeps
 MAX_K_TOTAL = 1024    # largest k: above MAX_K the library runs ceil(k / 64) sweeps
 FLOOR_NONE = -2**31
+DTYPE_F32, DTYPE_F16, DTYPE_BF16 = 0, 1, 2     # SEMGATE_DTYPE_* (semgate.h): element type of descriptors handed to K1
 GATE_FLAG, GATE_MASK = 0, 1
 EINVAL, EARCH, ENOMEM, EDRIVER, EINDEX = -1, -2, -3, -4, -5
 
 # every symbol include/semgate.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "semgate_version", "semgate_last_error", "semgate_create", "semgate_destroy", "semgate_device_info",
-    "semgate_set_option", "semgate_profile_read", "semgate_launch_count", "semgate_pad_dim", "semgate_normalize_cast",
+    "semgate_set_option", "semgate_profile_read", "semgate_launch_count", "semgate_pad_dim", "semgate_normalize_cast", "semgate_normalize_cast_dtype",
+    "semgate_find_loop_closures_host_dtype",
     "semgate_topk_workspace_bytes", "semgate_gated_topk", "semgate_merge_topk", "semgate_compact_workspace_bytes",
     "semgate_compact", "semgate_gate_candidates", "semgate_find_loop_closures_host", "semgate_query_host",
     "semgate_gate_candidates_host", "semgate_spatial_workspace_bytes", "semgate_spatial_count", "semgate_spatial_fill",
@@ -87,6 +89,7 @@ def load_library():
     lib.semgate_launch_count.restype = i64
     lib.semgate_pad_dim.argtypes = [C.c_int]
     lib.semgate_normalize_cast.argtypes = [vp, vp, i64, i32, i64, vp, i32, vp]
+    lib.semgate_normalize_cast_dtype.argtypes = [vp, vp, i32, i64, i32, i64, vp, i32, vp]
     lib.semgate_topk_workspace_bytes.argtypes = [vp, i64, i64, i32, P(TopkParams)]
     lib.semgate_topk_workspace_bytes.restype = sz
     lib.semgate_gated_topk.argtypes = [vp, vp, i64, vp, i64, i32, vp, vp, vp, vp, P(TopkParams), vp, sz,
@@ -97,6 +100,7 @@ def load_library():
     lib.semgate_compact.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.semgate_gate_candidates.argtypes = [vp, vp, i64, vp, vp, i64, i32, vp, vp, vp]
     lib.semgate_find_loop_closures_host.argtypes = [vp, vp, i64, i32, vp, vp, P(TopkParams), vp, vp, vp, vp, i64, P(i64)]
+    lib.semgate_find_loop_closures_host_dtype.argtypes = [vp, vp, i32, i64, i32, vp, vp, P(TopkParams), vp, vp, vp, vp, i64, P(i64)]
     lib.semgate_query_host.argtypes = [vp, vp, i64, vp, i64, i32, vp, vp, P(TopkParams), vp, vp, vp]
     lib.semgate_gate_candidates_host.argtypes = [vp, vp, i64, vp, vp, i64, i32, vp, vp]
     lib.semgate_spatial_workspace_bytes.argtypes = [i64]
@@ -267,10 +271,12 @@ class Engine:
 
     # ------------------------------------------------------------------ K1
     def normalize_cast(self, x, out=None):
-        """fp32 [n,d] CUDA tensor -> row-normalised bf16 [n,pad64(d)] (zero padded)."""
+        """fp32 (or fp16 / bf16) [n,d] CUDA tensor -> row-normalised bf16 [n,pad64(d)] (zero padded).  Half-precision
+        rows are widened exactly: the result equals that of their fp32 image bit for bit."""
         torch = self._torch()
-        if x.dim() != 2 or x.dtype != torch.float32 or not x.is_cuda or x.stride(1) != 1:
-            raise TypeError("normalize_cast: expected a 2-D fp32 CUDA tensor with unit inner stride")
+        dtypes = {torch.float32: DTYPE_F32, torch.float16: DTYPE_F16, torch.bfloat16: DTYPE_BF16}
+        if x.dim() != 2 or x.dtype not in dtypes or not x.is_cuda or x.stride(1) != 1:
+            raise TypeError("normalize_cast: expected a 2-D fp32 / fp16 / bf16 CUDA tensor with unit inner stride")
         n, d = x.shape
         dp = pad_dim(d)
         if out is None:
@@ -279,7 +285,8 @@ class Engine:
         if out.shape[0] < n or out.shape[1] != dp:
             raise ValueError("normalize_cast: out has the wrong shape")
         if n:
-            _check(self.lib.semgate_normalize_cast(self._h, self._ptr(x), n, d, x.stride(0), self._ptr(out), dp, self._stream()))
+            _check(self.lib.semgate_normalize_cast_dtype(self._h, self._ptr(x), dtypes[x.dtype], n, d, x.stride(0), self._ptr(out),
+                                                         dp, self._stream()))
         return out
 
     # ------------------------------------------------------------------ K2 + K3
@@ -552,8 +559,25 @@ class Engine:
     def find_loop_closures_host(self, descriptors: np.ndarray, timestamps: Optional[np.ndarray],
                                 floor_labels: Optional[np.ndarray], params: TopkParams, out=None):
         """Whole find_loop_closures on host arrays (H2D, kernels, D2H inside the call).
-        Returns (query_idx, match_idx, similarity, is_valid) numpy arrays."""
-        desc = np.ascontiguousarray(descriptors, dtype=np.float32)
+        Returns (query_idx, match_idx, similarity, is_valid) numpy arrays.  `descriptors`: fp32, or half precision as
+        a numpy float16 array or a CPU torch tensor (float16 / bfloat16; numpy has no bf16) -- half the PCIe bytes,
+        candidates bit-identical to the call on the widened rows."""
+        dtype = DTYPE_F32
+        if hasattr(descriptors, "data_ptr"):                   # a CPU torch tensor
+            torch = self._torch()
+            if descriptors.is_cuda:
+                raise TypeError("find_loop_closures_host: descriptors live on the GPU; use normalize_cast + gated_topk")
+            if descriptors.dtype in (torch.float16, torch.bfloat16):
+                dtype = DTYPE_F16 if descriptors.dtype == torch.float16 else DTYPE_BF16
+                keep = descriptors.contiguous()                # keeps the storage alive over the call
+                desc = keep.view(torch.int16).numpy()
+            else:
+                desc = np.ascontiguousarray(descriptors.numpy(), dtype=np.float32)
+        elif isinstance(descriptors, np.ndarray) and descriptors.dtype == np.float16:
+            dtype = DTYPE_F16
+            desc = np.ascontiguousarray(descriptors)
+        else:
+            desc = np.ascontiguousarray(descriptors, dtype=np.float32)
         n, d = desc.shape if desc.ndim == 2 else (0, 0)
         ts = None if timestamps is None else np.ascontiguousarray(timestamps, dtype=np.float64)
         fl = None if floor_labels is None else np.ascontiguousarray(floor_labels, dtype=np.int32)
@@ -562,9 +586,9 @@ class Engine:
             out = (np.empty(cap, np.int32), np.empty(cap, np.int32), np.empty(cap, np.float32), np.empty(cap, np.uint8))
         oq, om, os_, ov = out
         total = C.c_int64(0)
-        _check(self.lib.semgate_find_loop_closures_host(self._h, _np_ptr(desc), n, d, _np_ptr(ts), _np_ptr(fl),
-                                                        C.byref(params), _np_ptr(oq), _np_ptr(om), _np_ptr(os_), _np_ptr(ov),
-                                                        min(cap, oq.shape[0]), C.byref(total)))
+        _check(self.lib.semgate_find_loop_closures_host_dtype(self._h, _np_ptr(desc), dtype, n, d, _np_ptr(ts), _np_ptr(fl),
+                                                              C.byref(params), _np_ptr(oq), _np_ptr(om), _np_ptr(os_),
+                                                              _np_ptr(ov), min(cap, oq.shape[0]), C.byref(total)))
         t = total.value
         return oq[:t], om[:t], os_[:t], ov[:t].astype(bool)
 

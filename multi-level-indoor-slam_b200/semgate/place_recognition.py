@@ -174,7 +174,9 @@ class _PackedDB:
         keep = min(self.n, self._first_difference(self._refs, descriptors), self._first_difference(self._drefs, drefs))
         if n > keep:
             new = drefs[keep:]
-            x = np.ascontiguousarray(np.vstack([np.asarray(a).reshape(1, -1) for a in new]), dtype=np.float32)
+            x = np.vstack([np.asarray(a).reshape(1, -1) for a in new])
+            # fp16 descriptors (extractors under autocast) cross PCIe as they are: K1 widens them exactly
+            x = np.ascontiguousarray(x, dtype=np.float16 if x.dtype == np.float16 else np.float32)
             d = x.shape[1]
             self.n = keep                      # rows beyond `keep` are stale: _grow must not carry them over
             self._grow(n, d)

@@ -108,6 +108,80 @@ def test_normalize_cast_strided_and_unaligned(eng):
     assert np.max(np.abs(got - want)) <= 2.0 ** -7
 
 
+@pytest.mark.parametrize("d", [100, 512, 4096, 8448, 49152])
+@pytest.mark.parametrize("half", ["float16", "bfloat16"])
+def test_normalize_cast_half_input_equals_its_fp32_image(eng, half, d):
+    """fp16 / bf16 descriptors (an extractor under autocast, place_recognition.py:291-297) are widened exactly and
+    summed in the fp32 form's order: bit-identical rows, both K1 forms (one block per row, cluster per row)."""
+    import torch
+    n = 37 if d > 8448 else 301
+    g = torch.Generator(device="cuda").manual_seed(d)
+    x = (torch.randn(n, d, device="cuda", generator=g) * (torch.rand(n, 1, device="cuda", generator=g) * 30 + 0.1)).to(getattr(torch, half))
+    x[1] = 0
+    got = eng.normalize_cast(x)
+    want = eng.normalize_cast(x.float())
+    torch.cuda.synchronize()
+    assert got.dtype == torch.bfloat16 and torch.equal(got.view(torch.int16), want.view(torch.int16))
+    # strided rows, unaligned start: the scalar path
+    v = x[:, 3:3 + min(d - 3, 1001)]
+    assert torch.equal(eng.normalize_cast(v).view(torch.int16), eng.normalize_cast(v.float().contiguous()).view(torch.int16))
+    with pytest.raises(TypeError):
+        eng.normalize_cast(x.double())
+
+
+def test_host_abi_half_precision_descriptors(eng, monkeypatch):
+    """semgate_find_loop_closures_host_dtype: fp16 (numpy) and bf16 (CPU torch tensor) host databases give the fp32
+    call's candidates on the widened rows, bit for bit, chunked pipeline included; and the oracle's on those rows."""
+    import torch
+    from semgate import _native, synthetic
+    desc, ts, fl = synthetic.make_case(9000, 2048, 3, seed=46)          # 74 MB of fp32 -> 3 row chunks
+    fl32 = fl.astype(np.int32)
+    p = _native.make_params(k=25, similarity_threshold=0.5, min_time_gap=10.0, max_floor_diff=0)
+    d16 = desc.astype(np.float16)
+    want = eng.find_loop_closures_host(d16.astype(np.float32), ts, fl32, p)
+    got = eng.find_loop_closures_host(d16, ts, fl32, p)
+    assert len(want[0]) > 1000
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    monkeypatch.setenv("SEMGATE_E2E_CHUNKS", "3,1,2,1")                 # other row cuts: same lists
+    for a, b in zip(eng.find_loop_closures_host(d16, ts, fl32, p), want):
+        assert np.array_equal(a, b)
+    monkeypatch.delenv("SEMGATE_E2E_CHUNKS")
+    ref = O.find_loop_closures(d16.astype(np.float32), ts, fl32, similarity_threshold=0.5, min_time_gap=10.0, k=25, bf16=True)
+    g = dict(query_idx=got[0].astype(np.int64), match_idx=got[1].astype(np.int64), similarity=got[2], is_valid=got[3])
+    parity.check_order(g)
+    rep = parity.compare_candidates(ref, g, 25, 0.5, tol=BF16_MODEL_TOL)
+    assert rep["boundary_diffs"] <= 2
+    parity.check_decisions_exact(g, ts, fl32, 10.0, 0)
+    # bf16 rows in host memory
+    tb = torch.from_numpy(desc[:3000]).to(torch.bfloat16)
+    got = eng.find_loop_closures_host(tb, ts[:3000], fl32[:3000], p)
+    want = eng.find_loop_closures_host(tb.float().numpy(), ts[:3000], fl32[:3000], p)
+    assert len(want[0]) > 100
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    # the C ABI refuses element types it does not know
+    tot = _native.C.c_int64(0)
+    rc = eng.lib.semgate_find_loop_closures_host_dtype(eng._h, None, 7, 10, 64, None, None, _native.C.byref(p), None, None, None,
+                                                       None, 0, _native.C.byref(tot))
+    assert rc == _native.EINVAL
+
+
+def test_mirrored_class_keeps_fp16_descriptors_fp16(eng):
+    """PlaceDescriptor.descriptor arrays of dtype float16 are uploaded as they are (half the PCIe bytes) and give the
+    lists of their fp32 image."""
+    from semgate import SemanticPlaceRecognition, synthetic
+    desc, ts, fl = synthetic.make_case(700, 512, 3, seed=47)
+    d16 = desc.astype(np.float16)
+    out = []
+    for rows in (d16, d16.astype(np.float32)):
+        spr = SemanticPlaceRecognition('mixvpr', 'cuda', similarity_threshold=0.5, min_time_gap=10.0, descriptor_dim=512)
+        for i in range(len(rows)):
+            spr.add_image(rows[i], float(ts[i]), int(fl[i]))
+        out.append([(m.query_idx, m.match_idx, m.similarity, m.is_valid) for m in spr.find_loop_closures(k=10)])
+    assert len(out[0]) > 100 and out[0] == out[1]
+
+
 # --------------------------------------------------------------------------- K2/K3 vs oracle
 SHAPES = [
     # Q,   N,    D,   k,  thr,  gap, floors
