@@ -87,7 +87,8 @@ int semgate_destroy(semgate_handle_t h);
 int semgate_device_info(semgate_handle_t h, int* sm_count, int* cc_major, int* cc_minor);
 /* options: "cta_group" (0 auto | 1 | 2 | 4); "symmetric" (0 auto by size | 1 whenever the arguments allow |
  * -1 never: handle default for semgate_topk_params.symmetric == 0); "profile" (0|1): bracket every fused-kernel launch with CUDA
- * events on its own stream; "clock_probe" (0|1): see semgate_clock_probe_read */
+ * events on its own stream; "clock_probe" (0|1): see semgate_clock_probe_read; "k3_dense" (1|0, process-wide): lists
+ * handed to semgate_merge_topk* as arrays take the dense-list merge kernel (default) or the general one (A/B, tests) */
 int semgate_set_option(semgate_handle_t h, const char* name, int64_t value);
 /* sum of the fused kernel's (K2) device durations since the last read, and how many
  * launches that covers; synchronises on the recorded events and resets them. */

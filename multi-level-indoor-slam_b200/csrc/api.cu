@@ -350,6 +350,10 @@ int semgate_set_option(semgate_handle_t h, const char* name, int64_t value) {
     h->clk_ctas = 0;
     return 0;
   }
+  if (strcmp(name, "k3_dense") == 0) {       // process-wide: K3's dense-list kernel on (default) / off
+    set_merge_dense(value != 0);
+    return 0;
+  }
   return fail(SEMGATE_EINVAL, "unknown option '%s'", name);
 }
 

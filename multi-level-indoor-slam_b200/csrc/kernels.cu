@@ -6,11 +6,14 @@
 //   gate_candidates   : SemanticLoopClosureGate over explicit pairs     (loop_closure_gate.py:60-126)
 #include "launch.h"
 #include "merge.cuh"
+#include "ptx.cuh"
 #include "sortnet.cuh"
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
 
 namespace semgate {
 
@@ -458,6 +461,17 @@ __device__ __forceinline__ void bitonic_merge32_desc(uint64_t (&c)[32]) {
   }
 }
 
+template <int W>
+__device__ __forceinline__ void bitonic_merge_desc(uint64_t (&c)[32]) {     // the first W slots
+#pragma unroll
+  for (int stride = W / 2; stride >= 1; stride >>= 1) {
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      if ((i & stride) == 0) ce_desc(c[i], c[i | stride]);
+    }
+  }
+}
+
 // this thread's packed row (its first `cnt` of 32 slots in shared memory) -> registers -> sorting network -> folded
 // into its running top-32
 // Lists that are already sorted -- the per-GPU lists of a sharded sweep (each is a K3 output), a seeded list -- skip the
@@ -638,6 +652,181 @@ merge_net_kernel(const MergeLaunch a) {
   }
 }
 
+// K3, thread-per-row form for DENSE lists given explicitly (n_lists >= 0: the per-GPU lists of a sharded sweep, read from
+// one [G,Q,k] array or in place over NVLink through a pointer table, plus a seeded list).  Such lists are K3 outputs:
+// sorted, full or nearly full, rows contiguous.  The network kernel above spends most of its ~340 warp instructions per
+// row on moving keys (32 loads + 32 stores to stage a list, a data-dependent packing pass, a reload): here
+//  * a warp's 32 rows of one list are ONE contiguous block of 32 k keys: a single cp.async.bulk (TMA, one instruction,
+//    mbarrier completion) lands it in shared memory, two lists in flight per warp; rows are k keys apart, so with odd k
+//    (25) every thread reads its own row conflict-free; even k, a ragged last warp or an unaligned source take plain
+//    coalesced loads into rows pitched k | 1;
+//  * no packing: a list goes from shared memory straight into registers; sorted lists (31 compares and a warp vote;
+//    anything else runs the sorting network, so every input is still handled) fold into the running list with one
+//    max-against-the-reverse step and the bitonic merge; with k known at compile time (KT = 25) the slots beyond k are
+//    literal zeros and the compiler drops every compare-exchange that only feeds them;
+//  * outputs leave as the contiguous block they are: element e of the warp's 32 k outputs is row e / k, column e % k.
+constexpr int kDenseWarps = 4;
+// rows k keys apart are read by 32 threads at once, 8 bytes each: conflict-free for odd k, two-way for k = 2 mod 4 (kept:
+// a bulk copy needs rows unpitched); other k get an odd pitch and plain loads
+__host__ __device__ constexpr int dense_pitch(int k) { return (k & 1) || (k & 3) == 2 ? k : k | 1; }
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int KT>
+__global__ void __launch_bounds__(kDenseWarps * 32, 3)
+merge_dense_kernel(const MergeLaunch a) {
+  using namespace ptx;
+  constexpr int KK = KT > 0 ? KT : 32;                       // slots that can hold a key
+  constexpr int W = KK <= 8 ? 8 : KK <= 16 ? 16 : 32;        // width of the fold
+  extern __shared__ __align__(128) uint8_t dense_smem[];
+  const int k = KT > 0 ? KT : a.k;
+  const int pitch = dense_pitch(k);                          // keys between rows in shared memory
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t stage_bytes = 32u * pitch * 8u;
+  uint64_t* stage0 = reinterpret_cast<uint64_t*>(dense_smem + 128 + static_cast<size_t>(warp) * 2 * stage_bytes);
+  const uint32_t bar0 = smem_u32(dense_smem) + warp * 16;    // two mbarriers per warp
+  griddep_wait();
+  zero_handoff(a);
+  if (a.any_flag_out != nullptr && a.list_ptrs != nullptr && blockIdx.x == 0 && warp == 0) {
+    uint32_t f = 0;
+    for (int g = lane; g < a.n_lists; g += 32) f |= *reinterpret_cast<const volatile uint32_t*>(a.list_ptrs[g] + a.flag_offset);
+    f = __reduce_or_sync(0xffffffffu, f);
+    if (lane == 0) *a.any_flag_out = f;
+  }
+  const int64_t wrow0 = static_cast<int64_t>(blockIdx.x) * (kDenseWarps * 32) + warp * 32;    // first row of this warp
+  if (wrow0 >= a.Q) return;                                  // nothing below synchronises the block
+  const int64_t in_wrow0 = wrow0 + a.row_offset;
+  const int rows_here = static_cast<int>(min(static_cast<int64_t>(32), a.Q - wrow0));
+  const int n_keys = rows_here * k;
+  if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); fence_barrier_init(); }
+  __syncwarp();
+  // element e = lane + 32 t of the warp's block of rows_here x k keys is (row, column) = (e / k, e % k): one division
+  // here, then steps of 32
+  const int step_r = 32 / k, step_c = 32 - step_r * k;
+  const int r_first = lane / k, c_first = lane - r_first * k;
+
+  const int g0 = a.seed_keys != nullptr ? -1 : 0;            // source -1 is the seeded list (local rows)
+  const int n_src = a.n_lists - g0;
+  auto source = [&](int s) -> const uint64_t* {
+    const int g = g0 + s;
+    if (g < 0) return a.seed_keys + wrow0 * k;
+    if (a.list_ptrs != nullptr) return a.list_ptrs[g] + in_wrow0 * k;
+    return a.keys_in + g * a.list_stride + in_wrow0 * k;
+  };
+  // the warp's block of source s -> stage s & 1: one bulk copy, or coalesced loads into pitched rows
+  auto fetch = [&](int s) {
+    const uint64_t* src = source(s);
+    uint64_t* dst = stage0 + static_cast<size_t>(s & 1) * (stage_bytes / 8);
+    const bool bulk = pitch == k && rows_here == 32 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;     // warp-uniform
+    if (bulk) {
+      if (lane == 0) {
+        const uint32_t bar = bar0 + (s & 1) * 8;
+        fence_proxy_async();                                 // the stage may hold keys written by plain stores
+        mbar_arrive_expect_tx(bar, stage_bytes);
+        bulk_load(smem_u32(dst), src, stage_bytes, bar);
+      }
+    } else {
+      int r = r_first, c = c_first;
+      for (int e = lane; e < n_keys; e += 32) {
+        dst[r * pitch + c] = __ldg(src + e);
+        r += step_r; c += step_c;
+        if (c >= k) { c -= k; ++r; }
+      }
+    }
+    return bulk;
+  };
+
+  uint64_t best[32];
+  uint32_t bulk_mask = 0;                                    // bit s & 1: the stage was filled by a bulk copy
+  uint32_t phase = 0;                                        // bit s & 1: parity of that stage's barrier
+  for (int s = 0; s < n_src && s < 2; ++s) bulk_mask |= fetch(s) ? 1u << s : 0u;
+  for (int s = 0; s < n_src; ++s) {
+    const int st = s & 1;
+    if (bulk_mask >> st & 1) { mbar_wait(bar0 + st * 8, phase >> st & 1); phase ^= 1u << st; }
+    else __syncwarp();
+    const uint64_t* mine = stage0 + static_cast<size_t>(st) * (stage_bytes / 8) + lane * pitch;
+    uint64_t cur[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) cur[i] = (i < KK && i < k && lane < rows_here) ? mine[i] : 0ull;
+    __syncwarp();                                            // every lane has read its row: the stage may be refilled
+    if (s + 2 < n_src) bulk_mask = (bulk_mask & ~(1u << st)) | (fetch(s + 2) ? 1u << st : 0u);
+    bool sorted = true;
+#pragma unroll
+    for (int i = 0; i + 1 < KK; ++i) sorted &= cur[i] >= cur[i + 1];
+    if (!__all_sync(0xffffffffu, sorted)) sort32_desc(cur);
+#pragma unroll
+    for (int i = KK; i < 32; ++i) cur[i] = 0ull;             // zeros sort last: literal again after the network
+    if (s == 0) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) best[i] = cur[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < W; ++i) best[i] = best[i] > cur[W - 1 - i] ? best[i] : cur[W - 1 - i];   // bitonic
+      bitonic_merge_desc<W>(best);
+#pragma unroll
+      for (int i = KK; i < 32; ++i) best[i] = 0ull;          // only the top k go on
+    }
+  }
+  if (n_src <= 0) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) best[i] = 0ull;
+  }
+
+  // outputs: registers -> the warp's first stage (all fetches have been consumed) -> one contiguous block per array
+  __syncwarp();
+  uint64_t* outk = stage0;
+  int cnt = 0;
+#pragma unroll
+  for (int i = 0; i < KK; ++i) {
+    if (i < k) { outk[lane * pitch + i] = best[i]; cnt += best[i] != 0ull ? 1 : 0; }
+  }
+  __syncwarp();
+  if (a.count && lane < rows_here) a.count[wrow0 + lane] = a.count_add ? a.count[wrow0 + lane] + cnt : cnt;
+  const bool gate = a.valid != nullptr && a.max_floor_diff >= 0 && a.q_floor != nullptr && a.db_floor != nullptr;
+  int r = r_first, c = c_first;
+  for (int e = lane; e < n_keys; e += 32) {
+    const uint64_t key = outk[r * pitch + c];
+    const bool got = key != 0ull;
+    const int64_t o = a.out_stride > 0 ? (wrow0 + r) * a.out_stride + a.out_col + c : wrow0 * k + e;
+    if (a.keys_out) a.keys_out[o] = key;
+    const uint32_t gi = key_index(key);
+    if (a.scores) a.scores[o] = got ? key_score(key) : __int_as_float(0xff800000);
+    if (a.idx) a.idx[o] = got ? static_cast<int32_t>(gi) : -1;
+    if (a.valid) {
+      bool ok = got;
+      if (got && gate) {
+        // a key from outside the label array (lists seeded from other database slices) cannot be flagged here
+        const int64_t fi = static_cast<int64_t>(gi) - a.floor_index_offset;
+        ok = fi >= 0 && (a.floor_n <= 0 || fi < a.floor_n) && floor_ok(__ldg(a.q_floor + in_wrow0 + r), __ldg(a.db_floor + fi), a.max_floor_diff);
+      }
+      a.valid[o] = ok ? 1 : 0;
+    }
+    r += step_r; c += step_c;
+    if (c >= k) { c -= k; ++r; }
+  }
+}
+
+template <int KT>
+static int launch_merge_dense(const MergeLaunch& a, cudaStream_t st) {
+  const unsigned grid = static_cast<unsigned>((a.Q + kDenseWarps * 32 - 1) / (kDenseWarps * 32));
+  const size_t smem = 128 + static_cast<size_t>(kDenseWarps) * 2 * 32 * dense_pitch(a.k) * sizeof(uint64_t);   // k = 25: 51.3 KB
+  cudaError_t e = cudaFuncSetAttribute(merge_dense_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  return static_cast<int>(launch_maybe_pdl(a.pdl != 0, merge_dense_kernel<KT>, dim3(grid), dim3(kDenseWarps * 32), smem, st, a));
+}
+
+// process-wide switch (semgate_set_option "k3_dense"; first read: SEMGATE_K3_DENSE): A/B runs and tests of the general kernel
+static std::atomic<int> g_merge_dense{-1};
+void set_merge_dense(int on) { g_merge_dense.store(on != 0 ? 1 : 0); }
+static bool merge_dense_enabled() {
+  int v = g_merge_dense.load();
+  if (v < 0) { const char* e = getenv("SEMGATE_K3_DENSE"); v = (e == nullptr || atoi(e) != 0) ? 1 : 0; g_merge_dense.store(v); }
+  return v != 0;
+}
+
 int launch_merge_topk(const MergeLaunch& a, cudaStream_t st) {
   if (a.Q <= 0 && a.any_flag_out == nullptr) return 0;
   int lists = a.n_lists >= 0 ? a.n_lists : std::max(a.sc.s_main, a.sc.s_last);
@@ -651,6 +840,10 @@ int launch_merge_topk(const MergeLaunch& a, cudaStream_t st) {
   // sorting networks (1M x 4 full lists: 0.98 ms against the tournament's 1.3-1.9 ms); everything else -- in particular
   // the sparse lists of run-table sweeps -- goes to the warp-per-row kernel and its gather-and-rank fast path
   if (a.k <= 32 && a.Q >= 65536 && lists <= 8 && a.sym_flag == nullptr) {
+    // lists handed over as arrays (per-GPU lists, a seeded list) are K3 outputs -- sorted, mostly full, rows k keys apart:
+    // the dense form (1M x 4 sorted lists: 0.65 ms in the general network kernel); SEMGATE_K3_DENSE=0 keeps the latter
+    if (merge_dense_enabled() && a.n_lists >= 1 && (a.list_ptrs != nullptr || a.row_stride == a.k))
+      return a.k == 25 ? launch_merge_dense<25>(a, st) : a.k == 10 ? launch_merge_dense<10>(a, st) : a.k == 5 ? launch_merge_dense<5>(a, st) : launch_merge_dense<0>(a, st);
     const unsigned grid = static_cast<unsigned>(std::max<int64_t>(1, (a.Q + kNetRows - 1) / kNetRows));
     const size_t smem = 2 * static_cast<size_t>(kNetRows) * kNetPitch * sizeof(uint64_t);      // 67.6 KB: staging + pack rows
     cudaError_t e = cudaFuncSetAttribute(merge_net_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

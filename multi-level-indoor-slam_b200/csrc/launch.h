@@ -104,6 +104,7 @@ struct MergeLaunch {
   unsigned long long* zero_ptr; int zero_words; int pdl;
 };
 int launch_merge_topk(const MergeLaunch& a, cudaStream_t st);
+void set_merge_dense(int on);   // 0: dense explicit lists take the general network kernel too (A/B, tests); process-wide
 
 // K4: padded [Q,k] lists -> flat candidate arrays (query asc, score desc)
 size_t compact_workspace_bytes(int64_t Q);

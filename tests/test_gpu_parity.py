@@ -535,6 +535,78 @@ def test_merge_many_rows_sorted_lists(eng, G, k, order):
     assert np.array_equal(m.count.cpu().numpy(), (want != 0).sum(axis=1))
 
 
+@pytest.mark.parametrize("G,k,Q,order", [(4, 25, 65536 + 77, "sorted"), (8, 25, 65536 + 31, "mixed"), (3, 32, 65536 + 1, "sorted"),
+                                         (2, 10, 70000, "sorted"), (5, 7, 65537, "unsorted"), (1, 25, 65536, "sorted"),
+                                         (4, 25, 65536 + 96, "sparse")])
+def test_merge_dense_lists_kernel(eng, G, k, Q, order):
+    """K3's dense-list kernel (lists handed over as arrays: one bulk copy per warp and list, no packing pass, sorted lists
+    folded without the sorting network): odd k (bulk copies), even k (pitched rows), k = 32, ragged last warps, one list,
+    unsorted and nearly empty lists, a seeded list, a row slice that starts at an odd row (unaligned sources), the pointer
+    table form, strided outputs of a k > 64 pass -- against a numpy sort and against the general network kernel."""
+    import torch
+    rng = np.random.default_rng(G * 1000 + k + Q)
+    keys = rng.integers(1, 2 ** 62, size=(G, Q, k), dtype=np.int64).view(np.uint64)
+    fill = rng.integers(0, k + 1, size=(G, Q))
+    if order == "sparse":
+        fill = rng.integers(0, 3, size=(G, Q))
+    else:
+        fill[:, ::3] = k
+    keys[np.arange(k)[None, None, :] >= fill[:, :, None]] = 0
+    keys[0, 3] = 0
+    if order != "unsorted":
+        keys = np.sort(keys, axis=2)[:, :, ::-1].copy()
+    if order == "mixed":
+        sel = rng.uniform(size=Q) < 0.02
+        shuf = keys[:, sel].copy()
+        rng.shuffle(shuf, axis=2)
+        keys[:, sel] = shuf
+    tk = torch.from_numpy(keys.view(np.int64)).cuda()
+    nfl = 2 ** 20
+    fl = torch.from_numpy(rng.integers(1, 4, size=nfl).astype(np.int32)).cuda()
+    qf = torch.from_numpy(rng.integers(1, 4, size=Q).astype(np.int32)).cuda()
+    keys_m = keys.copy()
+    keys_m[keys_m != 0] = (keys_m[keys_m != 0] & ~np.uint64(0xFFFFFFFF)) | (np.uint64(0xFFFFFFFF) - (keys_m[keys_m != 0] % np.uint64(nfl)))
+    # ^ indices inside the label array (key = score bits << 32 | ~index); the order inside a list may change: re-sort
+    if order not in ("unsorted",):
+        keys_m = np.sort(keys_m, axis=2)[:, :, ::-1].copy()
+    tkm = torch.from_numpy(keys_m.view(np.int64)).cuda()
+    m = eng.merge_topk(tkm, k, q_floor=qf, db_floor_all=fl, max_floor_diff=0, want_keys=True)
+    torch.cuda.synchronize()
+    flat = keys_m.transpose(1, 0, 2).reshape(Q, G * k)
+    want = np.sort(flat, axis=1)[:, ::-1][:, :k]
+    got = m.keys.cpu().numpy().view(np.uint64)
+    assert np.array_equal(got, want)
+    assert np.array_equal(m.count.cpu().numpy(), (want != 0).sum(axis=1))
+    widx = np.where(want != 0, (np.uint64(0xFFFFFFFF) - (want & np.uint64(0xFFFFFFFF))).astype(np.int64), -1)
+    assert np.array_equal(m.idx.cpu().numpy(), widx)
+    wvalid = (want != 0) & (fl.cpu().numpy()[np.maximum(widx, 0)] == qf.cpu().numpy()[:, None])
+    assert np.array_equal(m.valid.cpu().numpy().astype(bool), wvalid)
+    # the general network kernel on the same lists: every output array bit for bit
+    eng.set_option("k3_dense", 0)
+    try:
+        n = eng.merge_topk(tkm, k, q_floor=qf, db_floor_all=fl, max_floor_diff=0, want_keys=True)
+        torch.cuda.synchronize()
+    finally:
+        eng.set_option("k3_dense", 1)
+    def same(x, y, f):       # random keys decode to NaN scores now and then: compare bits
+        x, y = getattr(x, f), getattr(y, f)
+        return torch.equal(x.view(torch.int32), y.view(torch.int32)) if f == "scores" else torch.equal(x, y)
+    for f in ("keys", "scores", "idx", "valid", "count"):
+        assert same(m, n, f), f
+    # the pointer-table form on a row slice that starts at an odd row (sources 8 bytes off a 16-byte boundary for odd k)
+    parts = [tkm[g].clone() for g in range(G)]
+    table = torch.tensor([p.data_ptr() for p in parts], dtype=torch.int64, device="cuda")
+    lo, rows = 33, Q - 40
+    mine = eng.merge_topk_peers_rows(table.data_ptr(), G, Q, k, lo, rows, q_floor=qf, db_floor_all=fl, max_floor_diff=0, want_keys=True)
+    torch.cuda.synchronize()
+    for f in ("keys", "idx", "valid", "count"):
+        assert torch.equal(getattr(mine, f), getattr(m, f)[lo:lo + rows]), f
+    assert torch.equal(mine.scores.view(torch.int32), m.scores[lo:lo + rows].view(torch.int32))
+    even = eng.merge_topk_peers_rows(table.data_ptr(), G, Q, k, 64, Q - 64, q_floor=qf, db_floor_all=fl, max_floor_diff=0, want_keys=True)
+    torch.cuda.synchronize()
+    assert torch.equal(even.keys, m.keys[64:]) and torch.equal(even.valid, m.valid[64:])
+
+
 def test_valid_only_compaction_and_device_statistics(eng):
     """§8f rank 4: the floor-consistent hand-off list (geometric_verification.py:709 skips cross-floor pairs) and
     get_statistics (place_recognition.py:913-933) reduced on the device, against the host path and the oracle."""
