@@ -899,13 +899,18 @@ __device__ __forceinline__ int row_emit_count(const int32_t* __restrict__ count,
 // already running or done.  One launch where count -> scan -> scatter were three: small sweeps are launch-bound.
 // state: [tiles] 64-bit words = value << 2 | flag (0 nothing yet, 1 tile total, 2 inclusive prefix), then the ticket
 // counter; zeroed by the caller per launch.
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+// (relaxed, gpu scope: a state word carries its whole message -- value and flag in one 64-bit word -- and guards no other
+// data, so neither side needs a fence: 1M x 25 full lists 0.205 -> 0.193 ms, 1M rows with one candidate each 0.082 ->
+// 0.067 ms.  Measured and dropped on the same box (tools/k4_bench.py): 256 tiles per look-back round instead of 32
+// (0.226 / 0.091 ms), one thread per INPUT slot with 4 or 8 loads issued before their stores and the first batch in flight
+// during the look-back (0.197 - 0.27 ms): the search-per-output form below stayed the fastest at every density.)
+__device__ __forceinline__ unsigned long long ld_state_u64(const unsigned long long* p) {
   unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_state_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 __global__ void __launch_bounds__(kScanBlock)
@@ -938,13 +943,13 @@ compact_onepass_kernel(const float* __restrict__ scores, const int32_t* __restri
     const unsigned long long tot = static_cast<unsigned long long>(tot_s);
     unsigned long long prefix = 0;
     if (tile > 0) {
-      if (lane == 0) st_release_u64(state + tile, (tot << 2) | 1ull);
+      if (lane == 0) st_state_u64(state + tile, (tot << 2) | 1ull);
       long long j = static_cast<long long>(tile) - 1;
       uint64_t t0 = 0;
       uint32_t spins = 0;
       while (true) {
         const long long at = j - lane;
-        const unsigned long long sv = at >= 0 ? ld_acquire_u64(state + at) : 2ull;
+        const unsigned long long sv = at >= 0 ? ld_state_u64(state + at) : 2ull;
         if (__any_sync(0xffffffffu, (sv & 3ull) == 0ull)) {   // some tile of the window has not published yet: it is
           if ((++spins & 0xFFFu) == 0) {                      // running (tickets).  Bounded like every wait here.
             uint64_t now;
@@ -965,7 +970,7 @@ compact_onepass_kernel(const float* __restrict__ scores, const int32_t* __restri
       }
     }
     if (lane == 0) {
-      st_release_u64(state + tile, ((prefix + tot) << 2) | 2ull);
+      st_state_u64(state + tile, ((prefix + tot) << 2) | 2ull);
       base_s = static_cast<long long>(prefix);
       if (tile == tiles - 1) *out_total = static_cast<int64_t>(prefix + tot);
     }
