@@ -633,7 +633,12 @@ def companions_leg(torch, eng, peak_hbm):
     om = om % fl.shape[0]
     oq = oq % fl.shape[0]
     ms = timeit(lambda: eng.gate_candidates(fl, oq[:M], om[:M], 0))
-    add("gate_candidates (pairs in the order K4 emits)", [M], ms, 9 * M, candidates_per_s=M / ms * 1e3)
+    add("gate_candidates (pairs in the order K4 emits; 2M labels: gathers from global memory)", [M], ms, 9 * M, candidates_per_s=M / ms * 1e3)
+    fl20 = fl[:20000].contiguous()                    # a trajectory-sized label table (the reference's 19 163 poses): kept in
+    oq20, om20 = oq[:M] % 20000, om[:M] % 20000       # shared memory by every block
+    ms = timeit(lambda: eng.gate_candidates(fl20, oq20, om20, 0))
+    add("gate_candidates (the same pairs, 20 000 labels: table in shared memory)", [M], ms, 9 * M, candidates_per_s=M / ms * 1e3)
+    del fl20, oq20, om20
     del res, oq, om, os_, ov, fl
     # K5: CricaVPR cross-correlation re-rank (place_recognition.py:669-757), DINOv2 shape (529 patches x 768-d), 25 candidates
     # per query -- tensor-bound: reported against the measured bf16 peak, useful FLOPs = 2 P^2 D per pair

@@ -1119,6 +1119,28 @@ __device__ __forceinline__ uint32_t gate_one(const int32_t* __restrict__ floors,
   if (ok) ++acc; else ++rej;
   return ok ? 1u : 0u;
 }
+// the same against a copy of the label table in shared memory
+__device__ __forceinline__ uint32_t gate_one_smem(const int32_t* tab, int n_floors, int32_t q, int32_t m, int max_floor_diff,
+                                                  unsigned& acc, unsigned& rej, unsigned& bad) {
+  if (static_cast<uint32_t>(q) >= static_cast<uint32_t>(n_floors) || static_cast<uint32_t>(m) >= static_cast<uint32_t>(n_floors)) { ++bad; return 0u; }
+  int64_t dfl = static_cast<int64_t>(tab[q]) - static_cast<int64_t>(tab[m]);
+  if (dfl < 0) dfl = -dfl;
+  const bool ok = dfl <= max_floor_diff;
+  if (ok) ++acc; else ++rej;
+  return ok ? 1u : 0u;
+}
+
+__device__ __forceinline__ void gate_counts_out(unsigned acc, unsigned rej, unsigned bad, unsigned long long* __restrict__ counts) {
+  acc = __reduce_add_sync(0xffffffffu, acc);
+  rej = __reduce_add_sync(0xffffffffu, rej);
+  bad = __reduce_add_sync(0xffffffffu, bad);
+  __shared__ unsigned s[3];
+  if (threadIdx.x < 3) s[threadIdx.x] = 0;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&s[0], acc); atomicAdd(&s[1], rej); atomicAdd(&s[2], bad); }
+  __syncthreads();
+  if (threadIdx.x < 3 && s[threadIdx.x]) atomicAdd(&counts[threadIdx.x], static_cast<unsigned long long>(s[threadIdx.x]));
+}
 
 // VEC: four candidates per thread per step (16-byte index loads, eight label gathers in
 // flight, one 4-byte store); needs 16-byte aligned index arrays and a 4-byte aligned output.
@@ -1147,15 +1169,40 @@ gate_candidates_kernel(const int32_t* __restrict__ floors, int64_t n_floors, con
     for (int64_t i = tid; i < M; i += nthreads)
       out_valid[i] = static_cast<uint8_t>(gate_one(floors, n_floors, q_idx[i], m_idx[i], max_floor_diff, acc, rej, bad));
   }
-  acc = __reduce_add_sync(0xffffffffu, acc);
-  rej = __reduce_add_sync(0xffffffffu, rej);
-  bad = __reduce_add_sync(0xffffffffu, bad);
-  __shared__ unsigned s[3];
-  if (threadIdx.x < 3) s[threadIdx.x] = 0;
+  gate_counts_out(acc, rej, bad, counts);
+}
+
+// Label table in shared memory.  Gathering labels from global memory costs a 32-byte L2 sector per 4-byte label: the kernel
+// above is bound by L2 sector traffic (ncu: lts throughput 73 %, DRAM 25 %; 0.31 of the copy bandwidth).  The label table of
+// a trajectory is small -- one int32 per keyframe, 77 KB for the 19 163 poses of the reference's published gate counts
+// (5.1 M candidates) -- so when it fits beside the block (<= 50 K labels) and there are enough candidates to pay for one
+// copy of it per block, every block keeps its own copy and the gathers become shared-memory loads: what remains is the
+// 9 bytes per candidate that must cross HBM.
+constexpr int kGateSmemThreads = 1024;
+constexpr int kGateSmemMaxLabels = 50 * 1024;
+__global__ void __launch_bounds__(kGateSmemThreads, 2)
+gate_candidates_smem_kernel(const int32_t* __restrict__ floors, int n_floors, const int32_t* __restrict__ q_idx,
+                            const int32_t* __restrict__ m_idx, int64_t M, int max_floor_diff, uint8_t* __restrict__ out_valid,
+                            unsigned long long* __restrict__ counts) {
+  extern __shared__ int32_t gate_tab[];
+  for (int i = threadIdx.x; i < n_floors; i += kGateSmemThreads) gate_tab[i] = __ldg(floors + i);
   __syncthreads();
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&s[0], acc); atomicAdd(&s[1], rej); atomicAdd(&s[2], bad); }
-  __syncthreads();
-  if (threadIdx.x < 3 && s[threadIdx.x]) atomicAdd(&counts[threadIdx.x], static_cast<unsigned long long>(s[threadIdx.x]));
+  unsigned acc = 0, rej = 0, bad = 0;
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * kGateSmemThreads + threadIdx.x;
+  const int64_t nthreads = static_cast<int64_t>(gridDim.x) * kGateSmemThreads;
+  const int64_t M4 = M >> 2;
+  for (int64_t i = tid; i < M4; i += nthreads) {
+    const int4 q = __ldcs(reinterpret_cast<const int4*>(q_idx) + i);
+    const int4 m = __ldcs(reinterpret_cast<const int4*>(m_idx) + i);
+    uint32_t r = gate_one_smem(gate_tab, n_floors, q.x, m.x, max_floor_diff, acc, rej, bad);
+    r |= gate_one_smem(gate_tab, n_floors, q.y, m.y, max_floor_diff, acc, rej, bad) << 8;
+    r |= gate_one_smem(gate_tab, n_floors, q.z, m.z, max_floor_diff, acc, rej, bad) << 16;
+    r |= gate_one_smem(gate_tab, n_floors, q.w, m.w, max_floor_diff, acc, rej, bad) << 24;
+    __stcs(reinterpret_cast<uint32_t*>(out_valid) + i, r);
+  }
+  for (int64_t i = (M4 << 2) + tid; i < M; i += nthreads)
+    out_valid[i] = static_cast<uint8_t>(gate_one_smem(gate_tab, n_floors, q_idx[i], m_idx[i], max_floor_diff, acc, rej, bad));
+  gate_counts_out(acc, rej, bad, counts);
 }
 
 int launch_gate_candidates(const int32_t* floors, int64_t n_floors, const int32_t* q_idx, const int32_t* m_idx, int64_t M,
@@ -1165,6 +1212,18 @@ int launch_gate_candidates(const int32_t* floors, int64_t n_floors, const int32_
   if (M <= 0) return 0;
   const bool vec = ((reinterpret_cast<uintptr_t>(q_idx) | reinterpret_cast<uintptr_t>(m_idx)) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(out_valid) & 3) == 0;
+  // one copy of the table per block is n_floors labels through L2; a gather costs 8 labels' worth (a sector) per label
+  if (vec && n_floors > 0 && n_floors <= kGateSmemMaxLabels && M >= 10 * n_floors) {
+    const size_t smem = static_cast<size_t>(n_floors) * sizeof(int32_t);
+    e = cudaFuncSetAttribute(gate_candidates_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    const int per_sm = smem + 1024 <= 113 * 1024 ? 2 : 1;
+    const int64_t want = (M / 4 + 4 * kGateSmemThreads - 1) / (4 * kGateSmemThreads);    // >= 4 steps per thread
+    const unsigned grid = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(want, 148 * per_sm)));
+    gate_candidates_smem_kernel<<<grid, kGateSmemThreads, smem, st>>>(floors, static_cast<int>(n_floors), q_idx, m_idx, M, max_floor_diff,
+                                                                      out_valid, counts);
+    return static_cast<int>(cudaGetLastError());
+  }
   const int64_t work = vec ? (M + 3) / 4 : M;
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>((work + 255) / 256, 148 * 8));
   if (vec)

@@ -890,6 +890,28 @@ def test_gate_candidates_kernel_paths(eng, M, shift):
     assert int(c[2].item()) == 1 and int(v[0].item()) == 0
 
 
+@pytest.mark.parametrize("nl,M", [(1, 5000), (2406, 87044), (19163, 600001), (50 * 1024, 600002), (50 * 1024 + 1, 600003), (300, 2999)])
+def test_gate_candidates_label_table_in_shared_memory(eng, nl, M):
+    """The pair gate keeps the label table in shared memory when it fits beside a block (<= 50 K labels) and there are at
+    least 10 candidates per label; otherwise it gathers from global memory.  Both forms, table sizes at the limit,
+    negative / too large indices, labels at the int32 extremes: decisions and counters bit-exact (LCG.py:89-101)."""
+    import torch
+    rng = np.random.default_rng(nl + M)
+    fl = rng.choice([1, 2, 4, 5, -2 ** 31, 2 ** 31 - 1], size=nl).astype(np.int32)
+    q = rng.integers(0, nl, size=M).astype(np.int32)
+    m = rng.integers(0, nl, size=M).astype(np.int32)
+    q[::1013] = -1
+    m[5::2027] = nl
+    m[7::4051] = 2 ** 31 - 1
+    bad = (q < 0) | (q >= nl) | (m < 0) | (m >= nl)
+    for mfd in (0, 1):
+        v, c = eng.gate_candidates(_t(fl), _t(q), _t(m), mfd)
+        torch.cuda.synchronize()
+        want = (np.abs(fl[np.clip(q, 0, nl - 1)].astype(np.int64) - fl[np.clip(m, 0, nl - 1)]) <= mfd) & ~bad
+        assert np.array_equal(v.cpu().numpy().astype(bool), want)
+        assert c.cpu().numpy().tolist() == [int(want.sum()), int((~want & ~bad).sum()), int(bad.sum())]
+
+
 @pytest.mark.parametrize("algo", ["lego_loam", "orb_slam3"])
 def test_spatial_candidates_and_gate_end_to_end(algo):
     """Poses -> radius join -> floor gate, all on the GPU, against the reference's published
