@@ -858,6 +858,7 @@ int launch_merge_topk(const MergeLaunch& a, cudaStream_t st) {
 
 // =========================================================================== K4
 constexpr int kScanBlock = 128;     // rows per block of the count / scatter kernels (many small blocks: all SMs busy)
+constexpr int kCompactMaxThreads = 512;   // K4: threads per block (a multiple of kScanBlock; the extra ones only scatter)
 
 __device__ __forceinline__ int block_exclusive_scan(int v, int* smem /*>=32*/, int* total) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -913,7 +914,7 @@ __device__ __forceinline__ void st_state_u64(unsigned long long* p, unsigned lon
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(kScanBlock)
+__global__ void __launch_bounds__(kCompactMaxThreads)
 compact_onepass_kernel(const float* __restrict__ scores, const int32_t* __restrict__ idx, const uint8_t* __restrict__ valid,
                        const int32_t* __restrict__ count, int64_t Q, int k, bool valid_only, unsigned long long* __restrict__ state,
                        int64_t q_offset, int32_t* __restrict__ out_q, int32_t* __restrict__ out_m, float* __restrict__ out_s,
@@ -931,10 +932,13 @@ compact_onepass_kernel(const float* __restrict__ scores, const int32_t* __restri
   const unsigned tile = tile_s;
   const int64_t row0 = static_cast<int64_t>(tile) * kScanBlock;
   const int64_t row = row0 + threadIdx.x;
-  const int v = row < Q ? row_emit_count(count, valid, row, k, valid_only) : 0;
+  const bool has_row = threadIdx.x < kScanBlock && row < Q;     // threads beyond the tile's rows only help to scatter
+  const int v = has_row ? row_emit_count(count, valid, row, k, valid_only) : 0;
   const int ex = block_exclusive_scan(v, sm, &tot_s);
-  offs[threadIdx.x] = ex;
-  cnts[threadIdx.x] = row < Q ? count[row] : 0;
+  if (threadIdx.x < kScanBlock) {
+    offs[threadIdx.x] = ex;
+    cnts[threadIdx.x] = has_row ? count[row] : 0;
+  }
   __syncthreads();
   if (threadIdx.x < 32) {
     // look-back by the first warp, 32 tiles at a time: lane l inspects tile j - l (a tile before tile 0 counts as an
@@ -983,7 +987,7 @@ compact_onepass_kernel(const float* __restrict__ scores, const int32_t* __restri
     // successor's offset and never win), its position in the row follows.  Loads of different elements are
     // independent and the stores are perfectly coalesced.
     const int total = tot_s;
-    for (int o = threadIdx.x; o < total; o += kScanBlock) {
+    for (int o = threadIdx.x; o < total; o += blockDim.x) {
       int lo = 0, hi = kScanBlock - 1;
       while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
@@ -999,7 +1003,7 @@ compact_onepass_kernel(const float* __restrict__ scores, const int32_t* __restri
     return;
   }
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int r = w; r < kScanBlock && row0 + r < Q; r += (kScanBlock >> 5)) {
+  for (int r = w; r < kScanBlock && row0 + r < Q; r += (blockDim.x >> 5)) {
     const int c = cnts[r];
     int64_t o = base + offs[r];
     const int64_t src = (row0 + r) * k;
@@ -1035,7 +1039,13 @@ int launch_compact(const float* scores, const int32_t* idx, const uint8_t* valid
     cudaError_t e = cudaMemsetAsync(state, 0, static_cast<size_t>(nb + 1) * sizeof(unsigned long long), st);
     if (e != cudaSuccess) return static_cast<int>(e);
   }
-  return static_cast<int>(launch_maybe_pdl(pdl, compact_onepass_kernel, dim3(static_cast<unsigned>(nb)), dim3(kScanBlock), 0, st, scores, idx, valid,
+  // A tile's scatter is a chain of dependent round trips per thread (search -> loads -> stores, 25 of them with 128 threads
+  // and full lists): with few tiles (one wave or so) the kernel's duration IS that chain, so 512 threads share a tile
+  // (config 1's graph step 68 -> 58 us, 20k x 1024-d 380 -> 371 us); with many tiles there are enough blocks per SM to
+  // hide it and the small block wins (1M x 25 full lists: 0.175 ms with 128 threads, 0.22 ms with 512).
+  static const int forced = [] { const char* e = getenv("SEMGATE_K4_THREADS"); const int v = e ? atoi(e) : 0; return (v == 128 || v == 256 || v == 512) ? v : 0; }();
+  const int threads = forced ? forced : (nb <= 4 * 148 ? kCompactMaxThreads : kScanBlock);
+  return static_cast<int>(launch_maybe_pdl(pdl, compact_onepass_kernel, dim3(static_cast<unsigned>(nb)), dim3(threads), 0, st, scores, idx, valid,
                                            count, Q, k, valid_only, state, q_offset, out_q, out_m, out_s, out_v, out_total));
 }
 int compact_state_words(int64_t Q) { return static_cast<int>((Q + kScanBlock - 1) / kScanBlock + 1); }
