@@ -914,6 +914,14 @@ __device__ __forceinline__ void st_state_u64(unsigned long long* p, unsigned lon
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+#ifdef SEMGATE_K4_TRACE   // tools/probe/k4_trace.cu: per-tile stage stamps (globaltimer ns), rounds and spins of the look-back
+__device__ unsigned long long k4_trace[8 * 65536];
+#define K4_STAMP(slot) do { if (threadIdx.x == 0 && tile < 65536u) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); k4_trace[8 * tile + (slot)] = t_; } } while (0)
+#define K4_NOTE(slot, v) do { if (tile < 65536u) k4_trace[8 * tile + (slot)] = (v); } while (0)
+#else
+#define K4_STAMP(slot) do { } while (0)
+#define K4_NOTE(slot, v) do { } while (0)
+#endif
 __global__ void __launch_bounds__(kCompactMaxThreads)
 compact_onepass_kernel(const float* __restrict__ scores, const int32_t* __restrict__ idx, const uint8_t* __restrict__ valid,
                        const int32_t* __restrict__ count, int64_t Q, int k, bool valid_only, unsigned long long* __restrict__ state,
@@ -927,9 +935,16 @@ compact_onepass_kernel(const float* __restrict__ scores, const int32_t* __restri
   __shared__ long long base_s;
   const unsigned tiles = gridDim.x;
   griddep_wait();
+#ifdef SEMGATE_K4_TRACE
+  unsigned long long t_top; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_top));
+#endif
   if (threadIdx.x == 0) tile_s = atomicAdd(reinterpret_cast<unsigned*>(state + tiles), 1u);
   __syncthreads();
   const unsigned tile = tile_s;
+#ifdef SEMGATE_K4_TRACE
+  if (threadIdx.x == 0) K4_NOTE(0, t_top);
+#endif
+  K4_STAMP(1);
   const int64_t row0 = static_cast<int64_t>(tile) * kScanBlock;
   const int64_t row = row0 + threadIdx.x;
   const bool has_row = threadIdx.x < kScanBlock && row < Q;     // threads beyond the tile's rows only help to scatter
@@ -940,6 +955,7 @@ compact_onepass_kernel(const float* __restrict__ scores, const int32_t* __restri
     cnts[threadIdx.x] = has_row ? count[row] : 0;
   }
   __syncthreads();
+  K4_STAMP(2);
   if (threadIdx.x < 32) {
     // look-back by the first warp, 32 tiles at a time: lane l inspects tile j - l (a tile before tile 0 counts as an
     // inclusive prefix of 0); the nearest inclusive prefix ends the walk, everything nearer contributes its total
@@ -951,7 +967,13 @@ compact_onepass_kernel(const float* __restrict__ scores, const int32_t* __restri
       long long j = static_cast<long long>(tile) - 1;
       uint64_t t0 = 0;
       uint32_t spins = 0;
+#ifdef SEMGATE_K4_TRACE
+      unsigned long long rounds = 0;
+#endif
       while (true) {
+#ifdef SEMGATE_K4_TRACE
+        ++rounds;
+#endif
         const long long at = j - lane;
         const unsigned long long sv = at >= 0 ? ld_state_u64(state + at) : 2ull;
         if (__any_sync(0xffffffffu, (sv & 3ull) == 0ull)) {   // some tile of the window has not published yet: it is
@@ -972,6 +994,9 @@ compact_onepass_kernel(const float* __restrict__ scores, const int32_t* __restri
         if (incl) break;
         j -= 32;
       }
+#ifdef SEMGATE_K4_TRACE
+      if (lane == 0) { K4_NOTE(5, rounds); K4_NOTE(6, static_cast<unsigned long long>(spins)); }
+#endif
     }
     if (lane == 0) {
       st_state_u64(state + tile, ((prefix + tot) << 2) | 2ull);
@@ -980,6 +1005,7 @@ compact_onepass_kernel(const float* __restrict__ scores, const int32_t* __restri
     }
   }
   __syncthreads();
+  K4_STAMP(3);
   const int64_t base = base_s;
   if (!valid_only) {
     // Everything is emitted: one thread per OUTPUT element.  The block's rows start at offs[]; a binary search over
@@ -1000,6 +1026,10 @@ compact_onepass_kernel(const float* __restrict__ scores, const int32_t* __restri
       out_s[base + o] = __ldg(scores + src);
       out_v[base + o] = __ldg(valid + src);
     }
+#ifdef SEMGATE_K4_TRACE
+    __syncthreads();
+    K4_STAMP(4);
+#endif
     return;
   }
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
