@@ -56,18 +56,21 @@ const T* opt_ptr(const c10::optional<Tensor>& t, at::ScalarType dtype, int64_t r
   return static_cast<const T*>(t->data_ptr());
 }
 
-// x fp32 [N, D] (row stride free) -> bf16 [N, pad64(D)], rows x / (||x|| + 1e-8)
+// x fp32 / fp16 / bf16 [N, D] (row stride free) -> bf16 [N, pad64(D)], rows x / (||x|| + 1e-8).  Half-precision rows (an
+// extractor under autocast, place_recognition.py:291-297) are widened exactly: same bits as the call on their fp32 image.
 Tensor normalize_cast(const Tensor& x) {
-  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kFloat && x.dim() == 2 && x.stride(1) == 1,
-              "normalize_cast: x must be a CUDA fp32 [N, D] tensor with unit column stride");
+  const auto st = x.scalar_type();
+  TORCH_CHECK(x.is_cuda() && (st == at::kFloat || st == at::kHalf || st == at::kBFloat16) && x.dim() == 2 && x.stride(1) == 1,
+              "normalize_cast: x must be a CUDA fp32 / fp16 / bf16 [N, D] tensor with unit column stride");
   c10::cuda::CUDAGuard guard(x.device());
   const int64_t n = x.size(0);
   const int d = static_cast<int>(x.size(1));
   const int dp = semgate_pad_dim(d);
+  const int32_t dtype = st == at::kFloat ? SEMGATE_DTYPE_F32 : st == at::kHalf ? SEMGATE_DTYPE_F16 : SEMGATE_DTYPE_BF16;
   Tensor out = at::empty({n, dp}, x.options().dtype(at::kBFloat16));
   if (n > 0)
-    ok(semgate_normalize_cast(handle_for(x.get_device()), x.data_ptr<float>(), n, d, x.stride(0), out.data_ptr(), dp, stream_of(x)),
-       "semgate_normalize_cast");
+    ok(semgate_normalize_cast_dtype(handle_for(x.get_device()), x.data_ptr(), dtype, n, d, x.stride(0), out.data_ptr(), dp, stream_of(x)),
+       "semgate_normalize_cast_dtype");
   return out;
 }
 

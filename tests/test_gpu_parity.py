@@ -1149,6 +1149,10 @@ def test_torch_ops_match_the_engine(eng):
     tts, tfl = _t(ts, torch.float64), _t(fl.astype(np.int32), torch.int32)
     xb = sg.normalize_cast(x)
     assert torch.equal(xb, eng.normalize_cast(x)) and xb.shape == (n, 256)
+    for half in (torch.float16, torch.bfloat16):      # an extractor under autocast hands over half-precision CUDA tensors
+        assert torch.equal(sg.normalize_cast(x.to(half)), eng.normalize_cast(x.to(half).float()))
+    with pytest.raises(RuntimeError):
+        sg.normalize_cast(x.double())
     p = _native.make_params(k=k, similarity_threshold=0.5, min_time_gap=10.0, max_floor_diff=0)
     want_ = eng.gated_topk(xb, xb, p, q_ts=tts, db_ts=tts, q_floor=tfl, db_floor=tfl, want_keys=True)
     sc, ix, va, ct, keys = sg.gated_topk(xb, xb, tfl, tfl, tts, tts, 10.0, 0.5, k, 0, 0, 0)
