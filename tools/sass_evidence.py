@@ -7,8 +7,8 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "multi-level-indoor-slam_b200", "semgate", "libsemgate.so")
-KEEP = re.compile(r"^(UTCHMMA|UTMALDG|UTMAPF|LDTM|UTCBAR|UTCATOMSWS|SYNCS|UCGABAR|REDUX|ELECT|MEMBAR|DADD|DSETP|HMMA|ATOMG|ATOMS|REDS|RED\b|SHFL)")
-SHOW = ("LDTM", "UTCBAR", "UTCHMMA", "UTMALDG")
+KEEP = re.compile(r"^(UTCHMMA|UTMALDG|UTMAPF|UBLKCP|LDTM|UTCBAR|UTCATOMSWS|SYNCS|UCGABAR|REDUX|ELECT|MEMBAR|DADD|DSETP|HMMA|ATOMG|ATOMS|REDS|RED\b|SHFL)")
+SHOW = ("LDTM", "UTCBAR", "UTCHMMA", "UTMALDG", "UBLKCP")
 
 
 def main():
@@ -18,6 +18,7 @@ def main():
     print("SASS evidence for libsemgate.so (sm_100a), round 2 (final code)")
     print("command: cuobjdump -sass multi-level-indoor-slam_b200/semgate/libsemgate.so   (nvcc 12.9, -gencode arch=compute_100a,code=sm_100a); tools/sass_evidence.py")
     print("mnemonics: UTCHMMA = tcgen05.mma (.2CTA = cta_group::2), UTMALDG = TMA tensor load (cp.async.bulk.tensor; .MULTICAST = multicast::cluster),")
+    print("           UBLKCP = cp.async.bulk (non-tensor TMA bulk copy global -> shared, mbarrier completion; K3's dense-list kernel),")
     print("           LDTM = tcgen05.ld (TMEM -> registers), UTCBAR = tcgen05.commit (mbarrier arrive), SYNCS = mbarrier ops, UCGABAR = barrier.cluster,")
     print("           REDUX = warp reduce, SHFL = warp shuffle, HMMA = legacy mma.sync (none expected)\n")
     cur, counts, ex = None, None, None
@@ -25,7 +26,7 @@ def main():
     def flush():
         if cur is None:
             return
-        if not any(k.startswith(("UTCHMMA", "UTMALDG", "LDTM")) for k in counts):
+        if not any(k.startswith(("UTCHMMA", "UTMALDG", "LDTM", "UBLKCP")) for k in counts):
             print(f"== {cur}\n   (no tensor-core / TMA instructions) " + ", ".join(f"{k} x{v}" for k, v in sorted(counts.items()) if k.startswith(("REDUX", "SHFL", "ATOM", "RED", "DADD"))))
             return
         print(f"== {cur}")
