@@ -4,7 +4,7 @@
 
 Variants: K1 (block / cluster form), K2 <1,1>, <2,1>, <2,2>, symmetric <2,1,SYM> (run table, super-rows, overflow ->
 armed full sweep, one part of a split), multi-pass k > 64, dense output, K3 (thread-per-row, block-per-row, peers'
-row slice, sorted lists), K4 (+ valid-only, row slice), statistics, gate, K5 re-rank (single-CTA and pair forms) + select,
+row slice, sorted lists, the dense-list kernel), K4 (+ valid-only, row slice), statistics, gate, K5 re-rank (single-CTA and pair forms) + select,
 K6 streaming query, spatial join, K2 with one / two epilogue sets, the one-call sweep (K3 -> K4 hand-off).
 Every result is compared with the plain path where one exists, so a silent corruption also fails the run.
 """
@@ -117,6 +117,24 @@ def main():
     ms = eng.merge_topk(ks, 25, want_keys=True)
     want = torch.sort(ks.permute(1, 0, 2).reshape(66000, 75), dim=1, descending=True).values[:, :25]
     assert torch.equal(ms.keys, want), "sorted-list merge"
+    # K3: that was the dense-list kernel (bulk copies); the network kernel on the same lists, a row slice that starts at an odd
+    # row (plain loads), even k (pitched rows), unsorted lists (sorting network)
+    eng.set_option("k3_dense", 0)
+    assert torch.equal(eng.merge_topk(ks, 25, want_keys=True).keys, want), "network kernel"
+    eng.set_option("k3_dense", 1)
+    tab = torch.tensor([ks[g].data_ptr() for g in range(3)], dtype=torch.int64, device=dev)
+    assert torch.equal(eng.merge_topk_peers_rows(tab.data_ptr(), 3, 66000, 25, 33, 65900, want_keys=True).keys, want[33:65933]), "dense rows"
+    k10 = torch.randint(1, 2 ** 62, (2, 65600, 10), device=dev, dtype=torch.int64)
+    w10 = torch.sort(k10.permute(1, 0, 2).reshape(65600, 20), dim=1, descending=True).values[:, :10]
+    assert torch.equal(eng.merge_topk(k10, 10, want_keys=True).keys, w10), "dense, even k, unsorted"
+    # pair gate with the label table in shared memory (>= 10 candidates per label)
+    gl = torch.randint(1, 5, (3000,), dtype=torch.int32, device=dev)
+    gq = torch.randint(-1, 3001, (40001,), dtype=torch.int32, device=dev)
+    gm = torch.randint(0, 3000, (40001,), dtype=torch.int32, device=dev)
+    gv, gc = eng.gate_candidates(gl, gq, gm, 0)
+    okq = (gq >= 0) & (gq < 3000)
+    wv = okq & (gl[gq.clamp(0, 2999).long()] == gl[gm.long()])
+    assert torch.equal(gv.bool(), wv) and int(gc[2].item()) == int((~okq).sum().item()), "gate, shared-memory table"
     # spatial join
     pos = np.cumsum(np.random.default_rng(0).normal(size=(600, 3)) * 0.3, axis=0)
     eng.spatial_candidates_host(pos, 2.0, 50)
