@@ -537,7 +537,8 @@ def test_merge_many_rows_sorted_lists(eng, G, k, order):
 
 @pytest.mark.parametrize("G,k,Q,order", [(4, 25, 65536 + 77, "sorted"), (8, 25, 65536 + 31, "mixed"), (3, 32, 65536 + 1, "sorted"),
                                          (2, 10, 70000, "sorted"), (5, 7, 65537, "unsorted"), (1, 25, 65536, "sorted"),
-                                         (4, 25, 65536 + 96, "sparse")])
+                                         (4, 25, 65536 + 96, "sparse"), (3, 5, 65536 + 5, "mixed"), (8, 10, 65536 + 130, "unsorted"),
+                                         (2, 1, 65536, "sorted"), (3, 30, 65536 + 64, "sorted")])
 def test_merge_dense_lists_kernel(eng, G, k, Q, order):
     """K3's dense-list kernel (lists handed over as arrays: one bulk copy per warp and list, no packing pass, sorted lists
     folded without the sorting network): odd k (bulk copies), even k (pitched rows), k = 32, ragged last warps, one list,
