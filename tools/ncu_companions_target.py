@@ -1,6 +1,6 @@
 """Short profiling target for the HBM-bound companions at the benchmark's shapes: K3 (dense-list kernel, 1M rows x 4 full
-sorted lists of 25), K4 (1M x 25 full lists), the pair gate over K4's output.  Three rounds; capture the third
-(ncu -k regex:"merge_dense|compact_onepass|gate_candidates" -s 6 -c 3)."""
+sorted lists of 25), K4 (1M x 25 full lists), the pair gate over K4's output (2M labels: global gathers; 20 000 labels: table in shared memory).  Three rounds; capture the third
+(ncu -k regex:"merge_dense|compact_onepass|gate_candidates" -s 8 -c 4)."""
 import os
 import sys
 
@@ -20,5 +20,6 @@ for _ in range(3):
     oq, om, os_, ov, tot = eng.compact(res)
     M = Q * k
     eng.gate_candidates(fl, oq[:M] % fl.shape[0], om[:M] % fl.shape[0], 0)
+    eng.gate_candidates(fl[:20000].contiguous(), oq[:M] % 20000, om[:M] % 20000, 0)      # label table in shared memory
 torch.cuda.synchronize()
 print("candidates", int(tot.item()))
