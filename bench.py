@@ -677,17 +677,26 @@ def c1_leg(torch, eng, peak_tf):
         for _ in range(5):
             res = eng.find_loop_closures_device(x, p, ts=ts, floor=fl, use_graph=True)
         side.synchronize()
-        reps = 200
+        reps = 100
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         eng.profile_read()
         l0 = eng.launch_count
-        e0.record(side)
-        for _ in range(reps):
-            res = eng.find_loop_closures_device(x, p, ts=ts, floor=fl, use_graph=True)
-        e1.record(side)
-        side.synchronize()
-        out["us_per_step_graph"] = e0.elapsed_time(e1) / reps * 1e3
-        out["launches_per_step"] = (eng.launch_count - l0) / reps
+        # five batches of 100 replays, median batch (the legs before this one leave the power controller in whatever state
+        # their last kernels put it: single batches of this 60 us step were seen between 57 and 71 us on the same code)
+        time.sleep(0.5)
+        batches = []
+        for _ in range(5):
+            e0.record(side)
+            for _ in range(reps):
+                res = eng.find_loop_closures_device(x, p, ts=ts, floor=fl, use_graph=True)
+            e1.record(side)
+            side.synchronize()
+            batches.append(e0.elapsed_time(e1) / reps * 1e3)
+        batches.sort()
+        out["us_per_step_graph"] = batches[len(batches) // 2]
+        out["us_per_step_graph_batches"] = [round(b, 2) for b in batches]
+        out["launches_per_step"] = (eng.launch_count - l0) / (5 * reps)
+        reps = 200
         e0.record(side)
         for _ in range(reps):
             res3 = eng.compact(eng.gated_topk(x, x, p, q_ts=ts, db_ts=ts, q_floor=fl, db_floor=fl))
