@@ -961,10 +961,12 @@ def run_ours(args):
         outs = tuple(torch.empty((cap,), dtype=dt, pin_memory=True).numpy()
                      for dt in (torch.int32, torch.int32, torch.float32, torch.uint8))
         qh = q_host.numpy()
+        ts_pin, fl_pin = torch.from_numpy(ts_h).pin_memory(), torch.from_numpy(fl_h).pin_memory()   # every input pinned
+        ts_p, fl_p = ts_pin.numpy(), fl_pin.numpy()
         p = mk(0)
 
         def e2e_step():
-            r = eng.find_loop_closures_host(qh, ts_h, fl_h, p, out=outs)   # semgate_find_loop_closures_host
+            r = eng.find_loop_closures_host(qh, ts_p, fl_p, p, out=outs)   # semgate_find_loop_closures_host
             return len(r[0])
         h2d = qh.nbytes + ts_h.nbytes + fl_h.nbytes
     else:
@@ -985,7 +987,8 @@ def run_ours(args):
             torch.cuda.synchronize()
             return t
         h2d = N_Q * DIM * 4 + (ts_h.nbytes + fl_h.nbytes) * world   # one fp32 row shard per rank
-    n_e2e = e2e_step()
+    for _ in range(max(args.warmup, 10)):         # the first calls after the device-resident legs run 5-8 % slower (same-box A/B,
+        n_e2e = e2e_step()                        # tools/e2e_pin_ab.py: 7.0 ms over calls 2-11, 6.5 ms from then on)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -1014,10 +1017,11 @@ def run_ours(args):
         try:
             q16 = torch.from_numpy(desc_h.astype(np.float16)).pin_memory()
             q16n = q16.numpy()
-            n16 = len(eng.find_loop_closures_host(q16n, ts_h, fl_h, p, out=outs)[0])
+            for _ in range(max(args.warmup, 10)):
+                n16 = len(eng.find_loop_closures_host(q16n, ts_p, fl_p, p, out=outs)[0])
             t0 = time.perf_counter()
             for _ in range(e2e_steps):
-                n16 = len(eng.find_loop_closures_host(q16n, ts_h, fl_h, p, out=outs)[0])
+                n16 = len(eng.find_loop_closures_host(q16n, ts_p, fl_p, p, out=outs)[0])
             s16 = time.perf_counter() - t0
             base["e2e_fp16_host_input"] = {
                 "value": pairs_per_step * e2e_steps / s16, "unit": UNIT, "ms_per_step": s16 / e2e_steps * 1e3,
