@@ -786,6 +786,33 @@ merge_dense_kernel(const MergeLaunch a) {
   __syncwarp();
   if (a.count && lane < rows_here) a.count[wrow0 + lane] = a.count_add ? a.count[wrow0 + lane] + cnt : cnt;
   const bool gate = a.valid != nullptr && a.max_floor_diff >= 0 && a.q_floor != nullptr && a.db_floor != nullptr;
+  if constexpr (KT > 0) {
+    // the common case -- a full warp of rows, plain [Q,k] outputs, k known at compile time -- unrolled: slot e = 32 j + lane of
+    // the warp's block sits at a literal offset of every array, its row is a division by a constant
+    if (rows_here == 32 && a.out_stride <= 0 && pitch == KT) {
+      const int64_t o0 = wrow0 * KT + lane;
+#pragma unroll
+      for (int j = 0; j < KT; ++j) {
+        const uint64_t key = outk[32 * j + lane];
+        const bool got = key != 0ull;
+        const int64_t o = o0 + 32 * j;
+        if (a.keys_out) a.keys_out[o] = key;
+        const uint32_t gi = key_index(key);
+        if (a.scores) a.scores[o] = got ? key_score(key) : __int_as_float(0xff800000);
+        if (a.idx) a.idx[o] = got ? static_cast<int32_t>(gi) : -1;
+        if (a.valid) {
+          bool ok = got;
+          if (got && gate) {
+            const int64_t fi = static_cast<int64_t>(gi) - a.floor_index_offset;
+            ok = fi >= 0 && (a.floor_n <= 0 || fi < a.floor_n) &&
+                 floor_ok(__ldg(a.q_floor + in_wrow0 + (32 * j + lane) / KT), __ldg(a.db_floor + fi), a.max_floor_diff);
+          }
+          a.valid[o] = ok ? 1 : 0;
+        }
+      }
+      return;
+    }
+  }
   int r = r_first, c = c_first;
   for (int e = lane; e < n_keys; e += 32) {
     const uint64_t key = outk[r * pitch + c];
